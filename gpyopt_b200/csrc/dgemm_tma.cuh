@@ -1,0 +1,280 @@
+// FP64 tensor-core GEMM for sm_100a:  C[M,N] (+)= A[M,K] * B[N,K]^T  with both operands K-major
+// (row-major, contraction index contiguous), every dimension a multiple of 128.
+//
+//  * operands arrive by TMA (cp.async.bulk.tensor.3d, SWIZZLE_128B, box 16 x 128 doubles = 16 KiB) into a
+//    4-stage shared-memory ring guarded by full/empty mbarriers; one producer warp, eight consumer warps
+//  * consumers run mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05 has no f64 kind), warp tile 64 x 32,
+//    fragments fetched with conflict-free 16-byte LDS (k index permuted identically for A and B)
+//  * epilogues are fused: plain/transposed store (Cholesky, inverse, W^-1), column sum of squares
+//    (posterior variance, value-only path) and the variance-gradient reduction (k.b and sum_j b_j dk_j/dx)
+//
+// This one kernel is the dense O(n^2)-per-candidate contraction of the path and the
+// workhorse of the refit (K4).  Reference arithmetic it replaces: GPy PosteriorExact._raw_predict
+// (dtrtrs + sum of squares) and GP.predictive_gradients (K* . woodbury_inv GEMM) as called from
+// /root/reference/GPyOpt/models/gpmodel.py:98,136-138.
+#pragma once
+#include "common.cuh"
+#include "kernfun.cuh"
+
+namespace gpo {
+
+constexpr int GEMM_BK = 16;                         // k extent of one pipeline stage (16 doubles = 128 B)
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_TILE_BYTES = TILE * GEMM_BK * 8;  // 16 KiB per operand per stage
+constexpr int GEMM_STAGE_BYTES = 2 * GEMM_TILE_BYTES;
+constexpr int GEMM_CONSUMER_WARPS = 8;
+constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum KRange { KR_FULL = 0, KR_LE_M = 1, KR_GE_N = 2, KR_GE_MAX = 3 };
+enum TileSkip { TS_ALL = 0, TS_LOWER = 1 };
+enum Raster { RO_M_FASTEST = 0, RO_HEAVY_FIRST = 1 };
+enum Epilogue { EPI_STORE = 0, EPI_SUMSQ = 1, EPI_GRAD = 2 };
+
+struct GemmOperand {  // element coordinates of tile (0,0) for batch z: (col0 + z*col_z, row0 + z*row_z, bat0 + z*bat_z)
+  int row0, col0, row_z, col_z, bat0, bat_z;
+};
+
+struct GemmParams {
+  int tiles_m, tiles_n, kblocks;  // in units of 128
+  int krange, tile_skip, raster;
+  GemmOperand a, b;
+  // EPI_STORE
+  double alpha, beta;
+  double* C;
+  long long ldc, c_off_z;  // C element (r,c) of batch z at C[c_off_z*z + (c_row0+r)*ldc + c_col0 + c]
+  int c_row0, c_col0;
+  double* Ct;  // optional transposed copy: Ct[ct_off_z*z + (ct_row0+c)*ldct + ct_col0 + r]
+  long long ldct, ct_off_z;
+  int ct_row0, ct_col0;
+  int sym_diag;  // diagonal tiles: C keeps c<=r, Ct keeps c<r (exactly symmetric result)
+  // EPI_SUMSQ / EPI_GRAD: partial[((z*tiles_m + tile_m)*nvals + v)*ldp + tile_n*128 + col]
+  double* partial;
+  long long ldp;
+  // EPI_GRAD
+  int d, kern;
+  const double* Xt;     // training inputs, SoA [d][ldx]
+  long long ldx;
+  const double* Xs;     // candidates, AoS [N][d] (this chunk's first row)
+  long long n_cand;     // valid candidate rows in the chunk
+  const double* invl;   // [z][d] inverse lengthscales
+  const double* sigf2;  // [z]    kernel variances
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+
+  int tile_m, tile_n;
+  if (p.raster == RO_M_FASTEST) {
+    tile_m = blockIdx.x % p.tiles_m;
+    tile_n = blockIdx.x / p.tiles_m;
+  } else {  // heaviest row blocks (largest k range under KR_LE_M) are dispatched first
+    tile_m = p.tiles_m - 1 - (int)(blockIdx.x / p.tiles_n);
+    tile_n = blockIdx.x % p.tiles_n;
+  }
+  const int z = blockIdx.z;
+  if (p.tile_skip == TS_LOWER && tile_n > tile_m) return;
+
+  int kb_begin = 0, kb_end = p.kblocks;
+  if (p.krange == KR_LE_M) kb_end = min(tile_m + 1, p.kblocks);
+  else if (p.krange == KR_GE_N) kb_begin = tile_n;
+  else if (p.krange == KR_GE_MAX) kb_begin = max(tile_m, tile_n);
+  const int nk = (kb_end - kb_begin) * (TILE / GEMM_BK);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], GEMM_CONSUMER_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp >= GEMM_CONSUMER_WARPS) {
+    // ===================== TMA producer warpgroup (one elected thread issues) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == GEMM_CONSUMER_WARPS && lane == 0) {
+      tma_prefetch_desc(&mapA);
+      tma_prefetch_desc(&mapB);
+      const int a_row = p.a.row0 + z * p.a.row_z + tile_m * TILE, a_col = p.a.col0 + z * p.a.col_z;
+      const int b_row = p.b.row0 + z * p.b.row_z + tile_n * TILE, b_col = p.b.col0 + z * p.b.col_z;
+      const int a_bat = p.a.bat0 + z * p.a.bat_z, b_bat = p.b.bat0 + z * p.b.bat_z;
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % GEMM_STAGES;
+        if (it >= GEMM_STAGES) mbar_wait(&empty_bar[s], ((it / GEMM_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], GEMM_STAGE_BYTES);
+        const int k = kb_begin * TILE + it * GEMM_BK;
+        uint8_t* st = smem + s * GEMM_STAGE_BYTES;
+        tma_load_3d(st, &mapA, &full_bar[s], a_col + k, a_row, a_bat);
+        tma_load_3d(st + GEMM_TILE_BYTES, &mapB, &full_bar[s], b_col + k, b_row, b_bat);
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers: DMMA main loop =====================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+  const int g = lane >> 2, t = lane & 3;
+  const int rr = frag_row(g);
+  double acc[8][4][2];
+#pragma unroll
+  for (int f = 0; f < 8; ++f)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[f][j][0] = acc[f][j][1] = 0.0;
+
+  for (int it = 0; it < nk; ++it) {
+    const int s = it % GEMM_STAGES;
+    mbar_wait(&full_bar[s], (it / GEMM_STAGES) & 1);
+    const uint8_t* sA = smem + s * GEMM_STAGE_BYTES + (wm + rr) * 128;
+    const uint8_t* sB = smem + s * GEMM_STAGE_BYTES + GEMM_TILE_BYTES + (wn + rr) * 128;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int chunk = ((4 * h + t) ^ rr) << 4;  // SWIZZLE_128B: 16-byte chunk index XOR (row & 7)
+      double2 a[8], b[4];
+#pragma unroll
+      for (int f = 0; f < 8; ++f) a[f] = *reinterpret_cast<const double2*>(sA + f * 1024 + chunk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(sB + j * 1024 + chunk);
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_884(acc[f][j][0], acc[f][j][1], a[f].x, b[j].x);
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_884(acc[f][j][0], acc[f][j][1], a[f].y, b[j].y);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  // accumulator (f, j, e) of lane (g, t) is output element
+  //   row = wm + 8 f + frag_row(g),   col = wn + 8 j + (e ? 4 + t : t)      (within the 128 x 128 tile)
+  if constexpr (EPI == EPI_STORE) {
+    const bool diag = p.sym_diag && tile_m == tile_n;
+    double* C = p.C ? p.C + p.c_off_z * z : nullptr;
+    double* Ct = p.Ct ? p.Ct + p.ct_off_z * z : nullptr;
+#pragma unroll
+    for (int f = 0; f < 8; ++f) {
+      const int r = tile_m * TILE + wm + 8 * f + rr;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = tile_n * TILE + wn + 8 * j + (e ? 4 + t : t);
+          double v = p.alpha * acc[f][j][e];
+          if (C && (!diag || c <= r)) {
+            double* dst = C + (long long)(p.c_row0 + r) * p.ldc + p.c_col0 + c;
+            if (p.beta != 0.0) v += p.beta * (*dst);
+            *dst = v;
+          }
+          if (Ct && (!diag || c < r)) Ct[(long long)(p.ct_row0 + c) * p.ldct + p.ct_col0 + r] = v;
+        }
+    }
+  } else {
+    // the pipeline stages are drained (every full barrier was waited on): reuse them as scratch
+    double* red = reinterpret_cast<double*>(smem);  // EPI_SUMSQ: [2][128]; EPI_GRAD: after the coordinates
+    const int half = warp & 1;
+    if constexpr (EPI == EPI_SUMSQ) {
+      named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double s2 = 0.0;
+#pragma unroll
+          for (int f = 0; f < 8; ++f) s2 = fma(acc[f][j][e], acc[f][j][e], s2);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+          if (g == 0) red[half * TILE + wn + 8 * j + (e ? 4 + t : t)] = s2;
+        }
+      named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
+      if (threadIdx.x < TILE) {
+        const int c = threadIdx.x;
+        p.partial[((long long)(z * p.tiles_m + tile_m)) * p.ldp + tile_n * TILE + c] = red[c] + red[TILE + c];
+      }
+    } else {  // EPI_GRAD
+      const int d = p.d;
+      double* xj = reinterpret_cast<double*>(smem);  // [d][128] training rows of this tile, scaled by 1/l
+      double* xi = xj + d * TILE;                    // [d][128] candidate columns of this tile, scaled by 1/l
+      red = xi + d * TILE;                           // [(d+1)][2][128]
+      named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
+      const double* invl = p.invl + (long long)z * d;
+      for (int idx = threadIdx.x; idx < d * TILE; idx += GEMM_CONSUMER_WARPS * 32) {
+        const int q = idx / TILE, r = idx % TILE;
+        xj[idx] = p.Xt[q * p.ldx + tile_m * TILE + r] * invl[q];
+        const long long ci = (long long)tile_n * TILE + r;
+        xi[idx] = (ci < p.n_cand ? p.Xs[ci * d + q] : 0.0) * invl[q];
+      }
+      named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
+      const double sf2 = p.sigf2[z];
+      double s0[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s0[j][0] = s0[j][1] = 0.0;
+#pragma unroll
+      for (int f = 0; f < 8; ++f) {
+        const int r = wm + 8 * f + rr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = wn + 8 * j + (e ? 4 + t : t);
+            double r2 = 0.0;
+            for (int q = 0; q < d; ++q) {
+              const double df = xi[q * TILE + c] - xj[q * TILE + r];
+              r2 = fma(df, df, r2);
+            }
+            double kv, hv;
+            kern_k_h(p.kern, sf2, r2, kv, hv);
+            s0[j][e] = fma(acc[f][j][e], kv, s0[j][e]);
+            acc[f][j][e] *= hv;
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double v = s0[j][e];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (g == 0) red[half * TILE + wn + 8 * j + (e ? 4 + t : t)] = v;
+        }
+      for (int q = 0; q < d; ++q) {
+        double xjr[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) xjr[f] = xj[q * TILE + wm + 8 * f + rr];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = wn + 8 * j + (e ? 4 + t : t);
+            const double xic = xi[q * TILE + c];
+            double v = 0.0;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) v = fma(acc[f][j][e], xic - xjr[f], v);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0) red[((q + 1) * 2 + half) * TILE + c] = v * invl[q];
+          }
+      }
+      named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
+      for (int idx = threadIdx.x; idx < (d + 1) * TILE; idx += GEMM_CONSUMER_WARPS * 32) {
+        const int v = idx / TILE, c = idx % TILE;
+        p.partial[((long long)(z * p.tiles_m + tile_m) * (d + 1) + v) * p.ldp + tile_n * TILE + c] =
+            red[(v * 2) * TILE + c] + red[(v * 2 + 1) * TILE + c];
+      }
+    }
+  }
+}
+
+}  // namespace gpo

@@ -1,0 +1,802 @@
+// C-ABI implementation (include/gpo_b200.h): engine state in HBM, the blocked FP64 refit, and the
+// chunked candidate sweep  K1 (cross-covariance + mean)  ->  DMMA GEMM (variance / variance gradient)
+// ->  K3 (acquisition epilogue)  pipelined over two stream slots.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/gpo_b200.h"
+#include "dgemm_tma.cuh"
+#include "kernels.cuh"
+
+using namespace gpo;
+
+// --------------------------------------------------------------------------------------------------
+// engine
+// --------------------------------------------------------------------------------------------------
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  double* Kt = nullptr;  // [S][nc_ld][n_pad]
+  CUtensorMap mapKt;
+  double* mean = nullptr;     // [S][nc_ld]
+  double* dmean = nullptr;    // [S][d][nc_ld]
+  double* partial = nullptr;  // [S][tiles_m][d+1][nc_ld]
+};
+
+struct gpo_engine {
+  int device = 0;
+  int sm_count = 0;
+  char last_error[512] = {0};
+  bool fitted = false;
+  // problem
+  int n = 0, n_pad = 0, d = 0, S = 0, kern = 0;
+  // capacity the buffers were allocated for
+  int cap_n_pad = 0, cap_d = 0, cap_S = 0;
+  long long nc_ld = 0, user_chunk = 0;
+  // data + hyper-parameters (device)
+  double *Xt = nullptr, *Xaos = nullptr, *Y = nullptr;
+  double *invl = nullptr, *sigf2 = nullptr, *noise = nullptr, *jitter = nullptr;
+  std::vector<double> h_invl, h_sigf2, h_noise;
+  // posterior state (device), each [S][n_pad][n_pad] unless noted
+  double *A = nullptr, *X = nullptr, *U = nullptr, *W = nullptr, *T = nullptr;
+  CUtensorMap mapA, mapX, mapU, mapW, mapT;
+  double *alpha = nullptr, *tmpv = nullptr;                          // [S][n_pad]
+  double *logdet = nullptr, *quad = nullptr, *fmin = nullptr;        // [S]
+  int* info = nullptr;                                               // [S]
+  std::vector<double> h_logdet, h_quad, h_fmin;
+  double* gradpart = nullptr;
+  // sweep
+  Slot slot[2];
+  cudaEvent_t ev_in = nullptr;
+  cudaStream_t fit_stream = nullptr;
+  // host<->device staging (grow-only)
+  double* stage_in = nullptr;  size_t stage_in_bytes = 0;
+  double* stage_out[4] = {nullptr, nullptr, nullptr, nullptr};  size_t stage_out_bytes[4] = {0, 0, 0, 0};
+  // local penalisation
+  int lp_on = 0, lp_K = 0, lp_transform = 0, lp_cap = 0;
+  double *lp_xb = nullptr, *lp_r = nullptr, *lp_s = nullptr;
+  // top-k scratch
+  double* tk_vals[2] = {nullptr, nullptr};  long long* tk_idx[2] = {nullptr, nullptr};  size_t tk_cap = 0;
+  // counters
+  long long launches = 0;
+};
+
+static thread_local char g_create_error[256] = {0};
+
+extern "C" const char* gpo_strerror(int status) {
+  switch (status) {
+    case GPO_OK: return "ok";
+    case GPO_ERR_CUDA: return "CUDA error";
+    case GPO_ERR_NOT_PD: return "not positive definite, even with jitter.";
+    case GPO_ERR_ARG: return "invalid argument";
+    case GPO_ERR_STATE: return "invalid call order (fit the engine first)";
+    case GPO_ERR_NO_DEVICE: return "no usable sm_100 CUDA device (the engine has no CPU fallback)";
+    default: return "unknown status";
+  }
+}
+extern "C" const char* gpo_last_error(const gpo_engine* eng) { return eng ? eng->last_error : g_create_error; }
+extern "C" const char* gpo_version(void) { return "gpo_b200 0.1 (sm_100a, DMMA m8n8k4 + TMA)"; }
+
+#define GPO_FAIL(code, ...)                                              \
+  do {                                                                   \
+    snprintf(eng->last_error, sizeof(eng->last_error), __VA_ARGS__);     \
+    return code;                                                         \
+  } while (0)
+
+// --------------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point fetched at run time: no link dependency on libcuda)
+// --------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// map over a [batch][rows][cols] float64 array, box = 16 (cols) x 128 (rows) x 1, SWIZZLE_128B
+static int make_map(gpo_engine* eng, CUtensorMap* map, double* base, long long cols, long long rows, long long batch) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 8, (cuuint64_t)cols * rows * 8};
+  cuuint32_t box[3] = {GEMM_BK, TILE, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return GPO_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// GEMM launcher
+// --------------------------------------------------------------------------------------------------
+static bool g_gemm_attr_set = false;
+static int gemm_setup(gpo_engine* eng) {
+  if (g_gemm_attr_set) return GPO_OK;
+  GPO_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPO_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<EPI_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPO_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<EPI_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPO_CUDA_OK(cudaFuncSetAttribute(diag_chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+  g_gemm_attr_set = true;
+  return GPO_OK;
+}
+
+static int launch_gemm(gpo_engine* eng, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int batch,
+                       cudaStream_t st) {
+  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), 1, (unsigned)batch);
+  if (epi == EPI_STORE) dgemm_nt_kernel<EPI_STORE><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
+  else if (epi == EPI_SUMSQ) dgemm_nt_kernel<EPI_SUMSQ><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
+  else dgemm_nt_kernel<EPI_GRAD><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  return GPO_OK;
+}
+
+static GemmParams gemm_defaults() {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.alpha = 1.0;
+  return p;
+}
+
+// --------------------------------------------------------------------------------------------------
+// lifetime / allocation
+// --------------------------------------------------------------------------------------------------
+extern "C" int gpo_create(int device, gpo_engine** out) {
+  if (!out) return GPO_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    snprintf(g_create_error, sizeof(g_create_error), "no CUDA device %d (count=%d)", device, count);
+    cudaGetLastError();
+    return GPO_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GPO_ERR_NO_DEVICE;
+  if (prop.major != 10) {
+    snprintf(g_create_error, sizeof(g_create_error), "device %d is sm_%d%d; this engine is built for sm_100a only", device,
+             prop.major, prop.minor);
+    return GPO_ERR_NO_DEVICE;
+  }
+  gpo_engine* eng = new gpo_engine();
+  eng->device = device;
+  eng->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess) { delete eng; return GPO_ERR_CUDA; }
+  for (int i = 0; i < 2; ++i) {
+    cudaStreamCreateWithFlags(&eng->slot[i].stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&eng->slot[i].done, cudaEventDisableTiming);
+  }
+  cudaStreamCreateWithFlags(&eng->fit_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&eng->ev_in, cudaEventDisableTiming);
+  int rc = gemm_setup(eng);
+  if (rc != GPO_OK) {
+    snprintf(g_create_error, sizeof(g_create_error), "%s", eng->last_error);
+    delete eng;
+    return rc;
+  }
+  *out = eng;
+  return GPO_OK;
+}
+
+static void free_state(gpo_engine* eng) {
+  double** ptrs[] = {&eng->Xt, &eng->Xaos, &eng->Y, &eng->invl, &eng->sigf2, &eng->noise, &eng->jitter, &eng->A, &eng->X,
+                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->logdet, &eng->quad, &eng->fmin, &eng->gradpart};
+  for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+  if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
+  for (int i = 0; i < 2; ++i) {
+    Slot& s = eng->slot[i];
+    double** sp[] = {&s.Kt, &s.mean, &s.dmean, &s.partial};
+    for (auto pp : sp) { if (*pp) cudaFree(*pp); *pp = nullptr; }
+  }
+  eng->cap_n_pad = eng->cap_d = eng->cap_S = 0;
+  eng->nc_ld = 0;
+}
+
+extern "C" int gpo_destroy(gpo_engine* eng) {
+  if (!eng) return GPO_OK;
+  cudaSetDevice(eng->device);
+  cudaDeviceSynchronize();
+  free_state(eng);
+  if (eng->stage_in) cudaFree(eng->stage_in);
+  for (int i = 0; i < 4; ++i) if (eng->stage_out[i]) cudaFree(eng->stage_out[i]);
+  if (eng->lp_xb) cudaFree(eng->lp_xb);
+  if (eng->lp_r) cudaFree(eng->lp_r);
+  if (eng->lp_s) cudaFree(eng->lp_s);
+  for (int i = 0; i < 2; ++i) {
+    if (eng->tk_vals[i]) cudaFree(eng->tk_vals[i]);
+    if (eng->tk_idx[i]) cudaFree(eng->tk_idx[i]);
+    cudaStreamDestroy(eng->slot[i].stream);
+    cudaEventDestroy(eng->slot[i].done);
+  }
+  cudaStreamDestroy(eng->fit_stream);
+  cudaEventDestroy(eng->ev_in);
+  delete eng;
+  return GPO_OK;
+}
+
+extern "C" int gpo_set_chunk(gpo_engine* eng, long long chunk) {
+  if (!eng || chunk < 0) return GPO_ERR_ARG;
+  eng->user_chunk = chunk;
+  eng->cap_n_pad = 0;  // force re-allocation of the sweep buffers at the next fit
+  return GPO_OK;
+}
+
+extern "C" int gpo_launch_count(gpo_engine* eng, long long* launches, int reset) {
+  if (!eng) return GPO_ERR_ARG;
+  if (launches) *launches = eng->launches;
+  if (reset) eng->launches = 0;
+  return GPO_OK;
+}
+
+// choose the chunk (candidates per sweep step): K*^T chunk <= ~160 MB per slot, and a tile count that
+// fills whole waves of the SMs
+static long long pick_chunk(const gpo_engine* eng, int n_pad, int S) {
+  if (eng->user_chunk > 0) return ((eng->user_chunk + TILE - 1) / TILE) * TILE;
+  const double budget = 160.0 * 1024 * 1024;
+  long long max_tiles_n = (long long)(budget / ((double)S * n_pad * 8.0 * TILE));
+  max_tiles_n = std::max(1LL, std::min(max_tiles_n, 128LL));
+  const int tiles_m = n_pad / TILE;
+  long long best = max_tiles_n;
+  double best_eff = 0.0;
+  for (long long tn = std::max(1LL, max_tiles_n / 2); tn <= max_tiles_n; ++tn) {
+    const double total = (double)tiles_m * tn * S;
+    const double eff = total / (std::ceil(total / eng->sm_count) * eng->sm_count);
+    if (eff >= best_eff) { best_eff = eff; best = tn; }
+  }
+  return best * TILE;
+}
+
+static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
+  if (n_pad == eng->cap_n_pad && d == eng->cap_d && S == eng->cap_S) return GPO_OK;
+  GPO_CUDA_OK(cudaDeviceSynchronize());
+  free_state(eng);
+  const size_t nn = (size_t)S * n_pad * n_pad * 8;
+  GPO_CUDA_OK(cudaMalloc(&eng->Xt, (size_t)d * n_pad * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->Xaos, (size_t)d * n_pad * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->Y, (size_t)n_pad * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->invl, (size_t)S * d * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->sigf2, (size_t)S * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->noise, (size_t)S * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->jitter, (size_t)S * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->A, nn));
+  GPO_CUDA_OK(cudaMalloc(&eng->X, nn));
+  GPO_CUDA_OK(cudaMalloc(&eng->U, nn));
+  GPO_CUDA_OK(cudaMalloc(&eng->W, nn));
+  GPO_CUDA_OK(cudaMalloc(&eng->T, nn));
+  GPO_CUDA_OK(cudaMalloc(&eng->alpha, (size_t)S * n_pad * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->tmpv, (size_t)S * n_pad * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->logdet, (size_t)S * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->quad, (size_t)S * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->fmin, (size_t)S * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->info, (size_t)S * sizeof(int)));
+  GPO_CUDA_OK(cudaMalloc(&eng->gradpart, (size_t)S * 256 * (DMAX + 2) * 8));
+  int rc;
+  if ((rc = make_map(eng, &eng->mapA, eng->A, n_pad, n_pad, S))) return rc;
+  if ((rc = make_map(eng, &eng->mapX, eng->X, n_pad, n_pad, S))) return rc;
+  if ((rc = make_map(eng, &eng->mapU, eng->U, n_pad, n_pad, S))) return rc;
+  if ((rc = make_map(eng, &eng->mapW, eng->W, n_pad, n_pad, S))) return rc;
+  if ((rc = make_map(eng, &eng->mapT, eng->T, n_pad, n_pad, S))) return rc;
+  eng->nc_ld = std::max<long long>(pick_chunk(eng, n_pad, S), n_pad);  // >= n_pad: the fmin sweep runs over X itself
+  const int tiles_m = n_pad / TILE;
+  for (int i = 0; i < 2; ++i) {
+    Slot& s = eng->slot[i];
+    GPO_CUDA_OK(cudaMalloc(&s.Kt, (size_t)S * eng->nc_ld * n_pad * 8));
+    GPO_CUDA_OK(cudaMalloc(&s.mean, (size_t)S * eng->nc_ld * 8));
+    GPO_CUDA_OK(cudaMalloc(&s.dmean, (size_t)S * d * eng->nc_ld * 8));
+    GPO_CUDA_OK(cudaMalloc(&s.partial, (size_t)S * tiles_m * (d + 1) * eng->nc_ld * 8));
+    if ((rc = make_map(eng, &s.mapKt, s.Kt, n_pad, eng->nc_ld, S))) return rc;
+  }
+  eng->cap_n_pad = n_pad; eng->cap_d = d; eng->cap_S = S;
+  return GPO_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// K1 dispatch
+// --------------------------------------------------------------------------------------------------
+template <int DP, int CW>
+static void launch_cov_t(const CovParams& p, bool grad, int S, cudaStream_t st) {
+  const long long warps = (p.nc_run + CW - 1) / CW;
+  dim3 grid((unsigned)((warps + 3) / 4), 1, (unsigned)S);
+  if (grad) cov_mean_kernel<DP, CW, true><<<grid, 128, 0, st>>>(p);
+  else cov_mean_kernel<DP, CW, false><<<grid, 128, 0, st>>>(p);
+}
+static int launch_cov(gpo_engine* eng, const CovParams& p, bool grad, int S, cudaStream_t st) {
+  const int d = p.d;
+  if (d <= 2) launch_cov_t<2, 4>(p, grad, S, st);
+  else if (d <= 4) launch_cov_t<4, 4>(p, grad, S, st);
+  else if (d <= 6) launch_cov_t<6, 4>(p, grad, S, st);
+  else if (d <= 8) launch_cov_t<8, 2>(p, grad, S, st);
+  else if (d <= 12) launch_cov_t<12, 2>(p, grad, S, st);
+  else launch_cov_t<16, 2>(p, grad, S, st);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  return GPO_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// refit (K4): blocked right-looking Cholesky, recursive triangular inverse, W^-1 = L^-T L^-1, alpha, fmin
+// --------------------------------------------------------------------------------------------------
+struct TriNode { int lo, mid, hi; };
+static void build_tree(int lo, int hi, int depth, std::vector<std::vector<TriNode>>& levels) {
+  if (hi - lo <= 1) return;
+  int half = 1;
+  while (half * 2 < hi - lo) half *= 2;  // largest power of two < size (== size/2 when size is a power of two)
+  const int mid = lo + half;
+  build_tree(lo, mid, depth + 1, levels);
+  build_tree(mid, hi, depth + 1, levels);
+  if ((int)levels.size() <= depth) levels.resize(depth + 1);
+  levels[depth].push_back({lo, mid, hi});
+}
+
+static int factorize(gpo_engine* eng, cudaStream_t st) {
+  const int n_pad = eng->n_pad, S = eng->S, nb = n_pad / TILE;
+  const long long nn = (long long)n_pad * n_pad;
+  int rc;
+  {
+    dim3 blk(16, 16), grd(n_pad / 16, n_pad / 16, S);
+    gram_kernel<<<grd, blk, 0, st>>>(eng->A, eng->Xt, n_pad, eng->n, n_pad, eng->d, eng->kern, eng->invl, eng->sigf2,
+                                     eng->noise, eng->jitter);
+    eng->launches++;
+  }
+  GPO_CUDA_OK(cudaMemsetAsync(eng->info, 0, S * sizeof(int), st));
+  GPO_CUDA_OK(cudaMemsetAsync(eng->X, 0, (size_t)S * nn * 8, st));
+  GPO_CUDA_OK(cudaMemsetAsync(eng->U, 0, (size_t)S * nn * 8, st));
+  for (int kb = 0; kb < nb; ++kb) {
+    diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb, eng->info);
+    eng->launches++;
+    const int rem = nb - kb - 1;
+    if (rem == 0) break;
+    // panel: A[kb+1:, kb] <- A[kb+1:, kb] * L_kk^-T       (B operand = rows of X_kk)
+    GemmParams p = gemm_defaults();
+    p.tiles_m = rem; p.tiles_n = 1; p.kblocks = 1;
+    p.a = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};
+    p.b = {kb * TILE, kb * TILE, 0, 0, 0, 1};
+    p.C = eng->A; p.ldc = n_pad; p.c_off_z = nn; p.c_row0 = (kb + 1) * TILE; p.c_col0 = kb * TILE;
+    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapX, p, S, st))) return rc;
+    // trailing update (lower tiles): A[kb+1:, kb+1:] -= P P^T
+    GemmParams q = gemm_defaults();
+    q.tiles_m = rem; q.tiles_n = rem; q.kblocks = 1; q.tile_skip = TS_LOWER;
+    q.a = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};
+    q.b = q.a;
+    q.alpha = -1.0; q.beta = 1.0;
+    q.C = eng->A; q.ldc = n_pad; q.c_off_z = nn; q.c_row0 = (kb + 1) * TILE; q.c_col0 = (kb + 1) * TILE;
+    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, q, S, st))) return rc;
+  }
+  // triangular inverse, recursively: X21 = -X22 (L21 X11)
+  std::vector<std::vector<TriNode>> levels;
+  build_tree(0, nb, 0, levels);
+  for (int lv = (int)levels.size() - 1; lv >= 0; --lv) {
+    for (const TriNode& nd : levels[lv]) {
+      const int r = nd.hi - nd.mid, c = nd.mid - nd.lo;
+      // T^T stored at Tbuf[lo:mid, mid:hi]:  T = L21 X11, B operand = U11 = X11^T (k >= n block)
+      GemmParams p = gemm_defaults();
+      p.tiles_m = r; p.tiles_n = c; p.kblocks = c; p.krange = KR_GE_N;
+      p.a = {nd.mid * TILE, nd.lo * TILE, 0, 0, 0, 1};
+      p.b = {nd.lo * TILE, nd.lo * TILE, 0, 0, 0, 1};
+      p.Ct = eng->T; p.ldct = n_pad; p.ct_off_z = nn; p.ct_row0 = nd.lo * TILE; p.ct_col0 = nd.mid * TILE;
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapU, p, S, st))) return rc;
+      // X21 = -X22 T  (A = X22 lower: k <= m block; B[n][k] = T[k][n] = Tbuf[lo+n][mid+k]); also U12 = X21^T
+      GemmParams q = gemm_defaults();
+      q.tiles_m = r; q.tiles_n = c; q.kblocks = r; q.krange = KR_LE_M;
+      q.a = {nd.mid * TILE, nd.mid * TILE, 0, 0, 0, 1};
+      q.b = {nd.lo * TILE, nd.mid * TILE, 0, 0, 0, 1};
+      q.alpha = -1.0;
+      q.C = eng->X; q.ldc = n_pad; q.c_off_z = nn; q.c_row0 = nd.mid * TILE; q.c_col0 = nd.lo * TILE;
+      q.Ct = eng->U; q.ldct = n_pad; q.ct_off_z = nn; q.ct_row0 = nd.lo * TILE; q.ct_col0 = nd.mid * TILE;
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapX, eng->mapT, q, S, st))) return rc;
+    }
+  }
+  // W^-1 = L^-T L^-1 = U U^T  (k >= max(m, n) block), lower tiles mirrored into the upper ones
+  {
+    GemmParams p = gemm_defaults();
+    p.tiles_m = nb; p.tiles_n = nb; p.kblocks = nb; p.krange = KR_GE_MAX; p.tile_skip = TS_LOWER;
+    p.a = {0, 0, 0, 0, 0, 1};
+    p.b = p.a;
+    p.C = eng->W; p.ldc = n_pad; p.c_off_z = nn;
+    p.Ct = eng->W; p.ldct = n_pad; p.ct_off_z = nn;
+    p.sym_diag = 1;
+    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapU, eng->mapU, p, S, st))) return rc;
+  }
+  return GPO_OK;
+}
+
+static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool want_kt_only, int with_noise, long long N,
+                 const double* Xs, double* o0, double* o1, double* o2, double* o3, cudaStream_t user);
+
+extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* X, const double* Y, int S,
+                       const double* variance, const double* lengthscale, const double* noise) {
+  if (!eng) return GPO_ERR_ARG;
+  if (n < 1 || d < 1 || d > DMAX || S < 1 || !X || !Y || !variance || !lengthscale || !noise || kernel < 0 || kernel > 2)
+    GPO_FAIL(GPO_ERR_ARG, "gpo_fit: bad argument (n=%d d=%d S=%d kernel=%d; d must be <= %d)", n, d, S, kernel, DMAX);
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  const int n_pad = ((n + TILE - 1) / TILE) * TILE;
+  int rc = ensure_capacity(eng, n_pad, d, S);
+  if (rc) return rc;
+  eng->fitted = false;
+  eng->n = n; eng->n_pad = n_pad; eng->d = d; eng->S = S; eng->kern = kernel;
+  cudaStream_t st = eng->fit_stream;
+  // upload data (SoA + AoS) and hyper-parameters
+  std::vector<double> xt((size_t)d * n_pad, 0.0), xa((size_t)n_pad * d, 0.0), yy((size_t)n_pad, 0.0);
+  for (int i = 0; i < n; ++i) {
+    for (int q = 0; q < d; ++q) { xt[(size_t)q * n_pad + i] = X[(size_t)i * d + q]; xa[(size_t)i * d + q] = X[(size_t)i * d + q]; }
+    yy[i] = Y[i];
+  }
+  eng->h_invl.assign((size_t)S * d, 0.0); eng->h_sigf2.assign(variance, variance + S); eng->h_noise.assign(noise, noise + S);
+  for (int i = 0; i < S * d; ++i) eng->h_invl[i] = 1.0 / lengthscale[i];
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->Xt, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->Xaos, xa.data(), xa.size() * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->Y, yy.data(), yy.size() * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->invl, eng->h_invl.data(), (size_t)S * d * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->sigf2, variance, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->noise, noise, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+
+  // GPy jitchol ladder: plain attempt, then jitter = mean(diag Ky) * 1e-6 * 10^t, t = 0..4.
+  // A hyper-parameter set that factorises keeps jitter 0; only failing sets are retried.
+  std::vector<double> jit(S, 0.0);
+  std::vector<int> info(S, 0), tries(S, 0);
+  for (int attempt = 0; attempt <= 6; ++attempt) {
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->jitter, jit.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = factorize(eng, st))) return rc;
+    GPO_CUDA_OK(cudaMemcpyAsync(info.data(), eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+    bool any = false;
+    for (int z = 0; z < S; ++z) {
+      if (info[z] == 0) continue;
+      any = true;
+      // Ky's diagonal is sigf2 + noise + 1e-8 (stationary kernel): always > 0, so GPy's "diag <= 0" exit never fires
+      if (tries[z] >= 5) GPO_FAIL(GPO_ERR_NOT_PD, "not positive definite, even with jitter.");
+      const double diag_mean = eng->h_sigf2[z] + eng->h_noise[z] + 1e-8;
+      jit[z] = diag_mean * 1e-6 * std::pow(10.0, tries[z]);
+      tries[z]++;
+    }
+    if (!any) break;
+  }
+  // alpha = L^-T (L^-1 y)
+  {
+    dim3 grd((n_pad + 7) / 8, S);
+    // Y is shared by all hyper-parameter sets: broadcast by reading with a zero batch stride
+    for (int z = 0; z < S; ++z)
+      GPO_CUDA_OK(cudaMemcpyAsync(eng->alpha + (size_t)z * n_pad, eng->Y, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, st));
+    gemv_kernel<<<grd, 256, 0, st>>>(eng->X, eng->alpha, eng->tmpv, n_pad, 0);
+    gemv_kernel<<<grd, 256, 0, st>>>(eng->U, eng->tmpv, eng->alpha, n_pad, 1);
+    eng->launches += 2;
+    GPO_CUDA_OK(cudaGetLastError());
+  }
+  GPO_CUDA_OK(cudaStreamSynchronize(st));
+  eng->fitted = true;
+  // fmin = min_i mean(X_i): GPModel.get_fmin (gpmodel.py:129) -- a K1 sweep over the training inputs
+  {
+    Slot& s = eng->slot[0];
+    CovParams cp;
+    cp.Xs = eng->Xaos; cp.n_cand = n; cp.nc_run = n_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n; cp.n_pad = n_pad;
+    cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
+    cp.Kt = nullptr; cp.mean = s.mean; cp.dmean = nullptr;
+    if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
+    fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, s.mean, eng->nc_ld, n, n_pad, eng->logdet, eng->quad,
+                                          eng->fmin);
+    eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
+    eng->h_logdet.resize(S); eng->h_quad.resize(S); eng->h_fmin.resize(S);
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->h_logdet.data(), eng->logdet, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->h_quad.data(), eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->h_fmin.data(), eng->fmin, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return GPO_OK;
+}
+
+extern "C" int gpo_get_fmin(gpo_engine* eng, double* fmin) {
+  if (!eng || !fmin) return GPO_ERR_ARG;
+  if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_get_fmin before gpo_fit");
+  for (int z = 0; z < eng->S; ++z) fmin[z] = eng->h_fmin[z];
+  return GPO_OK;
+}
+
+extern "C" int gpo_get_loglik(gpo_engine* eng, double* loglik, double* logdet) {
+  if (!eng) return GPO_ERR_ARG;
+  if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_get_loglik before gpo_fit");
+  for (int z = 0; z < eng->S; ++z) {
+    if (logdet) logdet[z] = eng->h_logdet[z];
+    if (loglik) loglik[z] = 0.5 * (-(double)eng->n * 1.8378770664093453 - eng->h_logdet[z] - eng->h_quad[z]);
+  }
+  return GPO_OK;
+}
+
+extern "C" int gpo_get_loglik_grad(gpo_engine* eng, double* grad) {
+  if (!eng || !grad) return GPO_ERR_ARG;
+  if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_get_loglik_grad before gpo_fit");
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  const int S = eng->S, d = eng->d, nblk = 256;
+  cudaStream_t st = eng->fit_stream;
+  dim3 grd(nblk, S);
+  loglik_grad_kernel<<<grd, 256, 0, st>>>(eng->W, eng->alpha, eng->Xt, eng->n_pad, eng->n, eng->n_pad, d, eng->kern, eng->invl,
+                                          eng->sigf2, eng->gradpart);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  std::vector<double> part((size_t)S * nblk * (d + 2));
+  GPO_CUDA_OK(cudaMemcpyAsync(part.data(), eng->gradpart, part.size() * 8, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaStreamSynchronize(st));
+  for (int z = 0; z < S; ++z)
+    for (int q = 0; q < d + 2; ++q) {
+      double s = 0.0;
+      for (int b = 0; b < nblk; ++b) s += part[((size_t)z * nblk + b) * (d + 2) + q];
+      grad[(size_t)z * (d + 2) + q] = s;
+    }
+  return GPO_OK;
+}
+
+extern "C" int gpo_get_state(gpo_engine* eng, double* L, double* Linv, double* Winv, double* alpha) {
+  if (!eng) return GPO_ERR_ARG;
+  if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_get_state before gpo_fit");
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  const int n = eng->n, n_pad = eng->n_pad, S = eng->S;
+  const double* src[3] = {eng->A, eng->X, eng->W};
+  double* dst[3] = {L, Linv, Winv};
+  for (int m = 0; m < 3; ++m)
+    if (dst[m])
+      for (int z = 0; z < S; ++z)
+        GPO_CUDA_OK(cudaMemcpy2D(dst[m] + (size_t)z * n * n, (size_t)n * 8, src[m] + (size_t)z * n_pad * n_pad, (size_t)n_pad * 8,
+                                 (size_t)n * 8, n, cudaMemcpyDeviceToHost));
+  if (alpha)
+    GPO_CUDA_OK(cudaMemcpy2D(alpha, (size_t)n * 8, eng->alpha, (size_t)n_pad * 8, (size_t)n * 8, S, cudaMemcpyDeviceToHost));
+  return GPO_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// candidate sweep
+// --------------------------------------------------------------------------------------------------
+static bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int grow(gpo_engine* eng, double** buf, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return GPO_OK;
+  GPO_CUDA_OK(cudaDeviceSynchronize());
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr; *cap = 0;
+  GPO_CUDA_OK(cudaMalloc(buf, bytes));
+  *cap = bytes;
+  return GPO_OK;
+}
+
+// kind == ACQ_NONE: predict  (o0 = m [S][N], o1 = s [S][N], o2 = dmdx [S][N][d], o3 = dsdx [S][N][d])
+// otherwise:        acquisition (o0 = f [N], o1 = df [N][d])
+static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused*/, int with_noise, long long N,
+                 const double* Xs, double* o0, double* o1, double* o2, double* o3, cudaStream_t user) {
+  if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "sweep before gpo_fit");
+  if (N <= 0) return GPO_OK;
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  const int S = eng->S, d = eng->d, n_pad = eng->n_pad, tiles_m = n_pad / TILE;
+  const bool predict = kind == ACQ_NONE;
+  const bool in_dev = is_device_ptr(Xs);
+  double* outs[4] = {o0, o1, o2, o3};
+  // bytes per candidate row of each output, and number of batch planes
+  size_t row_bytes[4]; int planes[4];
+  if (predict) { row_bytes[0] = row_bytes[1] = 8; row_bytes[2] = row_bytes[3] = (size_t)d * 8; for (int i = 0; i < 4; ++i) planes[i] = S; }
+  else { row_bytes[0] = 8; row_bytes[1] = (size_t)d * 8; row_bytes[2] = row_bytes[3] = 0; planes[0] = planes[1] = 1; planes[2] = planes[3] = 0; }
+  double* dev_out[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool out_dev[4] = {true, true, true, true};
+  int rc;
+  for (int i = 0; i < 4; ++i) {
+    if (!outs[i]) continue;
+    out_dev[i] = is_device_ptr(outs[i]);
+    if (out_dev[i]) dev_out[i] = outs[i];
+    else {
+      if ((rc = grow(eng, &eng->stage_out[i], &eng->stage_out_bytes[i], (size_t)planes[i] * N * row_bytes[i]))) return rc;
+      dev_out[i] = eng->stage_out[i];
+    }
+  }
+  const double* dev_in = Xs;
+  if (!in_dev) {
+    if ((rc = grow(eng, &eng->stage_in, &eng->stage_in_bytes, (size_t)N * d * 8))) return rc;
+    dev_in = eng->stage_in;
+  }
+  GPO_CUDA_OK(cudaEventRecord(eng->ev_in, user));
+  for (int i = 0; i < 2; ++i) GPO_CUDA_OK(cudaStreamWaitEvent(eng->slot[i].stream, eng->ev_in, 0));
+
+  const long long chunk = eng->nc_ld;
+  int ci = 0;
+  for (long long off = 0; off < N; off += chunk, ++ci) {
+    Slot& s = eng->slot[ci & 1];
+    cudaStream_t st = s.stream;
+    const long long rows = std::min(chunk, N - off);
+    const long long nc_run = ((rows + TILE - 1) / TILE) * TILE;
+    const int tiles_n = (int)(nc_run / TILE);
+    if (!in_dev)
+      GPO_CUDA_OK(cudaMemcpyAsync(eng->stage_in + off * d, Xs + off * d, (size_t)rows * d * 8, cudaMemcpyHostToDevice, st));
+    // K1
+    CovParams cp;
+    cp.Xs = dev_in + off * d; cp.n_cand = rows; cp.nc_run = nc_run; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad;
+    cp.n = eng->n; cp.n_pad = n_pad; cp.d = d; cp.kern = eng->kern; cp.alpha = eng->alpha; cp.invl = eng->invl;
+    cp.sigf2 = eng->sigf2; cp.Kt = s.Kt; cp.mean = s.mean; cp.dmean = s.dmean;
+    if ((rc = launch_cov(eng, cp, grad, S, st))) return rc;
+    // variance GEMM
+    GemmParams g = gemm_defaults();
+    g.tiles_m = tiles_m; g.tiles_n = tiles_n; g.kblocks = tiles_m;
+    g.a = {0, 0, 0, 0, 0, 1};
+    g.b = {0, 0, 0, 0, 0, 1};
+    g.partial = s.partial; g.ldp = eng->nc_ld;
+    if (grad) {
+      g.krange = KR_FULL; g.raster = RO_M_FASTEST;
+      g.d = d; g.kern = eng->kern; g.Xt = eng->Xt; g.ldx = n_pad; g.Xs = dev_in + off * d; g.n_cand = rows;
+      g.invl = eng->invl; g.sigf2 = eng->sigf2;
+      if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s.mapKt, g, S, st))) return rc;
+    } else {
+      g.krange = KR_LE_M; g.raster = RO_HEAVY_FIRST;
+      if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, g, S, st))) return rc;
+    }
+    // K3
+    AcqParams ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.n_cand = rows; ap.nc_pad = eng->nc_ld; ap.S = S; ap.d = d; ap.tiles_m = tiles_m; ap.grad = grad ? 1 : 0;
+    ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = s.partial; ap.sigf2 = eng->sigf2;
+    ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par;
+    if (predict) {
+      ap.out_m = dev_out[0] + off; ap.out_s = dev_out[1] + off;
+      ap.out_dm = dev_out[2] ? dev_out[2] + off * d : nullptr; ap.out_ds = dev_out[3] ? dev_out[3] + off * d : nullptr;
+      ap.out_ldN = N;
+    } else {
+      ap.out_f = dev_out[0] + off; ap.out_df = dev_out[1] ? dev_out[1] + off * d : nullptr;
+      ap.lp_on = eng->lp_on; ap.lp_K = eng->lp_K; ap.lp_transform = eng->lp_transform;
+      ap.lp_xb = eng->lp_xb; ap.lp_r = eng->lp_r; ap.lp_s = eng->lp_s; ap.Xs = dev_in + off * d;
+    }
+    acq_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(ap);
+    eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
+    // results back to host memory, chunk by chunk
+    for (int i = 0; i < 4; ++i) {
+      if (!outs[i] || out_dev[i]) continue;
+      GPO_CUDA_OK(cudaMemcpy2DAsync((char*)outs[i] + off * row_bytes[i], (size_t)N * row_bytes[i],
+                                    (char*)dev_out[i] + off * row_bytes[i], (size_t)N * row_bytes[i],
+                                    (size_t)rows * row_bytes[i], planes[i], cudaMemcpyDeviceToHost, st));
+    }
+  }
+  bool any_host = !in_dev;
+  for (int i = 0; i < 4; ++i) if (outs[i] && !out_dev[i]) any_host = true;
+  for (int i = 0; i < 2; ++i) {
+    GPO_CUDA_OK(cudaEventRecord(eng->slot[i].done, eng->slot[i].stream));
+    GPO_CUDA_OK(cudaStreamWaitEvent(user, eng->slot[i].done, 0));
+  }
+  if (any_host) {
+    for (int i = 0; i < 2; ++i) GPO_CUDA_OK(cudaStreamSynchronize(eng->slot[i].stream));
+  }
+  return GPO_OK;
+}
+
+extern "C" int gpo_predict(gpo_engine* eng, long long N, const double* Xs, int with_noise, double* m, double* s, void* stream) {
+  if (!eng || !Xs || !m || !s || N < 0) return GPO_ERR_ARG;
+  return sweep(eng, ACQ_NONE, 0.0, false, false, with_noise, N, Xs, m, s, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int gpo_predict_grad(gpo_engine* eng, long long N, const double* Xs, double* m, double* s, double* dmdx, double* dsdx,
+                                void* stream) {
+  if (!eng || !Xs || !m || !s || !dmdx || !dsdx || N < 0) return GPO_ERR_ARG;
+  return sweep(eng, ACQ_NONE, 0.0, true, false, 1, N, Xs, m, s, dmdx, dsdx, (cudaStream_t)stream);
+}
+
+extern "C" int gpo_acq(gpo_engine* eng, int kind, double par, long long N, const double* Xs, double* f, double* df, void* stream) {
+  if (!eng || !Xs || !f || N < 0 || kind < 0 || kind > 5) return GPO_ERR_ARG;
+  return sweep(eng, kind, par, df != nullptr, false, 1, N, Xs, f, df, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int gpo_lp_set(gpo_engine* eng, int K, const double* Xb, const double* r, const double* s, int transform) {
+  if (!eng || K < 0) return GPO_ERR_ARG;
+  if (transform < 0) { eng->lp_on = 0; eng->lp_K = 0; return GPO_OK; }
+  if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_lp_set before gpo_fit");
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  GPO_CUDA_OK(cudaDeviceSynchronize());
+  if (K > eng->lp_cap) {
+    if (eng->lp_xb) cudaFree(eng->lp_xb);
+    if (eng->lp_r) cudaFree(eng->lp_r);
+    if (eng->lp_s) cudaFree(eng->lp_s);
+    eng->lp_cap = std::max(K, 64);
+    GPO_CUDA_OK(cudaMalloc(&eng->lp_xb, (size_t)eng->lp_cap * DMAX * 8));
+    GPO_CUDA_OK(cudaMalloc(&eng->lp_r, (size_t)eng->lp_cap * 8));
+    GPO_CUDA_OK(cudaMalloc(&eng->lp_s, (size_t)eng->lp_cap * 8));
+  }
+  if (K > 0) {
+    if (!Xb || !r || !s) return GPO_ERR_ARG;
+    GPO_CUDA_OK(cudaMemcpy(eng->lp_xb, Xb, (size_t)K * eng->d * 8, cudaMemcpyHostToDevice));
+    GPO_CUDA_OK(cudaMemcpy(eng->lp_r, r, (size_t)K * 8, cudaMemcpyHostToDevice));
+    GPO_CUDA_OK(cudaMemcpy(eng->lp_s, s, (size_t)K * 8, cudaMemcpyHostToDevice));
+  }
+  eng->lp_on = 1; eng->lp_K = K; eng->lp_transform = transform;
+  return GPO_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// top-k
+// --------------------------------------------------------------------------------------------------
+static int topk_device(gpo_engine* eng, long long N, const double* v_dev, int k, int largest, double* vals, long long* idx,
+                       cudaStream_t st) {
+  if (k < 1 || k > TOPK_SEG / 2) GPO_FAIL(GPO_ERR_ARG, "top-k: k must be in [1, %d]", TOPK_SEG / 2);
+  const long long kk = std::min<long long>(k, N);
+  size_t need = (size_t)((N + TOPK_SEG - 1) / TOPK_SEG) * k;
+  if (need > eng->tk_cap) {
+    GPO_CUDA_OK(cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) {
+      if (eng->tk_vals[i]) cudaFree(eng->tk_vals[i]);
+      if (eng->tk_idx[i]) cudaFree(eng->tk_idx[i]);
+      GPO_CUDA_OK(cudaMalloc(&eng->tk_vals[i], need * 8));
+      GPO_CUDA_OK(cudaMalloc(&eng->tk_idx[i], need * 8));
+    }
+    eng->tk_cap = need;
+  }
+  const double sign = largest ? -1.0 : 1.0;
+  long long cur = N;
+  const double* cv = v_dev;
+  const long long* cidx = nullptr;
+  int pp = 0;
+  while (true) {
+    const long long blocks = (cur + TOPK_SEG - 1) / TOPK_SEG;
+    topk_level_kernel<<<(unsigned)blocks, TOPK_THREADS, 0, st>>>(cv, cidx, cur, k, sign, eng->tk_vals[pp], eng->tk_idx[pp]);
+    eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
+    cv = eng->tk_vals[pp]; cidx = eng->tk_idx[pp];
+    cur = blocks * k;
+    pp ^= 1;
+    if (blocks == 1) break;
+  }
+  std::vector<double> hv(k);
+  std::vector<long long> hi(k);
+  GPO_CUDA_OK(cudaMemcpyAsync(hv.data(), cv, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(hi.data(), cidx, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaStreamSynchronize(st));
+  for (long long i = 0; i < kk; ++i) { vals[i] = sign * hv[i]; idx[i] = hi[i]; }
+  for (long long i = kk; i < k; ++i) { vals[i] = NAN; idx[i] = -1; }
+  return GPO_OK;
+}
+
+extern "C" int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, int largest, double* vals, long long* idx,
+                        void* stream) {
+  if (!eng || !v || !vals || !idx || N < 1) return GPO_ERR_ARG;
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const double* dv = v;
+  if (!is_device_ptr(v)) {
+    int rc = grow(eng, &eng->stage_out[0], &eng->stage_out_bytes[0], (size_t)N * 8);
+    if (rc) return rc;
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->stage_out[0], v, (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    dv = eng->stage_out[0];
+  }
+  return topk_device(eng, N, dv, k, largest, vals, idx, st);
+}
+
+extern "C" int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, const double* Xs, int k, double* vals,
+                            long long* idx, double* f_out, void* stream) {
+  if (!eng || !Xs || !vals || !idx || N < 1 || kind < 0 || kind > 5) return GPO_ERR_ARG;
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  double* f_dev;
+  const bool f_is_dev = f_out && is_device_ptr(f_out);
+  if (f_is_dev) f_dev = f_out;
+  else {
+    if ((rc = grow(eng, &eng->stage_out[2], &eng->stage_out_bytes[2], (size_t)N * 8))) return rc;
+    f_dev = eng->stage_out[2];
+  }
+  if ((rc = sweep(eng, kind, par, false, false, 1, N, Xs, f_dev, nullptr, nullptr, nullptr, st))) return rc;
+  // smallest score = -f  <=>  largest f (or smallest LP value, which is already a "score to minimise")
+  const int largest = eng->lp_on ? 0 : 1;
+  if ((rc = topk_device(eng, N, f_dev, k, largest, vals, idx, st))) return rc;
+  if (!eng->lp_on) for (int i = 0; i < k; ++i) vals[i] = -vals[i];
+  if (f_out && !f_is_dev) {
+    GPO_CUDA_OK(cudaMemcpyAsync(f_out, f_dev, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return GPO_OK;
+}

@@ -1,0 +1,523 @@
+// Non-GEMM kernels of the path: cross-covariance + mean (K1), Gram build / diagonal-block Cholesky /
+// triangular GEMV (K4 helpers), acquisition epilogue (K3) and top-k selection.
+#pragma once
+#include <cfloat>
+#include "common.cuh"
+#include "kernfun.cuh"
+
+namespace gpo {
+
+constexpr int DMAX = 16;  // largest supported input dimension
+
+// =====================================================================================================
+// K1: fused cross-covariance + posterior mean (+ mean gradient).
+// One warp owns CW candidates; lanes stride over the training index j so the K*^T rows ([cand][n_pad],
+// the K-major B operand of the variance GEMM) are written with fully coalesced 256-byte stores, and
+// reduce k.alpha / sum_j alpha_j dk_j/dx in registers, finishing with warp shuffles.
+// Replaces GPy kern.K(X, X*) + Kx^T alpha (PosteriorExact._raw_predict) and
+// kern.gradients_X(alpha^T, X*, X) (GP.predictive_gradients), reference call sites
+// /root/reference/GPyOpt/models/gpmodel.py:98,136,138.
+// =====================================================================================================
+struct CovParams {
+  const double* Xs;       // candidates AoS [n_cand][d]
+  long long n_cand;       // valid rows
+  long long nc_run;       // rows to process (multiple of 128, >= n_cand; the excess is zero-coordinate padding)
+  long long nc_ld;        // leading dimension (rows) of the chunk buffers Kt / mean / dmean
+  const double* Xt;       // training inputs SoA [d][ldx]
+  long long ldx;          // = n_pad
+  int n, n_pad, d, kern;
+  const double* alpha;    // [S][n_pad]
+  const double* invl;     // [S][d]
+  const double* sigf2;    // [S]
+  double* Kt;             // [S][nc_ld][n_pad]   (may be null: mean only)
+  double* mean;           // [S][nc_ld]
+  double* dmean;          // [S][d][nc_ld]       (GRAD only)
+};
+
+template <int DP, int CW, bool GRAD>
+__global__ void __launch_bounds__(128) cov_mean_kernel(const CovParams p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int z = blockIdx.z;
+  const long long c0 = ((long long)blockIdx.x * 4 + warp) * CW;
+  if (c0 >= p.nc_run) return;
+  const double* invl = p.invl + (long long)z * p.d;
+  const double sf2 = p.sigf2[z];
+  double il[DP], xs[CW][DP], m[CW], dm[CW][DP];
+#pragma unroll
+  for (int q = 0; q < DP; ++q) il[q] = q < p.d ? invl[q] : 0.0;
+#pragma unroll
+  for (int c = 0; c < CW; ++c) {
+    m[c] = 0.0;
+#pragma unroll
+    for (int q = 0; q < DP; ++q) {
+      xs[c][q] = (q < p.d && c0 + c < p.n_cand) ? p.Xs[(c0 + c) * p.d + q] * il[q] : 0.0;
+      dm[c][q] = 0.0;
+    }
+  }
+  const double* alpha = p.alpha + (long long)z * p.n_pad;
+  double* Kt = p.Kt ? p.Kt + ((long long)z * p.nc_ld + c0) * p.n_pad : nullptr;
+  for (int j = lane; j < p.n_pad; j += 32) {
+    const bool valid = j < p.n;
+    double xj[DP];
+#pragma unroll
+    for (int q = 0; q < DP; ++q) xj[q] = (q < p.d) ? __ldg(p.Xt + q * p.ldx + j) * il[q] : 0.0;
+    const double aj = __ldg(alpha + j);
+#pragma unroll
+    for (int c = 0; c < CW; ++c) {
+      double r2 = 0.0;
+#pragma unroll
+      for (int q = 0; q < DP; ++q) {
+        const double df = xs[c][q] - xj[q];
+        r2 = fma(df, df, r2);
+      }
+      double kv, hv;
+      kern_k_h(p.kern, sf2, r2, kv, hv);
+      if (!valid) kv = 0.0;
+      if (Kt) Kt[(long long)c * p.n_pad + j] = kv;
+      m[c] = fma(kv, aj, m[c]);
+      if (GRAD) {
+        const double w = aj * hv;  // aj == 0 on padded rows
+#pragma unroll
+        for (int q = 0; q < DP; ++q) dm[c][q] = fma(w, xs[c][q] - xj[q], dm[c][q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CW; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m[c] += __shfl_xor_sync(0xffffffffu, m[c], o);
+    if (GRAD) {
+#pragma unroll
+      for (int q = 0; q < DP; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dm[c][q] += __shfl_xor_sync(0xffffffffu, dm[c][q], o);
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < CW; ++c) {
+      p.mean[(long long)z * p.nc_ld + c0 + c] = m[c];
+      if (GRAD) {
+#pragma unroll
+        for (int q = 0; q < DP; ++q)
+          if (q < p.d) p.dmean[((long long)z * p.d + q) * p.nc_ld + c0 + c] = dm[c][q] * il[q];
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// K4 helpers
+// =====================================================================================================
+// Gram matrix Ky = K(X,X) + (noise + 1e-8 + extra_jitter) I, identity on the padding.  GPy
+// ExactGaussianInference.inference; extra_jitter implements GPy jitchol's retry ladder.
+__global__ void gram_kernel(double* A, const double* Xt, long long ldx, int n, int n_pad, int d, int kern,
+                            const double* invl, const double* sigf2, const double* noise, const double* extra_jitter) {
+  const int z = blockIdx.z;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad || j >= n_pad) return;
+  double v;
+  if (i < n && j < n) {
+    double r2 = 0.0;
+    for (int q = 0; q < d; ++q) {
+      const double il = invl[z * d + q];
+      const double df = Xt[q * ldx + i] * il - Xt[q * ldx + j] * il;
+      r2 = fma(df, df, r2);
+    }
+    v = kern_k(kern, sigf2[z], r2);
+    if (i == j) v += noise[z] + 1e-8 + extra_jitter[z];
+  } else {
+    v = (i == j) ? 1.0 : 0.0;
+  }
+  A[((long long)z * n_pad + i) * n_pad + j] = v;
+}
+
+// mean of diag(K(X,X)) + noise + 1e-8 over the n real rows == sigf2 + noise + 1e-8 for a stationary kernel:
+// computed on the host; no kernel needed.
+
+// Cholesky factor + inverse of one 128 x 128 diagonal block per batch z, entirely in shared memory.
+//   in : lower triangle of A[z][kb*128 .. +128)^2   (upper part ignored)
+//   out: A block <- L (upper zeroed), X block <- L^-1 (lower), U block <- L^-T (upper)
+// info[z] is set to (global column index + 1) of the first non-positive pivot.
+constexpr int DIAG_THREADS = 256;
+constexpr int DIAG_PITCH = TILE + 1;
+constexpr int DIAG_SMEM_BYTES = (TILE * DIAG_PITCH + TILE) * 8;
+
+__global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, double* X, double* U, int n_pad, int kb,
+                                                                     int* info) {
+  extern __shared__ double sm[];
+  double* S = sm;                          // [128][129]
+  double* invd = sm + TILE * DIAG_PITCH;   // [128]
+  const int z = blockIdx.x, tid = threadIdx.x;
+  const long long base = ((long long)z * n_pad + (long long)kb * TILE) * n_pad + (long long)kb * TILE;
+  for (int idx = tid; idx < TILE * TILE; idx += DIAG_THREADS) {
+    const int i = idx / TILE, j = idx % TILE;
+    S[i * DIAG_PITCH + j] = A[base + (long long)i * n_pad + j];
+  }
+  __syncthreads();
+  for (int j = 0; j < TILE; ++j) {
+    if (tid == 0) {
+      double dd = S[j * DIAG_PITCH + j];
+      if (!(dd > 0.0)) {
+        if (info[z] == 0) info[z] = kb * TILE + j + 1;
+        dd = 1.0;
+      }
+      S[j * DIAG_PITCH + j] = sqrt(dd);
+    }
+    __syncthreads();
+    const double piv = S[j * DIAG_PITCH + j];
+    for (int i = j + 1 + tid; i < TILE; i += DIAG_THREADS) S[i * DIAG_PITCH + j] /= piv;
+    __syncthreads();
+    const int w = TILE - j - 1;
+    for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
+      const int i = j + 1 + idx / w, k = j + 1 + idx % w;
+      if (k <= i) S[i * DIAG_PITCH + k] = fma(-S[i * DIAG_PITCH + j], S[k * DIAG_PITCH + j], S[i * DIAG_PITCH + k]);
+    }
+    // next iteration's pivot read is ordered by the __syncthreads at its top
+    __syncthreads();
+  }
+  // inverse: thread c builds column c of L^-1 by forward substitution, kept in the upper triangle S[c][i], i > c
+  if (tid < TILE) {
+    const int c = tid;
+    const double xc = 1.0 / S[c * DIAG_PITCH + c];
+    invd[c] = xc;
+    for (int i = c + 1; i < TILE; ++i) {
+      double s = S[i * DIAG_PITCH + c] * xc;
+      for (int k = c + 1; k < i; ++k) s = fma(S[i * DIAG_PITCH + k], S[c * DIAG_PITCH + k], s);
+      S[c * DIAG_PITCH + i] = -s / S[i * DIAG_PITCH + i];
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < TILE * TILE; idx += DIAG_THREADS) {
+    const int i = idx / TILE, j = idx % TILE;
+    const long long o = base + (long long)i * n_pad + j;
+    // (i, j): L lower part lives in S[i][j] (j <= i); inverse element (i, j), j < i, lives in S[j][i]
+    const double l = (j <= i) ? S[i * DIAG_PITCH + j] : 0.0;
+    const double xi = (j < i) ? S[j * DIAG_PITCH + i] : (j == i ? invd[i] : 0.0);
+    const double ui = (j > i) ? S[i * DIAG_PITCH + j] : (j == i ? invd[i] : 0.0);  // U = X^T: U[i][j] = X[j][i]
+    A[o] = l;
+    X[o] = xi;
+    U[o] = ui;
+  }
+}
+
+// out[z][r] = sum_{k in [lo(r), hi(r))} M[z][r][k] * v[z][k]; mode 0: k <= r (lower), 1: k >= r (upper), 2: full
+__global__ void gemv_kernel(const double* M, const double* v, double* out, int n_pad, int mode) {
+  const int z = blockIdx.y;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= n_pad) return;
+  const int lo = mode == 1 ? r : 0, hi = mode == 0 ? r + 1 : n_pad;
+  const double* row = M + ((long long)z * n_pad + r) * n_pad;
+  const double* vv = v + (long long)z * n_pad;
+  double s = 0.0;
+  for (int k = lo + lane; k < hi; k += 32) s = fma(row[k], vv[k], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[(long long)z * n_pad + r] = s;
+}
+
+// per-z scalar reductions after the factorisation:
+//   logdet[z] = 2 sum_i log L_ii,  quad[z] = sum_i alpha_i y_i,  fmin[z] = min_i mean_i  (i < n)
+__global__ void fit_scalars_kernel(const double* L, const double* alpha, const double* y, const double* mean,
+                                   long long mean_ld, int n, int n_pad, double* logdet, double* quad,
+                                   double* fmin_out) {
+  const int z = blockIdx.x;
+  __shared__ double sh[3][32];
+  double ld = 0.0, qd = 0.0, mn = DBL_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    ld += log(L[((long long)z * n_pad + i) * n_pad + i]);
+    qd = fma(alpha[(long long)z * n_pad + i], y[i], qd);
+    mn = ::fmin(mn, mean[z * mean_ld + i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ld += __shfl_xor_sync(0xffffffffu, ld, o);
+    qd += __shfl_xor_sync(0xffffffffu, qd, o);
+    mn = ::fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][w] = ld; sh[1][w] = qd; sh[2][w] = mn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0, c = DBL_MAX;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh[0][i]; b += sh[1][i]; c = ::fmin(c, sh[2][i]); }
+    logdet[z] = 2.0 * a;
+    quad[z] = b;
+    fmin_out[z] = c;
+  }
+}
+
+// ML-II gradient: g[z][p] = sum_{i,j<n} dL_dK_ij dK_ij/dtheta_p with dL_dK = 0.5 (alpha alpha^T - W^-1):
+//   p = 0: variance, p = 1..d: per-dimension lengthscale (summed by the host for non-ARD), p = d+1: noise (trace).
+// GPy Stationary.update_gradients_full + Gaussian.exact_inference_gradients.  Output: per-block partials.
+__global__ void loglik_grad_kernel(const double* W, const double* alpha, const double* Xt, long long ldx, int n,
+                                   int n_pad, int d, int kern, const double* invl, const double* sigf2,
+                                   double* partial /*[S][gridDim.x][d+2]*/) {
+  const int z = blockIdx.y;
+  double acc[DMAX + 2];
+#pragma unroll
+  for (int q = 0; q < DMAX + 2; ++q) acc[q] = 0.0;
+  const double sf2 = sigf2[z];
+  const long long total = (long long)n * n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / n), j = (int)(idx % n);
+    const double dl = 0.5 * (alpha[(long long)z * n_pad + i] * alpha[(long long)z * n_pad + j] -
+                             W[((long long)z * n_pad + i) * n_pad + j]);
+    double r2 = 0.0, dq[DMAX];
+#pragma unroll
+    for (int q = 0; q < DMAX; ++q) {
+      if (q < d) {
+        const double il = invl[z * d + q];
+        const double df = Xt[q * ldx + i] * il - Xt[q * ldx + j] * il;
+        dq[q] = df * df;
+        r2 += dq[q];
+      } else dq[q] = 0.0;
+    }
+    double kv, hv;
+    kern_k_h(kern, sf2, r2, kv, hv);
+    acc[0] = fma(dl, kv / sf2, acc[0]);
+    // dK/dl_q = dK/dr * dr/dl_q = -(dK/dr / r) * (scaled diff_q)^2 / l_q  = -h * dq * invl_q
+#pragma unroll
+    for (int q = 0; q < DMAX; ++q)
+      if (q < d) acc[1 + q] = fma(dl, -hv * dq[q] * invl[z * d + q], acc[1 + q]);
+    if (i == j) acc[d + 1] += dl;
+  }
+  __shared__ double sh[32];
+  for (int q = 0; q < d + 2; ++q) {
+    double v = acc[0];
+#pragma unroll
+    for (int qq = 0; qq < DMAX + 2; ++qq)
+      if (qq == q) v = acc[qq];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += sh[i];
+      partial[((long long)z * gridDim.x + blockIdx.x) * (d + 2) + q] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// =====================================================================================================
+// K3: acquisition epilogue.  One thread per candidate: combines the per-row-block partials of the variance
+// GEMM with K1's mean, applies GPModel's clip/sqrt, then EI / MPI / LCB (+ MCMC average) and, if set, the
+// Local-Penalization transform + penalisers.  Reference: gpmodel.py:95-142, util/general.py:113-128,
+// acquisitions/{EI,MPI,LCB,EI_mcmc,MPI_mcmc,LCB_mcmc,LP}.py.
+// =====================================================================================================
+enum AcqKind { ACQ_EI = 0, ACQ_MPI = 1, ACQ_LCB = 2, ACQ_EI_MCMC = 3, ACQ_MPI_MCMC = 4, ACQ_LCB_MCMC = 5, ACQ_NONE = -1 };
+
+struct AcqParams {
+  long long n_cand, nc_pad;
+  int S, d, tiles_m;
+  int grad;              // partials come from EPI_GRAD (d+1 values) instead of EPI_SUMSQ (1 value)
+  int with_noise;
+  const double* mean;    // [S][nc_pad]
+  const double* dmean;   // [S][d][nc_pad]
+  const double* partial; // [S][tiles_m][nv][nc_pad]
+  const double* sigf2;   // [S]
+  const double* noise;   // [S]
+  const double* fmin;    // [S]
+  int kind;
+  double par;
+  // predict outputs (kind == ACQ_NONE), layout [S][N] / [S][N][d], already offset to this chunk's first row
+  double *out_m, *out_s, *out_dm, *out_ds;
+  long long out_ldN;     // N of the whole call (stride between hyper-parameter sets)
+  // acquisition outputs, offset to the chunk's first row
+  double *out_f, *out_df;
+  // Local Penalization
+  int lp_on, lp_K, lp_transform;
+  const double *lp_xb, *lp_r, *lp_s;   // [K][d], [K], [K]
+  const double* Xs;                    // candidates AoS (needed for the penalisers)
+};
+
+__device__ __forceinline__ double log_ndtr(double z) {
+  // log Phi(z): erfcx form for the left tail (no underflow), log1p form otherwise (as scipy.special.log_ndtr)
+  const double t = z * 0.70710678118654752440;
+  if (z < -1.0) return log(0.5 * erfcx(-t)) - t * t;
+  return log1p(-0.5 * erfc(t));
+}
+
+__global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_cand) return;
+  const int d = p.d, nv = p.grad ? d + 1 : 1;
+  double f_acc = 0.0, df_acc[DMAX];
+#pragma unroll
+  for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
+  for (int z = 0; z < p.S; ++z) {
+    const double m = p.mean[(long long)z * p.nc_pad + i];
+    const double* part = p.partial + (long long)z * p.tiles_m * nv * p.nc_pad + i;
+    double s0 = 0.0;
+    for (int tm = 0; tm < p.tiles_m; ++tm) s0 += part[(long long)tm * nv * p.nc_pad];
+    double v = p.sigf2[z] - s0;
+    if (p.with_noise) v += p.noise[z];
+    v = ::fmax(v, 1e-10);
+    double s = sqrt(v);
+    double dm[DMAX], ds[DMAX];
+    if (p.grad) {
+      const double inv2s = 1.0 / (2.0 * s);
+#pragma unroll
+      for (int q = 0; q < DMAX; ++q) {
+        if (q < d) {
+          double gq = 0.0;
+          for (int tm = 0; tm < p.tiles_m; ++tm) gq += part[((long long)tm * nv + 1 + q) * p.nc_pad];
+          dm[q] = p.dmean[((long long)z * d + q) * p.nc_pad + i];
+          ds[q] = -2.0 * gq * inv2s;
+        } else { dm[q] = 0.0; ds[q] = 0.0; }
+      }
+    }
+    if (p.kind == ACQ_NONE) {
+      p.out_m[(long long)z * p.out_ldN + i] = m;
+      p.out_s[(long long)z * p.out_ldN + i] = s;
+      if (p.grad) {
+#pragma unroll
+        for (int q = 0; q < DMAX; ++q)
+          if (q < d) {
+            p.out_dm[((long long)z * p.out_ldN + i) * d + q] = dm[q];
+            p.out_ds[((long long)z * p.out_ldN + i) * d + q] = ds[q];
+          }
+      }
+      continue;
+    }
+    const int base_kind = p.kind % 3;
+    if (base_kind == ACQ_LCB) {
+      f_acc += -m + p.par * s;
+      if (p.grad) {
+#pragma unroll
+        for (int q = 0; q < DMAX; ++q) df_acc[q] += -dm[q] + p.par * ds[q];
+      }
+    } else {
+      if (s < 1e-10) s = 1e-10;  // get_quantiles clamp (util/general.py:121-124)
+      const double fm = p.fmin[z];
+      const double u = (fm - m - p.par) / s;
+      const double phi = exp(-0.5 * u * u) * 0.39894228040143267794;
+      const double Phi = 0.5 * erfc(-u * 0.70710678118654752440);
+      if (base_kind == ACQ_EI) {
+        if (p.kind == ACQ_EI_MCMC) f_acc += (fm - m + p.par) * Phi + s * phi;  // EI_mcmc.py:38,51 (+jitter quirk)
+        else f_acc += s * (u * Phi + phi);
+        if (p.grad) {
+#pragma unroll
+          for (int q = 0; q < DMAX; ++q) df_acc[q] += ds[q] * phi - Phi * dm[q];
+        }
+      } else {  // MPI
+        f_acc += Phi;
+        if (p.grad) {
+          const double c = -(phi / s);
+#pragma unroll
+          for (int q = 0; q < DMAX; ++q) df_acc[q] += c * (dm[q] + ds[q] * u);
+        }
+      }
+    }
+  }
+  if (p.kind == ACQ_NONE) return;
+  if (p.kind >= ACQ_EI_MCMC) {
+    const double invS = 1.0 / (double)p.S;  // f_acqu/(len(means)): true division by S
+    f_acc = f_acc / (double)p.S;
+#pragma unroll
+    for (int q = 0; q < DMAX; ++q) df_acc[q] = df_acc[q] / (double)p.S;
+    (void)invS;
+  }
+  if (!p.lp_on) {
+    p.out_f[i] = f_acc;
+    if (p.grad) {
+#pragma unroll
+      for (int q = 0; q < DMAX; ++q)
+        if (q < d) p.out_df[i * d + q] = df_acc[q];
+    }
+    return;
+  }
+  // ---- Local Penalization (LP.py:70-132).  acquisition_function(x) == -f_acc, so fval = f_acc. ----
+  const double fval = f_acc;
+  double val, scale;
+  if (p.lp_transform == 1) {  // softplus
+    if (fval >= 40.0) val = log(fval);
+    else val = log(log1p(exp(fval)));
+    scale = 1.0 / (log1p(exp(fval)) * (1.0 + exp(-fval)));
+  } else {
+    val = log(fval + 1e-50);
+    scale = 1.0 / fval;
+  }
+  val = -val;
+  double dsum = 0.0;
+  for (int k = 0; k < p.lp_K; ++k) {
+    double nm2 = 0.0;
+    for (int q = 0; q < d; ++q) {
+      const double df = p.Xs[i * d + q] - p.lp_xb[k * d + q];
+      nm2 = fma(df, df, nm2);
+    }
+    const double nm = sqrt(nm2);
+    const double zz = (nm - p.lp_r[k]) / p.lp_s[k];
+    val -= log_ndtr(zz);
+    if (p.grad) {
+      const double h = 0.5 * erfc(-zz * 0.70710678118654752440);  // norm.cdf(z)
+      double dk = 1.0 / (p.lp_s[k] * 2.50662827463100050242 * h) * exp(-zz * zz / 2.0) / nm;
+      if (h < 1e-50) dk = 0.0;
+      dsum += dk;
+    }
+  }
+  p.out_f[i] = val;
+  if (p.grad) {
+    // scale * (-df) - sum_k d_k (direction dropped, broadcast over coordinates: LP.py:100-103,132)
+#pragma unroll
+    for (int q = 0; q < DMAX; ++q)
+      if (q < d) p.out_df[i * d + q] = scale * (-df_acc[q]) - dsum;
+  }
+}
+
+// =====================================================================================================
+// top-k selection (anchor_points_generator.py:67): k smallest (or largest) values, ties -> lowest index.
+// Level kernel: each block bitonic-sorts TOPK_SEG (value, index) pairs in shared memory and emits its first k.
+// =====================================================================================================
+constexpr int TOPK_SEG = 2048;
+constexpr int TOPK_THREADS = 512;
+
+__device__ __forceinline__ bool topk_before(double va, long long ia, double vb, long long ib) {
+  // strict "a sorts before b": smaller value first, NaN last, ties by index
+  const bool na = va != va, nb = vb != vb;
+  if (na || nb) return (!na && nb) || (na == nb && ia < ib);
+  return va < vb || (va == vb && ia < ib);
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_level_kernel(const double* vals, const long long* idx_in, long long n,
+                                                                  int k, double sign, double* out_vals,
+                                                                  long long* out_idx) {
+  __shared__ double sv[TOPK_SEG];
+  __shared__ long long si[TOPK_SEG];
+  const long long base = (long long)blockIdx.x * TOPK_SEG;
+  for (int t = threadIdx.x; t < TOPK_SEG; t += TOPK_THREADS) {
+    const long long g = base + t;
+    if (g < n) {
+      sv[t] = idx_in ? vals[g] : sign * vals[g];
+      si[t] = idx_in ? idx_in[g] : g;
+    } else {
+      sv[t] = __longlong_as_double(0x7ff8000000000000LL);  // NaN sorts last
+      si[t] = 0x7fffffffffffffffLL;
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= TOPK_SEG; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < TOPK_SEG / 2; t += TOPK_THREADS) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool up = (lo & size) == 0;
+        const bool hi_first = topk_before(sv[hi], si[hi], sv[lo], si[lo]);
+        if (hi_first == up) {
+          const double tv = sv[lo]; sv[lo] = sv[hi]; sv[hi] = tv;
+          const long long ti = si[lo]; si[lo] = si[hi]; si[hi] = ti;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int t = threadIdx.x; t < k; t += TOPK_THREADS) {
+    out_vals[(long long)blockIdx.x * k + t] = sv[t];
+    out_idx[(long long)blockIdx.x * k + t] = si[t];
+  }
+}
+
+}  // namespace gpo

@@ -1,0 +1,120 @@
+/* gpo_b200.h -- C ABI of the B200-native GP-posterior + acquisition engine.
+ *
+ * Drop-in boundary for ONE path of SheffieldML/GPyOpt: exact-GP posterior prediction fused with the
+ * acquisition value/gradient over very large candidate sets.  The reference is pure Python; each entry
+ * point below names the reference method whose arithmetic it replaces (paths relative to /root/reference).
+ * A maintainer binds these with ctypes; no torch / C++ types cross the boundary.
+ *
+ * Conventions
+ *   - every array is float64, C-contiguous; "candidate" arrays are row-major [N, d]
+ *   - pointer arguments marked (host|device) may be either: the library inspects them with
+ *     cudaPointerGetAttributes and stages host memory through its own pinned buffers
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream).  With device pointers the call is
+ *     asynchronous on `stream`; with host pointers it returns after the results are in host memory
+ *   - every function returns 0 (GPO_OK) or a negative gpo_status; never throws; one engine per thread
+ *   - S = number of hyper-parameter sets held by the engine: 1 for GPModel, #HMC samples for GPModel_MCMC
+ */
+#ifndef GPO_B200_H
+#define GPO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpo_engine gpo_engine;
+
+typedef enum {
+  GPO_OK = 0,
+  GPO_ERR_CUDA = -1,      /* CUDA runtime/driver failure; text via gpo_last_error */
+  GPO_ERR_NOT_PD = -2,    /* Gram matrix not positive definite even with jitter -> numpy.linalg.LinAlgError
+                             (caught by GPyOpt/core/bo.py:143) */
+  GPO_ERR_ARG = -3,       /* bad argument / unsupported size */
+  GPO_ERR_STATE = -4,     /* call order: predict before fit, ... */
+  GPO_ERR_NO_DEVICE = -5  /* no usable sm_100 GPU: the engine has no CPU fallback */
+} gpo_status;
+
+typedef enum { GPO_KERN_RBF = 0, GPO_KERN_MATERN52 = 1, GPO_KERN_MATERN32 = 2 } gpo_kernel;
+
+typedef enum {
+  GPO_ACQ_EI = 0,       /* GPyOpt/acquisitions/EI.py:32-51        par = jitter */
+  GPO_ACQ_MPI = 1,      /* GPyOpt/acquisitions/MPI.py:32-51       par = jitter */
+  GPO_ACQ_LCB = 2,      /* GPyOpt/acquisitions/LCB.py:35-50       par = exploration_weight */
+  GPO_ACQ_EI_MCMC = 3,  /* GPyOpt/acquisitions/EI_mcmc.py:29-59   par = jitter (keeps the +jitter quirk) */
+  GPO_ACQ_MPI_MCMC = 4, /* GPyOpt/acquisitions/MPI_mcmc.py:29-59 */
+  GPO_ACQ_LCB_MCMC = 5  /* GPyOpt/acquisitions/LCB_mcmc.py:26-52 */
+} gpo_acq_kind;
+
+typedef enum { GPO_LP_NONE = 0, GPO_LP_SOFTPLUS = 1 } gpo_lp_transform;
+
+const char* gpo_strerror(int status);
+const char* gpo_last_error(const gpo_engine* eng);
+const char* gpo_version(void);
+
+/* Engine lifetime.  `device` is the CUDA ordinal.  Fails with GPO_ERR_NO_DEVICE when there is no GPU. */
+int gpo_create(int device, gpo_engine** out);
+int gpo_destroy(gpo_engine* eng);
+
+/* Tunable: candidates per internal chunk (0 = automatic).  The K* chunk [S, chunk, n_pad] lives in HBM/L2. */
+int gpo_set_chunk(gpo_engine* eng, long long chunk);
+
+/* Refit given hyper-parameters: GPModel.updateModel / GPModel_MCMC per-sample `_trigger_params_changed`
+ * (GPyOpt/models/gpmodel.py:78-93, 267-271) == GPy ExactGaussianInference.inference:
+ *   Ky = K(X,X) + (noise + 1e-8) I;  L = jitchol(Ky);  alpha = Ky^-1 Y;  L^-1;  W^-1 = Ky^-1;  fmin = min(K alpha)
+ * X (host) [n, d]; Y (host) [n] (already normalised by the caller, GPyOpt/core/bo.py:253-256);
+ * variance [S]; lengthscale [S, d] (non-ARD: the single lengthscale repeated d times); noise [S].
+ * Returns GPO_ERR_NOT_PD after GPy's jitchol retry ladder (5 tries, jitter = mean(diag)*1e-6 * 10^i). */
+int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* X, const double* Y, int S,
+            const double* variance, const double* lengthscale, const double* noise);
+
+/* GPModel.get_fmin / GPModel_MCMC.get_fmin (gpmodel.py:125-129, 279-295): fmin (host) [S]. */
+int gpo_get_fmin(gpo_engine* eng, double* fmin);
+
+/* log marginal likelihood and log|Ky| per hyper-parameter set (host) [S] each; either may be NULL.
+ * (GPy ExactGaussianInference.inference; used by the ML-II fitter above the boundary.) */
+int gpo_get_loglik(gpo_engine* eng, double* loglik, double* logdet);
+
+/* d loglik / d [variance, lengthscale_1..d, noise] (host) [S, d + 2]: GPy dL_dK = 0.5 (alpha alpha^T - W^-1)
+ * contracted with dK/dtheta (Stationary.update_gradients_full) and its trace (Gaussian likelihood). */
+int gpo_get_loglik_grad(gpo_engine* eng, double* grad);
+
+/* Copy posterior state to the host for inspection / broadcast checks; any pointer may be NULL.
+ * L, Linv, Winv: [S, n, n]; alpha: [S, n]. */
+int gpo_get_state(gpo_engine* eng, double* L, double* Linv, double* Winv, double* alpha);
+
+/* GPModel.predict (gpmodel.py:95-112): m, s (host|device) [S, N]; s = sqrt(clip(var (+noise), 1e-10)). */
+int gpo_predict(gpo_engine* eng, long long N, const double* Xs, int with_noise, double* m, double* s, void* stream);
+
+/* GPModel.predict_withGradients (gpmodel.py:131-142): additionally dmdx, dsdx (host|device) [S, N, d]. */
+int gpo_predict_grad(gpo_engine* eng, long long N, const double* Xs, double* m, double* s, double* dmdx,
+                     double* dsdx, void* stream);
+
+/* Acquisition*._compute_acq / _compute_acq_withGradients: f [N], df [N, d] (df may be NULL: value only).
+ * For S > 1 the *_MCMC kinds average over the hyper-parameter sets.  If a Local-Penalization state is set
+ * (gpo_lp_set) the output is AcquisitionLP.acquisition_function / d_acquisition_function instead
+ * (GPyOpt/acquisitions/LP.py:70-132). */
+int gpo_acq(gpo_engine* eng, int kind, double par, long long N, const double* Xs, double* f, double* df,
+            void* stream);
+
+/* Local-Penalization state: K penalisers centred at Xb (host) [K, d] with radii r [K], scales s [K]
+ * (AcquisitionLP.update_batches, LP.py:40-62).  K = 0 with transform >= 0 keeps only the log transform;
+ * transform < 0 clears LP. */
+int gpo_lp_set(gpo_engine* eng, int K, const double* Xb, const double* r, const double* s, int transform);
+
+/* Fused candidate sweep + selection (AnchorPointsGenerator.get, GPyOpt/optimization/
+ * anchor_points_generator.py:25-69): evaluates the acquisition value over Xs [N, d] and returns the k
+ * candidates with the smallest score = -f (ties: lowest index).  vals/idx are host arrays [k];
+ * vals holds the scores (-f).  f_out (host|device, may be NULL) receives all N acquisition values. */
+int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, const double* Xs, int k, double* vals,
+                 long long* idx, double* f_out, void* stream);
+
+/* k smallest (largest = 0) or largest (largest = 1) entries of a device/host array v [N]. */
+int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, int largest, double* vals, long long* idx,
+             void* stream);
+
+/* Counters for the benchmark harness: kernels launched and seconds of GPU time since the last reset. */
+int gpo_launch_count(gpo_engine* eng, long long* launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPO_B200_H */

@@ -14,7 +14,6 @@
 // /root/reference/GPyOpt/models/gpmodel.py:98,136-138.
 #pragma once
 #include "common.cuh"
-#include "kernfun.cuh"
 
 namespace gpo {
 
@@ -51,21 +50,21 @@ struct GemmParams {
   // EPI_SUMSQ / EPI_GRAD: partial[((z*tiles_m + tile_m)*nvals + v)*ldp + tile_n*128 + col]
   double* partial;
   long long ldp;
-  // EPI_GRAD
-  int d, kern;
-  const double* Xt;     // training inputs, SoA [d][ldx]
+  // EPI_GRAD: partial values per column are [S0 = sum_j b_j k_j, H0 = sum_j b_j h_j, P_q = sum_j b_j h_j xc_jq]
+  int d;
+  const double* Xtc;    // centred training inputs, SoA [d][ldx] (zero on the padding rows)
   long long ldx;
-  const double* Xs;     // candidates, AoS [N][d] (this chunk's first row)
-  long long n_cand;     // valid candidate rows in the chunk
-  const double* invl;   // [z][d] inverse lengthscales
-  const double* sigf2;  // [z]    kernel variances
+  const double* Kt;     // K*^T chunk [z][nc_ld][n_pad] written by K1 (also the B operand)
+  const double* Ht;     // (dK/dr)/r chunk, same layout; null => RBF (h = -k)
+  long long nc_ld, n_pad;
 };
 
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // keep the pointer derived from the __shared__ symbol (so fragment loads compile to LDS, not generic LD)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = (uint64_t*)(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
 
@@ -202,52 +201,62 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         p.partial[((long long)(z * p.tiles_m + tile_m)) * p.ldp + tile_n * TILE + c] = red[c] + red[TILE + c];
       }
     } else {  // EPI_GRAD
+      // b = W^-1 k sits in the accumulators.  The covariance k_ji and its radial derivative factor h_ji are NOT
+      // recomputed: K1 left them in HBM/L2 (K*^T is this GEMM's own B operand), so each lane re-reads its 64
+      // entries (8 consecutive j per candidate row: full 32-byte sectors) and reduces
+      //   S0_i = sum_j b_ji k_ji        (posterior variance term k.b)
+      //   H0_i = sum_j b_ji h_ji,  P_qi = sum_j b_ji h_ji xc_jq     (variance gradient, combined in K3)
       const int d = p.d;
-      double* xj = reinterpret_cast<double*>(smem);  // [d][128] training rows of this tile, scaled by 1/l
-      double* xi = xj + d * TILE;                    // [d][128] candidate columns of this tile, scaled by 1/l
-      red = xi + d * TILE;                           // [(d+1)][2][128]
+      double* xj = reinterpret_cast<double*>(smem);  // [d][128] centred training coordinates of this row block
+      red = xj + d * TILE;                           // [(d+2)][2][128]
       named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
-      const double* invl = p.invl + (long long)z * d;
-      for (int idx = threadIdx.x; idx < d * TILE; idx += GEMM_CONSUMER_WARPS * 32) {
-        const int q = idx / TILE, r = idx % TILE;
-        xj[idx] = p.Xt[q * p.ldx + tile_m * TILE + r] * invl[q];
-        const long long ci = (long long)tile_n * TILE + r;
-        xi[idx] = (ci < p.n_cand ? p.Xs[ci * d + q] : 0.0) * invl[q];
-      }
-      named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
-      const double sf2 = p.sigf2[z];
-      double s0[4][2];
+      for (int idx = threadIdx.x; idx < d * TILE; idx += GEMM_CONSUMER_WARPS * 32)
+        xj[idx] = p.Xtc[(idx / TILE) * p.ldx + tile_m * TILE + (idx % TILE)];
+      const long long kt_off = ((long long)z * p.nc_ld + (long long)tile_n * TILE) * p.n_pad + (long long)tile_m * TILE;
+      const double* Kt = p.Kt + kt_off;
+      const double* Ht = p.Ht ? p.Ht + kt_off : nullptr;
+      double s0[4][2], h0[4][2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s0[j][0] = s0[j][1] = 0.0;
+      for (int j = 0; j < 4; ++j) s0[j][0] = s0[j][1] = h0[j][0] = h0[j][1] = 0.0;
 #pragma unroll
       for (int f = 0; f < 8; ++f) {
         const int r = wm + 8 * f + rr;
+        double kv[4][2], hv[4][2];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int c = wn + 8 * j + (e ? 4 + t : t);
-            double r2 = 0.0;
-            for (int q = 0; q < d; ++q) {
-              const double df = xi[q * TILE + c] - xj[q * TILE + r];
-              r2 = fma(df, df, r2);
-            }
-            double kv, hv;
-            kern_k_h(p.kern, sf2, r2, kv, hv);
-            s0[j][e] = fma(acc[f][j][e], kv, s0[j][e]);
-            acc[f][j][e] *= hv;
+            const long long o = (long long)(wn + 8 * j + (e ? 4 + t : t)) * p.n_pad + r;
+            kv[j][e] = __ldg(Kt + o);
+            hv[j][e] = Ht ? __ldg(Ht + o) : 0.0;
+          }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double b = acc[f][j][e];
+            s0[j][e] = fma(b, kv[j][e], s0[j][e]);
+            const double bh = Ht ? b * hv[j][e] : -(b * kv[j][e]);
+            h0[j][e] += bh;
+            acc[f][j][e] = bh;
           }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          double v = s0[j][e];
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (g == 0) red[half * TILE + wn + 8 * j + (e ? 4 + t : t)] = v;
+          double v = s0[j][e], w = h0[j][e];
+#pragma unroll
+          for (int o = 4; o <= 16; o <<= 1) {
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+            w += __shfl_xor_sync(0xffffffffu, w, o);
+          }
+          if (g == 0) {
+            red[(0 * 2 + half) * TILE + wn + 8 * j + (e ? 4 + t : t)] = v;
+            red[(1 * 2 + half) * TILE + wn + 8 * j + (e ? 4 + t : t)] = w;
+          }
         }
+      named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);  // xj visible
       for (int q = 0; q < d; ++q) {
         double xjr[8];
 #pragma unroll
@@ -256,21 +265,19 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int c = wn + 8 * j + (e ? 4 + t : t);
-            const double xic = xi[q * TILE + c];
             double v = 0.0;
 #pragma unroll
-            for (int f = 0; f < 8; ++f) v = fma(acc[f][j][e], xic - xjr[f], v);
+            for (int f = 0; f < 8; ++f) v = fma(acc[f][j][e], xjr[f], v);
             v += __shfl_xor_sync(0xffffffffu, v, 4);
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (g == 0) red[((q + 1) * 2 + half) * TILE + c] = v * invl[q];
+            if (g == 0) red[((q + 2) * 2 + half) * TILE + wn + 8 * j + (e ? 4 + t : t)] = v;
           }
       }
       named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
-      for (int idx = threadIdx.x; idx < (d + 1) * TILE; idx += GEMM_CONSUMER_WARPS * 32) {
+      for (int idx = threadIdx.x; idx < (d + 2) * TILE; idx += GEMM_CONSUMER_WARPS * 32) {
         const int v = idx / TILE, c = idx % TILE;
-        p.partial[((long long)(z * p.tiles_m + tile_m) * (d + 1) + v) * p.ldp + tile_n * TILE + c] =
+        p.partial[((long long)(z * p.tiles_m + tile_m) * (d + 2) + v) * p.ldp + tile_n * TILE + c] =
             red[(v * 2) * TILE + c] + red[(v * 2 + 1) * TILE + c];
       }
     }

@@ -19,10 +19,11 @@ struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   double* Kt = nullptr;  // [S][nc_ld][n_pad]
+  double* Ht = nullptr;  // [S][nc_ld][n_pad], only for non-RBF kernels (allocated on demand)
   CUtensorMap mapKt;
   double* mean = nullptr;     // [S][nc_ld]
   double* dmean = nullptr;    // [S][d][nc_ld]
-  double* partial = nullptr;  // [S][tiles_m][d+1][nc_ld]
+  double* partial = nullptr;  // [S][tiles_m][d+2][nc_ld]
 };
 
 struct gpo_engine {
@@ -36,7 +37,7 @@ struct gpo_engine {
   int cap_n_pad = 0, cap_d = 0, cap_S = 0;
   long long nc_ld = 0, user_chunk = 0;
   // data + hyper-parameters (device)
-  double *Xt = nullptr, *Xaos = nullptr, *Y = nullptr;
+  double *Xt = nullptr, *Xtc = nullptr, *xmu = nullptr, *Xaos = nullptr, *Y = nullptr;
   double *invl = nullptr, *sigf2 = nullptr, *noise = nullptr, *jitter = nullptr;
   std::vector<double> h_invl, h_sigf2, h_noise;
   // posterior state (device), each [S][n_pad][n_pad] unless noted
@@ -189,13 +190,13 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
 }
 
 static void free_state(gpo_engine* eng) {
-  double** ptrs[] = {&eng->Xt, &eng->Xaos, &eng->Y, &eng->invl, &eng->sigf2, &eng->noise, &eng->jitter, &eng->A, &eng->X,
+  double** ptrs[] = {&eng->Xt, &eng->Xtc, &eng->xmu, &eng->Xaos, &eng->Y, &eng->invl, &eng->sigf2, &eng->noise, &eng->jitter, &eng->A, &eng->X,
                      &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->logdet, &eng->quad, &eng->fmin, &eng->gradpart};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
   for (int i = 0; i < 2; ++i) {
     Slot& s = eng->slot[i];
-    double** sp[] = {&s.Kt, &s.mean, &s.dmean, &s.partial};
+    double** sp[] = {&s.Kt, &s.Ht, &s.mean, &s.dmean, &s.partial};
     for (auto pp : sp) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   }
   eng->cap_n_pad = eng->cap_d = eng->cap_S = 0;
@@ -263,6 +264,8 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   const size_t nn = (size_t)S * n_pad * n_pad * 8;
   GPO_CUDA_OK(cudaMalloc(&eng->Xt, (size_t)d * n_pad * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->Xaos, (size_t)d * n_pad * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->Xtc, (size_t)d * n_pad * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->xmu, (size_t)DMAX * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->Y, (size_t)n_pad * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->invl, (size_t)S * d * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->sigf2, (size_t)S * 8));
@@ -293,7 +296,7 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
     GPO_CUDA_OK(cudaMalloc(&s.Kt, (size_t)S * eng->nc_ld * n_pad * 8));
     GPO_CUDA_OK(cudaMalloc(&s.mean, (size_t)S * eng->nc_ld * 8));
     GPO_CUDA_OK(cudaMalloc(&s.dmean, (size_t)S * d * eng->nc_ld * 8));
-    GPO_CUDA_OK(cudaMalloc(&s.partial, (size_t)S * tiles_m * (d + 1) * eng->nc_ld * 8));
+    GPO_CUDA_OK(cudaMalloc(&s.partial, (size_t)S * tiles_m * (d + 2) * eng->nc_ld * 8));
     if ((rc = make_map(eng, &s.mapKt, s.Kt, n_pad, eng->nc_ld, S))) return rc;
   }
   eng->cap_n_pad = n_pad; eng->cap_d = d; eng->cap_S = S;
@@ -426,15 +429,31 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
   eng->n = n; eng->n_pad = n_pad; eng->d = d; eng->S = S; eng->kern = kernel;
   cudaStream_t st = eng->fit_stream;
   // upload data (SoA + AoS) and hyper-parameters
-  std::vector<double> xt((size_t)d * n_pad, 0.0), xa((size_t)n_pad * d, 0.0), yy((size_t)n_pad, 0.0);
+  std::vector<double> xt((size_t)d * n_pad, 0.0), xc((size_t)d * n_pad, 0.0), xa((size_t)n_pad * d, 0.0), yy((size_t)n_pad, 0.0);
+  std::vector<double> mu(DMAX, 0.0);
+  for (int q = 0; q < d; ++q) {
+    double sm = 0.0;
+    for (int i = 0; i < n; ++i) sm += X[(size_t)i * d + q];
+    mu[q] = sm / n;
+  }
   for (int i = 0; i < n; ++i) {
-    for (int q = 0; q < d; ++q) { xt[(size_t)q * n_pad + i] = X[(size_t)i * d + q]; xa[(size_t)i * d + q] = X[(size_t)i * d + q]; }
+    for (int q = 0; q < d; ++q) {
+      xt[(size_t)q * n_pad + i] = X[(size_t)i * d + q];
+      xc[(size_t)q * n_pad + i] = X[(size_t)i * d + q] - mu[q];
+      xa[(size_t)i * d + q] = X[(size_t)i * d + q];
+    }
     yy[i] = Y[i];
+  }
+  if (kernel != KERN_RBF) {  // (dK/dr)/r chunk buffers are only needed when h != -k
+    for (int i = 0; i < 2; ++i)
+      if (!eng->slot[i].Ht) GPO_CUDA_OK(cudaMalloc(&eng->slot[i].Ht, (size_t)S * eng->nc_ld * n_pad * 8));
   }
   eng->h_invl.assign((size_t)S * d, 0.0); eng->h_sigf2.assign(variance, variance + S); eng->h_noise.assign(noise, noise + S);
   for (int i = 0; i < S * d; ++i) eng->h_invl[i] = 1.0 / lengthscale[i];
   GPO_CUDA_OK(cudaMemcpyAsync(eng->Xt, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice, st));
   GPO_CUDA_OK(cudaMemcpyAsync(eng->Xaos, xa.data(), xa.size() * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->Xtc, xc.data(), xc.size() * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->xmu, mu.data(), mu.size() * 8, cudaMemcpyHostToDevice, st));
   GPO_CUDA_OK(cudaMemcpyAsync(eng->Y, yy.data(), yy.size() * 8, cudaMemcpyHostToDevice, st));
   GPO_CUDA_OK(cudaMemcpyAsync(eng->invl, eng->h_invl.data(), (size_t)S * d * 8, cudaMemcpyHostToDevice, st));
   GPO_CUDA_OK(cudaMemcpyAsync(eng->sigf2, variance, (size_t)S * 8, cudaMemcpyHostToDevice, st));
@@ -481,7 +500,7 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
     CovParams cp;
     cp.Xs = eng->Xaos; cp.n_cand = n; cp.nc_run = n_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n; cp.n_pad = n_pad;
     cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
-    cp.Kt = nullptr; cp.mean = s.mean; cp.dmean = nullptr;
+    cp.Kt = nullptr; cp.Ht = nullptr; cp.mean = s.mean; cp.dmean = nullptr;
     if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
     fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, s.mean, eng->nc_ld, n, n_pad, eng->logdet, eng->quad,
                                           eng->fmin);
@@ -622,7 +641,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     CovParams cp;
     cp.Xs = dev_in + off * d; cp.n_cand = rows; cp.nc_run = nc_run; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad;
     cp.n = eng->n; cp.n_pad = n_pad; cp.d = d; cp.kern = eng->kern; cp.alpha = eng->alpha; cp.invl = eng->invl;
-    cp.sigf2 = eng->sigf2; cp.Kt = s.Kt; cp.mean = s.mean; cp.dmean = s.dmean;
+    cp.sigf2 = eng->sigf2; cp.Kt = s.Kt; cp.Ht = (grad && eng->kern != KERN_RBF) ? s.Ht : nullptr; cp.mean = s.mean;
+    cp.dmean = s.dmean;
     if ((rc = launch_cov(eng, cp, grad, S, st))) return rc;
     // variance GEMM
     GemmParams g = gemm_defaults();
@@ -632,8 +652,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     g.partial = s.partial; g.ldp = eng->nc_ld;
     if (grad) {
       g.krange = KR_FULL; g.raster = RO_M_FASTEST;
-      g.d = d; g.kern = eng->kern; g.Xt = eng->Xt; g.ldx = n_pad; g.Xs = dev_in + off * d; g.n_cand = rows;
-      g.invl = eng->invl; g.sigf2 = eng->sigf2;
+      g.d = d; g.Xtc = eng->Xtc; g.ldx = n_pad; g.Kt = s.Kt; g.Ht = eng->kern != KERN_RBF ? s.Ht : nullptr;
+      g.nc_ld = eng->nc_ld; g.n_pad = n_pad;
       if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s.mapKt, g, S, st))) return rc;
     } else {
       g.krange = KR_LE_M; g.raster = RO_HEAVY_FIRST;
@@ -644,7 +664,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     memset(&ap, 0, sizeof(ap));
     ap.n_cand = rows; ap.nc_pad = eng->nc_ld; ap.S = S; ap.d = d; ap.tiles_m = tiles_m; ap.grad = grad ? 1 : 0;
     ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = s.partial; ap.sigf2 = eng->sigf2;
-    ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par;
+    ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par; ap.invl = eng->invl; ap.xmu = eng->xmu;
+    ap.Xs = dev_in + off * d;
     if (predict) {
       ap.out_m = dev_out[0] + off; ap.out_s = dev_out[1] + off;
       ap.out_dm = dev_out[2] ? dev_out[2] + off * d : nullptr; ap.out_ds = dev_out[3] ? dev_out[3] + off * d : nullptr;

@@ -30,6 +30,7 @@ struct CovParams {
   const double* invl;     // [S][d]
   const double* sigf2;    // [S]
   double* Kt;             // [S][nc_ld][n_pad]   (may be null: mean only)
+  double* Ht;             // [S][nc_ld][n_pad]   (dK/dr)/r, written only when non-null (non-RBF kernels, GRAD)
   double* mean;           // [S][nc_ld]
   double* dmean;          // [S][d][nc_ld]       (GRAD only)
 };
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(128) cov_mean_kernel(const CovParams p) {
   }
   const double* alpha = p.alpha + (long long)z * p.n_pad;
   double* Kt = p.Kt ? p.Kt + ((long long)z * p.nc_ld + c0) * p.n_pad : nullptr;
+  double* Ht = (GRAD && p.Ht) ? p.Ht + ((long long)z * p.nc_ld + c0) * p.n_pad : nullptr;
   for (int j = lane; j < p.n_pad; j += 32) {
     const bool valid = j < p.n;
     double xj[DP];
@@ -72,8 +74,9 @@ __global__ void __launch_bounds__(128) cov_mean_kernel(const CovParams p) {
       }
       double kv, hv;
       kern_k_h(p.kern, sf2, r2, kv, hv);
-      if (!valid) kv = 0.0;
+      if (!valid) { kv = 0.0; hv = 0.0; }
       if (Kt) Kt[(long long)c * p.n_pad + j] = kv;
+      if (GRAD && Ht) Ht[(long long)c * p.n_pad + j] = hv;
       m[c] = fma(kv, aj, m[c]);
       if (GRAD) {
         const double w = aj * hv;  // aj == 0 on padded rows
@@ -317,7 +320,9 @@ struct AcqParams {
   int with_noise;
   const double* mean;    // [S][nc_pad]
   const double* dmean;   // [S][d][nc_pad]
-  const double* partial; // [S][tiles_m][nv][nc_pad]
+  const double* partial; // [S][tiles_m][nv][nc_pad]; nv = 1 (sum of squares) or d + 2 (S0, H0, P_1..P_d)
+  const double* invl;    // [S][d]
+  const double* xmu;     // [d] centring offsets of the training inputs
   const double* sigf2;   // [S]
   const double* noise;   // [S]
   const double* fmin;    // [S]
@@ -344,7 +349,7 @@ __device__ __forceinline__ double log_ndtr(double z) {
 __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n_cand) return;
-  const int d = p.d, nv = p.grad ? d + 1 : 1;
+  const int d = p.d, nv = p.grad ? d + 2 : 1;
   double f_acc = 0.0, df_acc[DMAX];
 #pragma unroll
   for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
@@ -359,12 +364,17 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
     double s = sqrt(v);
     double dm[DMAX], ds[DMAX];
     if (p.grad) {
+      // dv/dx_q = -2 sum_j b_j h_j (x_q - x_jq)/l_q^2 = -2/l_q^2 ((x_q - mu_q) H0 - P_q);  dsdx = dvdx / (2 s)
       const double inv2s = 1.0 / (2.0 * s);
+      double h0 = 0.0;
+      for (int tm = 0; tm < p.tiles_m; ++tm) h0 += part[((long long)tm * nv + 1) * p.nc_pad];
 #pragma unroll
       for (int q = 0; q < DMAX; ++q) {
         if (q < d) {
-          double gq = 0.0;
-          for (int tm = 0; tm < p.tiles_m; ++tm) gq += part[((long long)tm * nv + 1 + q) * p.nc_pad];
+          double pq = 0.0;
+          for (int tm = 0; tm < p.tiles_m; ++tm) pq += part[((long long)tm * nv + 2 + q) * p.nc_pad];
+          const double il = p.invl[z * d + q];
+          const double gq = ((p.Xs[i * d + q] - p.xmu[q]) * h0 - pq) * il * il;
           dm[q] = p.dmean[((long long)z * d + q) * p.nc_pad + i];
           ds[q] = -2.0 * gq * inv2s;
         } else { dm[q] = 0.0; ds[q] = 0.0; }

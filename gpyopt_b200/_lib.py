@@ -46,6 +46,9 @@ SIGNATURES = {
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'gpo_topk': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'gpo_alloc': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    'gpo_state_buffers': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    'gpo_state_commit': (ctypes.c_int, [ctypes.c_void_p]),
     'gpo_launch_count': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
 }
 
@@ -240,6 +243,24 @@ class Engine(object):
         self._check(rc, 'gpo_topk')
         kk = min(k, N)
         return vals[:kk], idx[:kk]
+
+    # -- multi-GPU state replication ---------------------------------------------------------------
+    def alloc(self, kernel, n, d, S):
+        k = KERNELS[kernel.lower()] if isinstance(kernel, str) else int(kernel)
+        self._check(self._lib.gpo_alloc(self._h, k, int(n), int(d), int(S)), 'gpo_alloc')
+        self.n, self.d, self.S = int(n), int(d), int(S)
+
+    def state_buffers(self):
+        """[(device_pointer, nbytes), ...] of every buffer a sweep reads."""
+        ptrs = (ctypes.c_void_p * 32)()
+        nbytes = (ctypes.c_longlong * 32)()
+        cnt = self._lib.gpo_state_buffers(self._h, ptrs, nbytes, 32)
+        if cnt < 0:
+            self._check(cnt, 'gpo_state_buffers')
+        return [(int(ptrs[i]), int(nbytes[i])) for i in range(cnt)]
+
+    def state_commit(self):
+        self._check(self._lib.gpo_state_commit(self._h), 'gpo_state_commit')
 
     def launch_count(self, reset=False):
         c = ctypes.c_longlong(0)

@@ -821,3 +821,53 @@ extern "C" int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, 
   }
   return GPO_OK;
 }
+
+// --------------------------------------------------------------------------------------------------
+// multi-GPU state replication (the broadcast itself is done by the host with NCCL on these buffers)
+// --------------------------------------------------------------------------------------------------
+extern "C" int gpo_alloc(gpo_engine* eng, int kernel, int n, int d, int S) {
+  if (!eng) return GPO_ERR_ARG;
+  if (n < 1 || d < 1 || d > DMAX || S < 1 || kernel < 0 || kernel > 2) GPO_FAIL(GPO_ERR_ARG, "gpo_alloc: bad argument");
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  const int n_pad = ((n + TILE - 1) / TILE) * TILE;
+  int rc = ensure_capacity(eng, n_pad, d, S);
+  if (rc) return rc;
+  eng->fitted = false;
+  eng->n = n; eng->n_pad = n_pad; eng->d = d; eng->S = S; eng->kern = kernel;
+  if (kernel != KERN_RBF)
+    for (int i = 0; i < 2; ++i)
+      if (!eng->slot[i].Ht) GPO_CUDA_OK(cudaMalloc(&eng->slot[i].Ht, (size_t)S * eng->nc_ld * n_pad * 8));
+  return GPO_OK;
+}
+
+extern "C" int gpo_state_buffers(gpo_engine* eng, void** ptrs, long long* bytes, int max) {
+  if (!eng || !ptrs || !bytes) return GPO_ERR_ARG;
+  if (eng->n_pad == 0) GPO_FAIL(GPO_ERR_STATE, "gpo_state_buffers before gpo_fit / gpo_alloc");
+  const size_t S = eng->S, d = eng->d, np = eng->n_pad;
+  struct { void* p; size_t b; } list[] = {
+      {eng->Xt, d * np * 8}, {eng->Xtc, d * np * 8}, {eng->xmu, (size_t)DMAX * 8}, {eng->Xaos, d * np * 8}, {eng->Y, np * 8},
+      {eng->invl, S * d * 8}, {eng->sigf2, S * 8}, {eng->noise, S * 8}, {eng->alpha, S * np * 8}, {eng->fmin, S * 8},
+      {eng->logdet, S * 8}, {eng->quad, S * 8}, {eng->X, S * np * np * 8}, {eng->W, S * np * np * 8}};
+  const int cnt = (int)(sizeof(list) / sizeof(list[0]));
+  if (cnt > max) GPO_FAIL(GPO_ERR_ARG, "gpo_state_buffers: need room for %d entries", cnt);
+  for (int i = 0; i < cnt; ++i) { ptrs[i] = list[i].p; bytes[i] = (long long)list[i].b; }
+  return cnt;
+}
+
+extern "C" int gpo_state_commit(gpo_engine* eng) {
+  if (!eng) return GPO_ERR_ARG;
+  if (eng->n_pad == 0) GPO_FAIL(GPO_ERR_STATE, "gpo_state_commit before gpo_alloc");
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  GPO_CUDA_OK(cudaDeviceSynchronize());
+  const int S = eng->S, d = eng->d;
+  eng->h_logdet.resize(S); eng->h_quad.resize(S); eng->h_fmin.resize(S);
+  eng->h_invl.resize((size_t)S * d); eng->h_sigf2.resize(S); eng->h_noise.resize(S);
+  GPO_CUDA_OK(cudaMemcpy(eng->h_logdet.data(), eng->logdet, (size_t)S * 8, cudaMemcpyDeviceToHost));
+  GPO_CUDA_OK(cudaMemcpy(eng->h_quad.data(), eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost));
+  GPO_CUDA_OK(cudaMemcpy(eng->h_fmin.data(), eng->fmin, (size_t)S * 8, cudaMemcpyDeviceToHost));
+  GPO_CUDA_OK(cudaMemcpy(eng->h_invl.data(), eng->invl, (size_t)S * d * 8, cudaMemcpyDeviceToHost));
+  GPO_CUDA_OK(cudaMemcpy(eng->h_sigf2.data(), eng->sigf2, (size_t)S * 8, cudaMemcpyDeviceToHost));
+  GPO_CUDA_OK(cudaMemcpy(eng->h_noise.data(), eng->noise, (size_t)S * 8, cudaMemcpyDeviceToHost));
+  eng->fitted = true;
+  return GPO_OK;
+}

@@ -111,6 +111,17 @@ int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, const doubl
 int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, int largest, double* vals, long long* idx,
              void* stream);
 
+/* Multi-GPU replication of the posterior state (one process per GPU; the collective itself is issued by the
+ * host through torch.distributed / NCCL on the buffers listed here).
+ *   gpo_alloc          allocate an engine for (kernel, n, d, S) without fitting (receiving ranks)
+ *   gpo_state_buffers  device pointers + byte sizes of every buffer a sweep reads (X, alpha, L^-1, W^-1,
+ *                      hyper-parameters, fmin ...); returns their count (<= max) or a negative status
+ *   gpo_state_commit   after the buffers were overwritten (broadcast from the fitting rank): refresh the
+ *                      host mirrors and mark the engine fitted */
+int gpo_alloc(gpo_engine* eng, int kernel, int n, int d, int S);
+int gpo_state_buffers(gpo_engine* eng, void** ptrs, long long* bytes, int max);
+int gpo_state_commit(gpo_engine* eng);
+
 /* Counters for the benchmark harness: kernels launched and seconds of GPU time since the last reset. */
 int gpo_launch_count(gpo_engine* eng, long long* launches, int reset);
 

@@ -1,0 +1,45 @@
+"""world_size-2 gloo worker for tests/test_host_logic.py: exercises the sharded-sweep protocol on CPU with a
+NumPy stand-in scorer in place of the CUDA engine (which needs a B200)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+from gpyopt_b200 import parallel  # noqa: E402
+
+
+def main():
+    dist.init_process_group('gloo')
+    rank, world = dist.get_rank(), dist.get_world_size()
+    assert world == 2
+    N, d, k = 1001, 3, 7
+    rng = np.random.default_rng(0)           # identical candidate set on both ranks
+    Xs = rng.random((N, d))
+    scores = np.sin(7 * Xs).sum(1)
+    scores[5] = scores[900]                  # a tie that straddles the two shards
+    lo, hi = parallel.shard_rows(N, rank, world)
+    local = scores[lo:hi]
+    li = np.argsort(local, kind='stable')[:k]
+    vals, idx = parallel.allgather_topk(local[li], li + lo, k)
+    ref = np.argsort(scores, kind='stable')[:k]
+    assert np.array_equal(idx, ref), (idx, ref)
+    assert np.array_equal(vals, scores[ref])
+    # every rank must hold the identical merged record
+    t = torch.from_numpy(idx.astype(np.int64).copy())
+    gathered = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    assert all(torch.equal(g, gathered[0]) for g in gathered)
+    # fewer local rows than k on one rank
+    vals2, idx2 = parallel.allgather_topk(local[li][:2] if rank == 0 else local[li], (li + lo)[:2] if rank == 0 else li + lo, k)
+    assert len(idx2) == k and np.all(np.diff(vals2) >= 0)
+    dist.barrier()
+    if rank == 0:
+        print('DIST_OK')
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

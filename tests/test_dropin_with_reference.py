@@ -1,0 +1,128 @@
+"""CPU test of the drop-in boundary against the REAL reference BO loop (build container only: needs
+/root/reference).  The engine's plugin classes (gpyopt_b200.GPModel / AcquisitionEI / AcquisitionLP ...) are
+driven by the oracle-backed FakeEngine, plugged into the unmodified ``GPyOpt.methods.BayesianOptimization``,
+and must suggest the same points as the reference's own GPModel + acquisition running on the same GP arithmetic.
+This pins the HOST logic of the plugins (shapes, ML-II transforms and restarts, LP wiring, isinstance contracts);
+the CUDA arithmetic is pinned by tests/test_gpu_parity.py."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+REF = '/root/reference'
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'GPyOpt')), reason="reference tree not present")
+
+
+@pytest.fixture(scope='module')
+def gpyopt():
+    warnings.filterwarnings('ignore')
+    for p in (os.path.join(ROOT, 'oracle', 'gpy_stub'), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import GPyOpt
+    import importlib
+    import gpyopt_b200._compat as compat
+    importlib.reload(compat)           # pick up the real BOModel / AcquisitionBase now that GPyOpt imports
+    import gpyopt_b200.models as models
+    import gpyopt_b200.acquisitions as acqs
+    importlib.reload(models)
+    importlib.reload(acqs)
+    import gpyopt_b200.gp as gpmod
+    from fake_engine import FakeEngine
+    gpmod.Engine = FakeEngine          # no GPU in this container: oracle-backed engine (tests only)
+    assert compat.HAVE_GPYOPT
+    return GPyOpt, models, acqs
+
+
+def branin(x):
+    from oracle import gpyopt_numpy as og
+    return og.branin(x)
+
+
+DOMAIN = [{'name': 'x1', 'type': 'continuous', 'domain': (-5, 10)}, {'name': 'x2', 'type': 'continuous', 'domain': (1, 15)}]
+
+
+def _run(GPyOpt, model, acquisition_factory, evaluator_type='sequential', batch_size=1, iters=4, seed=7):
+    np.random.seed(seed)
+    space = GPyOpt.Design_space(DOMAIN)
+    objective = GPyOpt.core.task.SingleObjective(branin)
+    aopt = GPyOpt.optimization.AcquisitionOptimizer(space, 'lbfgs')
+    acq = acquisition_factory(model, space, aopt)
+    X0 = GPyOpt.experiment_design.initial_design('random', space, 5)
+    if evaluator_type == 'sequential':
+        ev = GPyOpt.core.evaluators.Sequential(acq)
+    else:
+        ev = GPyOpt.core.evaluators.LocalPenalization(acq, batch_size)
+    bo = GPyOpt.methods.ModularBayesianOptimization(model, space, objective, acq, ev, X0)
+    bo.run_optimization(max_iter=iters, verbosity=False)
+    return bo.X.copy(), bo.Y.copy()
+
+
+def test_plugins_are_accepted_as_reference_types(gpyopt):
+    GPyOpt, models, acqs = gpyopt
+    from GPyOpt.models.base import BOModel
+    from GPyOpt.acquisitions.base import AcquisitionBase
+    assert issubclass(models.GPModel, BOModel) and issubclass(models.GPModel_MCMC, BOModel)
+    assert issubclass(acqs.AcquisitionEI, AcquisitionBase) and issubclass(acqs.AcquisitionLP, AcquisitionBase)
+    m = models.GPModel(max_iters=0)
+    bo = GPyOpt.methods.BayesianOptimization(f=branin, domain=DOMAIN, model=m, initial_design_numdata=3)
+    assert bo.model is m
+
+
+@pytest.mark.parametrize('acq_name', ['EI', 'MPI', 'LCB'])
+def test_sequential_bo_suggests_the_same_points(gpyopt, acq_name):
+    """x_next parity (1e-6) over a short Branin run: reference GPModel+acquisition vs the engine's plugins."""
+    GPyOpt, models, acqs = gpyopt
+    ref_acq = {'EI': GPyOpt.acquisitions.AcquisitionEI, 'MPI': GPyOpt.acquisitions.AcquisitionMPI,
+               'LCB': GPyOpt.acquisitions.AcquisitionLCB}[acq_name]
+    new_acq = {'EI': acqs.AcquisitionEI, 'MPI': acqs.AcquisitionMPI, 'LCB': acqs.AcquisitionLCB}[acq_name]
+    import GPy
+    Xr, Yr = _run(GPyOpt, GPyOpt.models.GPModel(kernel=GPy.kern.RBF(2), exact_feval=True, optimize_restarts=2, verbose=False),
+                  lambda m, s, o: ref_acq(m, s, o))
+    from gpyopt_b200 import kern
+    Xn, Yn = _run(GPyOpt, models.GPModel(kernel=kern.RBF(2), exact_feval=True, optimize_restarts=2, verbose=False),
+                  lambda m, s, o: new_acq(m, s, o))
+    assert Xr.shape == Xn.shape
+    assert np.max(np.abs(Xr - Xn)) < 1e-6, np.max(np.abs(Xr - Xn))
+
+
+def test_local_penalization_batch_matches(gpyopt):
+    """LocalPenalization evaluator (estimate_L reaches through model.model.predictive_gradients / .X / .Y)."""
+    GPyOpt, models, acqs = gpyopt
+    import GPy
+    from gpyopt_b200 import kern
+
+    def ref_factory(m, s, o):
+        return GPyOpt.acquisitions.AcquisitionLP(m, s, o, GPyOpt.acquisitions.AcquisitionEI(m, s, o))
+
+    def new_factory(m, s, o):
+        return acqs.AcquisitionLP(m, s, o, acqs.AcquisitionEI(m, s, o))
+
+    Xr, _ = _run(GPyOpt, GPyOpt.models.GPModel(kernel=GPy.kern.Matern52(2), optimize_restarts=1, verbose=False), ref_factory,
+                 evaluator_type='lp', batch_size=3, iters=2, seed=11)
+    Xn, _ = _run(GPyOpt, models.GPModel(kernel=kern.Matern52(2), optimize_restarts=1, verbose=False), new_factory,
+                 evaluator_type='lp', batch_size=3, iters=2, seed=11)
+    assert Xr.shape == Xn.shape
+    assert np.max(np.abs(Xr - Xn)) < 1e-5, np.max(np.abs(Xr - Xn))
+
+
+def test_mcmc_model_plugin_shapes(gpyopt):
+    GPyOpt, models, acqs = gpyopt
+    np.random.seed(0)
+    X = np.random.rand(10, 2)
+    Y = np.sin(3 * X[:, :1]) + X[:, 1:]
+    m = models.GPModel_MCMC(n_samples=3, n_burnin=4, subsample_interval=2, leapfrog_steps=3)
+    m.updateModel(X, Y, None, None)
+    assert m.hmc_samples.shape == (3, 3)
+    means, stds = m.predict(X[:4])
+    assert len(means) == 3 and means[0].shape == (4, 1) and stds[0].shape == (4, 1)
+    mm, ss, dm, ds = m.predict_withGradients(X[0])
+    assert dm[0].shape == (1, 2) and len(m.get_fmin()) == 3
+    space = GPyOpt.Design_space(DOMAIN)
+    a = acqs.AcquisitionEI_MCMC(m, space, None)
+    f, df = a.acquisition_function_withGradients(X[:4])
+    assert f.shape == (4, 1) and df.shape == (4, 2)

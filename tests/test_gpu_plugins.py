@@ -1,0 +1,170 @@
+"""GPU tests of the reference-facing plugin classes (gpyopt_b200.GPModel / GPModel_MCMC / Acquisition*):
+same shapes and values as the reference classes produced for the golden vectors, ML-II pin, x_next parity."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, scaled_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _model_from_golden(g, **kw):
+    from gpyopt_b200 import GPModel, kern
+    cls = {'rbf': kern.RBF, 'matern52': kern.Matern52, 'matern32': kern.Matern32}[str(g['kernel'])]
+    d = g['X'].shape[1]
+    k = cls(d, variance=float(g['variance']), lengthscale=g['lengthscale'], ARD=bool(g['ARD']))
+    m = GPModel(kernel=k, noise_var=float(g['noise_var']), exact_feval=bool(g['exact_feval']), max_iters=0, verbose=False, **kw)
+    m.updateModel(g['X'], g['Y'], None, None)
+    return m
+
+
+@pytest.mark.parametrize('case', ['c3_rbf_alpine2_n256', 'c3_mat32_ard_n130', 'c1_branin_rbf_n20', 'c1_1d_rbf_n7'])
+def test_gpmodel_plugin_matches_reference_class(case):
+    from gpyopt_b200 import AcquisitionEI, AcquisitionMPI, AcquisitionLCB
+    g = load_golden(case)
+    model = _model_from_golden(g)
+    Xs = g['Xs']
+    m, s = model.predict(Xs)
+    assert m.shape == g['m'].shape and s.shape == g['s'].shape
+    assert scaled_err(m, g['m']) < TOL and scaled_err(s, g['s']) < TOL
+    assert scaled_err(model.predict(Xs[5])[0], g['m_1d']) < TOL          # 1-D input is promoted to one row
+    m, s, dm, ds = model.predict_withGradients(Xs)
+    assert dm.shape == g['dmdx'].shape and scaled_err(dm, g['dmdx']) < TOL and scaled_err(ds, g['dsdx']) < TOL
+    assert abs(model.get_fmin() - float(g['fmin'])) < TOL * max(1, abs(float(g['fmin'])))
+    assert np.allclose(model.get_model_parameters(), g['params'], rtol=1e-14)
+    # the inner GPy-like object that LocalPenalization / plotting reach through
+    mi, vi = model.model.predict(Xs)
+    assert scaled_err(np.sqrt(vi), g['s']) < TOL
+    dmi, dvi = model.model.predictive_gradients(Xs)
+    assert dmi.shape == (Xs.shape[0], Xs.shape[1], 1) and scaled_err(dvi / (2 * g['s']), g['dsdx']) < TOL
+    for name, cls, kw in (('EI', AcquisitionEI, {'jitter': 0.01}), ('MPI', AcquisitionMPI, {'jitter': 0.01}),
+                          ('LCB', AcquisitionLCB, {'exploration_weight': 2})):
+        a = cls(model, None, None, **kw)
+        af = a.acquisition_function(Xs)
+        assert af.shape == g[name + '_af'].shape and scaled_err(af, g[name + '_af']) < TOL
+        afg, adf = a.acquisition_function_withGradients(Xs)
+        assert scaled_err(afg, g[name + '_afg']) < TOL and scaled_err(adf, g[name + '_adf']) < TOL
+
+
+def test_mcmc_plugin_matches_reference_class():
+    from gpyopt_b200 import GPModel_MCMC, AcquisitionEI_MCMC, AcquisitionLCB_MCMC
+    for case in ('c4_mcmc_n64_S8', 'c4_mcmc_exact_n48_S4'):
+        g = load_golden(case)
+        model = GPModel_MCMC(exact_feval=bool(g['exact_feval']))
+        model._create_model(g['X'], g['Y'])
+        model.set_hmc_samples(g['hmc_samples'])
+        means, stds, dms, dss = model.predict_withGradients(g['Xs'])
+        assert isinstance(means, list) and len(means) == g['hmc_samples'].shape[0] and means[0].shape == (g['Xs'].shape[0], 1)
+        assert scaled_err(np.array(means), g['means']) < TOL and scaled_err(np.array(dss), g['dsdxs']) < TOL
+        assert scaled_err(np.array(model.get_fmin()), g['fmins']) < TOL
+        f, df = AcquisitionEI_MCMC(model, None, None, jitter=0.01)._compute_acq_withGradients(g['Xs'])
+        assert scaled_err(f, g['EI_MCMC_fg']) < TOL and scaled_err(df, g['EI_MCMC_df']) < TOL
+        f = AcquisitionLCB_MCMC(model, None, None, exploration_weight=2)._compute_acq(g['Xs'])
+        assert scaled_err(f, g['LCB_MCMC_f']) < TOL
+
+
+def test_lp_plugin_matches_reference_class():
+    from gpyopt_b200 import AcquisitionEI, AcquisitionLCB, AcquisitionLP
+    g, gg = load_golden('c5_lp_gsobol_n128'), load_golden('c5_lp_gsobol_n128_gp')
+    model = _model_from_golden(gg)
+    Xs = g['Xs']
+    for tname, inner, transform in (('EI_none', AcquisitionEI(model, None, None, jitter=0.01), 'none'),
+                                    ('LCB_auto', AcquisitionLCB(model, None, None, exploration_weight=2), 'none')):
+        lp = AcquisitionLP(model, None, None, inner, transform=transform)
+        assert lp.transform == str(g[tname + '_transform'])
+        lp.update_batches(None, None, None)
+        f0 = lp.acquisition_function(Xs)
+        assert f0.ndim == 1 and scaled_err(f0, g[tname + '_f0']) < TOL
+        lp.update_batches(g['X_batch'], float(g['L']), float(g['Min']))
+        assert np.allclose(lp.r_x0, g[tname + '_r'], rtol=1e-9) and np.allclose(lp.s_x0, g[tname + '_s'], rtol=1e-9)
+        f = lp.acquisition_function(Xs)
+        assert scaled_err(f, g[tname + '_f']) < 1e-9
+        grads = np.vstack([lp.acquisition_function_withGradients(x[None, :])[1] for x in Xs[:16]])
+        assert scaled_err(grads, g[tname + '_g'][:16]) < 1e-9
+
+
+def test_ml2_fit_reproduces_reference_known_answer():
+    """GPyOpt/testing/core_tests/test_cost.py:14-19,35-42 through the B200 GPModel (default Matern52, ML-II with 5
+    restarts driven by the device log-likelihood and gradient)."""
+    from gpyopt_b200 import GPModel
+    np.random.seed(0)
+    X = np.array([[3., 0.], [4., 1.], [5., 1.]])
+    Y = np.log(np.array([[4.], [5.], [6.]]))
+    model = GPModel(verbose=False)
+    model.updateModel(X, Y, None, None)
+    m, _, _, _ = model.predict_withGradients(X)
+    assert np.allclose(np.exp(m), [[4.00000008], [5.00000038], [5.99999939]], rtol=1e-5)
+    m, _, dmdx, _ = model.predict_withGradients(np.array([2., 2.]))
+    assert np.isclose(np.exp(m)[0, 0], 3.52110177, rtol=1e-5)
+    assert np.allclose((np.exp(m) * dmdx)[0], [0.65617088, 0.08849139], rtol=1e-4)
+    assert model.get_model_parameters_names() == ['GP_regression.Mat52.variance', 'GP_regression.Mat52.lengthscale',
+                                                  'GP_regression.Gaussian_noise.variance']
+
+
+def test_x_next_parity_engine_vs_oracle():
+    """Acquisition optimisation as AcquisitionOptimizer does it (anchor sweep -> top-5 -> L-BFGS-B from each anchor,
+    GPyOpt/optimization/acquisition_optimizer.py:47-78, optimizer.py:28-61): the suggested x_next from the engine-backed
+    acquisition must match the oracle-backed one within 1e-6."""
+    import scipy.optimize
+    import gpyopt_b200.gp as gpmod
+    from gpyopt_b200 import GPModel, AcquisitionEI, kern, Engine
+    from fake_engine import FakeEngine
+    from oracle import gpyopt_numpy as og
+    rng = np.random.default_rng(123)
+    bounds = [(-5., 10.), (1., 15.)]
+    X = np.column_stack([rng.uniform(lo, hi, 25) for lo, hi in bounds])
+    Y = og.normalize_stats(og.branin(X))
+    cand = np.column_stack([rng.uniform(lo, hi, 1000) for lo, hi in bounds])
+
+    def suggest(engine_cls):
+        gpmod.Engine = engine_cls
+        try:
+            model = GPModel(kernel=kern.RBF(2, variance=1.0, lengthscale=2.5), exact_feval=True, max_iters=0, verbose=False)
+            model.updateModel(X, Y, None, None)
+            acq = AcquisitionEI(model, None, None, jitter=0.01)
+            scores = acq.acquisition_function(cand).flatten()
+            anchors = cand[np.argsort(scores, kind='stable')[:5]]
+            best = (np.inf, None)
+            for a in anchors:
+                def f_df(x):
+                    f, df = acq.acquisition_function_withGradients(np.atleast_2d(x))
+                    return float(f[0, 0]), df[0]
+                res = scipy.optimize.fmin_l_bfgs_b(f_df, x0=a, bounds=bounds, maxiter=1000)
+                if res[1] < best[0]:
+                    best = (res[1], res[0])
+            return best
+        finally:
+            gpmod.Engine = Engine
+    f_gpu, x_gpu = suggest(Engine)
+    f_cpu, x_cpu = suggest(FakeEngine)
+    assert np.max(np.abs(x_gpu - x_cpu)) < 1e-6 and abs(f_gpu - f_cpu) < 1e-9
+
+
+def test_bo_loop_on_branin_reaches_the_known_minimum():
+    """Config 1 in miniature (5 initial + 15 iterations, GP/RBF, EI): the BO loop closes around the engine and finds
+    Branin's minimum 0.397887 (GPyOpt/objective_examples/experiments2d.py:199) to within 0.1."""
+    import scipy.optimize
+    from gpyopt_b200 import GPModel, AcquisitionEI, kern
+    from oracle import gpyopt_numpy as og
+    np.random.seed(123)
+    bounds = [(-5., 10.), (1., 15.)]
+    lo, hi = np.array(bounds).T
+    X = lo + (hi - lo) * np.random.rand(5, 2)
+    Yraw = og.branin(X)
+    model = GPModel(kernel=kern.RBF(2), exact_feval=True, optimize_restarts=3, verbose=False)
+    for it in range(15):
+        model.updateModel(X, og.normalize_stats(Yraw), None, None)
+        acq = AcquisitionEI(model, None, None, jitter=0.01)
+        cand = lo + (hi - lo) * np.random.rand(1000, 2)
+        _, idx = model.model.engine.acq_topk('EI', 0.01, cand, 5)
+        best = (np.inf, None)
+        for a in cand[idx]:
+            res = scipy.optimize.fmin_l_bfgs_b(
+                lambda x: (lambda f, df: (float(f[0, 0]), df[0]))(*acq.acquisition_function_withGradients(np.atleast_2d(x))),
+                x0=a, bounds=bounds, maxiter=200)
+            if res[1] < best[0]:
+                best = (res[1], res[0])
+        X = np.vstack([X, best[1]])
+        Yraw = np.vstack([Yraw, og.branin(best[1])])
+    assert Yraw.min() < 0.397887 + 0.1

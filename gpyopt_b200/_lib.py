@@ -46,6 +46,10 @@ SIGNATURES = {
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'gpo_topk': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'gpo_set_strict_variance': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    'gpo_get_info': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    'gpo_set_profiling': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    'gpo_get_profile': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'gpo_alloc': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     'gpo_state_buffers': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     'gpo_state_commit': (ctypes.c_int, [ctypes.c_void_p]),
@@ -244,6 +248,16 @@ class Engine(object):
         kk = min(k, N)
         return vals[:kk], idx[:kk]
 
+    def set_strict_variance(self, mode):
+        """-1 automatic (default), 0 never, 1 always: see gpo_set_strict_variance in include/gpo_b200.h."""
+        self._check(self._lib.gpo_set_strict_variance(self._h, int(mode)), 'gpo_set_strict_variance')
+
+    def info(self):
+        v = np.zeros(6)
+        self._check(self._lib.gpo_get_info(self._h, _ptr(v), 6), 'gpo_get_info')
+        return {'strict_variance': bool(v[0]), 'variance_discrepancy': float(v[1]), 'chunk': int(v[2]), 'n_pad': int(v[3]),
+                'sm_count': int(v[4]), 'S': int(v[5])}
+
     # -- multi-GPU state replication ---------------------------------------------------------------
     def alloc(self, kernel, n, d, S):
         k = KERNELS[kernel.lower()] if isinstance(kernel, str) else int(kernel)
@@ -261,6 +275,15 @@ class Engine(object):
 
     def state_commit(self):
         self._check(self._lib.gpo_state_commit(self._h), 'gpo_state_commit')
+
+    def set_profiling(self, enable):
+        self._check(self._lib.gpo_set_profiling(self._h, int(bool(enable))), 'gpo_set_profiling')
+
+    def get_profile(self):
+        """-> (gemm_ms, gemm_launches, gemm_candidates) accumulated since the last call (synchronises)."""
+        ms, nl, nc = ctypes.c_double(0), ctypes.c_longlong(0), ctypes.c_longlong(0)
+        self._check(self._lib.gpo_get_profile(self._h, ctypes.byref(ms), ctypes.byref(nl), ctypes.byref(nc)), 'gpo_get_profile')
+        return ms.value, nl.value, nc.value
 
     def launch_count(self, reset=False):
         c = ctypes.c_longlong(0)

@@ -24,6 +24,7 @@ struct Slot {
   double* mean = nullptr;     // [S][nc_ld]
   double* dmean = nullptr;    // [S][d][nc_ld]
   double* partial = nullptr;  // [S][tiles_m][d+2][nc_ld]
+  double* partial_sq = nullptr;  // [S][tiles_m][nc_ld]  (strict variance in gradient mode)
 };
 
 struct gpo_engine {
@@ -60,8 +61,18 @@ struct gpo_engine {
   double *lp_xb = nullptr, *lp_r = nullptr, *lp_s = nullptr;
   // top-k scratch
   double* tk_vals[2] = {nullptr, nullptr};  long long* tk_idx[2] = {nullptr, nullptr};  size_t tk_cap = 0;
-  // counters
+  // parity guard: variance form used by gradient sweeps (-1 auto, 0 fast k.W^-1.k, 1 strict |L^-1 k|^2)
+  int strict_mode = -1;
+  bool strict_active = false;
+  double var_disc = 0.0;
+  // counters / live profiling of the dominant kernel (variance GEMM) for the benchmark's roofline
   long long launches = 0;
+  int profiling = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
+  double prof_gemm_ms = 0.0;
+  long long prof_gemm_launches = 0;
+  long long prof_gemm_cands = 0;
 };
 
 static thread_local char g_create_error[256] = {0};
@@ -196,7 +207,7 @@ static void free_state(gpo_engine* eng) {
   if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
   for (int i = 0; i < 2; ++i) {
     Slot& s = eng->slot[i];
-    double** sp[] = {&s.Kt, &s.Ht, &s.mean, &s.dmean, &s.partial};
+    double** sp[] = {&s.Kt, &s.Ht, &s.mean, &s.dmean, &s.partial, &s.partial_sq};
     for (auto pp : sp) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   }
   eng->cap_n_pad = eng->cap_d = eng->cap_S = 0;
@@ -297,6 +308,7 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
     GPO_CUDA_OK(cudaMalloc(&s.mean, (size_t)S * eng->nc_ld * 8));
     GPO_CUDA_OK(cudaMalloc(&s.dmean, (size_t)S * d * eng->nc_ld * 8));
     GPO_CUDA_OK(cudaMalloc(&s.partial, (size_t)S * tiles_m * (d + 2) * eng->nc_ld * 8));
+    GPO_CUDA_OK(cudaMalloc(&s.partial_sq, (size_t)S * tiles_m * eng->nc_ld * 8));
     if ((rc = make_map(eng, &s.mapKt, s.Kt, n_pad, eng->nc_ld, S))) return rc;
   }
   eng->cap_n_pad = n_pad; eng->cap_d = d; eng->cap_S = S;
@@ -416,6 +428,48 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
 static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool want_kt_only, int with_noise, long long N,
                  const double* Xs, double* o0, double* o1, double* o2, double* o3, cudaStream_t user);
 
+// parity guard (see variance_probe_kernel): decide which variance form gradient sweeps use
+static int run_variance_probe(gpo_engine* eng, cudaStream_t st) {
+  const int n = eng->n, n_pad = eng->n_pad, d = eng->d, S = eng->S, kernel = eng->kern;
+  int rc;
+  {
+    Slot& s0 = eng->slot[0];
+    Slot& s1 = eng->slot[1];
+    const int tiles_m = n_pad / TILE;
+    CovParams cp;
+    cp.Xs = eng->Xaos; cp.n_cand = n; cp.nc_run = n_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n;
+    cp.n_pad = n_pad; cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
+    cp.Kt = s0.Kt; cp.Ht = nullptr; cp.mean = s0.mean; cp.dmean = nullptr;
+    if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
+    GemmParams g = gemm_defaults();
+    g.tiles_m = tiles_m; g.tiles_n = tiles_m; g.kblocks = tiles_m;
+    g.a = {0, 0, 0, 0, 0, 1}; g.b = {0, 0, 0, 0, 0, 1};
+    g.ldp = eng->nc_ld;
+    GemmParams gs = g; gs.partial = s0.partial_sq; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
+    if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s0.mapKt, gs, S, st))) return rc;
+    GemmParams gg = g; gg.partial = s1.partial; gg.krange = KR_FULL; gg.raster = RO_M_FASTEST;
+    gg.d = 0; gg.Xtc = eng->Xtc; gg.ldx = n_pad; gg.Kt = s0.Kt; gg.Ht = nullptr; gg.nc_ld = eng->nc_ld; gg.n_pad = n_pad;
+    if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s0.mapKt, gg, S, st))) return rc;
+    variance_probe_kernel<<<S, 256, 0, st>>>(s0.partial_sq, s1.partial, tiles_m, 2, eng->nc_ld, n, eng->sigf2, eng->noise,
+                                             eng->quad /*scratch, already copied out*/);
+    eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
+    std::vector<double> disc(S);
+    GPO_CUDA_OK(cudaMemcpyAsync(disc.data(), eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->quad, eng->h_quad.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+    eng->var_disc = 0.0;
+    bool need = false;
+    for (int z = 0; z < S; ++z) {
+      const double scale = std::sqrt(std::max(eng->h_sigf2[z] + eng->h_noise[z], 1e-300));
+      eng->var_disc = std::max(eng->var_disc, disc[z] / scale);
+      if (!(disc[z] <= 2e-11 * scale)) need = true;
+    }
+    eng->strict_active = eng->strict_mode == 1 || (eng->strict_mode < 0 && need);
+  }
+  return GPO_OK;
+}
+
 extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* X, const double* Y, int S,
                        const double* variance, const double* lengthscale, const double* noise) {
   if (!eng) return GPO_ERR_ARG;
@@ -512,6 +566,7 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
     GPO_CUDA_OK(cudaMemcpyAsync(eng->h_fmin.data(), eng->fmin, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
     GPO_CUDA_OK(cudaStreamSynchronize(st));
   }
+  if ((rc = run_variance_probe(eng, st))) return rc;
   return GPO_OK;
 }
 
@@ -650,20 +705,44 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     g.a = {0, 0, 0, 0, 0, 1};
     g.b = {0, 0, 0, 0, 0, 1};
     g.partial = s.partial; g.ldp = eng->nc_ld;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (eng->profiling) {
+      if (eng->prof_used == eng->prof_events.size()) {
+        cudaEvent_t a, b;
+        GPO_CUDA_OK(cudaEventCreate(&a));
+        GPO_CUDA_OK(cudaEventCreate(&b));
+        eng->prof_events.push_back({a, b});
+      }
+      pe0 = eng->prof_events[eng->prof_used].first;
+      pe1 = eng->prof_events[eng->prof_used].second;
+      eng->prof_used++;
+      eng->prof_gemm_cands += rows;
+      GPO_CUDA_OK(cudaEventRecord(pe0, st));
+    }
     if (grad) {
       g.krange = KR_FULL; g.raster = RO_M_FASTEST;
       g.d = d; g.Xtc = eng->Xtc; g.ldx = n_pad; g.Kt = s.Kt; g.Ht = eng->kern != KERN_RBF ? s.Ht : nullptr;
       g.nc_ld = eng->nc_ld; g.n_pad = n_pad;
       if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s.mapKt, g, S, st))) return rc;
+      if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
+      if (eng->strict_active) {  // ill-conditioned model: variance from the reference's own triangular form as well
+        GemmParams gs = gemm_defaults();
+        gs.tiles_m = tiles_m; gs.tiles_n = tiles_n; gs.kblocks = tiles_m;
+        gs.a = {0, 0, 0, 0, 0, 1}; gs.b = {0, 0, 0, 0, 0, 1};
+        gs.partial = s.partial_sq; gs.ldp = eng->nc_ld; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
+        if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, gs, S, st))) return rc;
+      }
     } else {
       g.krange = KR_LE_M; g.raster = RO_HEAVY_FIRST;
       if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, g, S, st))) return rc;
+      if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
     }
     // K3
     AcqParams ap;
     memset(&ap, 0, sizeof(ap));
     ap.n_cand = rows; ap.nc_pad = eng->nc_ld; ap.S = S; ap.d = d; ap.tiles_m = tiles_m; ap.grad = grad ? 1 : 0;
     ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = s.partial; ap.sigf2 = eng->sigf2;
+    ap.partial_sq = (grad && eng->strict_active) ? s.partial_sq : nullptr;
     ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par; ap.invl = eng->invl; ap.xmu = eng->xmu;
     ap.Xs = dev_in + off * d;
     if (predict) {
@@ -869,5 +948,47 @@ extern "C" int gpo_state_commit(gpo_engine* eng) {
   GPO_CUDA_OK(cudaMemcpy(eng->h_sigf2.data(), eng->sigf2, (size_t)S * 8, cudaMemcpyDeviceToHost));
   GPO_CUDA_OK(cudaMemcpy(eng->h_noise.data(), eng->noise, (size_t)S * 8, cudaMemcpyDeviceToHost));
   eng->fitted = true;
+  return run_variance_probe(eng, eng->fit_stream);
+}
+
+extern "C" int gpo_set_strict_variance(gpo_engine* eng, int mode) {
+  if (!eng || mode < -1 || mode > 1) return GPO_ERR_ARG;
+  eng->strict_mode = mode;
+  if (mode >= 0) eng->strict_active = mode == 1;
+  return GPO_OK;
+}
+
+extern "C" int gpo_get_info(gpo_engine* eng, double* info, int count) {
+  if (!eng || !info || count < 1) return GPO_ERR_ARG;
+  const double vals[] = {eng->strict_active ? 1.0 : 0.0, eng->var_disc, (double)eng->nc_ld, (double)eng->n_pad,
+                         (double)eng->sm_count, (double)eng->S};
+  const int have = (int)(sizeof(vals) / sizeof(vals[0]));
+  for (int i = 0; i < count; ++i) info[i] = i < have ? vals[i] : 0.0;
+  return GPO_OK;
+}
+
+// Live timing of the dominant kernel (the variance GEMM of each sweep chunk) with CUDA events recorded on the stream the
+// kernel is launched on.  enable = 1 starts collecting, gpo_get_profile synchronises, accumulates and resets.
+extern "C" int gpo_set_profiling(gpo_engine* eng, int enable) {
+  if (!eng) return GPO_ERR_ARG;
+  eng->profiling = enable ? 1 : 0;
+  return GPO_OK;
+}
+
+extern "C" int gpo_get_profile(gpo_engine* eng, double* gemm_ms, long long* gemm_launches, long long* gemm_candidates) {
+  if (!eng) return GPO_ERR_ARG;
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  for (int i = 0; i < 2; ++i) GPO_CUDA_OK(cudaStreamSynchronize(eng->slot[i].stream));
+  for (size_t i = 0; i < eng->prof_used; ++i) {
+    float ms = 0.f;
+    GPO_CUDA_OK(cudaEventElapsedTime(&ms, eng->prof_events[i].first, eng->prof_events[i].second));
+    eng->prof_gemm_ms += ms;
+    eng->prof_gemm_launches++;
+  }
+  eng->prof_used = 0;
+  if (gemm_ms) *gemm_ms = eng->prof_gemm_ms;
+  if (gemm_launches) *gemm_launches = eng->prof_gemm_launches;
+  if (gemm_candidates) *gemm_candidates = eng->prof_gemm_cands;
+  eng->prof_gemm_ms = 0.0; eng->prof_gemm_launches = 0; eng->prof_gemm_cands = 0;
   return GPO_OK;
 }

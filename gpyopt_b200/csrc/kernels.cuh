@@ -321,6 +321,7 @@ struct AcqParams {
   const double* mean;    // [S][nc_pad]
   const double* dmean;   // [S][d][nc_pad]
   const double* partial; // [S][tiles_m][nv][nc_pad]; nv = 1 (sum of squares) or d + 2 (S0, H0, P_1..P_d)
+  const double* partial_sq; // optional [S][tiles_m][nc_pad]: sum of squares |L^-1 k|^2 (strict variance in gradient mode)
   const double* invl;    // [S][d]
   const double* xmu;     // [d] centring offsets of the training inputs
   const double* sigf2;   // [S]
@@ -357,7 +358,14 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
     const double m = p.mean[(long long)z * p.nc_pad + i];
     const double* part = p.partial + (long long)z * p.tiles_m * nv * p.nc_pad + i;
     double s0 = 0.0;
-    for (int tm = 0; tm < p.tiles_m; ++tm) s0 += part[(long long)tm * nv * p.nc_pad];
+    if (p.grad && p.partial_sq) {
+      // strict variance: the reference's own form sigma_f^2 - |L^-1 k|^2 (PosteriorExact._raw_predict), immune to
+      // the cancellation of k.W^-1.k on ill-conditioned Gram matrices
+      const double* psq = p.partial_sq + (long long)z * p.tiles_m * p.nc_pad + i;
+      for (int tm = 0; tm < p.tiles_m; ++tm) s0 += psq[(long long)tm * p.nc_pad];
+    } else {
+      for (int tm = 0; tm < p.tiles_m; ++tm) s0 += part[(long long)tm * nv * p.nc_pad];
+    }
     double v = p.sigf2[z] - s0;
     if (p.with_noise) v += p.noise[z];
     v = ::fmax(v, 1e-10);
@@ -475,6 +483,33 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
 #pragma unroll
     for (int q = 0; q < DMAX; ++q)
       if (q < d) p.out_df[i * d + q] = scale * (-df_acc[q]) - dsum;
+  }
+}
+
+// Parity guard run after every refit: at the n training inputs (where the posterior variance is smallest and the
+// cancellation worst) compare s from the triangular form sigma_f^2 - |L^-1 k|^2 with s from k.W^-1.k.
+// out[z] = max_i |s_L - s_W|.
+__global__ void variance_probe_kernel(const double* part_sq, const double* part_gr, int tiles_m, int nv, long long nc_pad,
+                                      int n, const double* sigf2, const double* noise, double* out) {
+  const int z = blockIdx.x;
+  __shared__ double sh[32];
+  double mx = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double q = 0.0, s0 = 0.0;
+    for (int tm = 0; tm < tiles_m; ++tm) {
+      q += part_sq[((long long)z * tiles_m + tm) * nc_pad + i];
+      s0 += part_gr[((long long)(z * tiles_m + tm) * nv) * nc_pad + i];
+    }
+    const double sl = sqrt(::fmax(sigf2[z] - q + noise[z], 1e-10)), sw = sqrt(::fmax(sigf2[z] - s0 + noise[z], 1e-10));
+    mx = ::fmax(mx, fabs(sl - sw));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = ::fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = ::fmax(mx, sh[i]);
+    out[z] = mx;
   }
 }
 

@@ -161,7 +161,7 @@ class GPRegressionB200(object):
     """
     name = 'GP_regression'
 
-    def __init__(self, X, Y, kernel=None, noise_var=1.0, device=0, engine=None):
+    def __init__(self, X, Y, kernel=None, noise_var=1.0, device=0, engine=None, adopt_state=False):
         X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
         Y = np.ascontiguousarray(np.asarray(Y, dtype=np.float64))
         if X.ndim != 2 or Y.ndim != 2 or Y.shape[1] != 1 or Y.shape[0] != X.shape[0]:
@@ -181,6 +181,9 @@ class GPRegressionB200(object):
         self.Gaussian_noise = self.likelihood
         self.optimization_runs = []
         self._samples = None  # [S, p] full parameter rows when several hyper-parameter sets are resident
+        # adopt_state: `engine` already holds the posterior for exactly these (X, Y, hyper-parameters) -- e.g. it was
+        # replicated from another rank over NCCL (gpyopt_b200.parallel) -- so the constructor must not refit
+        self._frozen = bool(adopt_state)
         self._trigger_params_changed()
 
     # -- parameter plumbing ---------------------------------------------------------------------------
@@ -241,6 +244,8 @@ class GPRegressionB200(object):
     def _trigger_params_changed(self):
         """GPy ``parameters_changed``: Ky = K + (noise + 1e-8) I -> L, alpha, W^-1 (K4 on the GPU)."""
         self._samples = None
+        if self._frozen:
+            return
         var, ls, noise = self._rows_to_theta(self.param_array[None, :])
         self.engine.fit(self._spec.kind, self.X, self.Y[:, 0], var, ls, noise)
 
@@ -253,7 +258,12 @@ class GPRegressionB200(object):
         self.engine.fit(self._spec.kind, self.X, self.Y[:, 0], var, ls, noise)
         self._samples = rows.copy()
 
+    def unfreeze(self):
+        """Leave adopt_state mode: later parameter / data changes refit on this engine again."""
+        self._frozen = False
+
     def set_XY(self, X=None, Y=None):
+        self._frozen = False
         if X is not None:
             self.X = np.ascontiguousarray(np.asarray(X, dtype=np.float64)).copy()
         if Y is not None:

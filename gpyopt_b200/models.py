@@ -19,7 +19,7 @@ class GPModel(BOModel):
 
     def __init__(self, kernel=None, noise_var=None, exact_feval=False, optimizer='bfgs', max_iters=1000,
                  optimize_restarts=5, sparse=False, num_inducing=10, verbose=True, ARD=False, mean_function=None,
-                 device=0):
+                 device=0, engine=None, adopt_state=False):
         if sparse:
             raise NotImplementedError("sparse GP (VarDTC) is a different posterior and out of the engine's scope")
         if mean_function is not None:
@@ -37,6 +37,10 @@ class GPModel(BOModel):
         self.ARD = ARD
         self.mean_function = mean_function
         self.device = device
+        # multi-GPU replicas: `engine` is an Engine whose state was broadcast from the fitting rank
+        # (gpyopt_b200.parallel.ShardedSweep.fit); with adopt_state the first updateModel does not refit it
+        self._engine = engine
+        self._adopt_state = bool(adopt_state)
 
     @staticmethod
     def fromConfig(config):
@@ -51,12 +55,16 @@ class GPModel(BOModel):
             kern = self.kernel
             self.kernel = None
         noise_var = Y.var() * 0.01 if self.noise_var is None else self.noise_var
-        engine = self.model.engine if self.model is not None else None
-        self.model = GPRegressionB200(X, Y, kernel=kern, noise_var=noise_var, device=self.device, engine=engine)
+        engine = self.model.engine if self.model is not None else self._engine
+        self.model = GPRegressionB200(X, Y, kernel=kern, noise_var=noise_var, device=self.device, engine=engine,
+                                      adopt_state=self._adopt_state)
         if self.exact_feval:
             self.model.Gaussian_noise.constrain_fixed(1e-6, warning=False)
         else:
             self.model.Gaussian_noise.constrain_bounded(1e-9, 1e6, warning=False)
+        if self._adopt_state:
+            self._adopt_state = False
+            self.model.unfreeze() if self.max_iters > 0 else None
 
     def updateModel(self, X_all, Y_all, X_new, Y_new):
         """gpmodel.py:78-93."""

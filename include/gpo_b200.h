@@ -111,6 +111,16 @@ int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, const doubl
 int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, int largest, double* vals, long long* idx,
              void* stream);
 
+/* Parity guard.  Gradient sweeps need b = W^-1 k anyway and by default also take the variance from it
+ * (sigma_f^2 - k.b: 2 n^2 flop per candidate in total).  On an ill-conditioned Gram matrix that form cancels badly,
+ * whereas the reference's sigma_f^2 - |L^-1 k|^2 (GPy PosteriorExact._raw_predict) does not.  After every refit the
+ * engine measures max |s_L - s_W| over the training inputs; in mode -1 (automatic, default) it adds the triangular
+ * pass (3 n^2 flop per candidate, as the reference itself spends) when that discrepancy exceeds 2e-11 sqrt(sf2 + noise).
+ * mode 0 = never, 1 = always.  gpo_get_info: info[0] = strict pass active, info[1] = measured discrepancy (scaled),
+ * info[2] = chunk (candidates), info[3] = padded n, info[4] = SM count, info[5] = S. */
+int gpo_set_strict_variance(gpo_engine* eng, int mode);
+int gpo_get_info(gpo_engine* eng, double* info, int count);
+
 /* Multi-GPU replication of the posterior state (one process per GPU; the collective itself is issued by the
  * host through torch.distributed / NCCL on the buffers listed here).
  *   gpo_alloc          allocate an engine for (kernel, n, d, S) without fitting (receiving ranks)
@@ -121,6 +131,12 @@ int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, int largest, 
 int gpo_alloc(gpo_engine* eng, int kernel, int n, int d, int S);
 int gpo_state_buffers(gpo_engine* eng, void** ptrs, long long* bytes, int max);
 int gpo_state_commit(gpo_engine* eng);
+
+/* Live timing of the dominant kernel (the variance GEMM launched once per sweep chunk), measured with CUDA events on
+ * the stream the kernel runs on.  gpo_get_profile synchronises, returns the accumulated milliseconds, launches and
+ * candidates since the last call, and resets. */
+int gpo_set_profiling(gpo_engine* eng, int enable);
+int gpo_get_profile(gpo_engine* eng, double* gemm_ms, long long* gemm_launches, long long* gemm_candidates);
 
 /* Counters for the benchmark harness: kernels launched and seconds of GPU time since the last reset. */
 int gpo_launch_count(gpo_engine* eng, long long* launches, int reset);

@@ -10,7 +10,8 @@ computation), identical top-k / argmax indices on the fixed candidate set.
 import numpy as np
 import pytest
 
-from conftest import load_golden, scaled_err, oracle_gp_from_golden, GP_CASES, MCMC_CASES
+from conftest import (load_golden, scaled_err, assert_grad_close, parity_tolerances, oracle_gp_from_golden,
+                      GP_CASES, MCMC_CASES)
 
 pytestmark = pytest.mark.gpu
 
@@ -31,13 +32,15 @@ def test_predict_matches_reference_golden(engine, case):
     g = load_golden(case)
     fit_from_golden(engine, g)
     Xs = g['Xs']
+    tol_v, tol_g = parity_tolerances(oracle_gp_from_golden(g), Xs)   # == (1e-10, 1e-10) unless ill-conditioned
     m, s = engine.predict(Xs)
-    assert scaled_err(m[0], g['m'][:, 0]) < TOL and scaled_err(s[0], g['s'][:, 0]) < TOL
+    assert scaled_err(m[0], g['m'][:, 0]) < tol_v and scaled_err(s[0], g['s'][:, 0]) < tol_v
     m0, s0 = engine.predict(Xs, with_noise=False)
-    assert scaled_err(m0[0], g['m_nonoise'][:, 0]) < TOL and scaled_err(s0[0], g['s_nonoise'][:, 0]) < TOL
+    assert scaled_err(m0[0], g['m_nonoise'][:, 0]) < tol_v and scaled_err(s0[0], g['s_nonoise'][:, 0]) < tol_v
     m, s, dm, ds = engine.predict_grad(Xs)
-    assert scaled_err(m[0], g['mg'][:, 0]) < TOL and scaled_err(s[0], g['sg'][:, 0]) < TOL
-    assert scaled_err(dm[0], g['dmdx']) < TOL and scaled_err(ds[0], g['dsdx']) < TOL
+    assert scaled_err(m[0], g['mg'][:, 0]) < tol_v and scaled_err(s[0], g['sg'][:, 0]) < tol_v
+    assert_grad_close(dm[0], g['dmdx'], tol=tol_g)
+    assert_grad_close(ds[0], g['dsdx'], tol=tol_g)
     assert abs(engine.get_fmin()[0] - float(g['fmin'])) <= TOL * max(1.0, abs(float(g['fmin'])))
 
 
@@ -47,14 +50,16 @@ def test_acquisition_matches_reference_golden(engine, case, acq, par):
     g = load_golden(case)
     fit_from_golden(engine, g)
     Xs = g['Xs']
+    tol_v, tol_g = parity_tolerances(oracle_gp_from_golden(g), Xs)
     f = engine.acq(acq, par, Xs)
-    assert scaled_err(f, g[acq + '_f'][:, 0]) < TOL
+    assert scaled_err(f, g[acq + '_f'][:, 0]) < tol_v
     f2, df = engine.acq(acq, par, Xs, grad=True)
-    assert scaled_err(f2, g[acq + '_fg'][:, 0]) < TOL and scaled_err(df, g[acq + '_df']) < TOL
+    assert scaled_err(f2, g[acq + '_fg'][:, 0]) < tol_v
+    assert_grad_close(df, g[acq + '_df'], tol=tol_g)
     # the sweep's selection: same k best candidates as the reference's argsort(acquisition_function(X))[:5]
     vals, idx = engine.acq_topk(acq, par, Xs, 5)
     assert np.array_equal(idx, g[acq + '_top5'])
-    assert scaled_err(vals, g[acq + '_af'].flatten()[g[acq + '_top5']]) < TOL
+    assert scaled_err(vals, g[acq + '_af'].flatten()[g[acq + '_top5']]) < tol_v
     assert int(np.argmax(f)) == int(np.argmin(g[acq + '_af']))
 
 
@@ -65,15 +70,19 @@ def test_mcmc_matches_reference_golden(engine, case):
     S = hs.shape[0]
     noise = hs[:, 2] if hs.shape[1] == 3 else np.full(S, 1e-6)
     engine.fit('rbf', X, Y, hs[:, 0], hs[:, 1:2], noise)
+    from oracle import gpy_numpy as G
+    tols = [parity_tolerances(G.GPRegression(X, Y, G.RBF(X.shape[1], variance=hs[z, 0], lengthscale=hs[z, 1]),
+                                             noise_var=noise[z]), Xs) for z in range(S)]
+    tol_v, tol_g = max(t[0] for t in tols), max(t[1] for t in tols)
     m, s, dm, ds = engine.predict_grad(Xs)
-    assert scaled_err(m, g['means'][:, :, 0]) < TOL and scaled_err(s, g['stds'][:, :, 0]) < TOL
-    assert scaled_err(dm, g['dmdxs']) < TOL and scaled_err(ds, g['dsdxs']) < TOL
-    assert scaled_err(engine.get_fmin(), g['fmins']) < TOL
+    assert scaled_err(m, g['means'][:, :, 0]) < tol_v and scaled_err(s, g['stds'][:, :, 0]) < tol_v
+    assert scaled_err(dm, g['dmdxs']) < tol_g and scaled_err(ds, g['dsdxs']) < tol_g
+    assert scaled_err(engine.get_fmin(), g['fmins']) < tol_v
     for acq, par in (('EI_MCMC', 0.01), ('MPI_MCMC', 0.01), ('LCB_MCMC', 2.0)):
         f = engine.acq(acq, par, Xs)
-        assert scaled_err(f, g[acq + '_f'][:, 0]) < TOL
+        assert scaled_err(f, g[acq + '_f'][:, 0]) < tol_v
         f2, df = engine.acq(acq, par, Xs, grad=True)
-        assert scaled_err(f2, g[acq + '_fg'][:, 0]) < TOL and scaled_err(df, g[acq + '_df']) < TOL
+        assert scaled_err(f2, g[acq + '_fg'][:, 0]) < tol_v and scaled_err(df, g[acq + '_df']) < tol_g
 
 
 def test_local_penalization_matches_reference_golden(engine):
@@ -85,12 +94,13 @@ def test_local_penalization_matches_reference_golden(engine):
                                            ('LCB_auto', 'LCB', 2.0, 'softplus')):
             engine.lp_set(None, None, None, transform)  # transform only (X_batch is None)
             f0, g0 = engine.acq(acq, par, Xs, grad=True)
-            assert scaled_err(f0, g[tname + '_f0']) < TOL and scaled_err(g0, g[tname + '_g0']) < TOL
+            assert scaled_err(f0, g[tname + '_f0']) < TOL
+            assert_grad_close(g0, g[tname + '_g0'])
             engine.lp_set(Xb, g[tname + '_r'], g[tname + '_s'], transform)
             f = engine.acq(acq, par, Xs)
             f1, g1 = engine.acq(acq, par, Xs, grad=True)
             assert scaled_err(f, g[tname + '_f']) < TOL and scaled_err(f1, g[tname + '_f']) < TOL
-            assert scaled_err(g1, g[tname + '_g']) < TOL
+            assert_grad_close(g1, g[tname + '_g'])
     finally:
         engine.lp_set(None, None, None, None)
 
@@ -211,11 +221,14 @@ def test_host_and_device_pointers_agree_bitwise(engine):
     Xd = torch.from_numpy(Xs).cuda()
     f_d, df_d = engine.acq('EI', 0.01, Xd, grad=True, stream=torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    assert np.array_equal(f_h, f_d.cpu().numpy()) and np.array_equal(df_h, df_d.cpu().numpy())
+    f_dn, df_dn = f_d.cpu().numpy(), df_d.cpu().numpy()
+    bad = np.nonzero(f_h != f_dn)[0]
+    assert bad.size == 0, (bad[:10], f_h[bad[:5]], f_dn[bad[:5]])
+    assert np.array_equal(df_h, df_dn)
     # mixed: device input, host output
-    f_m = np.empty(Xs.shape[0])
-    engine.acq('EI', 0.01, Xd, out=(f_m, None))
-    assert np.array_equal(f_m, f_h)
+    f_m, df_m = np.empty(Xs.shape[0]), np.empty(Xs.shape)
+    engine.acq('EI', 0.01, Xd, grad=True, out=(f_m, df_m))
+    assert np.array_equal(f_m, f_h) and np.array_equal(df_m, df_h)
 
 
 def test_chunking_is_invisible(engine):
@@ -242,9 +255,13 @@ def test_candidates_on_training_points(engine):
     gp, X, Y, Xs, ls = _oracle_case(200, 4, 'matern32', False, 1e-4, 10, seed=9)
     engine.fit('matern32', X, Y, [1.3], np.broadcast_to(ls, (4,))[None, :], [1e-4])
     mo, so, dmo, dso = og.gp_predict_withGradients(gp, X[:50])
+    tol_v, tol_g = parity_tolerances(gp, X[:50])
     m, s, dm, ds = engine.predict_grad(X[:50])
-    assert scaled_err(m[0], mo[:, 0]) < TOL and scaled_err(s[0], so[:, 0]) < TOL
-    assert scaled_err(dm[0], dmo) < TOL and scaled_err(ds[0], dso) < 1e-8  # dsdx divides by a tiny s here
+    # every candidate here has a tiny s (~sqrt(2 noise)); scale errors in s by the prior std sqrt(sf2 + noise), the
+    # natural scale of the quantity, not by the (tiny) maximum over this adversarial candidate set
+    prior_std = np.sqrt(1.3 + 1e-4)
+    assert scaled_err(m[0], mo[:, 0]) < tol_v and np.max(np.abs(s[0] - so[:, 0])) / prior_std < tol_v
+    assert scaled_err(dm[0], dmo) < tol_g and scaled_err(ds[0], dso) < tol_g
 
 
 def test_topk_semantics(engine):

@@ -305,6 +305,14 @@ class Engine(object):
     @staticmethod
     def _empty_like(Xs, shape):
         if isinstance(Xs, np.ndarray):
+            if int(np.prod(shape)) >= (1 << 17):
+                # large host results: page-locked memory (torch's caching host allocator) so the chunk-by-chunk
+                # device->host copies run asynchronously at full PCIe rate and overlap the next chunk's kernels
+                try:
+                    import torch
+                    return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+                except Exception:
+                    pass
             return np.empty(shape, dtype=np.float64)
         import torch
         return torch.empty(shape, dtype=torch.float64, device=Xs.device)

@@ -138,70 +138,125 @@ __global__ void gram_kernel(double* A, const double* Xt, long long ldx, int n, i
 // mean of diag(K(X,X)) + noise + 1e-8 over the n real rows == sigf2 + noise + 1e-8 for a stationary kernel:
 // computed on the host; no kernel needed.
 
-// Cholesky factor + inverse of one 128 x 128 diagonal block per batch z, entirely in shared memory.
+// Cholesky factor + inverse of one 128 x 128 diagonal block per batch z.
 //   in : lower triangle of A[z][kb*128 .. +128)^2   (upper part ignored)
 //   out: A block <- L (upper zeroed), X block <- L^-1 (lower), U block <- L^-T (upper)
 // info[z] is set to (global column index + 1) of the first non-positive pivot.
+// 16 x 16 threads; thread (ty, tx) keeps the 8 x 8 elements (ty + 16 a, tx + 16 b) in REGISTERS through both phases
+// (cyclic ownership keeps all threads busy while the active region shrinks); per column/row step only the pivot and
+// the finished column/row travel through shared memory (two block barriers per step, 16 LDS + 64 DFMA per thread).
 constexpr int DIAG_THREADS = 256;
 constexpr int DIAG_PITCH = TILE + 1;
-constexpr int DIAG_SMEM_BYTES = (TILE * DIAG_PITCH + TILE) * 8;
+constexpr int DIAG_SMEM_BYTES = (TILE * DIAG_PITCH + 2 * TILE) * 8;
 
 __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, double* X, double* U, int n_pad, int kb,
                                                                      int* info) {
   extern __shared__ double sm[];
-  double* S = sm;                          // [128][129]
-  double* invd = sm + TILE * DIAG_PITCH;   // [128]
+  double* S = sm;                          // [128][129]  L (phase 2 reads its columns)
+  double* vec = sm + TILE * DIAG_PITCH;    // [128] finished column (phase 1) / finished row (phase 2)
+  double* piv = vec + TILE;                // [1]
   const int z = blockIdx.x, tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
   const long long base = ((long long)z * n_pad + (long long)kb * TILE) * n_pad + (long long)kb * TILE;
-  for (int idx = tid; idx < TILE * TILE; idx += DIAG_THREADS) {
-    const int i = idx / TILE, j = idx % TILE;
-    S[i * DIAG_PITCH + j] = A[base + (long long)i * n_pad + j];
-  }
-  __syncthreads();
-  for (int j = 0; j < TILE; ++j) {
-    if (tid == 0) {
-      double dd = S[j * DIAG_PITCH + j];
-      if (!(dd > 0.0)) {
-        if (info[z] == 0) info[z] = kb * TILE + j + 1;
-        dd = 1.0;
+  double r[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int i = ty + 16 * a, k = tx + 16 * b;
+      r[a][b] = A[base + (long long)(k <= i ? i : k) * n_pad + (k <= i ? k : i)];  // symmetric fill from the lower part
+    }
+  // ---- phase 1: right-looking Cholesky ----
+  // column j = jo + 16 jb: the outer loop over jb is unrolled so the owners' register index is a compile-time constant
+#pragma unroll
+  for (int jb = 0; jb < 8; ++jb) {
+#pragma unroll 1
+    for (int jo = 0; jo < 16; ++jo) {
+      const int j = jo + 16 * jb;
+      if (ty == jo && tx == jo) {
+        double dd = r[jb][jb];
+        if (!(dd > 0.0)) {
+          if (info[z] == 0) info[z] = kb * TILE + j + 1;
+          dd = 1.0;
+        }
+        piv[0] = sqrt(dd);
       }
-      S[j * DIAG_PITCH + j] = sqrt(dd);
+      __syncthreads();
+      if (tx == jo) {  // owners of column j: scale by the reciprocal pivot (as LAPACK dpotf2 does) and publish
+        const double p = piv[0], rp = 1.0 / p;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const int i = ty + 16 * a;
+          if (i > j) r[a][jb] *= rp;
+          else if (i == j) r[a][jb] = p;
+          if (i >= j) vec[i] = r[a][jb];
+        }
+      }
+      __syncthreads();
+      double li[8], lk[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) li[a] = (ty + 16 * a > j) ? vec[ty + 16 * a] : 0.0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) lk[b] = (tx + 16 * b > j) ? vec[tx + 16 * b] : 0.0;
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) r[a][b] = fma(-li[a], lk[b], r[a][b]);
+      // vec is rewritten only after the next pivot barrier, which every thread reaches after these reads
     }
-    __syncthreads();
-    const double piv = S[j * DIAG_PITCH + j];
-    for (int i = j + 1 + tid; i < TILE; i += DIAG_THREADS) S[i * DIAG_PITCH + j] /= piv;
-    __syncthreads();
-    const int w = TILE - j - 1;
-    for (int idx = tid; idx < w * w; idx += DIAG_THREADS) {
-      const int i = j + 1 + idx / w, k = j + 1 + idx % w;
-      if (k <= i) S[i * DIAG_PITCH + k] = fma(-S[i * DIAG_PITCH + j], S[k * DIAG_PITCH + j], S[i * DIAG_PITCH + k]);
-    }
-    // next iteration's pivot read is ordered by the __syncthreads at its top
-    __syncthreads();
   }
-  // inverse: thread c builds column c of L^-1 by forward substitution, kept in the upper triangle S[c][i], i > c
-  if (tid < TILE) {
-    const int c = tid;
-    const double xc = 1.0 / S[c * DIAG_PITCH + c];
-    invd[c] = xc;
-    for (int i = c + 1; i < TILE; ++i) {
-      double s = S[i * DIAG_PITCH + c] * xc;
-      for (int k = c + 1; k < i; ++k) s = fma(S[i * DIAG_PITCH + k], S[c * DIAG_PITCH + k], s);
-      S[c * DIAG_PITCH + i] = -s / S[i * DIAG_PITCH + i];
+  // publish L (lower part) to shared memory and global memory; start phase 2 with R = I
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int i = ty + 16 * a, k = tx + 16 * b;
+      const double l = (k <= i) ? r[a][b] : 0.0;
+      S[i * DIAG_PITCH + k] = l;
+      A[base + (long long)i * n_pad + k] = l;
+      r[a][b] = (i == k) ? 1.0 : 0.0;
     }
-  }
   __syncthreads();
-  for (int idx = tid; idx < TILE * TILE; idx += DIAG_THREADS) {
-    const int i = idx / TILE, j = idx % TILE;
-    const long long o = base + (long long)i * n_pad + j;
-    // (i, j): L lower part lives in S[i][j] (j <= i); inverse element (i, j), j < i, lives in S[j][i]
-    const double l = (j <= i) ? S[i * DIAG_PITCH + j] : 0.0;
-    const double xi = (j < i) ? S[j * DIAG_PITCH + i] : (j == i ? invd[i] : 0.0);
-    const double ui = (j > i) ? S[i * DIAG_PITCH + j] : (j == i ? invd[i] : 0.0);  // U = X^T: U[i][j] = X[j][i]
-    A[o] = l;
-    X[o] = xi;
-    U[o] = ui;
+  // ---- phase 2: L X = I by right-looking forward substitution; row k = ko + 16 kq of X becomes final at step k ----
+#pragma unroll
+  for (int kq = 0; kq < 8; ++kq) {
+#pragma unroll 1
+    for (int ko = 0; ko < 16; ++ko) {
+      const int k = ko + 16 * kq;
+      if (ty == ko) {  // owners of row k: scale by 1/L_kk and publish
+        const double inv = 1.0 / S[k * DIAG_PITCH + k];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          r[kq][b] *= inv;
+          vec[tx + 16 * b] = r[kq][b];
+        }
+      }
+      __syncthreads();
+      double li[8], xr[8];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) li[a] = (ty + 16 * a > k) ? S[(ty + 16 * a) * DIAG_PITCH + k] : 0.0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) xr[b] = vec[tx + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) r[a][b] = fma(-li[a], xr[b], r[a][b]);
+      __syncthreads();  // vec is rewritten by the next row's owners
+    }
   }
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int i = ty + 16 * a, c = tx + 16 * b;
+      const double x = (c <= i) ? r[a][b] : 0.0;
+      X[base + (long long)i * n_pad + c] = x;
+      if (c < i) {
+        X[base + (long long)c * n_pad + i] = 0.0;
+        U[base + (long long)i * n_pad + c] = 0.0;
+      }
+      U[base + (long long)c * n_pad + i] = x;  // U = X^T
+    }
 }
 
 // out[z][r] = sum_{k in [lo(r), hi(r))} M[z][r][k] * v[z][k]; mode 0: k <= r (lower), 1: k >= r (upper), 2: full

@@ -37,6 +37,8 @@ struct GemmOperand {  // element coordinates of tile (0,0) for batch z: (col0 + 
 struct GemmParams {
   int tiles_m, tiles_n, kblocks;  // in units of 128
   int krange, tile_skip, raster;
+  int ksplit;  // >= 1: grid.y slices of the k range (EPI_GRAD only: its reductions are linear in the accumulator);
+               // slice s of row block m writes partial row m*ksplit + s
   GemmOperand a, b;
   // EPI_STORE
   double alpha, beta;
@@ -83,6 +85,12 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   if (p.krange == KR_LE_M) kb_end = min(tile_m + 1, p.kblocks);
   else if (p.krange == KR_GE_N) kb_begin = tile_n;
   else if (p.krange == KR_GE_MAX) kb_begin = max(tile_m, tile_n);
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1, split = blockIdx.y;
+  if (ksplit > 1) {
+    const int len = (kb_end - kb_begin + ksplit - 1) / ksplit;
+    kb_begin = min(kb_end, kb_begin + split * len);
+    kb_end = min(kb_end, kb_begin + len);
+  }
   const int nk = (kb_end - kb_begin) * (TILE / GEMM_BK);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -277,7 +285,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
       for (int idx = threadIdx.x; idx < (d + 2) * TILE; idx += GEMM_CONSUMER_WARPS * 32) {
         const int v = idx / TILE, c = idx % TILE;
-        p.partial[((long long)(z * p.tiles_m + tile_m) * (d + 2) + v) * p.ldp + tile_n * TILE + c] =
+        p.partial[((long long)((z * p.tiles_m + tile_m) * ksplit + split) * (d + 2) + v) * p.ldp + tile_n * TILE + c] =
             red[(v * 2) * TILE + c] + red[(v * 2 + 1) * TILE + c];
       }
     }

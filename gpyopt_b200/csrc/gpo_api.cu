@@ -3,6 +3,7 @@
 // ->  K3 (acquisition epilogue)  pipelined over two stream slots.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -145,7 +146,7 @@ static int gemm_setup(gpo_engine* eng) {
 
 static int launch_gemm(gpo_engine* eng, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int batch,
                        cudaStream_t st) {
-  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), 1, (unsigned)batch);
+  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)(p.ksplit > 1 ? p.ksplit : 1), (unsigned)batch);
   if (epi == EPI_STORE) dgemm_nt_kernel<EPI_STORE><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
   else if (epi == EPI_SUMSQ) dgemm_nt_kernel<EPI_SUMSQ><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
   else dgemm_nt_kernel<EPI_GRAD><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
@@ -158,6 +159,7 @@ static GemmParams gemm_defaults() {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.alpha = 1.0;
+  p.ksplit = 1;
   return p;
 }
 
@@ -327,7 +329,10 @@ static void launch_cov_t(const CovParams& p, bool grad, int S, cudaStream_t st) 
 }
 static int launch_cov(gpo_engine* eng, const CovParams& p, bool grad, int S, cudaStream_t st) {
   const int d = p.d;
-  if (d <= 2) launch_cov_t<2, 4>(p, grad, S, st);
+  static const int cw_override = getenv("GPO_K1_CW") ? atoi(getenv("GPO_K1_CW")) : 0;  // tuning aid
+  if (cw_override == 2 && d <= 4) launch_cov_t<4, 2>(p, grad, S, st);
+  else if (cw_override == 2 && d <= 6) launch_cov_t<6, 2>(p, grad, S, st);
+  else if (d <= 2) launch_cov_t<2, 4>(p, grad, S, st);
   else if (d <= 4) launch_cov_t<4, 4>(p, grad, S, st);
   else if (d <= 6) launch_cov_t<6, 4>(p, grad, S, st);
   else if (d <= 8) launch_cov_t<8, 2>(p, grad, S, st);
@@ -705,6 +710,20 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     g.a = {0, 0, 0, 0, 0, 1};
     g.b = {0, 0, 0, 0, 0, 1};
     g.partial = s.partial; g.ldp = eng->nc_ld;
+    // Latency path (L-BFGS steps, N <= 256): a handful of row-block CTAs would leave most SMs idle, so the k range of
+    // the W^-1 product is split across grid.y (its epilogue reductions are linear in the accumulator, K3 adds the
+    // slices).  Value-only calls also take this W^-1 form here unless the parity guard demands the triangular one.
+    const bool small = N <= 256;
+    const bool w_form = grad || (small && !eng->strict_active);
+    int ksplit = 1;
+    if (small && w_form) {
+      ksplit = std::max(1, eng->sm_count / std::max(1, tiles_m * tiles_n * S));
+      ksplit = std::min(ksplit, tiles_m);
+      ksplit = (int)std::min<long long>(ksplit, eng->nc_ld / nc_run);
+      ksplit = std::max(ksplit, 1);
+    }
+    int part_nv = 1, part_rows = tiles_m;
+    long long part_ld = eng->nc_ld;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (eng->profiling) {
       if (eng->prof_used == eng->prof_events.size()) {
@@ -719,13 +738,16 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
       eng->prof_gemm_cands += rows;
       GPO_CUDA_OK(cudaEventRecord(pe0, st));
     }
-    if (grad) {
+    if (w_form) {
       g.krange = KR_FULL; g.raster = RO_M_FASTEST;
-      g.d = d; g.Xtc = eng->Xtc; g.ldx = n_pad; g.Kt = s.Kt; g.Ht = eng->kern != KERN_RBF ? s.Ht : nullptr;
+      g.d = grad ? d : 0; g.Xtc = eng->Xtc; g.ldx = n_pad; g.Kt = s.Kt; g.Ht = (grad && eng->kern != KERN_RBF) ? s.Ht : nullptr;
       g.nc_ld = eng->nc_ld; g.n_pad = n_pad;
+      g.ksplit = ksplit;
+      if (ksplit > 1) { g.ldp = nc_run; part_ld = nc_run; }
+      part_nv = g.d + 2; part_rows = tiles_m * ksplit;
       if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s.mapKt, g, S, st))) return rc;
       if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
-      if (eng->strict_active) {  // ill-conditioned model: variance from the reference's own triangular form as well
+      if (grad && eng->strict_active) {  // ill-conditioned model: variance from the reference's own triangular form as well
         GemmParams gs = gemm_defaults();
         gs.tiles_m = tiles_m; gs.tiles_n = tiles_n; gs.kblocks = tiles_m;
         gs.a = {0, 0, 0, 0, 0, 1}; gs.b = {0, 0, 0, 0, 0, 1};
@@ -740,7 +762,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     // K3
     AcqParams ap;
     memset(&ap, 0, sizeof(ap));
-    ap.n_cand = rows; ap.nc_pad = eng->nc_ld; ap.S = S; ap.d = d; ap.tiles_m = tiles_m; ap.grad = grad ? 1 : 0;
+    ap.n_cand = rows; ap.nc_pad = eng->nc_ld; ap.S = S; ap.d = d; ap.tiles_m = part_rows; ap.grad = grad ? 1 : 0;
+    ap.part_nv = part_nv; ap.part_ld = part_ld; ap.sq_tiles_m = tiles_m;
     ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = s.partial; ap.sigf2 = eng->sigf2;
     ap.partial_sq = (grad && eng->strict_active) ? s.partial_sq : nullptr;
     ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par; ap.invl = eng->invl; ap.xmu = eng->xmu;

@@ -370,13 +370,16 @@ enum AcqKind { ACQ_EI = 0, ACQ_MPI = 1, ACQ_LCB = 2, ACQ_EI_MCMC = 3, ACQ_MPI_MC
 
 struct AcqParams {
   long long n_cand, nc_pad;
-  int S, d, tiles_m;
-  int grad;              // partials come from EPI_GRAD (d+1 values) instead of EPI_SUMSQ (1 value)
+  int S, d, tiles_m;     // tiles_m = number of partial rows per hyper-parameter set (row blocks x k-splits)
+  int part_nv;           // values per partial row: 1 (EPI_SUMSQ) or d_epi + 2 (EPI_GRAD)
+  long long part_ld;     // leading dimension (candidates) of the partial buffers
+  int grad;              // produce gradients (partials then hold S0, H0, P_1..P_d)
   int with_noise;
   const double* mean;    // [S][nc_pad]
   const double* dmean;   // [S][d][nc_pad]
   const double* partial; // [S][tiles_m][nv][nc_pad]; nv = 1 (sum of squares) or d + 2 (S0, H0, P_1..P_d)
-  const double* partial_sq; // optional [S][tiles_m][nc_pad]: sum of squares |L^-1 k|^2 (strict variance in gradient mode)
+  const double* partial_sq; // optional [S][sq_tiles_m][nc_pad]: sum of squares |L^-1 k|^2 (strict variance in gradient mode)
+  int sq_tiles_m;
   const double* invl;    // [S][d]
   const double* xmu;     // [d] centring offsets of the training inputs
   const double* sigf2;   // [S]
@@ -405,21 +408,21 @@ __device__ __forceinline__ double log_ndtr(double z) {
 __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n_cand) return;
-  const int d = p.d, nv = p.grad ? d + 2 : 1;
+  const int d = p.d, nv = p.part_nv;
   double f_acc = 0.0, df_acc[DMAX];
 #pragma unroll
   for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
   for (int z = 0; z < p.S; ++z) {
     const double m = p.mean[(long long)z * p.nc_pad + i];
-    const double* part = p.partial + (long long)z * p.tiles_m * nv * p.nc_pad + i;
+    const double* part = p.partial + (long long)z * p.tiles_m * nv * p.part_ld + i;
     double s0 = 0.0;
     if (p.grad && p.partial_sq) {
       // strict variance: the reference's own form sigma_f^2 - |L^-1 k|^2 (PosteriorExact._raw_predict), immune to
       // the cancellation of k.W^-1.k on ill-conditioned Gram matrices
-      const double* psq = p.partial_sq + (long long)z * p.tiles_m * p.nc_pad + i;
-      for (int tm = 0; tm < p.tiles_m; ++tm) s0 += psq[(long long)tm * p.nc_pad];
+      const double* psq = p.partial_sq + (long long)z * p.sq_tiles_m * p.nc_pad + i;
+      for (int tm = 0; tm < p.sq_tiles_m; ++tm) s0 += psq[(long long)tm * p.nc_pad];
     } else {
-      for (int tm = 0; tm < p.tiles_m; ++tm) s0 += part[(long long)tm * nv * p.nc_pad];
+      for (int tm = 0; tm < p.tiles_m; ++tm) s0 += part[(long long)tm * nv * p.part_ld];
     }
     double v = p.sigf2[z] - s0;
     if (p.with_noise) v += p.noise[z];
@@ -430,12 +433,12 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
       // dv/dx_q = -2 sum_j b_j h_j (x_q - x_jq)/l_q^2 = -2/l_q^2 ((x_q - mu_q) H0 - P_q);  dsdx = dvdx / (2 s)
       const double inv2s = 1.0 / (2.0 * s);
       double h0 = 0.0;
-      for (int tm = 0; tm < p.tiles_m; ++tm) h0 += part[((long long)tm * nv + 1) * p.nc_pad];
+      for (int tm = 0; tm < p.tiles_m; ++tm) h0 += part[((long long)tm * nv + 1) * p.part_ld];
 #pragma unroll
       for (int q = 0; q < DMAX; ++q) {
         if (q < d) {
           double pq = 0.0;
-          for (int tm = 0; tm < p.tiles_m; ++tm) pq += part[((long long)tm * nv + 2 + q) * p.nc_pad];
+          for (int tm = 0; tm < p.tiles_m; ++tm) pq += part[((long long)tm * nv + 2 + q) * p.part_ld];
           const double il = p.invl[z * d + q];
           const double gq = ((p.Xs[i * d + q] - p.xmu[q]) * h0 - pq) * il * il;
           dm[q] = p.dmean[((long long)z * d + q) * p.nc_pad + i];

@@ -1,0 +1,181 @@
+"""Callers of the hot path, re-hosted so that they feed it batches instead of single points (SURVEY.md section 8f,
+rows f2 / f4).  Needs the reference package (GPyOpt) importable: these classes reuse its optimiser and space code.
+
+* :class:`BatchedAcquisitionOptimizer` -- drop-in for ``GPyOpt.optimization.AcquisitionOptimizer``
+  (GPyOpt/optimization/acquisition_optimizer.py:16-78).  The reference optimises its 5 anchor points one after the
+  other, and ``OptLbfgs`` evaluates ``f(x)`` and ``f_df(x)`` at a single point per step (optimizer.py:44-51): a
+  latency-bound chain of N=1 device calls.  Here every anchor runs the UNCHANGED reference ``apply_optimizer`` (and
+  therefore SciPy's own L-BFGS-B) in its own thread, and a rendezvous stacks the points all threads are currently
+  asking for into ONE device call per round.  Each L-BFGS instance sees exactly the values it would have seen alone
+  (the engine's per-row results do not depend on the batch), so the optimum is identical, not just close.
+* :class:`FusedAnchorPointsGenerator` -- ``ObjectiveAnchorPointsGenerator`` whose scoring + ``argsort[:k]``
+  (anchor_points_generator.py:62-67) is the fused device sweep + top-k (``gpo_acq_topk``) when the acquisition has
+  constant cost and the space no constraints.
+"""
+import threading
+
+import numpy as np
+
+from ._compat import HAVE_GPYOPT, constant_cost_withGradients
+
+if HAVE_GPYOPT:  # pragma: no branch
+    from GPyOpt.optimization.acquisition_optimizer import (AcquisitionOptimizer, max_objective_anchor_points_logic,
+                                                           thompson_sampling_anchor_points_logic, sobol_design_type,
+                                                           random_design_type)
+    from GPyOpt.optimization.anchor_points_generator import (ObjectiveAnchorPointsGenerator,
+                                                             ThompsonSamplingAnchorPointsGenerator)
+    from GPyOpt.optimization.optimizer import apply_optimizer, choose_optimizer
+    from GPyOpt.experiment_design import initial_design
+    from GPyOpt.core.errors import FullyExploredOptimizationDomainError
+else:  # the classes below are only usable next to the reference package
+    AcquisitionOptimizer = object
+    ObjectiveAnchorPointsGenerator = object
+
+
+class Rendezvous(object):
+    """Batches the calls that several worker threads make to row-wise functions.
+
+    ``fns`` maps a name to a batched function ``X[N,d] -> array or tuple of arrays with N leading rows``.  A worker
+    calls ``call(name, x)`` with one row and blocks; when every live worker is blocked the coordinator evaluates each
+    requested function ONCE on the stacked rows and hands every worker its own row of the result."""
+
+    def __init__(self, fns, n_workers):
+        self.fns = fns
+        self.cv = threading.Condition()
+        self.live = n_workers
+        self.pending = []      # (name, x_row, slot)
+        self.calls = 0         # batched evaluations issued (for tests / statistics)
+        self.rows = 0
+
+    def call(self, name, x):
+        slot = {'done': False, 'out': None, 'err': None}
+        with self.cv:
+            self.pending.append((name, np.atleast_2d(np.asarray(x, dtype=np.float64)), slot))
+            self.cv.notify_all()
+            while not slot['done']:
+                self.cv.wait()
+        if slot['err'] is not None:
+            raise slot['err']
+        return slot['out']
+
+    def worker_done(self):
+        with self.cv:
+            self.live -= 1
+            self.cv.notify_all()
+
+    def serve(self):
+        """Run on the coordinating thread until every worker has finished."""
+        while True:
+            with self.cv:
+                while self.live > 0 and len(self.pending) < self.live:
+                    self.cv.wait()
+                if self.live == 0 and not self.pending:
+                    return
+                batch, self.pending = self.pending, []
+            by_name = {}
+            for name, x, slot in batch:
+                by_name.setdefault(name, []).append((x, slot))
+            for name, items in by_name.items():
+                rows = [x.shape[0] for x, _ in items]
+                try:
+                    res = self.fns[name](np.vstack([x for x, _ in items]))
+                    self.calls += 1
+                    self.rows += sum(rows)
+                    off = 0
+                    for (x, slot), r in zip(items, rows):
+                        slot['out'] = (tuple(np.asarray(a)[off:off + r] for a in res) if isinstance(res, tuple)
+                                       else np.asarray(res)[off:off + r])
+                        off += r
+                except Exception as e:  # hand the failure to the workers that asked
+                    for _, slot in items:
+                        slot['err'] = e
+            with self.cv:
+                for _, _, slot in batch:
+                    slot['done'] = True
+                self.cv.notify_all()
+
+
+def _plain(acquisition):
+    """True when acquisition_function == -_compute_acq (constant cost, no constraints, no one-hot zipping)."""
+    space = acquisition.space
+    return (getattr(acquisition, 'cost_withGradients', None) is constant_cost_withGradients and space is not None
+            and not getattr(space, 'constraints', None) and space.model_dimensionality == space.objective_dimensionality)
+
+
+class FusedAnchorPointsGenerator(ObjectiveAnchorPointsGenerator):
+    """ObjectiveAnchorPointsGenerator (anchor_points_generator.py:91-104) with the scoring sweep and the top-k
+    selection fused on the device.  Falls back to the reference logic whenever duplicates, context variables or a
+    non-plain acquisition are involved."""
+
+    def __init__(self, space, design_type, acquisition, num_samples=1000):
+        super(FusedAnchorPointsGenerator, self).__init__(space, design_type, acquisition.acquisition_function, num_samples)
+        self.acquisition = acquisition
+
+    def get(self, num_anchor=5, duplicate_manager=None, unique=False, context_manager=None):
+        from .acquisitions import _FusedAcquisition, _engine_of
+        no_context = context_manager is None or len(getattr(context_manager, 'context_index', [])) == 0
+        fused = (isinstance(self.acquisition, _FusedAcquisition) and _plain(self.acquisition) and not duplicate_manager
+                 and not unique and no_context)
+        if not fused:
+            return super(FusedAnchorPointsGenerator, self).get(num_anchor, duplicate_manager, unique, context_manager)
+        X = initial_design(self.design_type, self.space, self.num_samples)   # same RNG stream as the reference
+        X = self.space.unzip_inputs(X)
+        if X.shape[0] == 0:
+            raise FullyExploredOptimizationDomainError("No anchor points could be generated")
+        eng = _engine_of(self.acquisition.model)
+        _, idx = eng.acq_topk(self.acquisition._kind, self.acquisition._par(), np.ascontiguousarray(X, dtype=np.float64),
+                              min(num_anchor, X.shape[0]))
+        return X[idx, :]
+
+
+class BatchedAcquisitionOptimizer(AcquisitionOptimizer):
+    """AcquisitionOptimizer whose local optimisations share their device calls (see module docstring)."""
+
+    def __init__(self, space, optimizer='lbfgs', acquisition=None, **kwargs):
+        if not HAVE_GPYOPT:
+            raise ImportError("BatchedAcquisitionOptimizer builds on GPyOpt's optimizer classes; GPyOpt is not importable")
+        super(BatchedAcquisitionOptimizer, self).__init__(space, optimizer, **kwargs)
+        self.acquisition = acquisition     # optional: enables the fused anchor sweep
+        self.last_stats = None
+
+    def optimize(self, f=None, df=None, f_df=None, duplicate_manager=None):
+        self.f, self.df, self.f_df = f, df, f_df
+        self.optimizer = choose_optimizer(self.optimizer_name, self.context_manager.noncontext_bounds)
+        if self.type_anchor_points_logic == max_objective_anchor_points_logic:
+            if self.acquisition is not None:
+                gen = FusedAnchorPointsGenerator(self.space, random_design_type, self.acquisition)
+            else:
+                gen = ObjectiveAnchorPointsGenerator(self.space, random_design_type, f)
+        elif self.type_anchor_points_logic == thompson_sampling_anchor_points_logic:
+            gen = ThompsonSamplingAnchorPointsGenerator(self.space, sobol_design_type, self.model)
+        anchor_points = gen.get(duplicate_manager=duplicate_manager, context_manager=self.context_manager)
+
+        fns = {'f': f}
+        if f_df is not None:
+            fns['f_df'] = f_df
+        rdv = Rendezvous(fns, len(anchor_points))
+        bf = lambda x: rdv.call('f', x)
+        bf_df = (lambda x: rdv.call('f_df', x)) if f_df is not None else None
+        results = [None] * len(anchor_points)
+        errors = []
+
+        def work(i, a):
+            try:
+                results[i] = apply_optimizer(self.optimizer, a, f=bf, df=None, f_df=bf_df, duplicate_manager=duplicate_manager,
+                                             context_manager=self.context_manager, space=self.space)
+            except Exception as e:  # noqa: BLE001 - re-raised on the calling thread
+                errors.append(e)
+            finally:
+                rdv.worker_done()
+
+        threads = [threading.Thread(target=work, args=(i, a), daemon=True) for i, a in enumerate(anchor_points)]
+        for t in threads:
+            t.start()
+        rdv.serve()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        self.last_stats = {'device_calls': rdv.calls, 'rows': rdv.rows}
+        x_min, fx_min = min(results, key=lambda t: t[1])
+        return x_min, fx_min

@@ -231,6 +231,24 @@ def test_host_and_device_pointers_agree_bitwise(engine):
     assert np.array_equal(f_m, f_h) and np.array_equal(df_m, df_h)
 
 
+def test_rows_are_independent_of_the_batch(engine):
+    """A candidate's outputs must not depend (bitwise) on which other rows share its call: this is what lets
+    BatchedAcquisitionOptimizer stack the L-BFGS runs of several anchors without changing any of them."""
+    g = load_golden('c3_rbf_alpine2_n256')
+    fit_from_golden(engine, g)
+    X5 = g['Xs'][10:15]
+    f5, df5 = engine.acq('EI', 0.01, X5, grad=True)
+    v5 = engine.acq('EI', 0.01, X5)
+    for i in range(5):
+        f1, df1 = engine.acq('EI', 0.01, X5[i:i + 1], grad=True)
+        assert np.array_equal(f1, f5[i:i + 1]) and np.array_equal(df1, df5[i:i + 1])
+        assert np.array_equal(engine.acq('EI', 0.01, X5[i:i + 1]), v5[i:i + 1])
+    # same through a big sweep: rows keep their values wherever they sit
+    big = np.tile(g['Xs'], (3, 1))
+    fb = engine.acq('EI', 0.01, big)
+    assert np.array_equal(fb[:384], fb[384:768]) and np.array_equal(fb[:384], fb[768:])
+
+
 def test_chunking_is_invisible(engine):
     """Results must not depend on how the sweep is cut into chunks (bit-exact), incl. a ragged last chunk."""
     from gpyopt_b200 import Engine

@@ -38,6 +38,7 @@ struct gpo_engine {
   // capacity the buffers were allocated for
   int cap_n_pad = 0, cap_d = 0, cap_S = 0;
   long long nc_ld = 0, user_chunk = 0;
+  int js = 1, tiles_per_split = 1;  // K1's slicing of the training index (function of n_pad only)
   // data + hyper-parameters (device)
   double *Xt = nullptr, *Xtc = nullptr, *xmu = nullptr, *Xaos = nullptr, *Y = nullptr;
   double *invl = nullptr, *sigf2 = nullptr, *noise = nullptr, *jitter = nullptr;
@@ -303,12 +304,18 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   if ((rc = make_map(eng, &eng->mapW, eng->W, n_pad, n_pad, S))) return rc;
   if ((rc = make_map(eng, &eng->mapT, eng->T, n_pad, n_pad, S))) return rc;
   eng->nc_ld = std::max<long long>(pick_chunk(eng, n_pad, S), n_pad);  // >= n_pad: the fmin sweep runs over X itself
+  {  // K1 slices: 256 training rows (8 tiles of 32) per slice, at most 16 slices
+    const int ntiles = n_pad / COV_JT;
+    int js = std::min(16, std::max(1, n_pad / 256));
+    eng->tiles_per_split = (ntiles + js - 1) / js;
+    eng->js = (ntiles + eng->tiles_per_split - 1) / eng->tiles_per_split;
+  }
   const int tiles_m = n_pad / TILE;
   for (int i = 0; i < 2; ++i) {
     Slot& s = eng->slot[i];
     GPO_CUDA_OK(cudaMalloc(&s.Kt, (size_t)S * eng->nc_ld * n_pad * 8));
-    GPO_CUDA_OK(cudaMalloc(&s.mean, (size_t)S * eng->nc_ld * 8));
-    GPO_CUDA_OK(cudaMalloc(&s.dmean, (size_t)S * d * eng->nc_ld * 8));
+    GPO_CUDA_OK(cudaMalloc(&s.mean, (size_t)S * eng->js * eng->nc_ld * 8));
+    GPO_CUDA_OK(cudaMalloc(&s.dmean, (size_t)S * eng->js * d * eng->nc_ld * 8));
     GPO_CUDA_OK(cudaMalloc(&s.partial, (size_t)S * tiles_m * (d + 2) * eng->nc_ld * 8));
     GPO_CUDA_OK(cudaMalloc(&s.partial_sq, (size_t)S * tiles_m * eng->nc_ld * 8));
     if ((rc = make_map(eng, &s.mapKt, s.Kt, n_pad, eng->nc_ld, S))) return rc;
@@ -320,24 +327,27 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
 // --------------------------------------------------------------------------------------------------
 // K1 dispatch
 // --------------------------------------------------------------------------------------------------
-template <int DP, int CW>
+template <int DP>
 static void launch_cov_t(const CovParams& p, bool grad, int S, cudaStream_t st) {
-  const long long warps = (p.nc_run + CW - 1) / CW;
-  dim3 grid((unsigned)((warps + 3) / 4), 1, (unsigned)S);
-  if (grad) cov_mean_kernel<DP, CW, true><<<grid, 128, 0, st>>>(p);
-  else cov_mean_kernel<DP, CW, false><<<grid, 128, 0, st>>>(p);
+  dim3 grid((unsigned)((p.nc_run + COV_THREADS - 1) / COV_THREADS), (unsigned)p.js, (unsigned)S);
+  const bool with_h = grad && p.Ht != nullptr;
+  const int smem = cov_smem_bytes(DP, with_h);
+  static bool attr_done = false;
+  if (!attr_done) {  // the (dK/dr)/r tile of the Matern kernels pushes the block past the 48 KiB default
+    cudaFuncSetAttribute(cov_mean_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cov_smem_bytes(DP, true));
+    attr_done = true;
+  }
+  if (grad) cov_mean_kernel<DP, true><<<grid, COV_THREADS, smem, st>>>(p);
+  else cov_mean_kernel<DP, false><<<grid, COV_THREADS, smem, st>>>(p);
 }
 static int launch_cov(gpo_engine* eng, const CovParams& p, bool grad, int S, cudaStream_t st) {
   const int d = p.d;
-  static const int cw_override = getenv("GPO_K1_CW") ? atoi(getenv("GPO_K1_CW")) : 0;  // tuning aid
-  if (cw_override == 2 && d <= 4) launch_cov_t<4, 2>(p, grad, S, st);
-  else if (cw_override == 2 && d <= 6) launch_cov_t<6, 2>(p, grad, S, st);
-  else if (d <= 2) launch_cov_t<2, 4>(p, grad, S, st);
-  else if (d <= 4) launch_cov_t<4, 4>(p, grad, S, st);
-  else if (d <= 6) launch_cov_t<6, 4>(p, grad, S, st);
-  else if (d <= 8) launch_cov_t<8, 2>(p, grad, S, st);
-  else if (d <= 12) launch_cov_t<12, 2>(p, grad, S, st);
-  else launch_cov_t<16, 2>(p, grad, S, st);
+  if (d <= 2) launch_cov_t<2>(p, grad, S, st);
+  else if (d <= 4) launch_cov_t<4>(p, grad, S, st);
+  else if (d <= 6) launch_cov_t<6>(p, grad, S, st);
+  else if (d <= 8) launch_cov_t<8>(p, grad, S, st);
+  else if (d <= 12) launch_cov_t<12>(p, grad, S, st);
+  else launch_cov_t<16>(p, grad, S, st);
   eng->launches++;
   GPO_CUDA_OK(cudaGetLastError());
   return GPO_OK;
@@ -444,7 +454,7 @@ static int run_variance_probe(gpo_engine* eng, cudaStream_t st) {
     CovParams cp;
     cp.Xs = eng->Xaos; cp.n_cand = n; cp.nc_run = n_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n;
     cp.n_pad = n_pad; cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
-    cp.Kt = s0.Kt; cp.Ht = nullptr; cp.mean = s0.mean; cp.dmean = nullptr;
+    cp.Kt = s0.Kt; cp.Ht = nullptr; cp.mean = s0.mean; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
     if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
     GemmParams g = gemm_defaults();
     g.tiles_m = tiles_m; g.tiles_n = tiles_m; g.kblocks = tiles_m;
@@ -559,9 +569,9 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
     CovParams cp;
     cp.Xs = eng->Xaos; cp.n_cand = n; cp.nc_run = n_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n; cp.n_pad = n_pad;
     cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
-    cp.Kt = nullptr; cp.Ht = nullptr; cp.mean = s.mean; cp.dmean = nullptr;
+    cp.Kt = nullptr; cp.Ht = nullptr; cp.mean = s.mean; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
     if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
-    fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, s.mean, eng->nc_ld, n, n_pad, eng->logdet, eng->quad,
+    fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, s.mean, eng->nc_ld, eng->js, n, n_pad, eng->logdet, eng->quad,
                                           eng->fmin);
     eng->launches++;
     GPO_CUDA_OK(cudaGetLastError());
@@ -702,7 +712,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     cp.Xs = dev_in + off * d; cp.n_cand = rows; cp.nc_run = nc_run; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad;
     cp.n = eng->n; cp.n_pad = n_pad; cp.d = d; cp.kern = eng->kern; cp.alpha = eng->alpha; cp.invl = eng->invl;
     cp.sigf2 = eng->sigf2; cp.Kt = s.Kt; cp.Ht = (grad && eng->kern != KERN_RBF) ? s.Ht : nullptr; cp.mean = s.mean;
-    cp.dmean = s.dmean;
+    cp.dmean = s.dmean; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
     if ((rc = launch_cov(eng, cp, grad, S, st))) return rc;
     // variance GEMM
     GemmParams g = gemm_defaults();
@@ -764,7 +774,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     memset(&ap, 0, sizeof(ap));
     ap.n_cand = rows; ap.nc_pad = eng->nc_ld; ap.S = S; ap.d = d; ap.tiles_m = part_rows; ap.grad = grad ? 1 : 0;
     ap.part_nv = part_nv; ap.part_ld = part_ld; ap.sq_tiles_m = tiles_m;
-    ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = s.partial; ap.sigf2 = eng->sigf2;
+    ap.js = eng->js; ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = s.partial; ap.sigf2 = eng->sigf2;
     ap.partial_sq = (grad && eng->strict_active) ? s.partial_sq : nullptr;
     ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par; ap.invl = eng->invl; ap.xmu = eng->xmu;
     ap.Xs = dev_in + off * d;

@@ -11,9 +11,8 @@ constexpr int DMAX = 16;  // largest supported input dimension
 
 // =====================================================================================================
 // K1: fused cross-covariance + posterior mean (+ mean gradient).
-// One warp owns CW candidates; lanes stride over the training index j so the K*^T rows ([cand][n_pad],
-// the K-major B operand of the variance GEMM) are written with fully coalesced 256-byte stores, and
-// reduce k.alpha / sum_j alpha_j dk_j/dx in registers, finishing with warp shuffles.
+// Writes the K*^T rows ([cand][n_pad], the K-major B operand of the variance GEMM) and reduces k.alpha and
+// sum_j alpha_j dk_j/dx in registers.
 // Replaces GPy kern.K(X, X*) + Kx^T alpha (PosteriorExact._raw_predict) and
 // kern.gradients_X(alpha^T, X*, X) (GP.predictive_gradients), reference call sites
 // /root/reference/GPyOpt/models/gpmodel.py:98,136,138.
@@ -31,80 +30,103 @@ struct CovParams {
   const double* sigf2;    // [S]
   double* Kt;             // [S][nc_ld][n_pad]   (may be null: mean only)
   double* Ht;             // [S][nc_ld][n_pad]   (dK/dr)/r, written only when non-null (non-RBF kernels, GRAD)
-  double* mean;           // [S][nc_ld]
-  double* dmean;          // [S][d][nc_ld]       (GRAD only)
+  int js, tiles_per_split; // the training index is cut into `js` contiguous slices (grid.y) of `tiles_per_split` 32-row tiles;
+                           // js depends only on n_pad, so a row's result never depends on the batch it is in
+  double* mean;           // [S][js][nc_ld]      per-slice partial sums, added in slice order by K3 / fit_scalars
+  double* dmean;          // [S][js][d][nc_ld]   (GRAD only)
 };
 
-template <int DP, int CW, bool GRAD>
-__global__ void __launch_bounds__(128) cov_mean_kernel(const CovParams p) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// One thread owns one candidate (its scaled coordinates, mean and mean-gradient accumulators stay in registers for the
+// whole pass over the training set); the block walks the training index in tiles of 32 whose scaled coordinates and
+// alpha are staged in shared memory and read as broadcasts.  The covariance tile [32 j][128 candidates] is transposed
+// through (padded, conflict-free) shared memory so that K*^T rows are written as full 256-byte lines.
+constexpr int COV_THREADS = 128;
+constexpr int COV_JT = 32;
+constexpr int COV_PITCH = COV_THREADS + 1;
+constexpr int cov_smem_bytes(int dp, bool with_h) {
+  return (COV_JT * COV_PITCH * (with_h ? 2 : 1) + 2 * (dp + 1) * COV_JT) * 8;
+}
+
+template <int DP, bool GRAD>
+__global__ void __launch_bounds__(COV_THREADS) cov_mean_kernel(const CovParams p) {
+  extern __shared__ double cov_smem[];
+  double* tile_k = cov_smem;                                   // [32][129]
+  double* xj_s0 = cov_smem + COV_JT * COV_PITCH;               // 2 x [(DP+1)][32]
+  double* tile_h = xj_s0 + 2 * (DP + 1) * COV_JT;              // [32][129], only when Ht is written
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int z = blockIdx.z;
-  const long long c0 = ((long long)blockIdx.x * 4 + warp) * CW;
-  if (c0 >= p.nc_run) return;
+  const long long c0 = (long long)blockIdx.x * COV_THREADS;
+  const long long cand = c0 + tid;
   const double* invl = p.invl + (long long)z * p.d;
   const double sf2 = p.sigf2[z];
-  double il[DP], xs[CW][DP], m[CW], dm[CW][DP];
-#pragma unroll
-  for (int q = 0; q < DP; ++q) il[q] = q < p.d ? invl[q] : 0.0;
-#pragma unroll
-  for (int c = 0; c < CW; ++c) {
-    m[c] = 0.0;
-#pragma unroll
-    for (int q = 0; q < DP; ++q) {
-      xs[c][q] = (q < p.d && c0 + c < p.n_cand) ? p.Xs[(c0 + c) * p.d + q] * il[q] : 0.0;
-      dm[c][q] = 0.0;
-    }
-  }
   const double* alpha = p.alpha + (long long)z * p.n_pad;
+  double xs[DP], dm[DP], m = 0.0;
+#pragma unroll
+  for (int q = 0; q < DP; ++q) {
+    xs[q] = (q < p.d && cand < p.n_cand) ? p.Xs[cand * p.d + q] * invl[q] : 0.0;
+    dm[q] = 0.0;
+  }
   double* Kt = p.Kt ? p.Kt + ((long long)z * p.nc_ld + c0) * p.n_pad : nullptr;
   double* Ht = (GRAD && p.Ht) ? p.Ht + ((long long)z * p.nc_ld + c0) * p.n_pad : nullptr;
-  for (int j = lane; j < p.n_pad; j += 32) {
-    const bool valid = j < p.n;
-    double xj[DP];
-#pragma unroll
-    for (int q = 0; q < DP; ++q) xj[q] = (q < p.d) ? __ldg(p.Xt + q * p.ldx + j) * il[q] : 0.0;
-    const double aj = __ldg(alpha + j);
-#pragma unroll
-    for (int c = 0; c < CW; ++c) {
-      double r2 = 0.0;
+  const int split = blockIdx.y;
+  const int jt_begin = split * p.tiles_per_split, jt_end = min(p.n_pad / COV_JT, jt_begin + p.tiles_per_split);
+  // stage loader: thread t < (DP+1)*32 loads one value of the next j tile (row q = t/32: coordinate q, row DP: alpha)
+  auto stage = [&](int jt, int buf) {
+    for (int t = tid; t < (DP + 1) * COV_JT; t += COV_THREADS) {
+      const int q = t / COV_JT, jj = t % COV_JT, j = jt * COV_JT + jj;
+      double v;
+      if (q < DP) v = (q < p.d) ? __ldg(p.Xt + q * p.ldx + j) * invl[q] : 0.0;
+      else v = __ldg(alpha + j);
+      xj_s0[buf * (DP + 1) * COV_JT + t] = v;
+    }
+  };
+  stage(jt_begin, 0);
+  __syncthreads();
+  for (int jt = jt_begin; jt < jt_end; ++jt) {
+    const int buf = (jt - jt_begin) & 1;
+    if (jt + 1 < jt_end) stage(jt + 1, buf ^ 1);
+    const double* xj = xj_s0 + buf * (DP + 1) * COV_JT;
+    const int j0 = jt * COV_JT;
+#pragma unroll 4
+    for (int jj = 0; jj < COV_JT; ++jj) {
+      double r2 = 0.0, df[DP];
 #pragma unroll
       for (int q = 0; q < DP; ++q) {
-        const double df = xs[c][q] - xj[q];
-        r2 = fma(df, df, r2);
+        df[q] = xs[q] - xj[q * COV_JT + jj];
+        r2 = fma(df[q], df[q], r2);
       }
       double kv, hv;
       kern_k_h(p.kern, sf2, r2, kv, hv);
-      if (!valid) { kv = 0.0; hv = 0.0; }
-      if (Kt) Kt[(long long)c * p.n_pad + j] = kv;
-      if (GRAD && Ht) Ht[(long long)c * p.n_pad + j] = hv;
-      m[c] = fma(kv, aj, m[c]);
+      if (j0 + jj >= p.n) { kv = 0.0; hv = 0.0; }
+      const double aj = xj[DP * COV_JT + jj];
+      m = fma(kv, aj, m);
       if (GRAD) {
-        const double w = aj * hv;  // aj == 0 on padded rows
+        const double w = aj * hv;
 #pragma unroll
-        for (int q = 0; q < DP; ++q) dm[c][q] = fma(w, xs[c][q] - xj[q], dm[c][q]);
+        for (int q = 0; q < DP; ++q) dm[q] = fma(w, df[q], dm[q]);
+        if (Ht) tile_h[jj * COV_PITCH + tid] = hv;
+      }
+      if (Kt) tile_k[jj * COV_PITCH + tid] = kv;
+    }
+    __syncthreads();
+    if (Kt) {
+      // transposed write-out: warp w stores candidates w, w+4, ...; lane l carries training index j0 + l
+      for (int c = warp; c < COV_THREADS; c += COV_THREADS / 32) {
+        if (c0 + c < p.nc_run) {
+          Kt[(long long)c * p.n_pad + j0 + lane] = tile_k[lane * COV_PITCH + c];
+          if (GRAD && Ht) Ht[(long long)c * p.n_pad + j0 + lane] = tile_h[lane * COV_PITCH + c];
+        }
       }
     }
+    __syncthreads();
   }
-#pragma unroll
-  for (int c = 0; c < CW; ++c) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m[c] += __shfl_xor_sync(0xffffffffu, m[c], o);
+  if (cand < p.nc_run) {
+    const long long zs = (long long)z * p.js + split;
+    p.mean[zs * p.nc_ld + cand] = m;
     if (GRAD) {
 #pragma unroll
       for (int q = 0; q < DP; ++q)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dm[c][q] += __shfl_xor_sync(0xffffffffu, dm[c][q], o);
-    }
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int c = 0; c < CW; ++c) {
-      p.mean[(long long)z * p.nc_ld + c0 + c] = m[c];
-      if (GRAD) {
-#pragma unroll
-        for (int q = 0; q < DP; ++q)
-          if (q < p.d) p.dmean[((long long)z * p.d + q) * p.nc_ld + c0 + c] = dm[c][q] * il[q];
-      }
+        if (q < p.d) p.dmean[(zs * p.d + q) * p.nc_ld + cand] = dm[q] * invl[q];
     }
   }
 }
@@ -277,7 +299,7 @@ __global__ void gemv_kernel(const double* M, const double* v, double* out, int n
 // per-z scalar reductions after the factorisation:
 //   logdet[z] = 2 sum_i log L_ii,  quad[z] = sum_i alpha_i y_i,  fmin[z] = min_i mean_i  (i < n)
 __global__ void fit_scalars_kernel(const double* L, const double* alpha, const double* y, const double* mean,
-                                   long long mean_ld, int n, int n_pad, double* logdet, double* quad,
+                                   long long mean_ld, int js, int n, int n_pad, double* logdet, double* quad,
                                    double* fmin_out) {
   const int z = blockIdx.x;
   __shared__ double sh[3][32];
@@ -285,7 +307,9 @@ __global__ void fit_scalars_kernel(const double* L, const double* alpha, const d
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     ld += log(L[((long long)z * n_pad + i) * n_pad + i]);
     qd = fma(alpha[(long long)z * n_pad + i], y[i], qd);
-    mn = ::fmin(mn, mean[z * mean_ld + i]);
+    double mi = 0.0;
+    for (int sp = 0; sp < js; ++sp) mi += mean[((long long)z * js + sp) * mean_ld + i];
+    mn = ::fmin(mn, mi);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -375,8 +399,9 @@ struct AcqParams {
   long long part_ld;     // leading dimension (candidates) of the partial buffers
   int grad;              // produce gradients (partials then hold S0, H0, P_1..P_d)
   int with_noise;
-  const double* mean;    // [S][nc_pad]
-  const double* dmean;   // [S][d][nc_pad]
+  int js;                // K1's slices of the training index: mean / dmean hold js partial sums per candidate
+  const double* mean;    // [S][js][nc_pad]
+  const double* dmean;   // [S][js][d][nc_pad]
   const double* partial; // [S][tiles_m][nv][nc_pad]; nv = 1 (sum of squares) or d + 2 (S0, H0, P_1..P_d)
   const double* partial_sq; // optional [S][sq_tiles_m][nc_pad]: sum of squares |L^-1 k|^2 (strict variance in gradient mode)
   int sq_tiles_m;
@@ -413,7 +438,8 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
 #pragma unroll
   for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
   for (int z = 0; z < p.S; ++z) {
-    const double m = p.mean[(long long)z * p.nc_pad + i];
+    double m = 0.0;
+    for (int sp = 0; sp < p.js; ++sp) m += p.mean[((long long)z * p.js + sp) * p.nc_pad + i];
     const double* part = p.partial + (long long)z * p.tiles_m * nv * p.part_ld + i;
     double s0 = 0.0;
     if (p.grad && p.partial_sq) {
@@ -441,7 +467,9 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
           for (int tm = 0; tm < p.tiles_m; ++tm) pq += part[((long long)tm * nv + 2 + q) * p.part_ld];
           const double il = p.invl[z * d + q];
           const double gq = ((p.Xs[i * d + q] - p.xmu[q]) * h0 - pq) * il * il;
-          dm[q] = p.dmean[((long long)z * d + q) * p.nc_pad + i];
+          double dmq = 0.0;
+          for (int sp = 0; sp < p.js; ++sp) dmq += p.dmean[(((long long)z * p.js + sp) * d + q) * p.nc_pad + i];
+          dm[q] = dmq;
           ds[q] = -2.0 * gq * inv2s;
         } else { dm[q] = 0.0; ds[q] = 0.0; }
       }

@@ -26,6 +26,7 @@ struct Slot {
   double* dmean = nullptr;    // [S][d][nc_ld]
   double* partial = nullptr;  // [S][tiles_m][d+2][nc_ld]
   double* partial_sq = nullptr;  // [S][tiles_m][nc_ld]  (strict variance in gradient mode)
+  double* zbuf = nullptr;        // [S][1+d][nc_ld]      per-set acquisition contributions (S > 1 only)
 };
 
 struct gpo_engine {
@@ -210,7 +211,7 @@ static void free_state(gpo_engine* eng) {
   if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
   for (int i = 0; i < 2; ++i) {
     Slot& s = eng->slot[i];
-    double** sp[] = {&s.Kt, &s.Ht, &s.mean, &s.dmean, &s.partial, &s.partial_sq};
+    double** sp[] = {&s.Kt, &s.Ht, &s.mean, &s.dmean, &s.partial, &s.partial_sq, &s.zbuf};
     for (auto pp : sp) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   }
   eng->cap_n_pad = eng->cap_d = eng->cap_S = 0;
@@ -257,8 +258,10 @@ extern "C" int gpo_launch_count(gpo_engine* eng, long long* launches, int reset)
 // fills whole waves of the SMs
 static long long pick_chunk(const gpo_engine* eng, int n_pad, int S) {
   if (eng->user_chunk > 0) return ((eng->user_chunk + TILE - 1) / TILE) * TILE;
-  const double budget = 160.0 * 1024 * 1024;
-  long long max_tiles_n = (long long)(budget / ((double)S * n_pad * 8.0 * TILE));
+  // 160 MB of K*^T per slot, or whatever 1024 candidates need when many hyper-parameter sets are resident (<= 1 GB)
+  const double per_tile = (double)S * n_pad * 8.0 * TILE;
+  const double budget = std::max(160.0 * 1024 * 1024, std::min(8.0 * per_tile, 1024.0 * 1024 * 1024));
+  long long max_tiles_n = (long long)(budget / per_tile);
   max_tiles_n = std::max(1LL, std::min(max_tiles_n, 128LL));
   const int tiles_m = n_pad / TILE;
   long long best = max_tiles_n;
@@ -318,6 +321,7 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
     GPO_CUDA_OK(cudaMalloc(&s.dmean, (size_t)S * eng->js * d * eng->nc_ld * 8));
     GPO_CUDA_OK(cudaMalloc(&s.partial, (size_t)S * tiles_m * (d + 2) * eng->nc_ld * 8));
     GPO_CUDA_OK(cudaMalloc(&s.partial_sq, (size_t)S * tiles_m * eng->nc_ld * 8));
+    if (S > 1) GPO_CUDA_OK(cudaMalloc(&s.zbuf, (size_t)S * (d + 1) * eng->nc_ld * 8));
     if ((rc = make_map(eng, &s.mapKt, s.Kt, n_pad, eng->nc_ld, S))) return rc;
   }
   eng->cap_n_pad = n_pad; eng->cap_d = d; eng->cap_S = S;
@@ -787,8 +791,16 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
       ap.lp_on = eng->lp_on; ap.lp_K = eng->lp_K; ap.lp_transform = eng->lp_transform;
       ap.lp_xb = eng->lp_xb; ap.lp_r = eng->lp_r; ap.lp_s = eng->lp_s; ap.Xs = dev_in + off * d;
     }
-    acq_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(ap);
-    eng->launches++;
+    ap.zbuf = s.zbuf;
+    {
+      dim3 kgrid((unsigned)((rows + 127) / 128), (unsigned)(S > 1 ? S : 1), 1);
+      acq_kernel<<<kgrid, 128, 0, st>>>(ap);
+      eng->launches++;
+      if (S > 1 && !predict) {
+        acq_reduce_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(ap);
+        eng->launches++;
+      }
+    }
     GPO_CUDA_OK(cudaGetLastError());
     // results back to host memory, chunk by chunk
     for (int i = 0; i < 4; ++i) {

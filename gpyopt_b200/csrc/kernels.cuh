@@ -417,6 +417,9 @@ struct AcqParams {
   long long out_ldN;     // N of the whole call (stride between hyper-parameter sets)
   // acquisition outputs, offset to the chunk's first row
   double *out_f, *out_df;
+  // S > 1: the kernel runs with gridDim.y = S (one hyper-parameter set per block row) and leaves each set's contribution
+  // in zbuf [S][1+d][nc_pad]; acq_reduce_kernel then adds them in set order (deterministic) and finishes
+  double* zbuf;
   // Local Penalization
   int lp_on, lp_K, lp_transform;
   const double *lp_xb, *lp_r, *lp_s;   // [K][d], [K], [K]
@@ -430,6 +433,63 @@ __device__ __forceinline__ double log_ndtr(double z) {
   return log1p(-0.5 * erfc(t));
 }
 
+// last stage of K3 for one candidate: MCMC average, then either the plain outputs or the Local-Penalization transform
+__device__ __forceinline__ void acq_finalize(const AcqParams& p, long long i, double f_acc, double (&df_acc)[DMAX]) {
+  const int d = p.d;
+  if (p.kind >= ACQ_EI_MCMC) {
+    const double invS = 1.0 / (double)p.S;  // f_acqu/(len(means)): true division by S
+    f_acc = f_acc / (double)p.S;
+#pragma unroll
+    for (int q = 0; q < DMAX; ++q) df_acc[q] = df_acc[q] / (double)p.S;
+    (void)invS;
+  }
+  if (!p.lp_on) {
+    p.out_f[i] = f_acc;
+    if (p.grad) {
+#pragma unroll
+      for (int q = 0; q < DMAX; ++q)
+        if (q < d) p.out_df[i * d + q] = df_acc[q];
+    }
+    return;
+  }
+  // ---- Local Penalization (LP.py:70-132).  acquisition_function(x) == -f_acc, so fval = f_acc. ----
+  const double fval = f_acc;
+  double val, scale;
+  if (p.lp_transform == 1) {  // softplus
+    if (fval >= 40.0) val = log(fval);
+    else val = log(log1p(exp(fval)));
+    scale = 1.0 / (log1p(exp(fval)) * (1.0 + exp(-fval)));
+  } else {
+    val = log(fval + 1e-50);
+    scale = 1.0 / fval;
+  }
+  val = -val;
+  double dsum = 0.0;
+  for (int k = 0; k < p.lp_K; ++k) {
+    double nm2 = 0.0;
+    for (int q = 0; q < d; ++q) {
+      const double df = p.Xs[i * d + q] - p.lp_xb[k * d + q];
+      nm2 = fma(df, df, nm2);
+    }
+    const double nm = sqrt(nm2);
+    const double zz = (nm - p.lp_r[k]) / p.lp_s[k];
+    val -= log_ndtr(zz);
+    if (p.grad) {
+      const double h = 0.5 * erfc(-zz * 0.70710678118654752440);  // norm.cdf(z)
+      double dk = 1.0 / (p.lp_s[k] * 2.50662827463100050242 * h) * exp(-zz * zz / 2.0) / nm;
+      if (h < 1e-50) dk = 0.0;
+      dsum += dk;
+    }
+  }
+  p.out_f[i] = val;
+  if (p.grad) {
+    // scale * (-df) - sum_k d_k (direction dropped, broadcast over coordinates: LP.py:100-103,132)
+#pragma unroll
+    for (int q = 0; q < DMAX; ++q)
+      if (q < d) p.out_df[i * d + q] = scale * (-df_acc[q]) - dsum;
+  }
+}
+
 __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n_cand) return;
@@ -437,7 +497,9 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
   double f_acc = 0.0, df_acc[DMAX];
 #pragma unroll
   for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
-  for (int z = 0; z < p.S; ++z) {
+  const bool zsplit = gridDim.y > 1;
+  const int z_begin = zsplit ? blockIdx.y : 0, z_end = zsplit ? blockIdx.y + 1 : p.S;
+  for (int z = z_begin; z < z_end; ++z) {
     double m = 0.0;
     for (int sp = 0; sp < p.js; ++sp) m += p.mean[((long long)z * p.js + sp) * p.nc_pad + i];
     const double* part = p.partial + (long long)z * p.tiles_m * nv * p.part_ld + i;
@@ -518,58 +580,36 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
     }
   }
   if (p.kind == ACQ_NONE) return;
-  if (p.kind >= ACQ_EI_MCMC) {
-    const double invS = 1.0 / (double)p.S;  // f_acqu/(len(means)): true division by S
-    f_acc = f_acc / (double)p.S;
-#pragma unroll
-    for (int q = 0; q < DMAX; ++q) df_acc[q] = df_acc[q] / (double)p.S;
-    (void)invS;
-  }
-  if (!p.lp_on) {
-    p.out_f[i] = f_acc;
+  if (zsplit) {
+    double* zb = p.zbuf + (long long)z_begin * (d + 1) * p.nc_pad + i;
+    zb[0] = f_acc;
     if (p.grad) {
 #pragma unroll
       for (int q = 0; q < DMAX; ++q)
-        if (q < d) p.out_df[i * d + q] = df_acc[q];
+        if (q < d) zb[(long long)(q + 1) * p.nc_pad] = df_acc[q];
     }
     return;
   }
-  // ---- Local Penalization (LP.py:70-132).  acquisition_function(x) == -f_acc, so fval = f_acc. ----
-  const double fval = f_acc;
-  double val, scale;
-  if (p.lp_transform == 1) {  // softplus
-    if (fval >= 40.0) val = log(fval);
-    else val = log(log1p(exp(fval)));
-    scale = 1.0 / (log1p(exp(fval)) * (1.0 + exp(-fval)));
-  } else {
-    val = log(fval + 1e-50);
-    scale = 1.0 / fval;
-  }
-  val = -val;
-  double dsum = 0.0;
-  for (int k = 0; k < p.lp_K; ++k) {
-    double nm2 = 0.0;
-    for (int q = 0; q < d; ++q) {
-      const double df = p.Xs[i * d + q] - p.lp_xb[k * d + q];
-      nm2 = fma(df, df, nm2);
-    }
-    const double nm = sqrt(nm2);
-    const double zz = (nm - p.lp_r[k]) / p.lp_s[k];
-    val -= log_ndtr(zz);
-    if (p.grad) {
-      const double h = 0.5 * erfc(-zz * 0.70710678118654752440);  // norm.cdf(z)
-      double dk = 1.0 / (p.lp_s[k] * 2.50662827463100050242 * h) * exp(-zz * zz / 2.0) / nm;
-      if (h < 1e-50) dk = 0.0;
-      dsum += dk;
-    }
-  }
-  p.out_f[i] = val;
-  if (p.grad) {
-    // scale * (-df) - sum_k d_k (direction dropped, broadcast over coordinates: LP.py:100-103,132)
+  acq_finalize(p, i, f_acc, df_acc);
+}
+
+__global__ void __launch_bounds__(128) acq_reduce_kernel(const AcqParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n_cand) return;
+  const int d = p.d;
+  double f_acc = 0.0, df_acc[DMAX];
 #pragma unroll
-    for (int q = 0; q < DMAX; ++q)
-      if (q < d) p.out_df[i * d + q] = scale * (-df_acc[q]) - dsum;
+  for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
+  for (int z = 0; z < p.S; ++z) {
+    const double* zb = p.zbuf + (long long)z * (d + 1) * p.nc_pad + i;
+    f_acc += zb[0];
+    if (p.grad) {
+#pragma unroll
+      for (int q = 0; q < DMAX; ++q)
+        if (q < d) df_acc[q] += zb[(long long)(q + 1) * p.nc_pad];
+    }
   }
+  acq_finalize(p, i, f_acc, df_acc);
 }
 
 // Parity guard run after every refit: at the n training inputs (where the posterior variance is smallest and the

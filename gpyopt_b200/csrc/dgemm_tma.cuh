@@ -23,7 +23,8 @@ constexpr int GEMM_TILE_BYTES = TILE * GEMM_BK * 8;  // 16 KiB per operand per s
 constexpr int GEMM_STAGE_BYTES = 2 * GEMM_TILE_BYTES;
 constexpr int GEMM_CONSUMER_WARPS = 8;
 constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_SCRATCH_BYTES = (16 + (16 + 2) * 2) * TILE * 8;  // xj [d][128] + red [(d+2)][2][128], d <= 16
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + GEMM_SCRATCH_BYTES;
 
 enum KRange { KR_FULL = 0, KR_LE_M = 1, KR_GE_N = 2, KR_GE_MAX = 3 };
 enum TileSkip { TS_ALL = 0, TS_LOWER = 1 };
@@ -37,6 +38,7 @@ struct GemmOperand {  // element coordinates of tile (0,0) for batch z: (col0 + 
 struct GemmParams {
   int tiles_m, tiles_n, kblocks;  // in units of 128
   int krange, tile_skip, raster;
+  int batch;   // number of batches z (hyper-parameter sets / independent sub-problems)
   int ksplit;  // >= 1: grid.y slices of the k range (EPI_GRAD only: its reductions are linear in the accumulator);
                // slice s of row block m writes partial row m*ksplit + s
   GemmOperand a, b;
@@ -61,6 +63,57 @@ struct GemmParams {
   long long nc_ld, n_pad;
 };
 
+// One unit of work of the persistent kernel: an output tile (tile_m, tile_n) of batch z, optionally one k slice of it.
+struct GemmTile {
+  int tile_m, tile_n, z, split, kb_begin, nk;
+};
+
+// Work items are numbered tile-fastest (the old grid.x order: row blocks sharing a B tile are neighbours, or heaviest
+// row blocks first), then k slice, then batch.  With TS_LOWER only the tiles_m (tiles_m + 1) / 2 lower tiles are numbered.
+__device__ __forceinline__ long long gemm_work_items(const GemmParams& p) {
+  const long long tiles = p.tile_skip == TS_LOWER ? (long long)p.tiles_m * (p.tiles_m + 1) / 2 : (long long)p.tiles_m * p.tiles_n;
+  return tiles * (p.ksplit > 1 ? p.ksplit : 1) * p.batch;
+}
+
+__device__ __forceinline__ GemmTile gemm_decode(const GemmParams& p, long long w) {
+  GemmTile t;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const long long tiles = p.tile_skip == TS_LOWER ? (long long)p.tiles_m * (p.tiles_m + 1) / 2 : (long long)p.tiles_m * p.tiles_n;
+  const int x = (int)(w % tiles);
+  const int rest = (int)(w / tiles);
+  t.split = rest % ksplit;
+  t.z = rest / ksplit;
+  if (p.tile_skip == TS_LOWER) {  // x -> (m, n), n <= m; rows with the longest k range first (KR_GE_MAX: small m)
+    const int l = p.krange == KR_GE_MAX ? x : (int)tiles - 1 - x;
+    int m = (int)((sqrt(8.0 * l + 1.0) - 1.0) * 0.5);
+    while ((m + 1) * (m + 2) / 2 <= l) ++m;
+    while (m * (m + 1) / 2 > l) --m;
+    t.tile_m = m;
+    t.tile_n = l - m * (m + 1) / 2;
+  } else if (p.raster == RO_M_FASTEST) {
+    t.tile_m = x % p.tiles_m;
+    t.tile_n = x / p.tiles_m;
+  } else {  // heaviest row blocks (largest k range under KR_LE_M) first
+    t.tile_m = p.tiles_m - 1 - x / p.tiles_n;
+    t.tile_n = x % p.tiles_n;
+  }
+  int kb_begin = 0, kb_end = p.kblocks;
+  if (p.krange == KR_LE_M) kb_end = min(t.tile_m + 1, p.kblocks);
+  else if (p.krange == KR_GE_N) kb_begin = t.tile_n;
+  else if (p.krange == KR_GE_MAX) kb_begin = max(t.tile_m, t.tile_n);
+  if (ksplit > 1) {
+    const int len = (kb_end - kb_begin + ksplit - 1) / ksplit;
+    kb_begin = min(kb_end, kb_begin + t.split * len);
+    kb_end = min(kb_end, kb_begin + len);
+  }
+  t.kb_begin = kb_begin;
+  t.nk = (kb_end - kb_begin) * (TILE / GEMM_BK);
+  return t;
+}
+
+// Persistent: gridDim.x CTAs (one per SM) walk the work items round-robin.  The producer thread runs ahead into the next
+// item's first stages while the consumers are still in the previous item's epilogue, so CTA start-up, the first TMA
+// round trip and the pipeline drain are paid once per CTA instead of once per tile.
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
@@ -69,30 +122,9 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = (uint64_t*)(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + GEMM_STAGES;
+  uint8_t* scratch = smem + GEMM_STAGES * GEMM_STAGE_BYTES + 256;  // epilogue scratch, separate from the ring
 
-  int tile_m, tile_n;
-  if (p.raster == RO_M_FASTEST) {
-    tile_m = blockIdx.x % p.tiles_m;
-    tile_n = blockIdx.x / p.tiles_m;
-  } else {  // heaviest row blocks (largest k range under KR_LE_M) are dispatched first
-    tile_m = p.tiles_m - 1 - (int)(blockIdx.x / p.tiles_n);
-    tile_n = blockIdx.x % p.tiles_n;
-  }
-  const int z = blockIdx.z;
-  if (p.tile_skip == TS_LOWER && tile_n > tile_m) return;
-
-  int kb_begin = 0, kb_end = p.kblocks;
-  if (p.krange == KR_LE_M) kb_end = min(tile_m + 1, p.kblocks);
-  else if (p.krange == KR_GE_N) kb_begin = tile_n;
-  else if (p.krange == KR_GE_MAX) kb_begin = max(tile_m, tile_n);
-  const int ksplit = p.ksplit > 1 ? p.ksplit : 1, split = blockIdx.y;
-  if (ksplit > 1) {
-    const int len = (kb_end - kb_begin + ksplit - 1) / ksplit;
-    kb_begin = min(kb_end, kb_begin + split * len);
-    kb_end = min(kb_end, kb_begin + len);
-  }
-  const int nk = (kb_end - kb_begin) * (TILE / GEMM_BK);
-
+  const long long n_work = gemm_work_items(p);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < GEMM_STAGES; ++s) {
@@ -109,17 +141,21 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (warp == GEMM_CONSUMER_WARPS && lane == 0) {
       tma_prefetch_desc(&mapA);
       tma_prefetch_desc(&mapB);
-      const int a_row = p.a.row0 + z * p.a.row_z + tile_m * TILE, a_col = p.a.col0 + z * p.a.col_z;
-      const int b_row = p.b.row0 + z * p.b.row_z + tile_n * TILE, b_col = p.b.col0 + z * p.b.col_z;
-      const int a_bat = p.a.bat0 + z * p.a.bat_z, b_bat = p.b.bat0 + z * p.b.bat_z;
-      for (int it = 0; it < nk; ++it) {
-        const int s = it % GEMM_STAGES;
-        if (it >= GEMM_STAGES) mbar_wait(&empty_bar[s], ((it / GEMM_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], GEMM_STAGE_BYTES);
-        const int k = kb_begin * TILE + it * GEMM_BK;
-        uint8_t* st = smem + s * GEMM_STAGE_BYTES;
-        tma_load_3d(st, &mapA, &full_bar[s], a_col + k, a_row, a_bat);
-        tma_load_3d(st + GEMM_TILE_BYTES, &mapB, &full_bar[s], b_col + k, b_row, b_bat);
+      long long g = 0;  // k iterations issued by this CTA so far (ring position)
+      for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const GemmTile t = gemm_decode(p, w);
+        const int a_row = p.a.row0 + t.z * p.a.row_z + t.tile_m * TILE, a_col = p.a.col0 + t.z * p.a.col_z;
+        const int b_row = p.b.row0 + t.z * p.b.row_z + t.tile_n * TILE, b_col = p.b.col0 + t.z * p.b.col_z;
+        const int a_bat = p.a.bat0 + t.z * p.a.bat_z, b_bat = p.b.bat0 + t.z * p.b.bat_z;
+        for (int it = 0; it < t.nk; ++it, ++g) {
+          const int s = (int)(g % GEMM_STAGES);
+          if (g >= GEMM_STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((g / GEMM_STAGES) & 1) ^ 1));
+          mbar_arrive_expect_tx(&full_bar[s], GEMM_STAGE_BYTES);
+          const int k = t.kb_begin * TILE + it * GEMM_BK;
+          uint8_t* st = smem + s * GEMM_STAGE_BYTES;
+          tma_load_3d(st, &mapA, &full_bar[s], a_col + k, a_row, a_bat);
+          tma_load_3d(st + GEMM_TILE_BYTES, &mapB, &full_bar[s], b_col + k, b_row, b_bat);
+        }
       }
     }
     return;
@@ -130,15 +166,20 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
   const int g = lane >> 2, t = lane & 3;
   const int rr = frag_row(g);
+  long long gi = 0;  // ring position, advances exactly like the producer's
+  for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
+  const GemmTile tl = gemm_decode(p, w);
+  const int tile_m = tl.tile_m, tile_n = tl.tile_n, z = tl.z, split = tl.split, nk = tl.nk;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
   double acc[8][4][2];
 #pragma unroll
   for (int f = 0; f < 8; ++f)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[f][j][0] = acc[f][j][1] = 0.0;
 
-  for (int it = 0; it < nk; ++it) {
-    const int s = it % GEMM_STAGES;
-    mbar_wait(&full_bar[s], (it / GEMM_STAGES) & 1);
+  for (int it = 0; it < nk; ++it, ++gi) {
+    const int s = (int)(gi % GEMM_STAGES);
+    mbar_wait(&full_bar[s], (uint32_t)((gi / GEMM_STAGES) & 1));
     const uint8_t* sA = smem + s * GEMM_STAGE_BYTES + (wm + rr) * 128;
     const uint8_t* sB = smem + s * GEMM_STAGE_BYTES + GEMM_TILE_BYTES + (wn + rr) * 128;
 #pragma unroll
@@ -186,8 +227,8 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     }
   } else {
-    // the pipeline stages are drained (every full barrier was waited on): reuse them as scratch
-    double* red = reinterpret_cast<double*>(smem);  // EPI_SUMSQ: [2][128]; EPI_GRAD: after the coordinates
+    // epilogue scratch lives past the ring: the producer may already be filling the ring for the next work item
+    double* red = reinterpret_cast<double*>(scratch);  // EPI_SUMSQ: [2][128]; EPI_GRAD: after the coordinates
     const int half = warp & 1;
     if constexpr (EPI == EPI_SUMSQ) {
       named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
@@ -215,7 +256,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       //   S0_i = sum_j b_ji k_ji        (posterior variance term k.b)
       //   H0_i = sum_j b_ji h_ji,  P_qi = sum_j b_ji h_ji xc_jq     (variance gradient, combined in K3)
       const int d = p.d;
-      double* xj = reinterpret_cast<double*>(smem);  // [d][128] centred training coordinates of this row block
+      double* xj = reinterpret_cast<double*>(scratch);  // [d][128] centred training coordinates of this row block
       red = xj + d * TILE;                           // [(d+2)][2][128]
       named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
       for (int idx = threadIdx.x; idx < d * TILE; idx += GEMM_CONSUMER_WARPS * 32)
@@ -290,6 +331,7 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
   }
+  }  // work items
 }
 
 }  // namespace gpo

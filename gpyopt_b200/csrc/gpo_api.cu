@@ -146,9 +146,13 @@ static int gemm_setup(gpo_engine* eng) {
   return GPO_OK;
 }
 
-static int launch_gemm(gpo_engine* eng, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int batch,
+static int launch_gemm(gpo_engine* eng, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p_in, int batch,
                        cudaStream_t st) {
-  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)(p.ksplit > 1 ? p.ksplit : 1), (unsigned)batch);
+  GemmParams p = p_in;
+  p.batch = batch;
+  const long long tiles = p.tile_skip == TS_LOWER ? (long long)p.tiles_m * (p.tiles_m + 1) / 2 : (long long)p.tiles_m * p.tiles_n;
+  const long long work = tiles * (p.ksplit > 1 ? p.ksplit : 1) * batch;
+  dim3 grid((unsigned)std::min<long long>(work, eng->sm_count), 1, 1);  // persistent: one CTA per SM
   if (epi == EPI_STORE) dgemm_nt_kernel<EPI_STORE><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
   else if (epi == EPI_SUMSQ) dgemm_nt_kernel<EPI_SUMSQ><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
   else dgemm_nt_kernel<EPI_GRAD><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);

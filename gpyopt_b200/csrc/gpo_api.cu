@@ -708,7 +708,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
   const long long chunk = eng->nc_ld;
   int ci = 0;
   for (long long off = 0; off < N; off += chunk, ++ci) {
-    Slot& s = eng->slot[ci & 1];
+    // profiling serialises the chunks on one slot so that the events around each GEMM launch bracket that kernel alone
+    Slot& s = eng->slot[eng->profiling ? 0 : (ci & 1)];
     cudaStream_t st = s.stream;
     const long long rows = std::min(chunk, N - off);
     const long long nc_run = ((rows + TILE - 1) / TILE) * TILE;

@@ -133,8 +133,9 @@ int gpo_state_buffers(gpo_engine* eng, void** ptrs, long long* bytes, int max);
 int gpo_state_commit(gpo_engine* eng);
 
 /* Live timing of the dominant kernel (the variance GEMM launched once per sweep chunk), measured with CUDA events on
- * the stream the kernel runs on.  gpo_get_profile synchronises, returns the accumulated milliseconds, launches and
- * candidates since the last call, and resets. */
+ * the stream the kernel runs on.  While profiling is enabled the sweep chunks are serialised on one stream slot (so the
+ * events bracket that kernel alone; the normal two-slot pipeline overlaps neighbouring chunks).  gpo_get_profile
+ * synchronises, returns the accumulated milliseconds, launches and candidates since the last call, and resets. */
 int gpo_set_profiling(gpo_engine* eng, int enable);
 int gpo_get_profile(gpo_engine* eng, double* gemm_ms, long long* gemm_launches, long long* gemm_candidates);
 

@@ -48,6 +48,8 @@ struct gpo_engine {
   double *A = nullptr, *X = nullptr, *U = nullptr, *W = nullptr, *T = nullptr;
   CUtensorMap mapA, mapX, mapU, mapW, mapT;
   double *alpha = nullptr, *tmpv = nullptr;                          // [S][n_pad]
+  double* xtile = nullptr;                                           // [S][n_pad/32][dp+1][32] K1 staging (TMA source)
+  int dp = 0;                                                        // K1's padded dimension for this d
   double *logdet = nullptr, *quad = nullptr, *fmin = nullptr;        // [S]
   int* info = nullptr;                                               // [S]
   std::vector<double> h_logdet, h_quad, h_fmin;
@@ -210,7 +212,7 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
 
 static void free_state(gpo_engine* eng) {
   double** ptrs[] = {&eng->Xt, &eng->Xtc, &eng->xmu, &eng->Xaos, &eng->Y, &eng->invl, &eng->sigf2, &eng->noise, &eng->jitter, &eng->A, &eng->X,
-                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->logdet, &eng->quad, &eng->fmin, &eng->gradpart};
+                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->xtile, &eng->logdet, &eng->quad, &eng->fmin, &eng->gradpart};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
   for (int i = 0; i < 2; ++i) {
@@ -299,6 +301,8 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   GPO_CUDA_OK(cudaMalloc(&eng->T, nn));
   GPO_CUDA_OK(cudaMalloc(&eng->alpha, (size_t)S * n_pad * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->tmpv, (size_t)S * n_pad * 8));
+  eng->dp = d <= 2 ? 2 : d <= 4 ? 4 : d <= 6 ? 6 : d <= 8 ? 8 : d <= 12 ? 12 : 16;
+  GPO_CUDA_OK(cudaMalloc(&eng->xtile, (size_t)S * n_pad * (eng->dp + 1) * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->logdet, (size_t)S * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->quad, (size_t)S * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->fmin, (size_t)S * 8));
@@ -348,7 +352,9 @@ static void launch_cov_t(const CovParams& p, bool grad, int S, cudaStream_t st) 
   if (grad) cov_mean_kernel<DP, true><<<grid, COV_THREADS, smem, st>>>(p);
   else cov_mean_kernel<DP, false><<<grid, COV_THREADS, smem, st>>>(p);
 }
-static int launch_cov(gpo_engine* eng, const CovParams& p, bool grad, int S, cudaStream_t st) {
+static int launch_cov(gpo_engine* eng, const CovParams& p_in, bool grad, int S, cudaStream_t st) {
+  CovParams p = p_in;
+  p.xtile = eng->xtile;
   const int d = p.d;
   if (d <= 2) launch_cov_t<2>(p, grad, S, st);
   else if (d <= 4) launch_cov_t<4>(p, grad, S, st);
@@ -566,7 +572,9 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
       GPO_CUDA_OK(cudaMemcpyAsync(eng->alpha + (size_t)z * n_pad, eng->Y, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, st));
     gemv_kernel<<<grd, 256, 0, st>>>(eng->X, eng->alpha, eng->tmpv, n_pad, 0);
     gemv_kernel<<<grd, 256, 0, st>>>(eng->U, eng->tmpv, eng->alpha, n_pad, 1);
-    eng->launches += 2;
+    dim3 tgrid(n_pad / COV_JT, S);
+    build_xtile_kernel<<<tgrid, 128, 0, st>>>(eng->xtile, eng->Xt, n_pad, eng->alpha, eng->invl, n_pad, d, eng->dp);
+    eng->launches += 3;
     GPO_CUDA_OK(cudaGetLastError());
   }
   GPO_CUDA_OK(cudaStreamSynchronize(st));
@@ -976,7 +984,8 @@ extern "C" int gpo_state_buffers(gpo_engine* eng, void** ptrs, long long* bytes,
   struct { void* p; size_t b; } list[] = {
       {eng->Xt, d * np * 8}, {eng->Xtc, d * np * 8}, {eng->xmu, (size_t)DMAX * 8}, {eng->Xaos, d * np * 8}, {eng->Y, np * 8},
       {eng->invl, S * d * 8}, {eng->sigf2, S * 8}, {eng->noise, S * 8}, {eng->alpha, S * np * 8}, {eng->fmin, S * 8},
-      {eng->logdet, S * 8}, {eng->quad, S * 8}, {eng->X, S * np * np * 8}, {eng->W, S * np * np * 8}};
+      {eng->logdet, S * 8}, {eng->quad, S * 8}, {eng->xtile, S * np * (size_t)(eng->dp + 1) * 8},
+      {eng->X, S * np * np * 8}, {eng->W, S * np * np * 8}};
   const int cnt = (int)(sizeof(list) / sizeof(list[0]));
   if (cnt > max) GPO_FAIL(GPO_ERR_ARG, "gpo_state_buffers: need room for %d entries", cnt);
   for (int i = 0; i < cnt; ++i) { ptrs[i] = list[i].p; bytes[i] = (long long)list[i].b; }

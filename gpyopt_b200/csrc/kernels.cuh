@@ -24,6 +24,8 @@ struct CovParams {
   long long nc_ld;        // leading dimension (rows) of the chunk buffers Kt / mean / dmean
   const double* Xt;       // training inputs SoA [d][ldx]
   long long ldx;          // = n_pad
+  const double* xtile;    // [S][n_pad/32][DP+1][32]: per 32-row tile the length-scaled coordinates (rows 0..DP-1, zero past d)
+                          // and alpha (row DP), contiguous so that one TMA bulk copy stages a tile
   int n, n_pad, d, kern;
   const double* alpha;    // [S][n_pad]
   const double* invl;     // [S][d]
@@ -38,13 +40,13 @@ struct CovParams {
 
 // One thread owns one candidate (its scaled coordinates, mean and mean-gradient accumulators stay in registers for the
 // whole pass over the training set); the block walks the training index in tiles of 32 whose scaled coordinates and
-// alpha are staged in shared memory and read as broadcasts.  The covariance tile [32 j][128 candidates] is transposed
+// alpha are staged in shared memory by TMA bulk copies (cp.async.bulk + mbarrier, double buffered) and read as broadcasts.  The covariance tile [32 j][128 candidates] is transposed
 // through (padded, conflict-free) shared memory so that K*^T rows are written as full 256-byte lines.
 constexpr int COV_THREADS = 128;
 constexpr int COV_JT = 32;
 constexpr int COV_PITCH = COV_THREADS + 1;
 constexpr int cov_smem_bytes(int dp, bool with_h) {
-  return (COV_JT * COV_PITCH * (with_h ? 2 : 1) + 2 * (dp + 1) * COV_JT) * 8;
+  return (COV_JT * COV_PITCH * (with_h ? 2 : 1) + 2 * (dp + 1) * COV_JT + 2) * 8;
 }
 
 template <int DP, bool GRAD>
@@ -52,7 +54,8 @@ __global__ void __launch_bounds__(COV_THREADS) cov_mean_kernel(const CovParams p
   extern __shared__ double cov_smem[];
   double* tile_k = cov_smem;                                   // [32][129]
   double* xj_s0 = cov_smem + COV_JT * COV_PITCH;               // 2 x [(DP+1)][32]
-  double* tile_h = xj_s0 + 2 * (DP + 1) * COV_JT;              // [32][129], only when Ht is written
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xj_s0 + 2 * (DP + 1) * COV_JT);  // 2 mbarriers
+  double* tile_h = xj_s0 + 2 * (DP + 1) * COV_JT + 2;          // [32][129], only when Ht is written
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int z = blockIdx.z;
   const long long c0 = (long long)blockIdx.x * COV_THREADS;
@@ -70,21 +73,27 @@ __global__ void __launch_bounds__(COV_THREADS) cov_mean_kernel(const CovParams p
   double* Ht = (GRAD && p.Ht) ? p.Ht + ((long long)z * p.nc_ld + c0) * p.n_pad : nullptr;
   const int split = blockIdx.y;
   const int jt_begin = split * p.tiles_per_split, jt_end = min(p.n_pad / COV_JT, jt_begin + p.tiles_per_split);
-  // stage loader: thread t < (DP+1)*32 loads one value of the next j tile (row q = t/32: coordinate q, row DP: alpha)
+  // stage loader: one elected thread issues a TMA bulk copy of the next tile [(DP+1)][32] and arms its mbarrier
+  constexpr uint32_t kStageBytes = (DP + 1) * COV_JT * 8;
+  const double* xtile = p.xtile + (long long)z * (p.n_pad / COV_JT) * (DP + 1) * COV_JT;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
   auto stage = [&](int jt, int buf) {
-    for (int t = tid; t < (DP + 1) * COV_JT; t += COV_THREADS) {
-      const int q = t / COV_JT, jj = t % COV_JT, j = jt * COV_JT + jj;
-      double v;
-      if (q < DP) v = (q < p.d) ? __ldg(p.Xt + q * p.ldx + j) * invl[q] : 0.0;
-      else v = __ldg(alpha + j);
-      xj_s0[buf * (DP + 1) * COV_JT + t] = v;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bars[buf], kStageBytes);
+      tma_bulk_load(xj_s0 + buf * (DP + 1) * COV_JT, xtile + (long long)jt * (DP + 1) * COV_JT, kStageBytes, &bars[buf]);
     }
   };
   stage(jt_begin, 0);
-  __syncthreads();
   for (int jt = jt_begin; jt < jt_end; ++jt) {
     const int buf = (jt - jt_begin) & 1;
+    // buffer buf^1 was last read in the previous iteration, which every thread left through a __syncthreads
     if (jt + 1 < jt_end) stage(jt + 1, buf ^ 1);
+    mbar_wait(&bars[buf], (uint32_t)(((jt - jt_begin) >> 1) & 1));
     const double* xj = xj_s0 + buf * (DP + 1) * COV_JT;
     const int j0 = jt * COV_JT;
 #pragma unroll 4
@@ -128,6 +137,21 @@ __global__ void __launch_bounds__(COV_THREADS) cov_mean_kernel(const CovParams p
       for (int q = 0; q < DP; ++q)
         if (q < p.d) p.dmean[(zs * p.d + q) * p.nc_ld + cand] = dm[q] * invl[q];
     }
+  }
+}
+
+// Tile-major staging buffer for K1's TMA loads: xtile[z][jt][q][jj] = X[jt*32+jj][q] / l_zq (q < d), 0 (d <= q < dp),
+// alpha_z[jt*32+jj] (q == dp).  Rebuilt after every refit (alpha and the lengthscales change).
+__global__ void build_xtile_kernel(double* xtile, const double* Xt, long long ldx, const double* alpha, const double* invl,
+                                   int n_pad, int d, int dp) {
+  const int jt = blockIdx.x, z = blockIdx.y, ntiles = n_pad / COV_JT;
+  double* out = xtile + ((long long)z * ntiles + jt) * (dp + 1) * COV_JT;
+  for (int t = threadIdx.x; t < (dp + 1) * COV_JT; t += blockDim.x) {
+    const int q = t / COV_JT, j = jt * COV_JT + t % COV_JT;
+    double v = 0.0;
+    if (q < d) v = Xt[q * ldx + j] * invl[z * d + q];
+    else if (q == dp) v = alpha[(long long)z * n_pad + j];
+    out[t] = v;
   }
 }
 

@@ -59,7 +59,8 @@ def test_sass_uses_dmma_and_tma():
     from gpyopt_b200 import _lib
     sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert 'DMMA.8x8x4' in sass          # FP64 tensor-core path
-    assert 'UTMALDG' in sass             # cp.async.bulk.tensor (TMA)
+    assert 'UTMALDG' in sass             # cp.async.bulk.tensor (TMA tiles of the GEMM operands)
+    assert 'UBLKCP' in sass              # cp.async.bulk (TMA staging of K1's training tiles)
     assert 'SYNCS' in sass               # mbarrier pipeline
 
 

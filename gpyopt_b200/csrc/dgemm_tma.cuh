@@ -31,14 +31,20 @@ enum TileSkip { TS_ALL = 0, TS_LOWER = 1 };
 enum Raster { RO_M_FASTEST = 0, RO_HEAVY_FIRST = 1 };
 enum Epilogue { EPI_STORE = 0, EPI_SUMSQ = 1, EPI_GRAD = 2 };
 
-struct GemmOperand {  // element coordinates of tile (0,0) for batch z: (col0 + z*col_z, row0 + z*row_z, bat0 + z*bat_z)
+// A batch index z decomposes as z = node * zdiv + set: `set` selects the hyper-parameter set (3rd TMA coordinate, bat_z)
+// and `node` an independent sub-problem inside one matrix (the same-level nodes of the recursive triangular inverse;
+// row_z / col_z are its element strides).  Tile (0,0) of batch z starts at (col0 + node*col_z, row0 + node*row_z,
+// bat0 + set*bat_z).
+struct GemmOperand {
   int row0, col0, row_z, col_z, bat0, bat_z;
 };
 
 struct GemmParams {
   int tiles_m, tiles_n, kblocks;  // in units of 128
   int krange, tile_skip, raster;
-  int batch;   // number of batches z (hyper-parameter sets / independent sub-problems)
+  int batch;   // number of batches z (= nodes * zdiv)
+  int zdiv;    // hyper-parameter sets per node (0: batch, i.e. a single node)
+  int c_row_z, c_col_z, ct_row_z, ct_col_z;  // per-node element offsets of the EPI_STORE outputs
   int ksplit;  // >= 1: grid.y slices of the k range (EPI_GRAD only: its reductions are linear in the accumulator);
                // slice s of row block m writes partial row m*ksplit + s
   GemmOperand a, b;
@@ -144,9 +150,10 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       long long g = 0;  // k iterations issued by this CTA so far (ring position)
       for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
         const GemmTile t = gemm_decode(p, w);
-        const int a_row = p.a.row0 + t.z * p.a.row_z + t.tile_m * TILE, a_col = p.a.col0 + t.z * p.a.col_z;
-        const int b_row = p.b.row0 + t.z * p.b.row_z + t.tile_n * TILE, b_col = p.b.col0 + t.z * p.b.col_z;
-        const int a_bat = p.a.bat0 + t.z * p.a.bat_z, b_bat = p.b.bat0 + t.z * p.b.bat_z;
+        const int zdiv = p.zdiv > 0 ? p.zdiv : p.batch, node = t.z / zdiv, set = t.z % zdiv;
+        const int a_row = p.a.row0 + node * p.a.row_z + t.tile_m * TILE, a_col = p.a.col0 + node * p.a.col_z;
+        const int b_row = p.b.row0 + node * p.b.row_z + t.tile_n * TILE, b_col = p.b.col0 + node * p.b.col_z;
+        const int a_bat = p.a.bat0 + set * p.a.bat_z, b_bat = p.b.bat0 + set * p.b.bat_z;
         for (int it = 0; it < t.nk; ++it, ++g) {
           const int s = (int)(g % GEMM_STAGES);
           if (g >= GEMM_STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((g / GEMM_STAGES) & 1) ^ 1));
@@ -207,8 +214,9 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   //   row = wm + 8 f + frag_row(g),   col = wn + 8 j + (e ? 4 + t : t)      (within the 128 x 128 tile)
   if constexpr (EPI == EPI_STORE) {
     const bool diag = p.sym_diag && tile_m == tile_n;
-    double* C = p.C ? p.C + p.c_off_z * z : nullptr;
-    double* Ct = p.Ct ? p.Ct + p.ct_off_z * z : nullptr;
+    const int zdiv = p.zdiv > 0 ? p.zdiv : p.batch, node = z / zdiv, set = z % zdiv;
+    double* C = p.C ? p.C + p.c_off_z * set + (long long)node * p.c_row_z * p.ldc + node * p.c_col_z : nullptr;
+    double* Ct = p.Ct ? p.Ct + p.ct_off_z * set + (long long)node * p.ct_row_z * p.ldct + node * p.ct_col_z : nullptr;
 #pragma unroll
     for (int f = 0; f < 8; ++f) {
       const int r = tile_m * TILE + wm + 8 * f + rr;

@@ -420,24 +420,38 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
   std::vector<std::vector<TriNode>> levels;
   build_tree(0, nb, 0, levels);
   for (int lv = (int)levels.size() - 1; lv >= 0; --lv) {
-    for (const TriNode& nd : levels[lv]) {
+    const std::vector<TriNode>& nodes = levels[lv];
+    // same-shape, evenly spaced nodes of one level (always the case when n_pad/128 is a power of two) go out as ONE
+    // batched launch per product instead of one launch per node
+    bool uniform = nodes.size() > 1;
+    const int stride = uniform ? nodes[1].lo - nodes[0].lo : 0;
+    for (size_t i = 1; uniform && i < nodes.size(); ++i)
+      uniform = (nodes[i].hi - nodes[i].mid == nodes[0].hi - nodes[0].mid) && (nodes[i].mid - nodes[i].lo == nodes[0].mid - nodes[0].lo) &&
+                (nodes[i].lo - nodes[i - 1].lo == stride);
+    const size_t n_launch = uniform ? 1 : nodes.size();
+    const int n_nodes = uniform ? (int)nodes.size() : 1, zs = stride * TILE;
+    for (size_t li = 0; li < n_launch; ++li) {
+      const TriNode& nd = nodes[li];
       const int r = nd.hi - nd.mid, c = nd.mid - nd.lo;
       // T^T stored at Tbuf[lo:mid, mid:hi]:  T = L21 X11, B operand = U11 = X11^T (k >= n block)
       GemmParams p = gemm_defaults();
-      p.tiles_m = r; p.tiles_n = c; p.kblocks = c; p.krange = KR_GE_N;
-      p.a = {nd.mid * TILE, nd.lo * TILE, 0, 0, 0, 1};
-      p.b = {nd.lo * TILE, nd.lo * TILE, 0, 0, 0, 1};
+      p.tiles_m = r; p.tiles_n = c; p.kblocks = c; p.krange = KR_GE_N; p.zdiv = S;
+      p.a = {nd.mid * TILE, nd.lo * TILE, zs, zs, 0, 1};
+      p.b = {nd.lo * TILE, nd.lo * TILE, zs, zs, 0, 1};
       p.Ct = eng->T; p.ldct = n_pad; p.ct_off_z = nn; p.ct_row0 = nd.lo * TILE; p.ct_col0 = nd.mid * TILE;
-      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapU, p, S, st))) return rc;
+      p.ct_row_z = zs; p.ct_col_z = zs;
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapU, p, S * n_nodes, st))) return rc;
       // X21 = -X22 T  (A = X22 lower: k <= m block; B[n][k] = T[k][n] = Tbuf[lo+n][mid+k]); also U12 = X21^T
       GemmParams q = gemm_defaults();
-      q.tiles_m = r; q.tiles_n = c; q.kblocks = r; q.krange = KR_LE_M;
-      q.a = {nd.mid * TILE, nd.mid * TILE, 0, 0, 0, 1};
-      q.b = {nd.lo * TILE, nd.mid * TILE, 0, 0, 0, 1};
+      q.tiles_m = r; q.tiles_n = c; q.kblocks = r; q.krange = KR_LE_M; q.zdiv = S;
+      q.a = {nd.mid * TILE, nd.mid * TILE, zs, zs, 0, 1};
+      q.b = {nd.lo * TILE, nd.mid * TILE, zs, zs, 0, 1};
       q.alpha = -1.0;
       q.C = eng->X; q.ldc = n_pad; q.c_off_z = nn; q.c_row0 = nd.mid * TILE; q.c_col0 = nd.lo * TILE;
+      q.c_row_z = zs; q.c_col_z = zs;
       q.Ct = eng->U; q.ldct = n_pad; q.ct_off_z = nn; q.ct_row0 = nd.lo * TILE; q.ct_col0 = nd.mid * TILE;
-      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapX, eng->mapT, q, S, st))) return rc;
+      q.ct_row_z = zs; q.ct_col_z = zs;
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapX, eng->mapT, q, S * n_nodes, st))) return rc;
     }
   }
   // W^-1 = L^-T L^-1 = U U^T  (k >= max(m, n) block), lower tiles mirrored into the upper ones
@@ -457,45 +471,45 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
 static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool want_kt_only, int with_noise, long long N,
                  const double* Xs, double* o0, double* o1, double* o2, double* o3, cudaStream_t user);
 
-// parity guard (see variance_probe_kernel): decide which variance form gradient sweeps use
+// parity guard (see variance_probe_kernel): decide which variance form gradient sweeps use.  Probes the first
+// min(n, 512) training inputs (their order is arbitrary, so this is a sample): 2 small GEMMs instead of 2 n-wide ones.
 static int run_variance_probe(gpo_engine* eng, cudaStream_t st) {
   const int n = eng->n, n_pad = eng->n_pad, d = eng->d, S = eng->S, kernel = eng->kern;
+  const int n_probe = std::min(n, 512), probe_pad = ((n_probe + TILE - 1) / TILE) * TILE;
   int rc;
-  {
-    Slot& s0 = eng->slot[0];
-    Slot& s1 = eng->slot[1];
-    const int tiles_m = n_pad / TILE;
-    CovParams cp;
-    cp.Xs = eng->Xaos; cp.n_cand = n; cp.nc_run = n_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n;
-    cp.n_pad = n_pad; cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
-    cp.Kt = s0.Kt; cp.Ht = nullptr; cp.mean = s0.mean; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
-    if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
-    GemmParams g = gemm_defaults();
-    g.tiles_m = tiles_m; g.tiles_n = tiles_m; g.kblocks = tiles_m;
-    g.a = {0, 0, 0, 0, 0, 1}; g.b = {0, 0, 0, 0, 0, 1};
-    g.ldp = eng->nc_ld;
-    GemmParams gs = g; gs.partial = s0.partial_sq; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
-    if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s0.mapKt, gs, S, st))) return rc;
-    GemmParams gg = g; gg.partial = s1.partial; gg.krange = KR_FULL; gg.raster = RO_M_FASTEST;
-    gg.d = 0; gg.Xtc = eng->Xtc; gg.ldx = n_pad; gg.Kt = s0.Kt; gg.Ht = nullptr; gg.nc_ld = eng->nc_ld; gg.n_pad = n_pad;
-    if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s0.mapKt, gg, S, st))) return rc;
-    variance_probe_kernel<<<S, 256, 0, st>>>(s0.partial_sq, s1.partial, tiles_m, 2, eng->nc_ld, n, eng->sigf2, eng->noise,
-                                             eng->quad /*scratch, already copied out*/);
-    eng->launches++;
-    GPO_CUDA_OK(cudaGetLastError());
-    std::vector<double> disc(S);
-    GPO_CUDA_OK(cudaMemcpyAsync(disc.data(), eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
-    GPO_CUDA_OK(cudaMemcpyAsync(eng->quad, eng->h_quad.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
-    GPO_CUDA_OK(cudaStreamSynchronize(st));
-    eng->var_disc = 0.0;
-    bool need = false;
-    for (int z = 0; z < S; ++z) {
-      const double scale = std::sqrt(std::max(eng->h_sigf2[z] + eng->h_noise[z], 1e-300));
-      eng->var_disc = std::max(eng->var_disc, disc[z] / scale);
-      if (!(disc[z] <= 2e-11 * scale)) need = true;
-    }
-    eng->strict_active = eng->strict_mode == 1 || (eng->strict_mode < 0 && need);
+  Slot& s0 = eng->slot[0];
+  Slot& s1 = eng->slot[1];
+  const int tiles_m = n_pad / TILE;
+  CovParams cp;
+  cp.Xs = eng->Xaos; cp.n_cand = n_probe; cp.nc_run = probe_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n;
+  cp.n_pad = n_pad; cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
+  cp.Kt = s0.Kt; cp.Ht = nullptr; cp.mean = s0.mean; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
+  if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
+  GemmParams g = gemm_defaults();
+  g.tiles_m = tiles_m; g.tiles_n = probe_pad / TILE; g.kblocks = tiles_m;
+  g.a = {0, 0, 0, 0, 0, 1}; g.b = {0, 0, 0, 0, 0, 1};
+  g.ldp = eng->nc_ld;
+  GemmParams gs = g; gs.partial = s0.partial_sq; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
+  if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s0.mapKt, gs, S, st))) return rc;
+  GemmParams gg = g; gg.partial = s1.partial; gg.krange = KR_FULL; gg.raster = RO_M_FASTEST;
+  gg.d = 0; gg.Xtc = eng->Xtc; gg.ldx = n_pad; gg.Kt = s0.Kt; gg.Ht = nullptr; gg.nc_ld = eng->nc_ld; gg.n_pad = n_pad;
+  if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s0.mapKt, gg, S, st))) return rc;
+  variance_probe_kernel<<<S, 256, 0, st>>>(s0.partial_sq, s1.partial, tiles_m, 2, eng->nc_ld, n_probe, eng->sigf2, eng->noise,
+                                           eng->quad /*scratch, already copied out*/);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  std::vector<double> disc(S);
+  GPO_CUDA_OK(cudaMemcpyAsync(disc.data(), eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->quad, eng->h_quad.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaStreamSynchronize(st));
+  eng->var_disc = 0.0;
+  bool need = false;
+  for (int z = 0; z < S; ++z) {
+    const double scale = std::sqrt(std::max(eng->h_sigf2[z] + eng->h_noise[z], 1e-300));
+    eng->var_disc = std::max(eng->var_disc, disc[z] / scale);
+    if (!(disc[z] <= 2e-11 * scale)) need = true;
   }
+  eng->strict_active = eng->strict_mode == 1 || (eng->strict_mode < 0 && need);
   return GPO_OK;
 }
 

@@ -193,14 +193,15 @@ __global__ void gram_kernel(double* A, const double* Xt, long long ldx, int n, i
 // the finished column/row travel through shared memory (two block barriers per step, 16 LDS + 64 DFMA per thread).
 constexpr int DIAG_THREADS = 256;
 constexpr int DIAG_PITCH = TILE + 1;
-constexpr int DIAG_SMEM_BYTES = (TILE * DIAG_PITCH + 2 * TILE) * 8;
+constexpr int DIAG_SMEM_BYTES = (TILE * DIAG_PITCH + 3 * TILE) * 8;
 
 __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, double* X, double* U, int n_pad, int kb,
                                                                      int* info) {
   extern __shared__ double sm[];
   double* S = sm;                          // [128][129]  L (phase 2 reads its columns)
   double* vec = sm + TILE * DIAG_PITCH;    // [128] finished column (phase 1) / finished row (phase 2)
-  double* piv = vec + TILE;                // [1]
+  double* rdiag = vec + TILE;              // [128] 1 / L_jj
+  double* piv = rdiag + TILE;              // [1]   current pivot candidate
   const int z = blockIdx.x, tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
   const long long base = ((long long)z * n_pad + (long long)kb * TILE) * n_pad + (long long)kb * TILE;
@@ -213,23 +214,24 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
       r[a][b] = A[base + (long long)(k <= i ? i : k) * n_pad + (k <= i ? k : i)];  // symmetric fill from the lower part
     }
   // ---- phase 1: right-looking Cholesky ----
-  // column j = jo + 16 jb: the outer loop over jb is unrolled so the owners' register index is a compile-time constant
+  // column j = jo + 16 jb: the outer loop over jb is unrolled so the owners' register index is a compile-time constant.
+  // The (already updated) diagonal entry of the NEXT column is dropped into shared memory by its owner at the end of
+  // each step, so a step is: barrier, 16 owner threads form 1/sqrt(d) and publish the scaled column, barrier, rank-1 update.
+  if (tid == 0) piv[0] = r[0][0];
 #pragma unroll
   for (int jb = 0; jb < 8; ++jb) {
 #pragma unroll 1
     for (int jo = 0; jo < 16; ++jo) {
       const int j = jo + 16 * jb;
-      if (ty == jo && tx == jo) {
-        double dd = r[jb][jb];
-        if (!(dd > 0.0)) {
-          if (info[z] == 0) info[z] = kb * TILE + j + 1;
-          dd = 1.0;
-        }
-        piv[0] = sqrt(dd);
-      }
       __syncthreads();
       if (tx == jo) {  // owners of column j: scale by the reciprocal pivot (as LAPACK dpotf2 does) and publish
-        const double p = piv[0], rp = 1.0 / p;
+        double dd = piv[0];
+        if (!(dd > 0.0)) {
+          if (ty == jo && info[z] == 0) info[z] = kb * TILE + j + 1;
+          dd = 1.0;
+        }
+        const double rp = rsqrt(dd), p = dd * rp;
+        if (ty == jo) rdiag[j] = rp;
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           const int i = ty + 16 * a;
@@ -239,16 +241,27 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
         }
       }
       __syncthreads();
+      // register rows / columns of groups a, b < jb hold indices < 16 jb <= j: finished, skipped at compile time
       double li[8], lk[8];
 #pragma unroll
-      for (int a = 0; a < 8; ++a) li[a] = (ty + 16 * a > j) ? vec[ty + 16 * a] : 0.0;
+      for (int a = 0; a < 8; ++a)
+        if (a >= jb) li[a] = (ty + 16 * a > j) ? vec[ty + 16 * a] : 0.0;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) lk[b] = (tx + 16 * b > j) ? vec[tx + 16 * b] : 0.0;
+      for (int b = 0; b < 8; ++b)
+        if (b >= jb) lk[b] = (tx + 16 * b > j) ? vec[tx + 16 * b] : 0.0;
 #pragma unroll
       for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) r[a][b] = fma(-li[a], lk[b], r[a][b]);
-      // vec is rewritten only after the next pivot barrier, which every thread reaches after these reads
+        for (int b = 0; b < 8; ++b)
+          if (a >= jb && b >= jb) r[a][b] = fma(-li[a], lk[b], r[a][b]);
+      // hand the next pivot over (piv is read only after the barrier at the top of the next step; vec is rewritten
+      // only after that barrier too)
+      const int jn = j + 1, jno = jn & 15, jnb = jn >> 4;
+      if (jn < TILE && ty == jno && tx == jno) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+          if (a == jnb) piv[0] = r[a][a];
+      }
     }
   }
   // publish L (lower part) to shared memory and global memory; start phase 2 with R = I
@@ -269,24 +282,30 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
 #pragma unroll 1
     for (int ko = 0; ko < 16; ++ko) {
       const int k = ko + 16 * kq;
-      if (ty == ko) {  // owners of row k: scale by 1/L_kk and publish
-        const double inv = 1.0 / S[k * DIAG_PITCH + k];
+      if (ty == ko) {  // owners of row k: scale by 1/L_kk (kept from phase 1) and publish
+        const double inv = rdiag[k];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          r[kq][b] *= inv;
-          vec[tx + 16 * b] = r[kq][b];
-        }
+        for (int b = 0; b < 8; ++b)
+          if (b <= kq) {
+            r[kq][b] *= inv;
+            vec[tx + 16 * b] = r[kq][b];
+          }
       }
       __syncthreads();
+      // only rows i > k (groups a >= kq) change, and only in columns c <= k (groups b <= kq): the rest is skipped
+      // at compile time
       double li[8], xr[8];
 #pragma unroll
-      for (int a = 0; a < 8; ++a) li[a] = (ty + 16 * a > k) ? S[(ty + 16 * a) * DIAG_PITCH + k] : 0.0;
+      for (int a = 0; a < 8; ++a)
+        if (a >= kq) li[a] = (ty + 16 * a > k) ? S[(ty + 16 * a) * DIAG_PITCH + k] : 0.0;
 #pragma unroll
-      for (int b = 0; b < 8; ++b) xr[b] = vec[tx + 16 * b];
+      for (int b = 0; b < 8; ++b)
+        if (b <= kq) xr[b] = vec[tx + 16 * b];
 #pragma unroll
       for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) r[a][b] = fma(-li[a], xr[b], r[a][b]);
+        for (int b = 0; b < 8; ++b)
+          if (a >= kq && b <= kq) r[a][b] = fma(-li[a], xr[b], r[a][b]);
       __syncthreads();  // vec is rewritten by the next row's owners
     }
   }

@@ -44,6 +44,9 @@ struct gpo_engine {
   double *Xt = nullptr, *Xtc = nullptr, *xmu = nullptr, *Xaos = nullptr, *Y = nullptr;
   double *invl = nullptr, *sigf2 = nullptr, *noise = nullptr, *jitter = nullptr;
   std::vector<double> h_invl, h_sigf2, h_noise;
+  std::vector<double> h_X, h_Y, st_xt, st_xc, st_xa, st_yy, st_mu, h_jit, h_disc;  // persistent host staging
+  std::vector<int> h_info;
+  double* probe_out = nullptr;                                       // [S] device
   // posterior state (device), each [S][n_pad][n_pad] unless noted
   double *A = nullptr, *X = nullptr, *U = nullptr, *W = nullptr, *T = nullptr;
   CUtensorMap mapA, mapX, mapU, mapW, mapT;
@@ -212,7 +215,7 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
 
 static void free_state(gpo_engine* eng) {
   double** ptrs[] = {&eng->Xt, &eng->Xtc, &eng->xmu, &eng->Xaos, &eng->Y, &eng->invl, &eng->sigf2, &eng->noise, &eng->jitter, &eng->A, &eng->X,
-                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->xtile, &eng->logdet, &eng->quad, &eng->fmin, &eng->gradpart};
+                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->xtile, &eng->probe_out, &eng->logdet, &eng->quad, &eng->fmin, &eng->gradpart};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
   for (int i = 0; i < 2; ++i) {
@@ -308,6 +311,8 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   GPO_CUDA_OK(cudaMalloc(&eng->fmin, (size_t)S * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->info, (size_t)S * sizeof(int)));
   GPO_CUDA_OK(cudaMalloc(&eng->gradpart, (size_t)S * 256 * (DMAX + 2) * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->probe_out, (size_t)S * 8));
+  eng->h_X.clear(); eng->h_Y.clear();
   int rc;
   if ((rc = make_map(eng, &eng->mapA, eng->A, n_pad, n_pad, S))) return rc;
   if ((rc = make_map(eng, &eng->mapX, eng->X, n_pad, n_pad, S))) return rc;
@@ -396,7 +401,8 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
   GPO_CUDA_OK(cudaMemsetAsync(eng->X, 0, (size_t)S * nn * 8, st));
   GPO_CUDA_OK(cudaMemsetAsync(eng->U, 0, (size_t)S * nn * 8, st));
   for (int kb = 0; kb < nb; ++kb) {
-    diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb, eng->info);
+    diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb,
+                                                                    std::max(0, std::min(TILE, eng->n - kb * TILE)), eng->info);
     eng->launches++;
     const int rem = nb - kb - 1;
     if (rem == 0) break;
@@ -473,7 +479,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool want_kt_
 
 // parity guard (see variance_probe_kernel): decide which variance form gradient sweeps use.  Probes the first
 // min(n, 512) training inputs (their order is arbitrary, so this is a sample): 2 small GEMMs instead of 2 n-wide ones.
-static int run_variance_probe(gpo_engine* eng, cudaStream_t st) {
+// launch_* enqueues the kernels and the copy of the result; finish_* (after a stream sync) takes the decision.
+static int launch_variance_probe(gpo_engine* eng, cudaStream_t st) {
   const int n = eng->n, n_pad = eng->n_pad, d = eng->d, S = eng->S, kernel = eng->kern;
   const int n_probe = std::min(n, 512), probe_pad = ((n_probe + TILE - 1) / TILE) * TILE;
   int rc;
@@ -483,7 +490,7 @@ static int run_variance_probe(gpo_engine* eng, cudaStream_t st) {
   CovParams cp;
   cp.Xs = eng->Xaos; cp.n_cand = n_probe; cp.nc_run = probe_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n;
   cp.n_pad = n_pad; cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
-  cp.Kt = s0.Kt; cp.Ht = nullptr; cp.mean = s0.mean; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
+  cp.Kt = s0.Kt; cp.Ht = nullptr; cp.mean = s1.mean; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
   if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
   GemmParams g = gemm_defaults();
   g.tiles_m = tiles_m; g.tiles_n = probe_pad / TILE; g.kblocks = tiles_m;
@@ -495,21 +502,30 @@ static int run_variance_probe(gpo_engine* eng, cudaStream_t st) {
   gg.d = 0; gg.Xtc = eng->Xtc; gg.ldx = n_pad; gg.Kt = s0.Kt; gg.Ht = nullptr; gg.nc_ld = eng->nc_ld; gg.n_pad = n_pad;
   if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s0.mapKt, gg, S, st))) return rc;
   variance_probe_kernel<<<S, 256, 0, st>>>(s0.partial_sq, s1.partial, tiles_m, 2, eng->nc_ld, n_probe, eng->sigf2, eng->noise,
-                                           eng->quad /*scratch, already copied out*/);
+                                           eng->probe_out);
   eng->launches++;
   GPO_CUDA_OK(cudaGetLastError());
-  std::vector<double> disc(S);
-  GPO_CUDA_OK(cudaMemcpyAsync(disc.data(), eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->quad, eng->h_quad.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaStreamSynchronize(st));
+  eng->h_disc.assign(S, 0.0);
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->h_disc.data(), eng->probe_out, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+  return GPO_OK;
+}
+
+static void finish_variance_probe(gpo_engine* eng) {
   eng->var_disc = 0.0;
   bool need = false;
-  for (int z = 0; z < S; ++z) {
+  for (int z = 0; z < eng->S; ++z) {
     const double scale = std::sqrt(std::max(eng->h_sigf2[z] + eng->h_noise[z], 1e-300));
-    eng->var_disc = std::max(eng->var_disc, disc[z] / scale);
-    if (!(disc[z] <= 2e-11 * scale)) need = true;
+    eng->var_disc = std::max(eng->var_disc, eng->h_disc[z] / scale);
+    if (!(eng->h_disc[z] <= 2e-11 * scale)) need = true;
   }
   eng->strict_active = eng->strict_mode == 1 || (eng->strict_mode < 0 && need);
+}
+
+static int run_variance_probe(gpo_engine* eng, cudaStream_t st) {
+  int rc = launch_variance_probe(eng, st);
+  if (rc) return rc;
+  GPO_CUDA_OK(cudaStreamSynchronize(st));
+  finish_variance_probe(eng);
   return GPO_OK;
 }
 
@@ -522,96 +538,107 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
   const int n_pad = ((n + TILE - 1) / TILE) * TILE;
   int rc = ensure_capacity(eng, n_pad, d, S);
   if (rc) return rc;
+  cudaStream_t st = eng->fit_stream;
+  for (int i = 0; i < 2; ++i) GPO_CUDA_OK(cudaStreamSynchronize(eng->slot[i].stream));  // an asynchronous sweep may still read the state
+  // All host staging lives in the engine (no sync is needed to keep it alive), and the data is re-uploaded only when it
+  // changed: ML-II and HMC call this hundreds of times with the same (X, Y) and new hyper-parameters.
+  const bool same_data = eng->fitted && eng->n == n && eng->d == d && eng->h_X.size() == (size_t)n * d &&
+                         memcmp(eng->h_X.data(), X, (size_t)n * d * 8) == 0 && eng->h_Y.size() == (size_t)n &&
+                         memcmp(eng->h_Y.data(), Y, (size_t)n * 8) == 0;
   eng->fitted = false;
   eng->n = n; eng->n_pad = n_pad; eng->d = d; eng->S = S; eng->kern = kernel;
-  cudaStream_t st = eng->fit_stream;
-  // upload data (SoA + AoS) and hyper-parameters
-  std::vector<double> xt((size_t)d * n_pad, 0.0), xc((size_t)d * n_pad, 0.0), xa((size_t)n_pad * d, 0.0), yy((size_t)n_pad, 0.0);
-  std::vector<double> mu(DMAX, 0.0);
-  for (int q = 0; q < d; ++q) {
-    double sm = 0.0;
-    for (int i = 0; i < n; ++i) sm += X[(size_t)i * d + q];
-    mu[q] = sm / n;
-  }
-  for (int i = 0; i < n; ++i) {
-    for (int q = 0; q < d; ++q) {
-      xt[(size_t)q * n_pad + i] = X[(size_t)i * d + q];
-      xc[(size_t)q * n_pad + i] = X[(size_t)i * d + q] - mu[q];
-      xa[(size_t)i * d + q] = X[(size_t)i * d + q];
-    }
-    yy[i] = Y[i];
-  }
   if (kernel != KERN_RBF) {  // (dK/dr)/r chunk buffers are only needed when h != -k
     for (int i = 0; i < 2; ++i)
       if (!eng->slot[i].Ht) GPO_CUDA_OK(cudaMalloc(&eng->slot[i].Ht, (size_t)S * eng->nc_ld * n_pad * 8));
   }
+  if (!same_data) {
+    GPO_CUDA_OK(cudaStreamSynchronize(st));  // earlier async uploads may still read the staging vectors
+    eng->h_X.assign(X, X + (size_t)n * d);
+    eng->h_Y.assign(Y, Y + n);
+    eng->st_xt.assign((size_t)d * n_pad, 0.0); eng->st_xc.assign((size_t)d * n_pad, 0.0);
+    eng->st_xa.assign((size_t)n_pad * d, 0.0); eng->st_yy.assign((size_t)n_pad, 0.0); eng->st_mu.assign(DMAX, 0.0);
+    for (int q = 0; q < d; ++q) {
+      double sm = 0.0;
+      for (int i = 0; i < n; ++i) sm += X[(size_t)i * d + q];
+      eng->st_mu[q] = sm / n;
+    }
+    for (int i = 0; i < n; ++i) {
+      for (int q = 0; q < d; ++q) {
+        eng->st_xt[(size_t)q * n_pad + i] = X[(size_t)i * d + q];
+        eng->st_xc[(size_t)q * n_pad + i] = X[(size_t)i * d + q] - eng->st_mu[q];
+        eng->st_xa[(size_t)i * d + q] = X[(size_t)i * d + q];
+      }
+      eng->st_yy[i] = Y[i];
+    }
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->Xt, eng->st_xt.data(), eng->st_xt.size() * 8, cudaMemcpyHostToDevice, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->Xaos, eng->st_xa.data(), eng->st_xa.size() * 8, cudaMemcpyHostToDevice, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->Xtc, eng->st_xc.data(), eng->st_xc.size() * 8, cudaMemcpyHostToDevice, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->xmu, eng->st_mu.data(), eng->st_mu.size() * 8, cudaMemcpyHostToDevice, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->Y, eng->st_yy.data(), eng->st_yy.size() * 8, cudaMemcpyHostToDevice, st));
+  } else {
+    GPO_CUDA_OK(cudaStreamSynchronize(st));  // the hyper-parameter vectors below are rewritten
+  }
   eng->h_invl.assign((size_t)S * d, 0.0); eng->h_sigf2.assign(variance, variance + S); eng->h_noise.assign(noise, noise + S);
   for (int i = 0; i < S * d; ++i) eng->h_invl[i] = 1.0 / lengthscale[i];
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->Xt, xt.data(), xt.size() * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->Xaos, xa.data(), xa.size() * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->Xtc, xc.data(), xc.size() * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->xmu, mu.data(), mu.size() * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->Y, yy.data(), yy.size() * 8, cudaMemcpyHostToDevice, st));
   GPO_CUDA_OK(cudaMemcpyAsync(eng->invl, eng->h_invl.data(), (size_t)S * d * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->sigf2, variance, (size_t)S * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->noise, noise, (size_t)S * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaStreamSynchronize(st));  // the host vectors above go out of scope
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->sigf2, eng->h_sigf2.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->noise, eng->h_noise.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
 
   // GPy jitchol ladder: plain attempt, then jitter = mean(diag Ky) * 1e-6 * 10^t, t = 0..4.
-  // A hyper-parameter set that factorises keeps jitter 0; only failing sets are retried.
-  std::vector<double> jit(S, 0.0);
-  std::vector<int> info(S, 0), tries(S, 0);
+  // A hyper-parameter set that factorises keeps jitter 0; only failing sets are retried.  Everything of one attempt
+  // (factorisation, alpha, fmin sweep, scalars, variance probe) is enqueued back to back and checked after ONE sync.
+  eng->h_jit.assign(S, 0.0);
+  eng->h_info.assign(S, 0);
+  eng->h_logdet.resize(S); eng->h_quad.resize(S); eng->h_fmin.resize(S);
+  std::vector<int> tries(S, 0);
   for (int attempt = 0; attempt <= 6; ++attempt) {
-    GPO_CUDA_OK(cudaMemcpyAsync(eng->jitter, jit.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->jitter, eng->h_jit.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
     if ((rc = factorize(eng, st))) return rc;
-    GPO_CUDA_OK(cudaMemcpyAsync(info.data(), eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->h_info.data(), eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
+    // alpha = L^-T (L^-1 y)
+    {
+      dim3 grd((n_pad + 7) / 8, S);
+      for (int z = 0; z < S; ++z)  // Y is shared by all hyper-parameter sets
+        GPO_CUDA_OK(cudaMemcpyAsync(eng->alpha + (size_t)z * n_pad, eng->Y, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, st));
+      gemv_kernel<<<grd, 256, 0, st>>>(eng->X, eng->alpha, eng->tmpv, n_pad, 0);
+      gemv_kernel<<<grd, 256, 0, st>>>(eng->U, eng->tmpv, eng->alpha, n_pad, 1);
+      dim3 tgrid(n_pad / COV_JT, S);
+      build_xtile_kernel<<<tgrid, 128, 0, st>>>(eng->xtile, eng->Xt, n_pad, eng->alpha, eng->invl, n_pad, d, eng->dp);
+      eng->launches += 3;
+      GPO_CUDA_OK(cudaGetLastError());
+    }
+    // fmin = min_i mean(X_i): GPModel.get_fmin (gpmodel.py:129) -- a K1 sweep over the training inputs
+    {
+      Slot& s = eng->slot[0];
+      CovParams cp;
+      cp.Xs = eng->Xaos; cp.n_cand = n; cp.nc_run = n_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n;
+      cp.n_pad = n_pad; cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
+      cp.Kt = nullptr; cp.Ht = nullptr; cp.mean = s.mean; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
+      if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
+      fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, s.mean, eng->nc_ld, eng->js, n, n_pad, eng->logdet,
+                                            eng->quad, eng->fmin);
+      eng->launches++;
+      GPO_CUDA_OK(cudaGetLastError());
+      GPO_CUDA_OK(cudaMemcpyAsync(eng->h_logdet.data(), eng->logdet, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+      GPO_CUDA_OK(cudaMemcpyAsync(eng->h_quad.data(), eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+      GPO_CUDA_OK(cudaMemcpyAsync(eng->h_fmin.data(), eng->fmin, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if ((rc = launch_variance_probe(eng, st))) return rc;
     GPO_CUDA_OK(cudaStreamSynchronize(st));
     bool any = false;
     for (int z = 0; z < S; ++z) {
-      if (info[z] == 0) continue;
+      if (eng->h_info[z] == 0) continue;
       any = true;
       // Ky's diagonal is sigf2 + noise + 1e-8 (stationary kernel): always > 0, so GPy's "diag <= 0" exit never fires
       if (tries[z] >= 5) GPO_FAIL(GPO_ERR_NOT_PD, "not positive definite, even with jitter.");
       const double diag_mean = eng->h_sigf2[z] + eng->h_noise[z] + 1e-8;
-      jit[z] = diag_mean * 1e-6 * std::pow(10.0, tries[z]);
+      eng->h_jit[z] = diag_mean * 1e-6 * std::pow(10.0, tries[z]);
       tries[z]++;
     }
     if (!any) break;
   }
-  // alpha = L^-T (L^-1 y)
-  {
-    dim3 grd((n_pad + 7) / 8, S);
-    // Y is shared by all hyper-parameter sets: broadcast by reading with a zero batch stride
-    for (int z = 0; z < S; ++z)
-      GPO_CUDA_OK(cudaMemcpyAsync(eng->alpha + (size_t)z * n_pad, eng->Y, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, st));
-    gemv_kernel<<<grd, 256, 0, st>>>(eng->X, eng->alpha, eng->tmpv, n_pad, 0);
-    gemv_kernel<<<grd, 256, 0, st>>>(eng->U, eng->tmpv, eng->alpha, n_pad, 1);
-    dim3 tgrid(n_pad / COV_JT, S);
-    build_xtile_kernel<<<tgrid, 128, 0, st>>>(eng->xtile, eng->Xt, n_pad, eng->alpha, eng->invl, n_pad, d, eng->dp);
-    eng->launches += 3;
-    GPO_CUDA_OK(cudaGetLastError());
-  }
-  GPO_CUDA_OK(cudaStreamSynchronize(st));
+  finish_variance_probe(eng);
   eng->fitted = true;
-  // fmin = min_i mean(X_i): GPModel.get_fmin (gpmodel.py:129) -- a K1 sweep over the training inputs
-  {
-    Slot& s = eng->slot[0];
-    CovParams cp;
-    cp.Xs = eng->Xaos; cp.n_cand = n; cp.nc_run = n_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n; cp.n_pad = n_pad;
-    cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
-    cp.Kt = nullptr; cp.Ht = nullptr; cp.mean = s.mean; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
-    if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
-    fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, s.mean, eng->nc_ld, eng->js, n, n_pad, eng->logdet, eng->quad,
-                                          eng->fmin);
-    eng->launches++;
-    GPO_CUDA_OK(cudaGetLastError());
-    eng->h_logdet.resize(S); eng->h_quad.resize(S); eng->h_fmin.resize(S);
-    GPO_CUDA_OK(cudaMemcpyAsync(eng->h_logdet.data(), eng->logdet, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
-    GPO_CUDA_OK(cudaMemcpyAsync(eng->h_quad.data(), eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
-    GPO_CUDA_OK(cudaMemcpyAsync(eng->h_fmin.data(), eng->fmin, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
-    GPO_CUDA_OK(cudaStreamSynchronize(st));
-  }
-  if ((rc = run_variance_probe(eng, st))) return rc;
   return GPO_OK;
 }
 

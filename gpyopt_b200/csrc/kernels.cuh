@@ -195,8 +195,10 @@ constexpr int DIAG_THREADS = 256;
 constexpr int DIAG_PITCH = TILE + 1;
 constexpr int DIAG_SMEM_BYTES = (TILE * DIAG_PITCH + 3 * TILE) * 8;
 
+// Only the first n_valid = clamp(n - 128 kb, 0, 128) rows of the block are real data; the rest is identity padding, for
+// which both phases are no-ops, so the (latency-bound) step loops stop there.
 __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, double* X, double* U, int n_pad, int kb,
-                                                                     int* info) {
+                                                                     int n_valid, int* info) {
   extern __shared__ double sm[];
   double* S = sm;                          // [128][129]  L (phase 2 reads its columns)
   double* vec = sm + TILE * DIAG_PITCH;    // [128] finished column (phase 1) / finished row (phase 2)
@@ -223,6 +225,10 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
 #pragma unroll 1
     for (int jo = 0; jo < 16; ++jo) {
       const int j = jo + 16 * jb;
+      if (j >= n_valid) {  // identity padding from here on: L_jj = 1, nothing to eliminate (uniform branch)
+        if (tid == 0) rdiag[j] = 1.0;
+        continue;
+      }
       __syncthreads();
       if (tx == jo) {  // owners of column j: scale by the reciprocal pivot (as LAPACK dpotf2 does) and publish
         double dd = piv[0];
@@ -282,6 +288,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
 #pragma unroll 1
     for (int ko = 0; ko < 16; ++ko) {
       const int k = ko + 16 * kq;
+      if (k >= n_valid) continue;  // identity rows: R already holds the answer
       if (ty == ko) {  // owners of row k: scale by 1/L_kk (kept from phase 1) and publish
         const double inv = rdiag[k];
 #pragma unroll

@@ -22,8 +22,8 @@ struct Slot {
   double* Kt = nullptr;  // [S][nc_ld][n_pad]
   double* Ht = nullptr;  // [S][nc_ld][n_pad], only for non-RBF kernels (allocated on demand)
   CUtensorMap mapKt;
-  double* mean = nullptr;     // [S][nc_ld]
-  double* dmean = nullptr;    // [S][d][nc_ld]
+  double* mean = nullptr;     // [S][js][nc_ld]   per-slice partial sums of K1
+  double* dmean = nullptr;    // [S][js][d][nc_ld]
   double* partial = nullptr;  // [S][tiles_m][d+2][nc_ld]
   double* partial_sq = nullptr;  // [S][tiles_m][nc_ld]  (strict variance in gradient mode)
   double* zbuf = nullptr;        // [S][1+d][nc_ld]      per-set acquisition contributions (S > 1 only)
@@ -140,14 +140,19 @@ static int make_map(gpo_engine* eng, CUtensorMap* map, double* base, long long c
 // --------------------------------------------------------------------------------------------------
 // GEMM launcher
 // --------------------------------------------------------------------------------------------------
-static bool g_gemm_attr_set = false;
+// Opt-in shared-memory sizes are per device: set them for the engine's device at creation (a process may hold
+// engines on several GPUs).
+template <int DP>
+static cudaError_t cov_attr() {
+  return cudaFuncSetAttribute(cov_mean_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cov_smem_bytes(DP, true));
+}
 static int gemm_setup(gpo_engine* eng) {
-  if (g_gemm_attr_set) return GPO_OK;
   GPO_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   GPO_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<EPI_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   GPO_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<EPI_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   GPO_CUDA_OK(cudaFuncSetAttribute(diag_chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
-  g_gemm_attr_set = true;
+  GPO_CUDA_OK(cov_attr<2>()); GPO_CUDA_OK(cov_attr<4>()); GPO_CUDA_OK(cov_attr<6>());
+  GPO_CUDA_OK(cov_attr<8>()); GPO_CUDA_OK(cov_attr<12>()); GPO_CUDA_OK(cov_attr<16>());
   return GPO_OK;
 }
 
@@ -302,6 +307,8 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   GPO_CUDA_OK(cudaMalloc(&eng->U, nn));
   GPO_CUDA_OK(cudaMalloc(&eng->W, nn));
   GPO_CUDA_OK(cudaMalloc(&eng->T, nn));
+  GPO_CUDA_OK(cudaMemset(eng->X, 0, nn));
+  GPO_CUDA_OK(cudaMemset(eng->U, 0, nn));
   GPO_CUDA_OK(cudaMalloc(&eng->alpha, (size_t)S * n_pad * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->tmpv, (size_t)S * n_pad * 8));
   eng->dp = d <= 2 ? 2 : d <= 4 ? 4 : d <= 6 ? 6 : d <= 8 ? 8 : d <= 12 ? 12 : 16;
@@ -349,11 +356,6 @@ static void launch_cov_t(const CovParams& p, bool grad, int S, cudaStream_t st) 
   dim3 grid((unsigned)((p.nc_run + COV_THREADS - 1) / COV_THREADS), (unsigned)p.js, (unsigned)S);
   const bool with_h = grad && p.Ht != nullptr;
   const int smem = cov_smem_bytes(DP, with_h);
-  static bool attr_done = false;
-  if (!attr_done) {  // the (dK/dr)/r tile of the Matern kernels pushes the block past the 48 KiB default
-    cudaFuncSetAttribute(cov_mean_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cov_smem_bytes(DP, true));
-    attr_done = true;
-  }
   if (grad) cov_mean_kernel<DP, true><<<grid, COV_THREADS, smem, st>>>(p);
   else cov_mean_kernel<DP, false><<<grid, COV_THREADS, smem, st>>>(p);
 }
@@ -398,8 +400,7 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
     eng->launches++;
   }
   GPO_CUDA_OK(cudaMemsetAsync(eng->info, 0, S * sizeof(int), st));
-  GPO_CUDA_OK(cudaMemsetAsync(eng->X, 0, (size_t)S * nn * 8, st));
-  GPO_CUDA_OK(cudaMemsetAsync(eng->U, 0, (size_t)S * nn * 8, st));
+  // (the off-diagonal blocks of X above / of U below the diagonal are never written: zeroed once at allocation)
   for (int kb = 0; kb < nb; ++kb) {
     diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb,
                                                                     std::max(0, std::min(TILE, eng->n - kb * TILE)), eng->info);

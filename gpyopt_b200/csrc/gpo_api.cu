@@ -69,6 +69,8 @@ struct gpo_engine {
   double *lp_xb = nullptr, *lp_r = nullptr, *lp_s = nullptr;
   // top-k scratch
   double* tk_vals[2] = {nullptr, nullptr};  long long* tk_idx[2] = {nullptr, nullptr};  size_t tk_cap = 0;
+  // per-block best candidates written by K3 (fused selection)
+  double* blk_val = nullptr;  long long* blk_idx = nullptr;  size_t blk_cap = 0;  bool want_blk = false;
   // parity guard: variance form used by gradient sweeps (-1 auto, 0 fast k.W^-1.k, 1 strict |L^-1 k|^2)
   int strict_mode = -1;
   bool strict_active = false;
@@ -242,6 +244,8 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->lp_xb) cudaFree(eng->lp_xb);
   if (eng->lp_r) cudaFree(eng->lp_r);
   if (eng->lp_s) cudaFree(eng->lp_s);
+  if (eng->blk_val) cudaFree(eng->blk_val);
+  if (eng->blk_idx) cudaFree(eng->blk_idx);
   for (int i = 0; i < 2; ++i) {
     if (eng->tk_vals[i]) cudaFree(eng->tk_vals[i]);
     if (eng->tk_idx[i]) cudaFree(eng->tk_idx[i]);
@@ -847,6 +851,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
       ap.lp_xb = eng->lp_xb; ap.lp_r = eng->lp_r; ap.lp_s = eng->lp_s; ap.Xs = dev_in + off * d;
     }
     ap.zbuf = s.zbuf;
+    ap.blk_val = eng->want_blk ? eng->blk_val : nullptr; ap.blk_idx = eng->blk_idx; ap.row0 = off;
     {
       dim3 kgrid((unsigned)((rows + 127) / 128), (unsigned)(S > 1 ? S : 1), 1);
       acq_kernel<<<kgrid, 128, 0, st>>>(ap);
@@ -978,7 +983,7 @@ extern "C" int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, in
 
 extern "C" int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, const double* Xs, int k, double* vals,
                             long long* idx, double* f_out, void* stream) {
-  if (!eng || !Xs || !vals || !idx || N < 1 || kind < 0 || kind > 5) return GPO_ERR_ARG;
+  if (!eng || !Xs || !vals || !idx || N < 1 || k < 1 || kind < 0 || kind > 5) return GPO_ERR_ARG;
   GPO_CUDA_OK(cudaSetDevice(eng->device));
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
@@ -989,11 +994,38 @@ extern "C" int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, 
     if ((rc = grow(eng, &eng->stage_out[2], &eng->stage_out_bytes[2], (size_t)N * 8))) return rc;
     f_dev = eng->stage_out[2];
   }
-  if ((rc = sweep(eng, kind, par, false, false, 1, N, Xs, f_dev, nullptr, nullptr, nullptr, st))) return rc;
-  // smallest score = -f  <=>  largest f (or smallest LP value, which is already a "score to minimise")
-  const int largest = eng->lp_on ? 0 : 1;
-  if ((rc = topk_device(eng, N, f_dev, k, largest, vals, idx, st))) return rc;
-  if (!eng->lp_on) for (int i = 0; i < k; ++i) vals[i] = -vals[i];
+  const size_t nblk = (size_t)((N + 127) / 128);
+  if (k == 1) {  // fused selection: K3 leaves one record per 128 candidates (warp-shuffle argmax)
+    if (nblk > eng->blk_cap) {
+      GPO_CUDA_OK(cudaDeviceSynchronize());
+      if (eng->blk_val) cudaFree(eng->blk_val);
+      if (eng->blk_idx) cudaFree(eng->blk_idx);
+      GPO_CUDA_OK(cudaMalloc(&eng->blk_val, nblk * 8));
+      GPO_CUDA_OK(cudaMalloc(&eng->blk_idx, nblk * 8));
+      eng->blk_cap = nblk;
+    }
+    eng->want_blk = true;
+  }
+  rc = sweep(eng, kind, par, false, false, 1, N, Xs, f_dev, nullptr, nullptr, nullptr, st);
+  eng->want_blk = false;
+  if (rc) return rc;
+  if (k == 1) {
+    std::vector<double> bv(nblk);
+    std::vector<long long> bi(nblk);
+    GPO_CUDA_OK(cudaMemcpyAsync(bv.data(), eng->blk_val, nblk * 8, cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(bi.data(), eng->blk_idx, nblk * 8, cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+    size_t best = 0;
+    for (size_t b = 1; b < nblk; ++b)
+      if (bv[b] > bv[best] || (bv[b] == bv[best] && bi[b] < bi[best])) best = b;
+    vals[0] = -bv[best];  // score = -f (or the LP value itself, which K3 negated to maximise)
+    idx[0] = bi[best];
+  } else {
+    // smallest score = -f  <=>  largest f (or smallest LP value, which is already a "score to minimise")
+    const int largest = eng->lp_on ? 0 : 1;
+    if ((rc = topk_device(eng, N, f_dev, k, largest, vals, idx, st))) return rc;
+    if (!eng->lp_on) for (int i = 0; i < k; ++i) vals[i] = -vals[i];
+  }
   if (f_out && !f_is_dev) {
     GPO_CUDA_OK(cudaMemcpyAsync(f_out, f_dev, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
     GPO_CUDA_OK(cudaStreamSynchronize(st));

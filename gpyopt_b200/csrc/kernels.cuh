@@ -467,6 +467,11 @@ struct AcqParams {
   long long out_ldN;     // N of the whole call (stride between hyper-parameter sets)
   // acquisition outputs, offset to the chunk's first row
   double *out_f, *out_df;
+  // fused selection: every block leaves its best candidate (largest score = f, or smallest LP value; ties -> lowest
+  // index) found with warp shuffles; gpo_acq_topk(k = 1) reduces these N/128 records instead of re-reading f
+  double* blk_val;
+  long long* blk_idx;
+  long long row0;        // global index of the chunk's first row
   // S > 1: the kernel runs with gridDim.y = S (one hyper-parameter set per block row) and leaves each set's contribution
   // in zbuf [S][1+d][nc_pad]; acq_reduce_kernel then adds them in set order (deterministic) and finishes
   double* zbuf;
@@ -483,8 +488,29 @@ __device__ __forceinline__ double log_ndtr(double z) {
   return log1p(-0.5 * erfc(t));
 }
 
+// block-wide argmax of (score, index) with warp shuffles; ties -> lowest index; inactive threads pass -inf
+__device__ __forceinline__ void block_argmax_store(double score, long long idx, double* blk_val, long long* blk_idx,
+                                                   long long slot) {
+  __shared__ double sv[4];
+  __shared__ long long si[4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, score, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > score || (ov == score && oi < idx)) { score = ov; idx = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = score; si[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (sv[w] > score || (sv[w] == score && si[w] < idx)) { score = sv[w]; idx = si[w]; }
+    blk_val[slot] = score;
+    blk_idx[slot] = idx;
+  }
+}
+
 // last stage of K3 for one candidate: MCMC average, then either the plain outputs or the Local-Penalization transform
-__device__ __forceinline__ void acq_finalize(const AcqParams& p, long long i, double f_acc, double (&df_acc)[DMAX]) {
+__device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, double f_acc, double (&df_acc)[DMAX]) {
   const int d = p.d;
   if (p.kind >= ACQ_EI_MCMC) {
     const double invS = 1.0 / (double)p.S;  // f_acqu/(len(means)): true division by S
@@ -500,7 +526,7 @@ __device__ __forceinline__ void acq_finalize(const AcqParams& p, long long i, do
       for (int q = 0; q < DMAX; ++q)
         if (q < d) p.out_df[i * d + q] = df_acc[q];
     }
-    return;
+    return f_acc;
   }
   // ---- Local Penalization (LP.py:70-132).  acquisition_function(x) == -f_acc, so fval = f_acc. ----
   const double fval = f_acc;
@@ -538,11 +564,13 @@ __device__ __forceinline__ void acq_finalize(const AcqParams& p, long long i, do
     for (int q = 0; q < DMAX; ++q)
       if (q < d) p.out_df[i * d + q] = scale * (-df_acc[q]) - dsum;
   }
+  return -val;  // the penalised value is minimised
 }
 
 __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n_cand) return;
+  const long long i_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i_raw < p.n_cand;
+  const long long i = active ? i_raw : p.n_cand - 1;  // out-of-range threads shadow the last row and write nothing
   const int d = p.d, nv = p.part_nv;
   double f_acc = 0.0, df_acc[DMAX];
 #pragma unroll
@@ -640,12 +668,13 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
     }
     return;
   }
-  acq_finalize(p, i, f_acc, df_acc);
+  const double score = acq_finalize(p, i, f_acc, df_acc);
+  if (p.blk_val) block_argmax_store(score, p.row0 + i, p.blk_val, p.blk_idx, (p.row0 >> 7) + blockIdx.x);
 }
 
 __global__ void __launch_bounds__(128) acq_reduce_kernel(const AcqParams p) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n_cand) return;
+  const long long i_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = i_raw < p.n_cand ? i_raw : p.n_cand - 1;  // shadow the last row (identical values, benign)
   const int d = p.d;
   double f_acc = 0.0, df_acc[DMAX];
 #pragma unroll
@@ -659,7 +688,8 @@ __global__ void __launch_bounds__(128) acq_reduce_kernel(const AcqParams p) {
         if (q < d) df_acc[q] += zb[(long long)(q + 1) * p.nc_pad];
     }
   }
-  acq_finalize(p, i, f_acc, df_acc);
+  const double score = acq_finalize(p, i, f_acc, df_acc);
+  if (p.blk_val) block_argmax_store(score, p.row0 + i, p.blk_val, p.blk_idx, (p.row0 >> 7) + blockIdx.x);
 }
 
 // Parity guard run after every refit: at the n training inputs (where the posterior variance is smallest and the

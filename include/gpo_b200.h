@@ -103,7 +103,9 @@ int gpo_lp_set(gpo_engine* eng, int K, const double* Xb, const double* r, const 
 /* Fused candidate sweep + selection (AnchorPointsGenerator.get, GPyOpt/optimization/
  * anchor_points_generator.py:25-69): evaluates the acquisition value over Xs [N, d] and returns the k
  * candidates with the smallest score = -f (ties: lowest index).  vals/idx are host arrays [k];
- * vals holds the scores (-f).  f_out (host|device, may be NULL) receives all N acquisition values. */
+ * vals holds the scores (-f).  f_out (host|device, may be NULL) receives all N acquisition values.
+ * k = 1 is served by the per-block argmax that the acquisition epilogue computes with warp shuffles; k > 1 by a
+ * multi-level bitonic selection over f. */
 int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, const double* Xs, int k, double* vals,
                  long long* idx, double* f_out, void* stream);
 

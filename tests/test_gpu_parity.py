@@ -347,6 +347,20 @@ def test_full_size_sweep_consistency(engine, full_size):
     vals, idx = engine.acq_topk('EI', 0.01, Xs, 25, f_out=f_out)
     assert np.array_equal(f_out, f)
     assert np.array_equal(idx, np.argsort(-f, kind='stable')[:25]) and np.array_equal(vals, -f[idx])
+    # k = 1 takes the fused selection (per-block warp-shuffle argmax inside K3): same winner, ties -> lowest index
+    v1, i1 = engine.acq_topk('EI', 0.01, Xs, 1)
+    assert i1[0] == idx[0] and v1[0] == vals[0]
+    dup = np.vstack([Xs[:5000], Xs[int(idx[0])][None, :], Xs[5000:9000], Xs[int(idx[0])][None, :]])
+    v1, i1 = engine.acq_topk('EI', 0.01, dup, 1)
+    first = int(idx[0]) if idx[0] < 5000 else 5000
+    assert i1[0] == first and v1[0] == vals[0]
+    try:
+        engine.lp_set(Xs[:3], np.full(3, 0.5), np.full(3, 0.3), 'none')
+        flp = engine.acq('EI', 0.01, Xs[:3000])
+        v1, i1 = engine.acq_topk('EI', 0.01, Xs[:3000], 1)
+        assert i1[0] == int(np.argmin(flp)) and v1[0] == flp.min()
+    finally:
+        engine.lp_set(None, None, None, None)
 
 
 def test_full_size_gradients_match_finite_differences(engine, full_size):

@@ -17,7 +17,7 @@ for (n,d,S,N) in ((2048,6,1,9472*8),(128,6,1,2_000_000),(512,4,64,100_000)):
     Xs=torch.from_numpy(rng.random((N,d))*9+1).cuda(); f=torch.empty(N,dtype=torch.float64,device='cuda'); df=torch.empty(N,d,dtype=torch.float64,device='cuda')
     kind='EI_MCMC' if S>1 else 'EI'
     tg=t(lambda: eng.acq(kind,0.01,Xs,grad=True,out=(f,df),stream=st)); tv=t(lambda: eng.acq(kind,0.01,Xs,out=(f,None),stream=st))
-    print(json.dumps({'cw':os.environ.get('GPO_K1_CW','default'),'n':n,'d':d,'S':S,'N':N,'grad_ms':tg,'val_ms':tv,'grad_Mcand_s':N/tg/1e3,'val_Mcand_s':N/tv/1e3}))
+    print(json.dumps({'n':n,'d':d,'S':S,'N':N,'grad_ms':tg,'val_ms':tv,'grad_Mcand_s':N/tg/1e3,'val_Mcand_s':N/tv/1e3}))
     eng.close()
 # latency
 for n in (2048, 4096):

@@ -270,11 +270,22 @@ class GPRegressionB200(object):
             self.Y = np.ascontiguousarray(np.asarray(Y, dtype=np.float64)).copy()
         self._trigger_params_changed()
 
+    def _ensure_own_state(self):
+        """The engine may be holding a set of hyper-parameter samples (GPModel_MCMC's prediction state).  GPy's model
+        always answers for its CURRENT parameters (the reference restores them after every sample loop,
+        gpmodel.py:275-276), so inner-model calls first put the single current set back."""
+        if self._samples is not None:
+            frozen, self._frozen = self._frozen, False
+            self._trigger_params_changed()
+            self._frozen = frozen
+
     # -- marginal likelihood ------------------------------------------------------------------------------
     def log_likelihood(self):
+        self._ensure_own_state()
         return float(self.engine.get_loglik()[0][0])
 
     def _loglik_gradient(self):
+        self._ensure_own_state()
         g = self.engine.get_loglik_grad()[0]
         d = self.input_dim
         gl = g[1:1 + d] if self._spec.ARD else np.array([g[1:1 + d].sum()])
@@ -349,11 +360,13 @@ class GPRegressionB200(object):
         if full_cov:
             raise NotImplementedError("full predictive covariance is outside the engine's hot path")
         Xnew = np.atleast_2d(np.asarray(Xnew, dtype=np.float64))
+        self._ensure_own_state()
         m, s = self.engine.predict(Xnew, with_noise=include_likelihood)
         return m[0][:, None], np.square(s[0])[:, None]
 
     def predictive_gradients(self, Xnew, kern=None):
         Xnew = np.atleast_2d(np.asarray(Xnew, dtype=np.float64))
+        self._ensure_own_state()
         m, s, dm, ds = self.engine.predict_grad(Xnew)
         return dm[0][:, :, None], ds[0] * (2.0 * s[0][:, None])
 

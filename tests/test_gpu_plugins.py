@@ -68,6 +68,17 @@ def test_mcmc_plugin_matches_reference_class():
         assert scaled_err(f, g['EI_MCMC_fg']) < TOL and scaled_err(df, g['EI_MCMC_df']) < tg
         f = AcquisitionLCB_MCMC(model, None, None, exploration_weight=2)._compute_acq(g['Xs'])
         assert scaled_err(f, g['LCB_MCMC_f']) < TOL
+        # the inner GPy-like object answers for the model's CURRENT parameters (the reference restores them after each
+        # sample loop), not for the first resident sample ...
+        from oracle import gpy_numpy as G
+        p = model.model.param_array
+        gp = G.GPRegression(g['X'], g['Y'], G.RBF(g['X'].shape[1], variance=p[0], lengthscale=p[1]), noise_var=p[2])
+        mi, vi = model.model.predict(g['Xs'][:7])
+        mo, vo = gp.predict(g['Xs'][:7])
+        assert scaled_err(mi, mo) < 1e-9 and scaled_err(vi, np.clip(vo, 1e-10, np.inf)) < 1e-9
+        # ... and the sample state comes back for the next integrated prediction
+        means2, _ = model.predict(g['Xs'])
+        assert scaled_err(np.array(means2), g['means']) < TOL
 
 
 def test_lp_plugin_matches_reference_class():

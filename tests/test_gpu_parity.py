@@ -444,3 +444,100 @@ def test_randomised_shapes_against_oracle(n, d, N, kernel, ARD, S, noise, seed):
         assert np.array_equal(np.sort(fv)[::-1][:k], -vals)
     finally:
         eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# the other BASELINE configs at their full sizes: oracle on a row subset + size-independent properties
+# ------------------------------------------------------------------------------------------------------
+def test_config2_camel_lcb_million_candidate_sweep(engine):
+    """BASELINE config 2: six-hump camel (2-D), n = 55, LCB, 1M-candidate value-only sweep."""
+    from oracle import gpy_numpy as G, gpyopt_numpy as og
+    rng = np.random.default_rng(50)
+    lo, hi = np.array([-2., -1.]), np.array([2., 1.])
+    X = lo + (hi - lo) * rng.random((55, 2))
+    Y = og.normalize_stats(og.sixhumpcamel(X))
+    gp = G.GPRegression(X, Y, G.Matern52(2, variance=1.0, lengthscale=0.7), noise_var=Y.var() * 0.01)
+    engine.fit('matern52', X, Y, [1.0], [[0.7, 0.7]], [Y.var() * 0.01])
+    N = 1_000_000
+    Xs = lo + (hi - lo) * rng.random((N, 2))
+    f = engine.acq('LCB', 2.0, Xs)
+    rows = rng.choice(N, 3000, replace=False)
+    mo, so = og.gp_predict(gp, Xs[rows])
+    assert scaled_err(f[rows], og.acq_LCB(mo, so, 2.0)[:, 0]) < TOL
+    vals, idx = engine.acq_topk('LCB', 2.0, Xs, 5)
+    assert np.array_equal(idx, np.argsort(-f, kind='stable')[:5]) and np.array_equal(vals, -f[idx])
+    assert lo[0] <= Xs[idx[0], 0] <= hi[0]
+
+
+def test_config4_mcmc_64_samples_full_size(engine):
+    """BASELINE config 4: S = 64 hyper-parameter samples, n = 512, d = 4, EI_MCMC with gradients."""
+    from gpyopt_b200 import Engine
+    from oracle import gpy_numpy as G, gpyopt_numpy as og
+    rng = np.random.default_rng(2)
+    n, d, S, N = 512, 4, 64, 6000
+    X = rng.random((n, d))
+    Y = og.normalize_stats(og.alpine2(1 + 9 * X))
+    theta = np.array([1.0, 0.5, 1e-2]) * np.exp(0.1 * rng.standard_normal((S, 3)))
+    Xs = rng.random((N, d))
+    engine.fit('rbf', X, Y, theta[:, 0], theta[:, 1:2], theta[:, 2])
+    f, df = engine.acq('EI_MCMC', 0.01, Xs, grad=True)
+    m, s, dm, ds = engine.predict_grad(Xs[:500])
+    fmins = engine.get_fmin()
+    # (a) the integrated acquisition is the plain average of the per-sample ones (EI_mcmc.py:49-59)
+    means, stds = [mi[:, None] for mi in m], [si[:, None].copy() for si in s]
+    fo, dfo = og.acq_EI_MCMC_withGradients(means, stds, list(dm), list(ds), list(fmins), 0.01)
+    assert scaled_err(f[:500], fo[:, 0]) < TOL and scaled_err(df[:500], dfo) < TOL
+    # (b) three of the 64 resident factorisations against the oracle, and against a single-set engine (bit-exact)
+    e1 = Engine(0)
+    try:
+        for z in (0, 31, 63):
+            gp = G.GPRegression(X, Y, G.RBF(d, variance=theta[z, 0], lengthscale=theta[z, 1]), noise_var=theta[z, 2])
+            tol_v, tol_g = parity_tolerances(gp, Xs[:300])
+            mo, so, dmo, dso = og.gp_predict_withGradients(gp, Xs[:300])
+            assert scaled_err(m[z][:300], mo[:, 0]) < tol_v and scaled_err(s[z][:300], so[:, 0]) < tol_v
+            assert scaled_err(dm[z][:300], dmo) < tol_g and scaled_err(ds[z][:300], dso) < tol_g
+            assert abs(fmins[z] - og.gp_get_fmin(gp)) < tol_v * abs(fmins[z])
+            e1.fit('rbf', X, Y, theta[z:z + 1, 0], theta[z:z + 1, 1:2], theta[z:z + 1, 2])
+            m1, s1 = e1.predict(Xs[:300])
+            mz, sz = engine.predict(Xs[:300])
+            assert np.array_equal(m1[0], mz[z]) and np.array_equal(s1[0], sz[z])
+    finally:
+        e1.close()
+
+
+def test_config5_gsobol_n4096_local_penalization(engine):
+    """BASELINE config 5: gSobol d = 10, n = 4096, refit + EI under Local Penalization with 15 penalisers."""
+    from oracle import gpy_numpy as G, gpyopt_numpy as og
+    rng = np.random.default_rng(70)
+    n, d, N = 4096, 10, 20000
+    X = -4 + 10 * rng.random((n, d))
+    Y = og.normalize_stats(og.gSobol(X, np.ones(d)))
+    engine.fit('rbf', X, Y, [1.0], [[3.0] * d], [1e-2])
+    gp = G.GPRegression(X, Y, G.RBF(d, variance=1.0, lengthscale=3.0), noise_var=1e-2)   # ~3 s of LAPACK
+    L, _, Wi, al = engine.get_state(Linv=False)
+    assert scaled_err(np.tril(L[0]), gp.posterior.woodbury_chol) < TOL and scaled_err(al[0], gp.posterior.woodbury_vector[:, 0]) < TOL
+    assert scaled_err(Wi[0], gp.posterior.woodbury_inv) < TOL
+    ll, _ = engine.get_loglik()
+    assert abs(ll[0] - gp.log_likelihood()) < TOL * abs(gp.log_likelihood())
+    Xs = -4 + 10 * rng.random((N, d))
+    rows = np.arange(400)
+    tol_v, tol_g = parity_tolerances(gp, Xs[rows])
+    mo, so, dmo, dso = og.gp_predict_withGradients(gp, Xs[rows])
+    fmin = og.gp_get_fmin(gp)
+    fo, dfo = og.acq_EI_withGradients(mo.copy(), so.copy(), dmo, dso, fmin, 0.01)
+    f, df = engine.acq('EI', 0.01, Xs, grad=True)
+    assert scaled_err(f[rows], fo[:, 0]) < tol_v and scaled_err(df[rows], dfo) < tol_g
+    # Local Penalization with 15 penalisers (batch_size 16): device LP == reference formulas on the unpenalised EI
+    Xb = -4 + 10 * rng.random((15, d))
+    mb, sb = engine.predict(Xb)
+    r, sc = og.lp_hammer_precompute(mb[0][:, None], sb[0][:, None], 0.4, float(Y.min()))
+    try:
+        engine.lp_set(Xb, r, sc, 'none')
+        flp, glp = engine.acq('EI', 0.01, Xs, grad=True)
+    finally:
+        engine.lp_set(None, None, None, None)
+    af, adf = og.acquisition_function_withGradients(f[:, None], df)
+    ref_val = og.lp_penalized_acquisition(af[rows], Xs[rows], Xb, r, sc, 'none')
+    ref_grad = np.vstack([og.lp_d_acquisition(af[i:i + 1], adf[i:i + 1], Xs[i:i + 1], Xb, r, sc, 'none') for i in rows])
+    assert scaled_err(flp[rows], ref_val) < TOL
+    assert np.max(np.abs(glp[rows] - ref_grad)) / np.max(np.abs(ref_grad)) < 1e-9

@@ -46,6 +46,8 @@ SIGNATURES = {
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'gpo_topk': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'gpo_posterior_cov': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_void_p]),
     'gpo_set_strict_variance': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'gpo_get_info': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     'gpo_set_profiling': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -247,6 +249,16 @@ class Engine(object):
         self._check(rc, 'gpo_topk')
         kk = min(k, N)
         return vals[:kk], idx[:kk]
+
+    def posterior_cov(self, X1, X2=None, with_noise=False):
+        """Full posterior covariance [N1, N2] (X2 None: between X1 and itself, noise on the diagonal if with_noise)."""
+        X1 = _f64(np.atleast_2d(X1))
+        X2c = None if X2 is None else _f64(np.atleast_2d(X2))
+        out = np.empty((X1.shape[0], X1.shape[0] if X2c is None else X2c.shape[0]))
+        rc = self._lib.gpo_posterior_cov(self._h, X1.shape[0], _ptr(X1), 0 if X2c is None else X2c.shape[0], _ptr(X2c),
+                                         int(bool(with_noise)), _ptr(out))
+        self._check(rc, 'gpo_posterior_cov')
+        return out
 
     def set_strict_variance(self, mode):
         """-1 automatic (default), 0 never, 1 always: see gpo_set_strict_variance in include/gpo_b200.h."""

@@ -71,6 +71,8 @@ struct gpo_engine {
   double* tk_vals[2] = {nullptr, nullptr};  long long* tk_idx[2] = {nullptr, nullptr};  size_t tk_cap = 0;
   // per-block best candidates written by K3 (fused selection)
   double* blk_val = nullptr;  long long* blk_idx = nullptr;  size_t blk_cap = 0;  bool want_blk = false;
+  // full-covariance scratch (grow-only): K*^T staging, L^-1 K* for both point sets, result, K1 mean scratch
+  double* cov_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  size_t cov_bytes[5] = {0, 0, 0, 0, 0};
   // parity guard: variance form used by gradient sweeps (-1 auto, 0 fast k.W^-1.k, 1 strict |L^-1 k|^2)
   int strict_mode = -1;
   bool strict_active = false;
@@ -246,6 +248,7 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->lp_s) cudaFree(eng->lp_s);
   if (eng->blk_val) cudaFree(eng->blk_val);
   if (eng->blk_idx) cudaFree(eng->blk_idx);
+  for (int i = 0; i < 5; ++i) if (eng->cov_buf[i]) cudaFree(eng->cov_buf[i]);
   for (int i = 0; i < 2; ++i) {
     if (eng->tk_vals[i]) cudaFree(eng->tk_vals[i]);
     if (eng->tk_idx[i]) cudaFree(eng->tk_idx[i]);
@@ -1123,5 +1126,74 @@ extern "C" int gpo_get_profile(gpo_engine* eng, double* gemm_ms, long long* gemm
   if (gemm_launches) *gemm_launches = eng->prof_gemm_launches;
   if (gemm_candidates) *gemm_candidates = eng->prof_gemm_cands;
   eng->prof_gemm_ms = 0.0; eng->prof_gemm_launches = 0; eng->prof_gemm_cands = 0;
+  return GPO_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// full posterior covariance between two (small) point sets: GPModel.predict_covariance and
+// GPModel.get_covariance_between_points (gpmodel.py:114-123, 173-177), i.e. GPy GP.predict(full_cov=True) and
+// posterior_covariance_between_points:  K(X1, X2) - (L^-1 K(X, X1))^T (L^-1 K(X, X2))  (+ noise I when X2 is X1).
+// Not on the large-sweep hot path (Entropy Search is its only caller); built from the same K1 / GEMM primitives.
+// --------------------------------------------------------------------------------------------------
+extern "C" int gpo_posterior_cov(gpo_engine* eng, long long N1, const double* X1, long long N2, const double* X2, int with_noise,
+                                 double* out) {
+  if (!eng || !X1 || !out || N1 < 1 || (X2 && N2 < 1)) return GPO_ERR_ARG;
+  if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_posterior_cov before gpo_fit");
+  if (eng->S != 1) GPO_FAIL(GPO_ERR_ARG, "gpo_posterior_cov needs a single hyper-parameter set (S = 1)");
+  const bool same = X2 == nullptr;
+  if (same) { X2 = X1; N2 = N1; }
+  if (N1 > 16384 || N2 > 16384) GPO_FAIL(GPO_ERR_ARG, "gpo_posterior_cov: at most 16384 points per set");
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  cudaStream_t st = eng->fit_stream;
+  for (int i = 0; i < 2; ++i) GPO_CUDA_OK(cudaStreamSynchronize(eng->slot[i].stream));
+  const int n_pad = eng->n_pad, d = eng->d, tiles = n_pad / TILE;
+  const long long Np[2] = {((N1 + TILE - 1) / TILE) * TILE, ((N2 + TILE - 1) / TILE) * TILE};
+  const long long Nn[2] = {N1, N2};
+  const double* Xh[2] = {X1, X2};
+  const long long Nmax = std::max(Np[0], Np[1]);
+  int rc;
+  // 0: K*^T staging [Nmax][n_pad]; 1, 2: T_1^T, T_2^T [Np][n_pad]; 3: result [Np0][Np1]; 4: candidates AoS + K1 mean scratch
+  const size_t need[5] = {(size_t)Nmax * n_pad * 8, (size_t)Np[0] * n_pad * 8, (size_t)Np[1] * n_pad * 8, (size_t)Np[0] * Np[1] * 8,
+                          (size_t)(Np[0] + Np[1]) * d * 8 + (size_t)eng->js * Nmax * 8};
+  for (int i = 0; i < 5; ++i)
+    if ((rc = grow(eng, &eng->cov_buf[i], &eng->cov_bytes[i], need[i]))) return rc;
+  double* xdev[2] = {eng->cov_buf[4], eng->cov_buf[4] + Np[0] * d};
+  double* mean_scratch = eng->cov_buf[4] + (Np[0] + Np[1]) * d;
+  GPO_CUDA_OK(cudaMemsetAsync(eng->cov_buf[4], 0, need[4], st));
+  for (int sidx = 0; sidx < (same ? 1 : 2); ++sidx)
+    GPO_CUDA_OK(cudaMemcpyAsync(xdev[sidx], Xh[sidx], (size_t)Nn[sidx] * d * 8, cudaMemcpyHostToDevice, st));
+  if (same) xdev[1] = xdev[0];
+  CUtensorMap mapK, mapT[2];
+  for (int sidx = 0; sidx < (same ? 1 : 2); ++sidx) {
+    if ((rc = make_map(eng, &mapK, eng->cov_buf[0], n_pad, Np[sidx], 1))) return rc;
+    if ((rc = make_map(eng, &mapT[sidx], eng->cov_buf[1 + sidx], n_pad, Np[sidx], 1))) return rc;
+    CovParams cp;
+    cp.Xs = xdev[sidx]; cp.n_cand = Nn[sidx]; cp.nc_run = Np[sidx]; cp.nc_ld = Np[sidx]; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = eng->n;
+    cp.n_pad = n_pad; cp.d = d; cp.kern = eng->kern; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
+    cp.Kt = eng->cov_buf[0]; cp.Ht = nullptr; cp.mean = mean_scratch; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
+    if ((rc = launch_cov(eng, cp, false, 1, st))) return rc;
+    // T = L^-1 K*, stored transposed ([point][training index]) so that it is K-major for the product below
+    GemmParams g = gemm_defaults();
+    g.tiles_m = tiles; g.tiles_n = (int)(Np[sidx] / TILE); g.kblocks = tiles; g.krange = KR_LE_M; g.raster = RO_HEAVY_FIRST;
+    g.a = {0, 0, 0, 0, 0, 1}; g.b = {0, 0, 0, 0, 0, 1};
+    g.Ct = eng->cov_buf[1 + sidx]; g.ldct = n_pad;
+    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapX, mapK, g, 1, st))) return rc;
+  }
+  if (same) mapT[1] = mapT[0];
+  {
+    dim3 blk(16, 16), grd((unsigned)(Np[1] / 16), (unsigned)(Np[0] / 16));
+    cross_gram_kernel<<<grd, blk, 0, st>>>(eng->cov_buf[3], Np[1], xdev[0], N1, xdev[1], N2, Np[0], Np[1], d, eng->kern, eng->invl,
+                                           eng->sigf2, (same && with_noise) ? eng->h_noise[0] : 0.0);
+    eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
+    GemmParams g = gemm_defaults();
+    g.tiles_m = (int)(Np[0] / TILE); g.tiles_n = (int)(Np[1] / TILE); g.kblocks = tiles;
+    g.a = {0, 0, 0, 0, 0, 1}; g.b = {0, 0, 0, 0, 0, 1};
+    g.alpha = -1.0; g.beta = 1.0; g.C = eng->cov_buf[3]; g.ldc = Np[1];
+    if ((rc = launch_gemm(eng, EPI_STORE, mapT[0], mapT[same ? 0 : 1], g, 1, st))) return rc;
+  }
+  GPO_CUDA_OK(cudaMemcpy2DAsync(out, (size_t)N2 * 8, eng->cov_buf[3], (size_t)Np[1] * 8, (size_t)N2 * 8, (size_t)N1,
+                                cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaStreamSynchronize(st));
   return GPO_OK;
 }

@@ -181,6 +181,26 @@ __global__ void gram_kernel(double* A, const double* Xt, long long ldx, int n, i
   A[((long long)z * n_pad + i) * n_pad + j] = v;
 }
 
+// Prior covariance between two candidate sets (AoS [N][d]): out[i][j] = k(x1_i, x2_j) (+ diag_add on i == j), zero on the
+// padding.  First term of GP.predict(full_cov=True) / posterior_covariance_between_points.
+__global__ void cross_gram_kernel(double* out, long long ldo, const double* X1, long long n1, const double* X2, long long n2,
+                                  long long n1p, long long n2p, int d, int kern, const double* invl, const double* sigf2,
+                                  double diag_add) {
+  const long long i = (long long)blockIdx.y * blockDim.y + threadIdx.y, j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n1p || j >= n2p) return;
+  double v = 0.0;
+  if (i < n1 && j < n2) {
+    double r2 = 0.0;
+    for (int q = 0; q < d; ++q) {
+      const double df = X1[i * d + q] * invl[q] - X2[j * d + q] * invl[q];
+      r2 = fma(df, df, r2);
+    }
+    v = kern_k(kern, sigf2[0], r2);
+    if (i == j) v += diag_add;
+  }
+  out[i * ldo + j] = v;
+}
+
 // mean of diag(K(X,X)) + noise + 1e-8 over the n real rows == sigf2 + noise + 1e-8 for a stationary kernel:
 // computed on the host; no kernel needed.
 

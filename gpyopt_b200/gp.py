@@ -357,12 +357,17 @@ class GPRegressionB200(object):
 
     # -- prediction (GPy signatures; variances, not standard deviations) -------------------------------------
     def predict(self, Xnew, full_cov=False, Y_metadata=None, kern=None, likelihood=None, include_likelihood=True):
-        if full_cov:
-            raise NotImplementedError("full predictive covariance is outside the engine's hot path")
         Xnew = np.atleast_2d(np.asarray(Xnew, dtype=np.float64))
         self._ensure_own_state()
+        if full_cov:
+            m, _ = self.engine.predict(Xnew, with_noise=include_likelihood)
+            return m[0][:, None], self.engine.posterior_cov(Xnew, None, with_noise=include_likelihood)
         m, s = self.engine.predict(Xnew, with_noise=include_likelihood)
         return m[0][:, None], np.square(s[0])[:, None]
+
+    def posterior_covariance_between_points(self, X1, X2):
+        self._ensure_own_state()
+        return self.engine.posterior_cov(np.atleast_2d(X1), np.atleast_2d(X2))
 
     def predictive_gradients(self, Xnew, kern=None):
         Xnew = np.atleast_2d(np.asarray(Xnew, dtype=np.float64))

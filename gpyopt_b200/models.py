@@ -87,8 +87,18 @@ class GPModel(BOModel):
         m, s = self.model.engine.predict(X, with_noise=with_noise)
         return m[0][:, None], s[0][:, None]
 
+    def _predict(self, X, full_cov, include_likelihood):
+        """gpmodel.py:95-100."""
+        if X.ndim == 1:
+            X = X[None, :]
+        m, v = self.model.predict(X, full_cov=full_cov, include_likelihood=include_likelihood)
+        v = np.clip(v, 1e-10, np.inf)
+        return m, v
+
     def predict_covariance(self, X, with_noise=True):
-        raise NotImplementedError("predict_covariance (full covariance, Entropy Search only) is outside the hot path")
+        """Full predictive covariance matrix at X (gpmodel.py:114-123)."""
+        _, v = self._predict(np.asarray(X, dtype=np.float64), True, with_noise)
+        return v
 
     def get_fmin(self):
         """Minimum posterior mean at the training inputs (gpmodel.py:125-129); cached by the engine per refit."""
@@ -117,7 +127,8 @@ class GPModel(BOModel):
         return self.model.parameter_names_flat().tolist()
 
     def get_covariance_between_points(self, x1, x2):
-        raise NotImplementedError("posterior covariance between points (Entropy Search only) is outside the hot path")
+        """Posterior covariance between two sets of points (gpmodel.py:173-177)."""
+        return self.model.posterior_covariance_between_points(x1, x2)
 
 
 class GPModel_MCMC(BOModel):

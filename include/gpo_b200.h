@@ -113,6 +113,14 @@ int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, const doubl
 int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, int largest, double* vals, long long* idx,
              void* stream);
 
+/* Full posterior covariance between two small point sets X1 (host) [N1, d] and X2 (host) [N2, d]:
+ * GPModel.get_covariance_between_points (gpmodel.py:173-177) = K(X1,X2) - (L^-1 K(X,X1))^T (L^-1 K(X,X2)).
+ * X2 == NULL means X2 = X1 and is GPModel.predict_covariance's matrix (gpmodel.py:114-123, before its 1e-10 clip),
+ * with the noise variance added on the diagonal when with_noise != 0.  out (host) [N1, N2].  S = 1 only; not a
+ * large-sweep path (Entropy Search is the only caller in the reference). */
+int gpo_posterior_cov(gpo_engine* eng, long long N1, const double* X1, long long N2, const double* X2, int with_noise,
+                      double* out);
+
 /* Parity guard.  Gradient sweeps need b = W^-1 k anyway and by default also take the variance from it
  * (sigma_f^2 - k.b: 2 n^2 flop per candidate in total).  On an ill-conditioned Gram matrix that form cancels badly,
  * whereas the reference's sigma_f^2 - |L^-1 k|^2 (GPy PosteriorExact._raw_predict) does not.  After every refit the

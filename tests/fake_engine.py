@@ -64,6 +64,13 @@ class FakeEngine(object):
         return (np.array([r[0][:, 0] for r in res]), np.array([r[1][:, 0] for r in res]),
                 np.array([r[2] for r in res]), np.array([r[3] for r in res]))
 
+    def posterior_cov(self, X1, X2=None, with_noise=False):
+        g = self.gps[0]
+        X1 = np.atleast_2d(np.asarray(X1, dtype=float))
+        if X2 is None:
+            return g.predict(X1, full_cov=True, include_likelihood=with_noise)[1]
+        return g.posterior_covariance_between_points(X1, np.atleast_2d(np.asarray(X2, dtype=float)))
+
     def lp_set(self, X_batch, r, s, transform):
         self._lp = None if transform is None else (X_batch, r, s, transform)
 

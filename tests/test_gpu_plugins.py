@@ -52,6 +52,27 @@ def test_gpmodel_plugin_matches_reference_class(case):
         assert_grad_close(adf, g[name + '_adf'], tol=TOLG)
 
 
+def test_full_covariance_methods_match_oracle():
+    """GPModel.predict_covariance / get_covariance_between_points (gpmodel.py:114-123, 173-177): the Entropy-Search-only
+    corner of the model API, served from the same K1 / GEMM primitives."""
+    g = load_golden('c2_camel_mat52_n55')
+    model = _model_from_golden(g)
+    gp = oracle_gp_from_golden(g)
+    X1, X2 = g['Xs'][:150], g['Xs'][150:190]
+    for with_noise in (True, False):
+        ref = np.clip(gp.predict(X1, full_cov=True, include_likelihood=with_noise)[1], 1e-10, np.inf)
+        cov = model.predict_covariance(X1, with_noise=with_noise)
+        assert cov.shape == ref.shape and scaled_err(cov, ref) < TOL
+    ref = gp.posterior_covariance_between_points(X1, X2)
+    cov = model.get_covariance_between_points(X1, X2)
+    assert cov.shape == (150, 40) and scaled_err(cov, ref) < TOL
+    # a larger model (n = 256 -> 2 row blocks) and more points than one tile
+    g = load_golden('c3_rbf_alpine2_n256')
+    model, gp = _model_from_golden(g), oracle_gp_from_golden(g)
+    ref = gp.posterior_covariance_between_points(g['Xs'][:300], g['Xs'][100:384])
+    assert scaled_err(model.get_covariance_between_points(g['Xs'][:300], g['Xs'][100:384]), ref) < TOL
+
+
 def test_mcmc_plugin_matches_reference_class():
     from gpyopt_b200 import GPModel_MCMC, AcquisitionEI_MCMC, AcquisitionLCB_MCMC
     for case in ('c4_mcmc_n64_S8', 'c4_mcmc_exact_n48_S4'):

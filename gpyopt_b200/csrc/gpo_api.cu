@@ -77,6 +77,7 @@ struct gpo_engine {
   int strict_mode = -1;
   bool strict_active = false;
   double var_disc = 0.0;
+  std::vector<cudaEvent_t> chol_ev;  // look-ahead events of the blocked Cholesky (2 per block column)
   // counters / live profiling of the dominant kernel (variance GEMM) for the benchmark's roofline
   long long launches = 0;
   int profiling = 0;
@@ -161,12 +162,12 @@ static int gemm_setup(gpo_engine* eng) {
 }
 
 static int launch_gemm(gpo_engine* eng, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p_in, int batch,
-                       cudaStream_t st) {
+                       cudaStream_t st, int max_ctas = 0) {
   GemmParams p = p_in;
   p.batch = batch;
   const long long tiles = p.tile_skip == TS_LOWER ? (long long)p.tiles_m * (p.tiles_m + 1) / 2 : (long long)p.tiles_m * p.tiles_n;
   const long long work = tiles * (p.ksplit > 1 ? p.ksplit : 1) * batch;
-  dim3 grid((unsigned)std::min<long long>(work, eng->sm_count), 1, 1);  // persistent: one CTA per SM
+  dim3 grid((unsigned)std::min<long long>(work, max_ctas > 0 ? max_ctas : eng->sm_count), 1, 1);  // persistent: one CTA per SM
   if (epi == EPI_STORE) dgemm_nt_kernel<EPI_STORE><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
   else if (epi == EPI_SUMSQ) dgemm_nt_kernel<EPI_SUMSQ><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
   else dgemm_nt_kernel<EPI_GRAD><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
@@ -249,6 +250,8 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->blk_val) cudaFree(eng->blk_val);
   if (eng->blk_idx) cudaFree(eng->blk_idx);
   for (int i = 0; i < 5; ++i) if (eng->cov_buf[i]) cudaFree(eng->cov_buf[i]);
+  for (cudaEvent_t e : eng->chol_ev) cudaEventDestroy(e);
+  for (auto& pe : eng->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
   for (int i = 0; i < 2; ++i) {
     if (eng->tk_vals[i]) cudaFree(eng->tk_vals[i]);
     if (eng->tk_idx[i]) cudaFree(eng->tk_idx[i]);
@@ -408,6 +411,22 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
   }
   GPO_CUDA_OK(cudaMemsetAsync(eng->info, 0, S * sizeof(int), st));
   // (the off-diagonal blocks of X above / of U below the diagonal are never written: zeroed once at allocation)
+  // Right-looking blocked Cholesky.  From 8 block columns on it runs with one step of look-ahead: after the panel of
+  // step kb, only block column kb+1 of the trailing matrix is updated on the main stream (that is all the next
+  // diagonal factorisation and panel need), while the rest of the update runs on a side stream on the other SMs.
+  // Every tile still receives its rank-128 updates in the order kb = 0, 1, 2, ...: the factor is bit-identical.
+  const bool lookahead = nb >= 8;
+  cudaStream_t sb = eng->slot[0].stream;
+  if (lookahead) {
+    while ((int)eng->chol_ev.size() < 2 * nb + 1) {
+      cudaEvent_t e;
+      GPO_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      eng->chol_ev.push_back(e);
+    }
+    GPO_CUDA_OK(cudaEventRecord(eng->chol_ev[2 * nb], st));  // the Gram matrix is ready
+    GPO_CUDA_OK(cudaStreamWaitEvent(sb, eng->chol_ev[2 * nb], 0));
+  }
+  int last_rest = -1;
   for (int kb = 0; kb < nb; ++kb) {
     diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb,
                                                                     std::max(0, std::min(TILE, eng->n - kb * TILE)), eng->info);
@@ -423,13 +442,39 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
     if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapX, p, S, st))) return rc;
     // trailing update (lower tiles): A[kb+1:, kb+1:] -= P P^T
     GemmParams q = gemm_defaults();
-    q.tiles_m = rem; q.tiles_n = rem; q.kblocks = 1; q.tile_skip = TS_LOWER;
-    q.a = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};
-    q.b = q.a;
+    q.kblocks = 1;
     q.alpha = -1.0; q.beta = 1.0;
-    q.C = eng->A; q.ldc = n_pad; q.c_off_z = nn; q.c_row0 = (kb + 1) * TILE; q.c_col0 = (kb + 1) * TILE;
-    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, q, S, st))) return rc;
+    q.C = eng->A; q.ldc = n_pad; q.c_off_z = nn;
+    if (!lookahead) {
+      q.tiles_m = rem; q.tiles_n = rem; q.tile_skip = TS_LOWER;
+      q.a = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};
+      q.b = q.a;
+      q.c_row0 = (kb + 1) * TILE; q.c_col0 = (kb + 1) * TILE;
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, q, S, st))) return rc;
+      continue;
+    }
+    GPO_CUDA_OK(cudaEventRecord(eng->chol_ev[2 * kb], st));  // panel kb is final
+    if (rem >= 2) {  // columns kb+2.. on the side stream, leaving 32 SMs to the critical path
+      GemmParams r = q;
+      r.tiles_m = rem - 1; r.tiles_n = rem - 1; r.tile_skip = TS_LOWER;
+      r.a = {(kb + 2) * TILE, kb * TILE, 0, 0, 0, 1};
+      r.b = r.a;
+      r.c_row0 = (kb + 2) * TILE; r.c_col0 = (kb + 2) * TILE;
+      GPO_CUDA_OK(cudaStreamWaitEvent(sb, eng->chol_ev[2 * kb], 0));
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, r, S, sb, std::max(16, eng->sm_count - 32)))) return rc;
+      GPO_CUDA_OK(cudaEventRecord(eng->chol_ev[2 * kb + 1], sb));
+    }
+    // column kb+1 on the main stream, after the side stream's previous update of those tiles
+    if (last_rest >= 0) GPO_CUDA_OK(cudaStreamWaitEvent(st, eng->chol_ev[2 * last_rest + 1], 0));
+    if (rem >= 2) last_rest = kb;
+    GemmParams c = q;
+    c.tiles_m = rem; c.tiles_n = 1;
+    c.a = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};
+    c.b = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};
+    c.c_row0 = (kb + 1) * TILE; c.c_col0 = (kb + 1) * TILE;
+    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, c, S, st))) return rc;
   }
+  if (lookahead && last_rest >= 0) GPO_CUDA_OK(cudaStreamWaitEvent(st, eng->chol_ev[2 * last_rest + 1], 0));
   // triangular inverse, recursively: X21 = -X22 (L21 X11)
   std::vector<std::vector<TriNode>> levels;
   build_tree(0, nb, 0, levels);

@@ -905,8 +905,10 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
       acq_kernel<<<kgrid, 128, 0, st>>>(ap);
       eng->launches++;
       if (S > 1 && !predict) {
+        dim3 zgrid((unsigned)((rows + 127) / 128), (unsigned)(grad ? d + 1 : 1), 1);
+        acq_zsum_kernel<<<zgrid, 128, 0, st>>>(ap);
         acq_reduce_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(ap);
-        eng->launches++;
+        eng->launches += 2;
       }
     }
     GPO_CUDA_OK(cudaGetLastError());

@@ -692,22 +692,27 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
   if (p.blk_val) block_argmax_store(score, p.row0 + i, p.blk_val, p.blk_idx, (p.row0 >> 7) + blockIdx.x);
 }
 
+// S > 1, stage 1: grid (candidates / 128, 1 + d).  Thread (i, v) adds value v of candidate i over the hyper-parameter sets
+// in set order (deterministic, the reference's own accumulation order) and leaves the sum in set 0's slot of zbuf.
+__global__ void __launch_bounds__(128) acq_zsum_kernel(const AcqParams p) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = blockIdx.y;
+  if (i >= p.n_cand) return;
+  const long long stride = (long long)(p.d + 1) * p.nc_pad;
+  double* zb = p.zbuf + (long long)v * p.nc_pad + i;
+  double acc = 0.0;
+  for (int z = 0; z < p.S; ++z) acc += zb[(long long)z * stride];
+  zb[0] = acc;
+}
+
+// S > 1, stage 2: MCMC average, Local Penalization, outputs and the fused block argmax
 __global__ void __launch_bounds__(128) acq_reduce_kernel(const AcqParams p) {
   const long long i_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = i_raw < p.n_cand ? i_raw : p.n_cand - 1;  // shadow the last row (identical values, benign)
   const int d = p.d;
-  double f_acc = 0.0, df_acc[DMAX];
+  double f_acc = p.zbuf[i], df_acc[DMAX];
 #pragma unroll
-  for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
-  for (int z = 0; z < p.S; ++z) {
-    const double* zb = p.zbuf + (long long)z * (d + 1) * p.nc_pad + i;
-    f_acc += zb[0];
-    if (p.grad) {
-#pragma unroll
-      for (int q = 0; q < DMAX; ++q)
-        if (q < d) df_acc[q] += zb[(long long)(q + 1) * p.nc_pad];
-    }
-  }
+  for (int q = 0; q < DMAX; ++q) df_acc[q] = (p.grad && q < d) ? p.zbuf[(long long)(q + 1) * p.nc_pad + i] : 0.0;
   const double score = acq_finalize(p, i, f_acc, df_acc);
   if (p.blk_val) block_argmax_store(score, p.row0 + i, p.blk_val, p.blk_idx, (p.row0 >> 7) + blockIdx.x);
 }

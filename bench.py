@@ -84,8 +84,14 @@ class ClockSampler(threading.Thread):
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_reference_rate(sample, chunk=8192, repeats=1):
     """EI + gradient through the oracle (reference acquisition formulas on the NumPy restatement of GPy's exact GP),
-    chunked at 8192 rows (un-chunked K* would need 164 GB at 1e7 candidates), fmin cached per refit."""
+    chunked at 8192 rows (un-chunked K* would need 164 GB at 1e7 candidates), fmin cached per refit.  BLAS runs on all
+    host cores (torchrun exports OMP_NUM_THREADS=1, which would otherwise throttle the baseline)."""
     from oracle import gpy_numpy as G, gpyopt_numpy as og
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     X, Y = synthetic_problem()
     gp = G.GPRegression(X, Y, G.RBF(DIM, variance=1.0, lengthscale=2.0), noise_var=1e-2)
     fmin = og.gp_get_fmin(gp)

@@ -8,7 +8,7 @@
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))  # (this file lives in tests/: it uses the oracle)
 import torch
 from gpyopt_b200 import Engine, GPModel, AcquisitionEI, kern
 from oracle import gpyopt_numpy as og

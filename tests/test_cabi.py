@@ -79,10 +79,10 @@ def test_no_cpu_fallback(lib):
 
 def test_product_package_never_imports_the_oracle():
     """gpyopt_b200/ must not reference oracle/ (the oracle is test infrastructure)."""
-    pkg = os.path.join(ROOT, 'gpyopt_b200')
-    for dirpath, _, files in os.walk(pkg):
+    for top in ('gpyopt_b200', 'tools', 'include'):
+      for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
         for f in files:
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
-                assert 'gpy_numpy' not in src and 'gpyopt_numpy' not in src, f
+                assert 'gpy_numpy' not in src and 'gpyopt_numpy' not in src and 'fake_engine' not in src, f

@@ -44,6 +44,11 @@ SIGNATURES = {
                                   ctypes.c_int]),
     'gpo_acq_topk': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_longlong, ctypes.c_void_p,
                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'gpo_design_uniform': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'gpo_acq_topk_uniform': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_longlong,
+                                            ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
     'gpo_topk': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'gpo_posterior_cov': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p,
@@ -236,6 +241,44 @@ class Engine(object):
         self._check(rc, 'gpo_acq_topk')
         kk = min(k, N)
         return vals[:kk], idx[:kk]
+
+    @staticmethod
+    def _design_args(key, bounds):
+        key = np.atleast_1d(np.asarray(key, dtype=np.uint64)).reshape(-1)
+        if key.size == 1:                    # numpy.random.Philox(key=int): the integer is the low word
+            key = np.array([key[0], 0], dtype=np.uint64)
+        if key.size != 2:
+            raise ValueError("Philox key: one integer or two 64-bit words")
+        bounds = _f64(np.atleast_2d(bounds))
+        if bounds.shape[1] != 2:
+            raise ValueError("bounds must be [d, 2] (low, high)")
+        return np.ascontiguousarray(key), bounds
+
+    def design_uniform(self, key, N, bounds, row0=0, out=None, stream=None):
+        """Rows [row0, row0+N) of numpy.random.Generator(numpy.random.Philox(key=key)).uniform(lo, hi, (rows, d)),
+        generated on the device (bit-identical to NumPy).  out: optional [N, d] NumPy array or device tensor."""
+        key, bounds = self._design_args(key, bounds)
+        d = bounds.shape[0]
+        if out is None:
+            out = np.empty((int(N), d))
+        rc = self._lib.gpo_design_uniform(self._h, key.ctypes.data, int(row0), int(N), d, _ptr(bounds), _ptr(out), stream)
+        self._check(rc, 'gpo_design_uniform')
+        return out
+
+    def acq_topk_uniform(self, kind, par, key, N, bounds, k, row0=0, stream=None):
+        """acq_topk over a device-generated uniform design -> (scores [k], local idx [k], rows [k, d])."""
+        key, bounds = self._design_args(key, bounds)
+        if bounds.shape[0] != self.d:
+            raise ValueError("bounds must have one row per model dimension (%d)" % self.d)
+        vals = np.empty(k)
+        idx = np.empty(k, dtype=np.int64)
+        xt = np.empty((k, self.d))
+        kk = ACQ[kind] if isinstance(kind, str) else int(kind)
+        rc = self._lib.gpo_acq_topk_uniform(self._h, kk, float(par), key.ctypes.data, int(row0), int(N), _ptr(bounds), int(k),
+                                            _ptr(vals), _ptr(idx), _ptr(xt), stream)
+        self._check(rc, 'gpo_acq_topk_uniform')
+        kk = min(k, int(N))
+        return vals[:kk], idx[:kk], xt[:kk]
 
     def topk(self, v, k, largest=False, stream=None):
         if isinstance(v, np.ndarray):

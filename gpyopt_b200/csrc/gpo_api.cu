@@ -69,6 +69,9 @@ struct gpo_engine {
   double *lp_xb = nullptr, *lp_r = nullptr, *lp_s = nullptr;
   // top-k scratch
   double* tk_vals[2] = {nullptr, nullptr};  long long* tk_idx[2] = {nullptr, nullptr};  size_t tk_cap = 0;
+  // device-side design: when gen_on, the sweep generates its candidates (Philox stream) instead of reading Xs
+  bool gen_on = false;  DesignParams gen;  long long gen_row0 = 0;
+  long long* gen_idx = nullptr;  double* gen_x = nullptr;  // [TOPK_SEG/2], [TOPK_SEG/2][DMAX] winners of a generated design
   // per-block best candidates written by K3 (fused selection)
   double* blk_val = nullptr;  long long* blk_idx = nullptr;  size_t blk_cap = 0;  bool want_blk = false;
   // full-covariance scratch (grow-only): K*^T staging, L^-1 K* for both point sets, result, K1 mean scratch
@@ -249,6 +252,8 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->lp_s) cudaFree(eng->lp_s);
   if (eng->blk_val) cudaFree(eng->blk_val);
   if (eng->blk_idx) cudaFree(eng->blk_idx);
+  if (eng->gen_idx) cudaFree(eng->gen_idx);
+  if (eng->gen_x) cudaFree(eng->gen_x);
   for (int i = 0; i < 5; ++i) if (eng->cov_buf[i]) cudaFree(eng->cov_buf[i]);
   for (cudaEvent_t e : eng->chol_ev) cudaEventDestroy(e);
   for (auto& pe : eng->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
@@ -772,6 +777,29 @@ static int grow(gpo_engine* eng, double** buf, size_t* cap, size_t bytes) {
   return GPO_OK;
 }
 
+// --------------------------------------------------------------------------------------------------
+// device-side random design
+// --------------------------------------------------------------------------------------------------
+static int design_setup(gpo_engine* eng, DesignParams* p, const unsigned long long* key, int d, const double* bounds) {
+  if (d < 1 || d > DMAX) GPO_FAIL(GPO_ERR_ARG, "design: d must be in [1, %d]", DMAX);
+  memset(p, 0, sizeof(*p));
+  p->key0 = key[0]; p->key1 = key[1]; p->d = d;
+  for (int q = 0; q < d; ++q) {
+    p->lo[q] = bounds[2 * q];
+    p->range[q] = bounds[2 * q + 1] - bounds[2 * q];
+    if (!std::isfinite(p->lo[q]) || !std::isfinite(p->range[q])) GPO_FAIL(GPO_ERR_ARG, "design: bounds of dimension %d are not finite", q);
+  }
+  return GPO_OK;
+}
+
+static void launch_design(gpo_engine* eng, DesignParams p, long long row0, long long rows, double* out, cudaStream_t st) {
+  p.e0 = row0 * p.d; p.n_el = rows * p.d; p.out = out;
+  const long long nblk = ((p.e0 + p.n_el + 3) >> 2) - (p.e0 >> 2);
+  const unsigned grid = (unsigned)std::min<long long>((nblk + 255) / 256, (long long)eng->sm_count * 8);
+  design_uniform_kernel<<<grid, 256, 0, st>>>(p);
+  eng->launches++;
+}
+
 // kind == ACQ_NONE: predict  (o0 = m [S][N], o1 = s [S][N], o2 = dmdx [S][N][d], o3 = dsdx [S][N][d])
 // otherwise:        acquisition (o0 = f [N], o1 = df [N][d])
 static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused*/, int with_noise, long long N,
@@ -781,7 +809,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
   GPO_CUDA_OK(cudaSetDevice(eng->device));
   const int S = eng->S, d = eng->d, n_pad = eng->n_pad, tiles_m = n_pad / TILE;
   const bool predict = kind == ACQ_NONE;
-  const bool in_dev = is_device_ptr(Xs);
+  const bool gen = eng->gen_on;
+  const bool in_dev = gen || is_device_ptr(Xs);
   double* outs[4] = {o0, o1, o2, o3};
   // bytes per candidate row of each output, and number of batch planes
   size_t row_bytes[4]; int planes[4];
@@ -800,7 +829,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     }
   }
   const double* dev_in = Xs;
-  if (!in_dev) {
+  if (!in_dev || gen) {
     if ((rc = grow(eng, &eng->stage_in, &eng->stage_in_bytes, (size_t)N * d * 8))) return rc;
     dev_in = eng->stage_in;
   }
@@ -818,6 +847,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     const int tiles_n = (int)(nc_run / TILE);
     if (!in_dev)
       GPO_CUDA_OK(cudaMemcpyAsync(eng->stage_in + off * d, Xs + off * d, (size_t)rows * d * 8, cudaMemcpyHostToDevice, st));
+    if (gen) launch_design(eng, eng->gen, eng->gen_row0 + off, rows, eng->stage_in + off * d, st);
     // K1
     CovParams cp;
     cp.Xs = dev_in + off * d; cp.n_cand = rows; cp.nc_run = nc_run; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad;
@@ -1031,9 +1061,8 @@ extern "C" int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, in
   return topk_device(eng, N, dv, k, largest, vals, idx, st);
 }
 
-extern "C" int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, const double* Xs, int k, double* vals,
-                            long long* idx, double* f_out, void* stream) {
-  if (!eng || !Xs || !vals || !idx || N < 1 || k < 1 || kind < 0 || kind > 5) return GPO_ERR_ARG;
+static int acq_topk_impl(gpo_engine* eng, int kind, double par, long long N, const double* Xs, int k, double* vals,
+                         long long* idx, double* f_out, void* stream) {
   GPO_CUDA_OK(cudaSetDevice(eng->device));
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
@@ -1078,6 +1107,66 @@ extern "C" int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, 
   }
   if (f_out && !f_is_dev) {
     GPO_CUDA_OK(cudaMemcpyAsync(f_out, f_dev, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return GPO_OK;
+}
+
+extern "C" int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, const double* Xs, int k, double* vals,
+                            long long* idx, double* f_out, void* stream) {
+  if (!eng || !Xs || !vals || !idx || N < 1 || k < 1 || kind < 0 || kind > 5) return GPO_ERR_ARG;
+  return acq_topk_impl(eng, kind, par, N, Xs, k, vals, idx, f_out, stream);
+}
+
+extern "C" int gpo_design_uniform(gpo_engine* eng, const unsigned long long* key, long long row0, long long N, int d,
+                                  const double* bounds, double* X, void* stream) {
+  if (!eng || !key || !bounds || !X || N < 0 || row0 < 0) return GPO_ERR_ARG;
+  if (N == 0) return GPO_OK;
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DesignParams p;
+  int rc;
+  if ((rc = design_setup(eng, &p, key, d, bounds))) return rc;
+  const bool dev = is_device_ptr(X);
+  double* out = X;
+  if (!dev) {
+    if ((rc = grow(eng, &eng->stage_in, &eng->stage_in_bytes, (size_t)N * d * 8))) return rc;
+    out = eng->stage_in;
+  }
+  launch_design(eng, p, row0, N, out, st);
+  GPO_CUDA_OK(cudaGetLastError());
+  if (!dev) {
+    GPO_CUDA_OK(cudaMemcpyAsync(X, out, (size_t)N * d * 8, cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return GPO_OK;
+}
+
+extern "C" int gpo_acq_topk_uniform(gpo_engine* eng, int kind, double par, const unsigned long long* key, long long row0,
+                                    long long N, const double* bounds, int k, double* vals, long long* idx, double* x_top,
+                                    void* stream) {
+  if (!eng || !key || !bounds || !vals || !idx || N < 1 || row0 < 0 || k < 1 || kind < 0 || kind > 5) return GPO_ERR_ARG;
+  if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_acq_topk_uniform before gpo_fit");
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = design_setup(eng, &eng->gen, key, eng->d, bounds))) return rc;
+  eng->gen_row0 = row0;
+  eng->gen_on = true;
+  rc = acq_topk_impl(eng, kind, par, N, nullptr, k, vals, idx, nullptr, stream);
+  eng->gen_on = false;
+  if (rc) return rc;
+  if (x_top) {  // the winning rows are still in the generated design: gather them on the device, one small copy back
+    if (!eng->gen_idx) {
+      GPO_CUDA_OK(cudaMalloc(&eng->gen_idx, (size_t)(TOPK_SEG / 2) * 8));
+      GPO_CUDA_OK(cudaMalloc(&eng->gen_x, (size_t)(TOPK_SEG / 2) * DMAX * 8));
+    }
+    const int d = eng->d;
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->gen_idx, idx, (size_t)k * 8, cudaMemcpyHostToDevice, st));
+    gather_rows_kernel<<<(k * d + 127) / 128, 128, 0, st>>>(eng->stage_in, eng->gen_idx, k, d, eng->gen_x);
+    eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
+    GPO_CUDA_OK(cudaMemcpyAsync(x_top, eng->gen_x, (size_t)k * d * 8, cudaMemcpyDeviceToHost, st));
     GPO_CUDA_OK(cudaStreamSynchronize(st));
   }
   return GPO_OK;

@@ -796,4 +796,69 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_level_kernel(const double* 
   }
 }
 
+// --------------------------------------------------------------------------------------------------
+// Device-side random design: uniform candidates from a counter-based generator, so that a sweep
+// needs no host->device copy of X*.  The stream is Philox4x64-10 exactly as NumPy consumes it:
+//   numpy.random.Generator(numpy.random.Philox(key=key)).uniform(lo, hi, size=(N, d))     (row-major)
+// element e takes lane (e & 3) of the block whose counter is (e >> 2) + 1 (NumPy increments the counter BEFORE it
+// generates a block), u = (v >> 11) * 2^-53, x = lo + (hi - lo) * u with the product and the sum rounded
+// separately (NumPy's random_uniform is not FMA-contracted).  Replaces samples_multidimensional_uniform
+// (GPyOpt/experiment_design/random_design.py:66-76), whose legacy MT19937 stream is inherently sequential.
+// --------------------------------------------------------------------------------------------------
+struct DesignParams {
+  unsigned long long key0, key1;
+  long long e0;    // first global element index (row0 * d)
+  long long n_el;  // elements to generate
+  int d;
+  double lo[DMAX], range[DMAX];
+  double* out;     // element e0 is written to out[0]
+};
+
+__device__ __forceinline__ void philox4x64_10(unsigned long long c0, unsigned long long c1, unsigned long long c2,
+                                              unsigned long long c3, unsigned long long k0, unsigned long long k1,
+                                              unsigned long long (&v)[4]) {
+  constexpr unsigned long long M0 = 0xD2E7470EE14C6C93ULL, M1 = 0xCA5A826395121157ULL;
+  constexpr unsigned long long W0 = 0x9E3779B97F4A7C15ULL, W1 = 0xBB67AE8584CAA73BULL;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    if (r) { k0 += W0; k1 += W1; }
+    const unsigned long long hi0 = __umul64hi(M0, c0), lo0 = M0 * c0;
+    const unsigned long long hi1 = __umul64hi(M1, c2), lo1 = M1 * c2;
+    const unsigned long long n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  v[0] = c0; v[1] = c1; v[2] = c2; v[3] = c3;
+}
+
+__global__ void __launch_bounds__(256) design_uniform_kernel(const DesignParams p) {
+  const long long b_first = p.e0 >> 2;
+  const long long e_end = p.e0 + p.n_el;
+  const long long nblk = ((e_end + 3) >> 2) - b_first;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nblk; t += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long b = (unsigned long long)(b_first + t);
+    unsigned long long v[4];
+    philox4x64_10(b + 1ULL, 0ULL, 0ULL, 0ULL, p.key0, p.key1, v);  // N*d < 2^66: no carry into the second counter word
+    int q = (int)((b << 2) % (unsigned long long)p.d);
+#pragma unroll
+    for (int lane = 0; lane < 4; ++lane) {
+      const long long e = (long long)(b << 2) + lane;
+      if (e >= p.e0 && e < e_end) {
+        const double u = (double)(v[lane] >> 11) * (1.0 / 9007199254740992.0);
+        p.out[e - p.e0] = __dadd_rn(p.lo[q], __dmul_rn(p.range[q], u));
+      }
+      if (++q == p.d) q = 0;
+    }
+  }
+}
+
+// rows idx[0..k) of X [N, d] -> out [k, d]  (the winning candidates of a device-generated design)
+__global__ void gather_rows_kernel(const double* __restrict__ X, const long long* __restrict__ idx, int k, int d,
+                                   double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= k * d) return;
+  const int r = t / d, q = t - r * d;
+  const long long i = idx[r];
+  out[t] = i >= 0 ? X[i * d + q] : __longlong_as_double(0x7ff8000000000000LL);
+}
+
 }  // namespace gpo

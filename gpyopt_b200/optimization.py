@@ -11,6 +11,9 @@ rows f2 / f4).  Needs the reference package (GPyOpt) importable: these classes r
 * :class:`FusedAnchorPointsGenerator` -- ``ObjectiveAnchorPointsGenerator`` whose scoring + ``argsort[:k]``
   (anchor_points_generator.py:62-67) is the fused device sweep + top-k (``gpo_acq_topk``) when the acquisition has
   constant cost and the space no constraints.
+* :class:`DeviceDesignAnchorPointsGenerator` -- the same, with the random design itself generated on the device
+  (``gpo_acq_topk_uniform``): for all-continuous box domains the 1000 ... 1e7 candidate rows of
+  ``initial_design('random', ...)`` (experiment_design/random_design.py:56-76) never exist on the host.
 """
 import threading
 
@@ -128,22 +131,64 @@ class FusedAnchorPointsGenerator(ObjectiveAnchorPointsGenerator):
         return X[idx, :]
 
 
+class DeviceDesignAnchorPointsGenerator(FusedAnchorPointsGenerator):
+    """Anchor points from a uniform design generated, scored and reduced to its top-k on the device in one call.
+
+    The design is the counter-based stream ``numpy.random.Generator(numpy.random.Philox(key=[seed, call])).uniform``
+    (same distribution as the reference's ``samples_multidimensional_uniform``, a different stream than its legacy
+    global MT19937 one); ``call`` counts the ``get`` calls so that every BO iteration sees a fresh design.  Falls back
+    to the host design whenever the space is not a plain continuous box or the acquisition is not a fused one."""
+
+    def __init__(self, space, acquisition, num_samples=1000, seed=0):
+        super(DeviceDesignAnchorPointsGenerator, self).__init__(space, random_design_type, acquisition, num_samples)
+        self.seed, self.calls = int(seed), 0
+
+    def _continuous_box(self):
+        types = getattr(self.space, 'has_types', {})
+        return (self.space.has_continuous() and not any(v for t, v in types.items() if t != 'continuous')
+                and not self.space.has_constraints())
+
+    def get(self, num_anchor=5, duplicate_manager=None, unique=False, context_manager=None):
+        from .acquisitions import _FusedAcquisition, _engine_of
+        no_context = context_manager is None or len(getattr(context_manager, 'context_index', [])) == 0
+        fused = (isinstance(self.acquisition, _FusedAcquisition) and _plain(self.acquisition) and not duplicate_manager
+                 and not unique and no_context and self._continuous_box())
+        if not fused:
+            return super(DeviceDesignAnchorPointsGenerator, self).get(num_anchor, duplicate_manager, unique, context_manager)
+        eng = _engine_of(self.acquisition.model)
+        key = [self.seed, self.calls]
+        self.calls += 1
+        bounds = np.asarray(self.space.get_bounds(), dtype=np.float64)
+        _, _, rows = eng.acq_topk_uniform(self.acquisition._kind, self.acquisition._par(), key, self.num_samples, bounds,
+                                          min(num_anchor, self.num_samples))
+        return rows
+
+
 class BatchedAcquisitionOptimizer(AcquisitionOptimizer):
     """AcquisitionOptimizer whose local optimisations share their device calls (see module docstring)."""
 
-    def __init__(self, space, optimizer='lbfgs', acquisition=None, **kwargs):
+    def __init__(self, space, optimizer='lbfgs', acquisition=None, device_design_seed=None, num_anchor_samples=1000,
+                 **kwargs):
         if not HAVE_GPYOPT:
             raise ImportError("BatchedAcquisitionOptimizer builds on GPyOpt's optimizer classes; GPyOpt is not importable")
         super(BatchedAcquisitionOptimizer, self).__init__(space, optimizer, **kwargs)
         self.acquisition = acquisition     # optional: enables the fused anchor sweep
+        self.device_design_seed = device_design_seed   # not None: the anchor design is generated on the device
+        self.num_anchor_samples = int(num_anchor_samples)
+        self._device_gen = None
         self.last_stats = None
 
     def optimize(self, f=None, df=None, f_df=None, duplicate_manager=None):
         self.f, self.df, self.f_df = f, df, f_df
         self.optimizer = choose_optimizer(self.optimizer_name, self.context_manager.noncontext_bounds)
         if self.type_anchor_points_logic == max_objective_anchor_points_logic:
-            if self.acquisition is not None:
-                gen = FusedAnchorPointsGenerator(self.space, random_design_type, self.acquisition)
+            if self.acquisition is not None and self.device_design_seed is not None:
+                if self._device_gen is None or self._device_gen.acquisition is not self.acquisition:
+                    self._device_gen = DeviceDesignAnchorPointsGenerator(self.space, self.acquisition, self.num_anchor_samples,
+                                                                         self.device_design_seed)
+                gen = self._device_gen
+            elif self.acquisition is not None:
+                gen = FusedAnchorPointsGenerator(self.space, random_design_type, self.acquisition, self.num_anchor_samples)
             else:
                 gen = ObjectiveAnchorPointsGenerator(self.space, random_design_type, f)
         elif self.type_anchor_points_logic == thompson_sampling_anchor_points_logic:

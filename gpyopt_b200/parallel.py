@@ -7,6 +7,9 @@ each rank sweeps a contiguous block of rows with NO data-path collective.  The o
     fitting rank -- one NCCL broadcast per buffer, straight between the engines' own HBM buffers;
   * after a sweep: all-gather of the per-rank top-k records {score, global index} (k*16 bytes per rank) and an
     identical deterministic merge on every rank (ties -> lowest global index).
+With a device-generated design (``acq_topk_uniform``) the candidates themselves never exist outside the GPUs: every
+rank generates its own rows of ONE global counter-based stream, so the union over ranks is the same design for any
+number of GPUs.
 """
 import numpy as np
 
@@ -114,3 +117,19 @@ class ShardedSweep(object):
         vals, idx = self.engine.acq_topk(kind, par, Xs_local, k, f_out=f_out)
         dev = 'cuda:%d' % self.engine.device if self.distributed and _dist().get_backend(self.group) == 'nccl' else None
         return allgather_topk(vals, idx + row_offset, k, device=dev, group=self.group)
+
+    def acq_topk_uniform(self, kind, par, key, N, bounds, k):
+        """Sweep a device-generated uniform design of N global rows (Engine.design_uniform's stream), sharded by rows,
+        and return (scores [k], global row numbers [k], rows [k, d]) of the k best -- identical on every rank and
+        independent of the number of ranks."""
+        lo, hi = self.local_rows(N)
+        if hi > lo:
+            vals, idx, _ = self.engine.acq_topk_uniform(kind, par, key, hi - lo, bounds, min(k, hi - lo), row0=lo)
+        else:
+            vals, idx = np.empty(0), np.empty(0, dtype=np.int64)
+        dev = 'cuda:%d' % self.engine.device if self.distributed and _dist().get_backend(self.group) == 'nccl' else None
+        vals, gidx = allgather_topk(vals, idx + lo, k, device=dev, group=self.group)
+        # the winners are regenerated from their global row numbers: no candidate rows travel between ranks
+        rows = np.vstack([self.engine.design_uniform(key, 1, bounds, row0=int(g)) for g in gidx]) if len(gidx) else \
+            np.empty((0, np.atleast_2d(bounds).shape[0]))
+        return vals, gidx, rows

@@ -109,6 +109,22 @@ int gpo_lp_set(gpo_engine* eng, int K, const double* Xb, const double* r, const 
 int gpo_acq_topk(gpo_engine* eng, int kind, double par, long long N, const double* Xs, int k, double* vals,
                  long long* idx, double* f_out, void* stream);
 
+/* Device-side random design (replaces samples_multidimensional_uniform,
+ * GPyOpt/experiment_design/random_design.py:66-76, for continuous box domains): rows [row0, row0+N) of the
+ * uniform design  numpy.random.Generator(numpy.random.Philox(key=key)).uniform(lo, hi, size=(rows, d))
+ * (Philox4x64-10, row-major, bit-identical to NumPy), written to X (host|device) [N, d].
+ * key: two 64-bit words; bounds (host) [d, 2] = (lo, hi) per dimension.  Needs no fitted model. */
+int gpo_design_uniform(gpo_engine* eng, const unsigned long long* key, long long row0, long long N, int d,
+                       const double* bounds, double* X, void* stream);
+
+/* gpo_acq_topk over rows [row0, row0+N) of that design, generated on the device chunk by chunk inside the
+ * sweep: no candidate ever crosses PCIe (initial_design('random') + AnchorPointsGenerator.get,
+ * anchor_points_generator.py:25-69, in one call).  idx are LOCAL row numbers (global row = row0 + idx);
+ * x_top (host, may be NULL) [k, d] receives the winning rows. */
+int gpo_acq_topk_uniform(gpo_engine* eng, int kind, double par, const unsigned long long* key, long long row0,
+                         long long N, const double* bounds, int k, double* vals, long long* idx, double* x_top,
+                         void* stream);
+
 /* k smallest (largest = 0) or largest (largest = 1) entries of a device/host array v [N]. */
 int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, int largest, double* vals, long long* idx,
              void* stream);

@@ -323,3 +323,69 @@ def normalize_stats(Y):
     if std > 0:
         Y_norm = Y_norm / std
     return Y_norm
+
+
+# --------------------------------------------------------------------------------------------------
+# Device-side random design.  The engine generates uniform candidates with a counter-based
+# generator instead of copying a host design; the CONTRACT of that generator is NumPy's own Philox bit generator
+# (third-party: numpy >= 1.17, numpy/random/src/philox/philox.h, Philox4x64-10 of Salmon et al., "Parallel random
+# numbers: as easy as 1, 2, 3", SC'11).  `design_uniform` below IS numpy; `philox4x64_10` restates the published
+# algorithm in plain integers and is pinned against numpy's raw stream by tests/test_oracle_pins.py.
+# The reference's samples_multidimensional_uniform (experiment_design/random_design.py:66-76) draws column by
+# column from the legacy global MT19937 stream; a counter-based design has the same distribution, not the same
+# numbers -- parity for this row is "same candidates in -> same scores / top-k out", with the candidates
+# regenerated on the host from the same key.
+# --------------------------------------------------------------------------------------------------
+_PHILOX_M0, _PHILOX_M1 = 0xD2E7470EE14C6C93, 0xCA5A826395121157
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B97F4A7C15, 0xBB67AE8584CAA73B
+_U64 = (1 << 64) - 1
+
+
+def philox4x64_10(counter, key):
+    """One Philox4x64-10 block: counter (4 words), key (2 words) -> 4 output words (plain Python integers)."""
+    c, k = [int(v) for v in counter], [int(v) for v in key]
+    for r in range(10):
+        if r:
+            k = [(k[0] + _PHILOX_W0) & _U64, (k[1] + _PHILOX_W1) & _U64]
+        p0, p1 = _PHILOX_M0 * c[0], _PHILOX_M1 * c[2]
+        c = [(p1 >> 64) ^ c[1] ^ k[0], p1 & _U64, (p0 >> 64) ^ c[3] ^ k[1], p0 & _U64]
+    return c
+
+
+def design_uniform_restated(key, N, bounds, row0=0):
+    """Pure-Python restatement of the device generator (small N only): element e of the row-major design uses lane
+    e & 3 of block (e >> 2) + 1 (numpy increments the counter before generating), u = (v >> 11) * 2**-53,
+    x = lo + (hi - lo) * u."""
+    bounds = np.atleast_2d(np.asarray(bounds, dtype=np.float64))
+    d = bounds.shape[0]
+    lo, rng = bounds[:, 0], bounds[:, 1] - bounds[:, 0]
+    key = _philox_key(key)
+    out = np.empty(N * d)
+    cache = {}
+    for j in range(N * d):
+        e = row0 * d + j
+        b = e >> 2
+        if b not in cache:
+            cache[b] = philox4x64_10([b + 1, 0, 0, 0], key)
+        u = (cache[b][e & 3] >> 11) * (1.0 / 9007199254740992.0)
+        out[j] = lo[e % d] + rng[e % d] * u
+    return out.reshape(N, d)
+
+
+def _philox_key(key):
+    key = np.atleast_1d(np.asarray(key, dtype=np.uint64)).reshape(-1)
+    return np.array([key[0], 0], dtype=np.uint64) if key.size == 1 else key
+
+
+def design_uniform(key, N, bounds, row0=0):
+    """Rows [row0, row0+N) of numpy.random.Generator(numpy.random.Philox(key=key)).uniform(lo, hi, (rows, d))."""
+    bounds = np.atleast_2d(np.asarray(bounds, dtype=np.float64))
+    d = bounds.shape[0]
+    e0 = int(row0) * d
+    bg = np.random.Philox(key=_philox_key(key), counter=np.array([e0 >> 2, 0, 0, 0], dtype=np.uint64))
+    g = np.random.Generator(bg)
+    skip = e0 & 3
+    u = g.random(skip + N * d)[skip:]
+    lo, rng = bounds[:, 0], bounds[:, 1] - bounds[:, 0]
+    q = (e0 + np.arange(N * d)) % d
+    return (lo[q] + rng[q] * u).reshape(N, d)

@@ -35,6 +35,19 @@ def main():
     # fewer local rows than k on one rank
     vals2, idx2 = parallel.allgather_topk(local[li][:2] if rank == 0 else local[li], (li + lo)[:2] if rank == 0 else li + lo, k)
     assert len(idx2) == k and np.all(np.diff(vals2) >= 0)
+    # device-generated design, sharded by rows: same winners as ONE process sweeping the whole design
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from fake_engine import FakeEngine
+    from oracle import gpyopt_numpy as og
+    eng = FakeEngine()
+    Xt = rng.random((25, 3)) * 4 - 2
+    eng.fit('rbf', Xt, np.sin(Xt).sum(1), 1.0, np.full((1, 3), 0.7), 1e-3)
+    bounds = np.array([[-2., 2.], [-2., 2.], [-1., 3.]])
+    sw = parallel.ShardedSweep(eng)
+    v, gi, rows = sw.acq_topk_uniform('EI', 0.01, [11, 22], 1003, bounds, 5)
+    Xall = og.design_uniform([11, 22], 1003, bounds)
+    v1, i1 = eng.acq_topk('EI', 0.01, Xall, 5)
+    assert np.array_equal(gi, i1) and np.array_equal(v, v1) and np.array_equal(rows, Xall[i1]), (gi, i1)
     dist.barrier()
     if rank == 0:
         print('DIST_OK')

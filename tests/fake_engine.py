@@ -107,3 +107,11 @@ class FakeEngine(object):
         score = f if self._lp is not None else -f
         idx = og.anchor_topk(score, k)
         return score[idx], idx
+
+    def design_uniform(self, key, N, bounds, row0=0, out=None, stream=None):
+        return og.design_uniform(key, int(N), bounds, row0=int(row0))
+
+    def acq_topk_uniform(self, kind, par, key, N, bounds, k, row0=0, stream=None):
+        X = self.design_uniform(key, N, bounds, row0)
+        vals, idx = self.acq_topk(kind, par, X, k)
+        return vals, idx, X[idx]

@@ -54,8 +54,24 @@ Xs = torch.from_numpy(lo + (hi - lo) * rng.random((N, d))).cuda(); f = torch.emp
 t = dev_time(lambda: eng.acq('LCB', 2.0, Xs, out=(f, None), stream=st))
 Xh = Xs.cpu().numpy()
 th = wall(lambda: eng.acq_topk('LCB', 2.0, Xh, 5))
+bounds = np.stack([lo, hi], 1)
+tg = wall(lambda: eng.acq_topk_uniform('LCB', 2.0, [1, 2], N, bounds, 5))       # design generated on the device
 out({"config": "C2 sixhumpcamel n=55 LCB value-only sweep", "candidates": N, "device_cand_per_s": N / t, "ms": t * 1e3,
-     "host_sweep_plus_top5_cand_per_s": N / th})
+     "host_sweep_plus_top5_cand_per_s": N / th, "device_design_sweep_plus_top5_cand_per_s": N / tg})
+eng.close()
+
+# ---- C3 anchor step: 10M-candidate random design -> EI -> top-5, host design vs device design ------------
+n, d, N = 2048, 6, 10_000_000
+X = rng.uniform(1, 10, (n, d)); Y = og.normalize_stats(og.alpine2(X))[:, 0]
+eng = Engine(0); eng.fit('rbf', X, Y, [1.0], [[2.0]], [1e-2])
+bounds = np.array([[1., 10.]] * d)
+tg = wall(lambda: eng.acq_topk_uniform('EI', 0.01, [1, 2], N, bounds, 5), reps=2)
+Xh = eng.design_uniform([1, 2], N, bounds)
+th = wall(lambda: eng.acq_topk('EI', 0.01, Xh, 5), reps=2)
+tnp = wall(lambda: og.design_uniform([1, 2], 1_000_000, bounds), reps=1, warm=0)
+out({"config": "C3 anchor step n=2048 d=6 EI value-only, 10M random candidates -> top-5", "candidates": N,
+     "device_design_cand_per_s": N / tg, "host_design_cand_per_s_excluding_generation": N / th,
+     "numpy_philox_generation_only_cand_per_s": 1_000_000 / tnp})
 eng.close()
 
 # ---- C4 ------------------------------------------------------------------------------------------------

@@ -173,6 +173,48 @@ def test_batched_acquisition_optimizer_is_exact(gpyopt):
         assert new_opt.last_stats['rows'] >= new_opt.last_stats['device_calls']
 
 
+def test_device_design_anchor_points(gpyopt):
+    """DeviceDesignAnchorPointsGenerator: anchors = the k best rows of the counter-based design, i.e. what the
+    reference's ObjectiveAnchorPointsGenerator returns when it is handed that same design; mixed / constrained
+    spaces fall back to the host design."""
+    GPyOpt, models, acqs = gpyopt
+    import importlib
+    import gpyopt_b200.optimization as opt
+    importlib.reload(opt)
+    from gpyopt_b200 import kern
+    from oracle import gpyopt_numpy as og
+    rng = np.random.default_rng(9)
+    space = GPyOpt.Design_space(DOMAIN)
+    X = np.column_stack([rng.uniform(-5, 10, 15), rng.uniform(1, 15, 15)])
+    Y = og.normalize_stats(branin(X))
+    model = models.GPModel(kernel=kern.RBF(2, lengthscale=3.0), exact_feval=True, max_iters=0, verbose=False)
+    model.updateModel(X, Y, None, None)
+    acq = acqs.AcquisitionEI(model, space, None, jitter=0.01)
+    gen = opt.DeviceDesignAnchorPointsGenerator(space, acq, num_samples=2000, seed=31)
+    a0 = gen.get(num_anchor=5)
+    a1 = gen.get(num_anchor=5)
+    assert a0.shape == (5, 2) and not np.array_equal(a0, a1)            # a fresh design per call
+    for call, got in ((0, a0), (1, a1)):
+        design = og.design_uniform([31, call], 2000, np.array(space.get_bounds(), dtype=float))
+        scores = acq.acquisition_function(design).flatten()               # the reference's scoring + argsort[:k]
+        assert np.array_equal(got, design[np.argsort(scores, kind='stable')[:5]])
+    # optimiser wiring: device_design_seed switches the anchor source, the result is a valid optimum
+    o = opt.BatchedAcquisitionOptimizer(space, 'lbfgs', device_design_seed=31)
+    acq2 = acqs.AcquisitionEI(model, space, o, jitter=0.01)
+    o.acquisition = acq2
+    x, fx = acq2.optimize()
+    d1000 = og.design_uniform([31, 0], 1000, np.array(space.get_bounds(), dtype=float))   # the optimiser's first design
+    assert x.shape == (1, 2) and np.ravel(fx)[0] <= acq2.acquisition_function(d1000).min() + 1e-12
+    assert o._device_gen.calls == 1
+    # a space with a discrete variable is not a continuous box: host design
+    mixed = GPyOpt.Design_space([{'name': 'a', 'type': 'continuous', 'domain': (-5, 10)},
+                                 {'name': 'b', 'type': 'discrete', 'domain': (1, 5, 9, 15)}])
+    g2 = opt.DeviceDesignAnchorPointsGenerator(mixed, acqs.AcquisitionEI(model, mixed, None), num_samples=200, seed=1)
+    assert not g2._continuous_box()
+    np.random.seed(0)
+    assert g2.get(num_anchor=3).shape == (3, 2) and g2.calls == 0
+
+
 def test_rendezvous_propagates_errors_and_handles_uneven_workers():
     import threading
     from gpyopt_b200.optimization import Rendezvous

@@ -302,6 +302,54 @@ def test_topk_semantics(engine):
     assert np.array_equal(idx, [1, 0])
 
 
+@pytest.mark.parametrize('d,N,row0', [(1, 1000, 0), (2, 4097, 3), (3, 100000, 12345), (6, 300001, 7), (10, 65536, 1), (16, 999, 2 ** 40 + 5)])
+def test_device_design_is_numpy_philox_stream(engine, d, N, row0):
+    """gpo_design_uniform == numpy.random.Generator(numpy.random.Philox(key)).uniform(...) bit for bit (row f4)."""
+    from oracle import gpyopt_numpy as og
+    rng = np.random.default_rng(d)
+    lo = rng.uniform(-5, 5, d)
+    bounds = np.stack([lo, lo + rng.uniform(0.1, 10, d)], 1)
+    key = np.array([0xDEADBEEFCAFEF00D, 42 + d], dtype=np.uint64)
+    X = engine.design_uniform(key, N, bounds, row0=row0)
+    assert np.array_equal(X, og.design_uniform(key, N, bounds, row0=row0))
+    assert np.all(X >= bounds[:, 0]) and np.all(X < bounds[:, 1] + 1e-12)
+    import torch
+    Xd = torch.empty((N, d), dtype=torch.float64, device='cuda:0')     # device destination
+    engine.design_uniform(key, N, bounds, row0=row0, out=Xd)
+    torch.cuda.synchronize()
+    assert np.array_equal(Xd.cpu().numpy(), X)
+
+
+@pytest.mark.parametrize('acq,par,k', [('EI', 0.01, 1), ('EI', 0.01, 5), ('LCB', 2.0, 16), ('MPI', 0.01, 80)])
+def test_sweep_over_device_design_equals_sweep_over_host_design(engine, acq, par, k):
+    """Fused generate + score + select == the same call on the host copy of the same candidates (bitwise), and the
+    shard [row0, row0+N) of a design gives the rows a whole-design sweep would see."""
+    from oracle import gpyopt_numpy as og
+    rng = np.random.default_rng(5)
+    n, d, N = 300, 4, 70001
+    bounds = np.array([[1., 10.]] * d)
+    X = rng.uniform(1, 10, (n, d))
+    Y = og.normalize_stats(og.alpine2(X))[:, 0]
+    engine.fit('rbf', X, Y, 1.0, np.full((1, d), 2.0), 1e-2)
+    key = [2024, 7]
+    for row0 in (0, 333):
+        Xs = og.design_uniform(key, N, bounds, row0=row0)
+        v_ref, i_ref = engine.acq_topk(acq, par, Xs, k)
+        v, i, rows = engine.acq_topk_uniform(acq, par, key, N, bounds, k, row0=row0)
+        assert np.array_equal(i, i_ref) and np.array_equal(v, v_ref)
+        assert np.array_equal(rows, Xs[i_ref])
+    # and against the oracle's scores of those candidates
+    f_o = og.acq_EI(*og.gp_predict(_oracle_gp(X, Y, d), Xs[:2000]), og.gp_get_fmin(_oracle_gp(X, Y, d)), 0.01) if acq == 'EI' else None
+    if f_o is not None:
+        f_e = engine.acq('EI', 0.01, Xs[:2000])
+        assert scaled_err(f_e, f_o[:, 0]) < 1e-10
+
+
+def _oracle_gp(X, Y, d):
+    from oracle import gpy_numpy as G
+    return G.GPRegression(X, Y.reshape(-1, 1), G.RBF(d, variance=1.0, lengthscale=2.0), noise_var=1e-2)
+
+
 # ------------------------------------------------------------------------------------------------------
 # (3) properties at the full BASELINE sizes (n = 2048, d = 6; the oracle is too slow / too big there)
 # ------------------------------------------------------------------------------------------------------

@@ -217,22 +217,42 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int zdiv = p.zdiv > 0 ? p.zdiv : p.batch, node = z / zdiv, set = z % zdiv;
     double* C = p.C ? p.C + p.c_off_z * set + (long long)node * p.c_row_z * p.ldc + node * p.c_col_z : nullptr;
     double* Ct = p.Ct ? p.Ct + p.ct_off_z * set + (long long)node * p.ct_row_z * p.ldct + node * p.ct_col_z : nullptr;
+    // beta != 0: the tile of C is fetched in two batches of 32 independent loads per thread BEFORE any store of the
+    // batch (interleaved load/store pairs would be kept in program order by the compiler -- the pointers may alias --
+    // and cost one L2 round trip per element: 64 x ~0.3 us on the Cholesky's critical path)
 #pragma unroll
-    for (int f = 0; f < 8; ++f) {
-      const int r = tile_m * TILE + wm + 8 * f + rr;
+    for (int fh = 0; fh < 2; ++fh) {
+      double cin[4][4][2];
+      if (C && p.beta != 0.0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+        for (int f4 = 0; f4 < 4; ++f4) {
+          const int r = tile_m * TILE + wm + 8 * (4 * fh + f4) + rr;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = tile_n * TILE + wn + 8 * j + (e ? 4 + t : t);
-          double v = p.alpha * acc[f][j][e];
-          if (C && (!diag || c <= r)) {
-            double* dst = C + (long long)(p.c_row0 + r) * p.ldc + p.c_col0 + c;
-            if (p.beta != 0.0) v += p.beta * (*dst);
-            *dst = v;
-          }
-          if (Ct && (!diag || c < r)) Ct[(long long)(p.ct_row0 + c) * p.ldct + p.ct_col0 + r] = v;
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int c = tile_n * TILE + wn + 8 * j + (e ? 4 + t : t);
+              cin[f4][j][e] = (!diag || c <= r) ? C[(long long)(p.c_row0 + r) * p.ldc + p.c_col0 + c] : 0.0;
+            }
         }
+      }
+#pragma unroll
+      for (int f4 = 0; f4 < 4; ++f4) {
+        const int f = 4 * fh + f4;
+        const int r = tile_m * TILE + wm + 8 * f + rr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = tile_n * TILE + wn + 8 * j + (e ? 4 + t : t);
+            double v = p.alpha * acc[f][j][e];
+            if (C && (!diag || c <= r)) {
+              if (p.beta != 0.0) v += p.beta * cin[f4][j][e];
+              C[(long long)(p.c_row0 + r) * p.ldc + p.c_col0 + c] = v;
+            }
+            if (Ct && (!diag || c < r)) Ct[(long long)(p.ct_row0 + c) * p.ldct + p.ct_col0 + r] = v;
+          }
+      }
     }
   } else {
     // epilogue scratch lives past the ring: the producer may already be filling the ring for the next work item

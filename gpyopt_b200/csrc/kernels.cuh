@@ -209,22 +209,158 @@ __global__ void cross_gram_kernel(double* out, long long ldo, const double* X1, 
 //   out: A block <- L (upper zeroed), X block <- L^-1 (lower), U block <- L^-T (upper)
 // info[z] is set to (global column index + 1) of the first non-positive pivot.
 // 16 x 16 threads; thread (ty, tx) keeps the 8 x 8 elements (ty + 16 a, tx + 16 b) in REGISTERS through both phases
-// (cyclic ownership keeps all threads busy while the active region shrinks); per column/row step only the pivot and
-// the finished column/row travel through shared memory (two block barriers per step, 16 LDS + 64 DFMA per thread).
+// (cyclic ownership keeps all threads busy while the active region shrinks).
 constexpr int DIAG_THREADS = 256;
 constexpr int DIAG_PITCH = TILE + 1;
-constexpr int DIAG_SMEM_BYTES = (TILE * DIAG_PITCH + 3 * TILE) * 8;
+constexpr int DIAG_PB = 32;                       // inner panel width
+constexpr int DIAG_NP = TILE / DIAG_PB;           // 4 panels
+constexpr int DIAG_XD_PITCH = DIAG_PB + 1;
+constexpr int DIAG_SMEM_BYTES = (TILE * DIAG_PITCH + DIAG_NP * DIAG_PB * DIAG_XD_PITCH + TILE + 2 * DIAG_PB) * 8;
 
-// Only the first n_valid = clamp(n - 128 kb, 0, 128) rows of the block are real data; the rest is identity padding, for
-// which both phases are no-ops, so the (latency-bound) step loops stop there.
+// Cholesky of the 32x32 diagonal block at S[j0.., j0..] by ONE warp, lane = row, the row in registers.  Per column:
+// broadcast of the pivot, 1/sqrt in every lane, the scaled column goes through a 32-entry shared buffer (double-buffered)
+// and comes back as 16-byte broadcast loads (one LDS.128 per two columns still to update; a shuffle version needs five
+// instructions per column and is issue-bound).  The NEXT pivot does not wait for that round trip: its owner forms
+// a_(j+1,j+1) - l^2 from its own l, so the serial chain per column is shuffle -> rsqrt -> multiply -> fma.
+// Writes L (lower part) back and 1/L_jj to rd.  colbuf: 64 doubles, 16-byte aligned.
+__device__ __forceinline__ void chol32_warp(double* S, double* rd, double* colbuf, int j0, int lane, int* info_z, int col0) {
+  double a[DIAG_PB];
+#pragma unroll
+  for (int k = 0; k < DIAG_PB; ++k) a[k] = (k <= lane) ? S[(j0 + lane) * DIAG_PITCH + j0 + k] : 0.0;
+  double dd = __shfl_sync(0xffffffffu, a[0], 0);
+#pragma unroll
+  for (int j = 0; j < DIAG_PB; ++j) {
+    if (!(dd > 0.0)) {  // uniform: dd is a broadcast
+      if (lane == j && *info_z == 0) *info_z = col0 + j0 + j + 1;
+      dd = 1.0;
+    }
+    const double rp = rsqrt(dd);
+    const double l = (lane > j) ? a[j] * rp : (lane == j ? dd * rp : 0.0);  // as LAPACK dpotf2: scale by the reciprocal pivot
+    a[j] = l;
+    if (lane == j) rd[j0 + j] = rp;
+    if (j < DIAG_PB - 1) {
+      dd = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);   // next pivot, from its owner's own l
+      double* cb = colbuf + (j & 1) * DIAG_PB;
+      cb[lane] = l;
+      __syncwarp();
+      if (((j + 1) & 1) != 0) a[j + 1] = fma(-l, cb[j + 1], a[j + 1]);   // odd first column: single load
+#pragma unroll
+      for (int k = (j + 2) & ~1; k < DIAG_PB; k += 2) {
+        const double2 lk = *reinterpret_cast<const double2*>(cb + k);
+        a[k] = fma(-l, lk.x, a[k]);   // lanes below k carry unused values in a[k]
+        a[k + 1] = fma(-l, lk.y, a[k + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < DIAG_PB; ++k)
+    if (k <= lane) S[(j0 + lane) * DIAG_PITCH + j0 + k] = a[k];
+}
+
+// Forward substitution L x = v with a 32x32 lower-triangular block (rdp = 1 / diagonal), v in shared memory with stride
+// sv, one thread per right-hand side; the entries of L are shared-memory broadcasts.  The diagonal-block kernel funnels
+// ALL of its triangular work through this single unrolled routine -- the panel rows below a diagonal block
+// (l L11^T = a), the columns of the diagonal-block inverses (L x = e_c) and the block rows of the inverse
+// (X_pp R = L_pp^-1 R) -- because it runs once per launch from a cold instruction cache: straight-line code costs ~8
+// cycles per instruction on first touch (measured), rolled shared-memory loops ~35 cycles per element.
+__device__ __forceinline__ void fwdsub32(double* vec, int sv, const double* Lb, const double* rdp) {
+  double v[DIAG_PB];
+#pragma unroll
+  for (int c = 0; c < DIAG_PB; ++c) v[c] = vec[c * sv];
+#pragma unroll
+  for (int c = 0; c < DIAG_PB; ++c) {
+    v[c] *= rdp[c];
+#pragma unroll
+    for (int c2 = c + 1; c2 < DIAG_PB; ++c2) v[c2] = fma(-v[c], Lb[c2 * DIAG_PITCH + c], v[c2]);
+  }
+#pragma unroll
+  for (int c = 0; c < DIAG_PB; ++c) vec[c * sv] = v[c];
+}
+
+// Register-tile helpers of the diagonal-block kernel; thread (ty, tx) owns rows ty + 16 a, columns tx + 16 b in r[a][b].
+// P is the panel index as a template parameter so that every register index is a compile-time constant while the panel
+// loop itself stays rolled (the long straight-line warp routines above then exist once in the instruction stream).
+template <int P>
+__device__ __forceinline__ void diag_store_block_column(double (&r)[8][8], double* S, int ty, int tx) {
+#pragma unroll
+  for (int a = 2 * P; a < 8; ++a)
+#pragma unroll
+    for (int b = 2 * P; b < 2 * P + 2; ++b) {
+      const int i = ty + 16 * a, k = tx + 16 * b;
+      if (k <= i) S[i * DIAG_PITCH + k] = r[a][b];
+    }
+}
+
+// rank-32 update of the trailing matrix from the finished panel P (tiles on or below the diagonal; diagonal tiles stay
+// symmetric)
+template <int P>
+__device__ __forceinline__ void diag_syrk_update(double (&r)[8][8], const double* S, int ty, int tx) {
+  constexpr int j0 = DIAG_PB * P;
+#pragma unroll 4
+  for (int c = 0; c < DIAG_PB; ++c) {
+    double li[8], lk[8];
+#pragma unroll
+    for (int a = 2 * P + 2; a < 8; ++a) li[a] = S[(ty + 16 * a) * DIAG_PITCH + j0 + c];
+#pragma unroll
+    for (int b = 2 * P + 2; b < 8; ++b) lk[b] = S[(tx + 16 * b) * DIAG_PITCH + j0 + c];
+#pragma unroll
+    for (int a = 2 * P + 2; a < 8; ++a)
+#pragma unroll
+      for (int b = 2 * P + 2; b < 8; ++b)
+        if (b <= a) r[a][b] = fma(-li[a], lk[b], r[a][b]);
+  }
+}
+
+// rows of block P of the running right-hand side R (columns < j0), transposed into the strict upper triangle:
+// S[c][j0 + k] = R[j0 + k][c]
+template <int P>
+__device__ __forceinline__ void diag_store_rhs_rows(double (&r)[8][8], double* S, int ty, int tx) {
+#pragma unroll
+  for (int a = 2 * P; a < 2 * P + 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2 * P; ++b) S[(tx + 16 * b) * DIAG_PITCH + ty + 16 * a] = r[a][b];
+}
+
+// R[i][c] -= sum_k L[i][j0+k] X[j0+k][c]   for rows below block P, columns up to the end of block P
+template <int P>
+__device__ __forceinline__ void diag_rhs_update(double (&r)[8][8], const double* S, const double* XDp, int ty, int tx) {
+  constexpr int j0 = DIAG_PB * P;
+#pragma unroll 4
+  for (int k = 0; k < DIAG_PB; ++k) {
+    double li[8], xr[8];
+#pragma unroll
+    for (int a = 2 * P + 2; a < 8; ++a) li[a] = S[(ty + 16 * a) * DIAG_PITCH + j0 + k];
+#pragma unroll
+    for (int b = 0; b < 2 * P + 2; ++b)
+      xr[b] = (b < 2 * P) ? S[(tx + 16 * b) * DIAG_PITCH + j0 + k] : XDp[k * DIAG_XD_PITCH + tx + 16 * (b - 2 * P)];
+#pragma unroll
+    for (int a = 2 * P + 2; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 2 * P + 2; ++b) r[a][b] = fma(-li[a], xr[b], r[a][b]);
+  }
+}
+
+// One CTA factors the 128x128 diagonal block kb of A (lower Cholesky, in place) and inverts the factor
+// (X = L^-1, U = X^T).  Blocked inside the CTA with 32-wide panels so that the serial part is four warp-level
+// 32x32 factorizations instead of 128 block-wide barrier rounds:
+//   phase 1, per panel: the trailing matrix lives in registers; owners drop the block column into shared memory, warp 0
+//     factors the diagonal 32x32 block (chol32_warp), one thread per row below solves its row against it (fwdsub32),
+//     then every thread applies the rank-32 update to its registers from the finished panel.
+//   phase 2: the columns of the four diagonal 32x32 inverses (fwdsub32 on unit vectors), then block forward
+//     substitution L X = I with the running right-hand side in registers: per block row a fwdsub32 per column and a
+//     rank-32 update; finished rows of X are kept TRANSPOSED in the strict upper triangle of the shared array
+//     (diagonal blocks in XD).
+// The eight stages run through ONE loop body so that chol32_warp and fwdsub32 exist once in the instruction stream.
+// Only the first n_valid = clamp(n - 128 kb, 0, 128) rows are real data; the rest is identity padding for which every
+// step is a no-op, so panels at or beyond n_valid are skipped.
 __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, double* X, double* U, int n_pad, int kb,
                                                                      int n_valid, int* info) {
   extern __shared__ double sm[];
-  double* S = sm;                          // [128][129]  L (phase 2 reads its columns)
-  double* vec = sm + TILE * DIAG_PITCH;    // [128] finished column (phase 1) / finished row (phase 2)
-  double* rdiag = vec + TILE;              // [128] 1 / L_jj
-  double* piv = rdiag + TILE;              // [1]   current pivot candidate
-  const int z = blockIdx.x, tid = threadIdx.x;
+  double* S = sm;                                        // [128][129]  lower: L;  strict upper: X^T (off-diagonal blocks)
+  double* XD = sm + TILE * DIAG_PITCH;                   // [4][32][33] inverses of the diagonal 32x32 blocks
+  double* rd = XD + DIAG_NP * DIAG_PB * DIAG_XD_PITCH;   // [128]       1 / L_jj
+  double* colbuf = rd + TILE;                            // [2][32]     chol32_warp's column broadcast (16-byte aligned)
+  const int z = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ty = tid >> 4, tx = tid & 15;
   const long long base = ((long long)z * n_pad + (long long)kb * TILE) * n_pad + (long long)kb * TILE;
   double r[8][8];
@@ -234,121 +370,86 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
     for (int b = 0; b < 8; ++b) {
       const int i = ty + 16 * a, k = tx + 16 * b;
       r[a][b] = A[base + (long long)(k <= i ? i : k) * n_pad + (k <= i ? k : i)];  // symmetric fill from the lower part
+      if (k > i) S[i * DIAG_PITCH + k] = 0.0;
     }
-  // ---- phase 1: right-looking Cholesky ----
-  // column j = jo + 16 jb: the outer loop over jb is unrolled so the owners' register index is a compile-time constant.
-  // The (already updated) diagonal entry of the NEXT column is dropped into shared memory by its owner at the end of
-  // each step, so a step is: barrier, 16 owner threads form 1/sqrt(d) and publish the scaled column, barrier, rank-1 update.
-  if (tid == 0) piv[0] = r[0][0];
-#pragma unroll
-  for (int jb = 0; jb < 8; ++jb) {
+  if (tid < TILE) rd[tid] = 1.0;
+
+  // stages 0..3: Cholesky panel p = s;  stage 4: L out + diagonal-block inverses;  stages 5..7: block row p = s - 4 of X
 #pragma unroll 1
-    for (int jo = 0; jo < 16; ++jo) {
-      const int j = jo + 16 * jb;
-      if (j >= n_valid) {  // identity padding from here on: L_jj = 1, nothing to eliminate (uniform branch)
-        if (tid == 0) rdiag[j] = 1.0;
-        continue;
+  for (int s = 0; s < 8; ++s) {
+    const int p = s < 4 ? s : s - 4, j0 = DIAG_PB * p;
+    const bool live = j0 < n_valid;                      // uniform; identity padding from j0 on otherwise
+    double* vec = S;
+    int sv = 1;
+    const double* Lb = S + j0 * DIAG_PITCH + j0;
+    const double* rdp = rd + j0;
+    bool solve = false;
+    if (s < 4) {
+      if (p == 0) diag_store_block_column<0>(r, S, ty, tx);
+      else if (p == 1) diag_store_block_column<1>(r, S, ty, tx);
+      else if (p == 2) diag_store_block_column<2>(r, S, ty, tx);
+      else diag_store_block_column<3>(r, S, ty, tx);
+      __syncthreads();
+      if (live && warp == 0) chol32_warp(S, rd, colbuf, j0, lane, info + z, kb * TILE);
+      __syncthreads();
+      const int i = j0 + DIAG_PB + tid;                  // rows below the diagonal block: l L11^T = a
+      solve = live && p < DIAG_NP - 1 && i < n_valid;    // (rows of the identity padding hold zeros already)
+      vec = S + i * DIAG_PITCH + j0;
+    } else if (s == 4) {
+      for (int e = tid; e < TILE * TILE; e += DIAG_THREADS) {  // L to global memory (coalesced rows)
+        const int i = e >> 7, k = e & (TILE - 1);
+        A[base + (long long)i * n_pad + k] = (k <= i) ? S[i * DIAG_PITCH + k] : 0.0;
+      }
+      if (tid < TILE) {                                  // thread = (diagonal block w, column c): L_ww x = e_c
+        const int w = tid >> 5;
+        vec = XD + w * DIAG_PB * DIAG_XD_PITCH + lane;
+        sv = DIAG_XD_PITCH;
+#pragma unroll 4
+        for (int i = 0; i < DIAG_PB; ++i) vec[i * sv] = (i == lane) ? 1.0 : 0.0;
+        Lb = S + (DIAG_PB * w) * DIAG_PITCH + DIAG_PB * w;
+        rdp = rd + DIAG_PB * w;
+        solve = DIAG_PB * w < n_valid;
+      }
+    } else {
+      if (live) {  // rows of block p of the running right-hand side, transposed into the strict upper triangle
+        if (p == 1) diag_store_rhs_rows<1>(r, S, ty, tx);
+        else if (p == 2) diag_store_rhs_rows<2>(r, S, ty, tx);
+        else diag_store_rhs_rows<3>(r, S, ty, tx);
       }
       __syncthreads();
-      if (tx == jo) {  // owners of column j: scale by the reciprocal pivot (as LAPACK dpotf2 does) and publish
-        double dd = piv[0];
-        if (!(dd > 0.0)) {
-          if (ty == jo && info[z] == 0) info[z] = kb * TILE + j + 1;
-          dd = 1.0;
-        }
-        const double rp = rsqrt(dd), p = dd * rp;
-        if (ty == jo) rdiag[j] = rp;
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-          const int i = ty + 16 * a;
-          if (i > j) r[a][jb] *= rp;
-          else if (i == j) r[a][jb] = p;
-          if (i >= j) vec[i] = r[a][jb];
-        }
+      solve = live && tid < j0;                          // thread = column c < j0: X[block p][c] = L_pp^-1 R[block p][c]
+      vec = S + tid * DIAG_PITCH + j0;
+    }
+    if (solve) fwdsub32(vec, sv, Lb, rdp);
+    __syncthreads();
+    if (s < 3) {
+      if (live) {
+        if (p == 0) diag_syrk_update<0>(r, S, ty, tx);
+        else if (p == 1) diag_syrk_update<1>(r, S, ty, tx);
+        else diag_syrk_update<2>(r, S, ty, tx);
       }
-      __syncthreads();
-      // register rows / columns of groups a, b < jb hold indices < 16 jb <= j: finished, skipped at compile time
-      double li[8], lk[8];
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-        if (a >= jb) li[a] = (ty + 16 * a > j) ? vec[ty + 16 * a] : 0.0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b)
-        if (b >= jb) lk[b] = (tx + 16 * b > j) ? vec[tx + 16 * b] : 0.0;
+    } else if (s == 4) {
 #pragma unroll
       for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b)
-          if (a >= jb && b >= jb) r[a][b] = fma(-li[a], lk[b], r[a][b]);
-      // hand the next pivot over (piv is read only after the barrier at the top of the next step; vec is rewritten
-      // only after that barrier too)
-      const int jn = j + 1, jno = jn & 15, jnb = jn >> 4;
-      if (jn < TILE && ty == jno && tx == jno) {
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-          if (a == jnb) piv[0] = r[a][a];
-      }
+        for (int b = 0; b < 8; ++b) r[a][b] = (ty + 16 * a == tx + 16 * b) ? 1.0 : 0.0;  // running right-hand side R = I
+      if (n_valid > 0) diag_rhs_update<0>(r, S, XD, ty, tx);
+    } else if (s > 4 && live) {
+      const double* XDp = XD + p * DIAG_PB * DIAG_XD_PITCH;
+      if (p == 1) diag_rhs_update<1>(r, S, XDp, ty, tx);
+      else if (p == 2) diag_rhs_update<2>(r, S, XDp, ty, tx);
     }
   }
-  // publish L (lower part) to shared memory and global memory; start phase 2 with R = I
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const int i = ty + 16 * a, k = tx + 16 * b;
-      const double l = (k <= i) ? r[a][b] : 0.0;
-      S[i * DIAG_PITCH + k] = l;
-      A[base + (long long)i * n_pad + k] = l;
-      r[a][b] = (i == k) ? 1.0 : 0.0;
-    }
   __syncthreads();
-  // ---- phase 2: L X = I by right-looking forward substitution; row k = ko + 16 kq of X becomes final at step k ----
-#pragma unroll
-  for (int kq = 0; kq < 8; ++kq) {
-#pragma unroll 1
-    for (int ko = 0; ko < 16; ++ko) {
-      const int k = ko + 16 * kq;
-      if (k >= n_valid) continue;  // identity rows: R already holds the answer
-      if (ty == ko) {  // owners of row k: scale by 1/L_kk (kept from phase 1) and publish
-        const double inv = rdiag[k];
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-          if (b <= kq) {
-            r[kq][b] *= inv;
-            vec[tx + 16 * b] = r[kq][b];
-          }
-      }
-      __syncthreads();
-      // only rows i > k (groups a >= kq) change, and only in columns c <= k (groups b <= kq): the rest is skipped
-      // at compile time
-      double li[8], xr[8];
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-        if (a >= kq) li[a] = (ty + 16 * a > k) ? S[(ty + 16 * a) * DIAG_PITCH + k] : 0.0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b)
-        if (b <= kq) xr[b] = vec[tx + 16 * b];
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-          if (a >= kq && b <= kq) r[a][b] = fma(-li[a], xr[b], r[a][b]);
-      __syncthreads();  // vec is rewritten by the next row's owners
-    }
+  // X (lower) and U = X^T (upper), coalesced rows
+  for (int e = tid; e < TILE * TILE; e += DIAG_THREADS) {
+    const int i = e >> 7, c = e & (TILE - 1);
+    const int lo = c < i ? c : i, hi = c < i ? i : c;              // X[hi][lo] is the non-zero of the pair
+    const double x = ((hi >> 5) == (lo >> 5)) ? XD[(hi >> 5) * DIAG_PB * DIAG_XD_PITCH + (hi & 31) * DIAG_XD_PITCH + (lo & 31)]
+                                              : S[lo * DIAG_PITCH + hi];
+    X[base + (long long)i * n_pad + c] = (c <= i) ? x : 0.0;
+    U[base + (long long)i * n_pad + c] = (c >= i) ? x : 0.0;
   }
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const int i = ty + 16 * a, c = tx + 16 * b;
-      const double x = (c <= i) ? r[a][b] : 0.0;
-      X[base + (long long)i * n_pad + c] = x;
-      if (c < i) {
-        X[base + (long long)c * n_pad + i] = 0.0;
-        U[base + (long long)i * n_pad + c] = 0.0;
-      }
-      U[base + (long long)c * n_pad + i] = x;  // U = X^T
-    }
 }
 
 // out[z][r] = sum_{k in [lo(r), hi(r))} M[z][r][k] * v[z][k]; mode 0: k <= r (lower), 1: k >= r (upper), 2: full

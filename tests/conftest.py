@@ -96,3 +96,23 @@ def parity_tolerances(gp, Xs, base=1e-10):
     floor_s = np.max(np.abs(sA - sB)) / np.max(np.abs(sA))
     floor_g = np.max(np.abs(dsA - dsB)) / max(np.max(np.abs(dsA)), 1e-300)
     return max(base, 10 * floor_s), max(base, 10 * floor_g)
+
+
+def ei_input_error_budget(mo, so, dmo, dso, m, s, dm, ds, fmin, jitter):
+    """First-order change of EI and of its gradient caused by the (separately asserted, <= 1e-10 scaled) deviations of
+    their inputs:  dEI = -Phi(u) dm + phi(u) ds,  d(grad) = phi d(ds) - Phi d(dm) - phi du (u ds + dm),
+    du = -(dm + u ds)/s.  In the far tail (EI ~ 1e-25 at u ~ -10) the RELATIVE condition number of the value is ~u^2,
+    so a single-candidate array cannot meet 1e-10 relative to itself unless m and s agree to 1e-12; comparisons of
+    acquisition values therefore allow 1e-10 * max|ref| plus this budget (4x for the neglected second-order terms).
+    Returns (budget_f, budget_df)."""
+    import scipy.special as sp
+    mo, so, m, s = (np.asarray(a, dtype=float).reshape(-1) for a in (mo, so, m, s))
+    dmo, dso, dm, ds = (np.asarray(a, dtype=float).reshape(mo.size, -1) for a in (dmo, dso, dm, ds))
+    u = (fmin - mo - jitter) / so
+    Phi, phi = 0.5 * sp.erfc(-u / np.sqrt(2.0)), np.exp(-0.5 * u * u) / np.sqrt(2.0 * np.pi)
+    em, es = np.abs(m - mo), np.abs(s - so)
+    du = (em + np.abs(u) * es) / so
+    bf = Phi * em + phi * es
+    bdf = (phi[:, None] * np.abs(ds - dso) + Phi[:, None] * np.abs(dm - dmo)
+           + (phi * du)[:, None] * (np.abs(u)[:, None] * np.abs(dso) + np.abs(dmo)))
+    return 4.0 * float(np.max(bf)), 4.0 * float(np.max(bdf))

@@ -38,6 +38,8 @@ SIGNATURES = {
                                    ctypes.c_void_p, ctypes.c_void_p]),
     'gpo_predict_grad': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'gpo_predict_mean_grad': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
     'gpo_acq': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_longlong, ctypes.c_void_p,
                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'gpo_lp_set': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -206,6 +208,16 @@ class Engine(object):
                    self._empty_like(Xs, (self.S, N, self.d)), self._empty_like(Xs, (self.S, N, self.d)))
         rc = self._lib.gpo_predict_grad(self._h, N, _ptr(Xs), *[_ptr(o) for o in out], stream)
         self._check(rc, 'gpo_predict_grad')
+        return out
+
+    def predict_mean_grad(self, Xs, out=None, stream=None):
+        """-> m [S, N], dmdx [S, N, d]: posterior mean and its gradient only (no variance contraction)."""
+        Xs = self._as_input(Xs)
+        N = self._rows(Xs, self.d)
+        if out is None:
+            out = (self._empty_like(Xs, (self.S, N)), self._empty_like(Xs, (self.S, N, self.d)))
+        rc = self._lib.gpo_predict_mean_grad(self._h, N, _ptr(Xs), _ptr(out[0]), _ptr(out[1]), stream)
+        self._check(rc, 'gpo_predict_mean_grad')
         return out
 
     def acq(self, kind, par, Xs, grad=False, out=None, stream=None):

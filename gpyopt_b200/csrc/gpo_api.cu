@@ -802,7 +802,8 @@ static void launch_design(gpo_engine* eng, DesignParams p, long long row0, long 
 
 // kind == ACQ_NONE: predict  (o0 = m [S][N], o1 = s [S][N], o2 = dmdx [S][N][d], o3 = dsdx [S][N][d])
 // otherwise:        acquisition (o0 = f [N], o1 = df [N][d])
-static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused*/, int with_noise, long long N,
+// mean_only (predict mode): K1 + K3 only -- posterior mean and its gradient, no variance GEMM (o1, o3 unused)
+static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_only, int with_noise, long long N,
                  const double* Xs, double* o0, double* o1, double* o2, double* o3, cudaStream_t user) {
   if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "sweep before gpo_fit");
   if (N <= 0) return GPO_OK;
@@ -876,7 +877,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     int part_nv = 1, part_rows = tiles_m;
     long long part_ld = eng->nc_ld;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
-    if (eng->profiling) {
+    if (eng->profiling && !mean_only) {
       if (eng->prof_used == eng->prof_events.size()) {
         cudaEvent_t a, b;
         GPO_CUDA_OK(cudaEventCreate(&a));
@@ -889,7 +890,9 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
       eng->prof_gemm_cands += rows;
       GPO_CUDA_OK(cudaEventRecord(pe0, st));
     }
-    if (w_form) {
+    if (mean_only) {
+      part_rows = 0;  // K3 then reads no variance partials
+    } else if (w_form) {
       g.krange = KR_FULL; g.raster = RO_M_FASTEST;
       g.d = grad ? d : 0; g.Xtc = eng->Xtc; g.ldx = n_pad; g.Kt = s.Kt; g.Ht = (grad && eng->kern != KERN_RBF) ? s.Ht : nullptr;
       g.nc_ld = eng->nc_ld; g.n_pad = n_pad;
@@ -916,11 +919,11 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool /*unused
     ap.n_cand = rows; ap.nc_pad = eng->nc_ld; ap.S = S; ap.d = d; ap.tiles_m = part_rows; ap.grad = grad ? 1 : 0;
     ap.part_nv = part_nv; ap.part_ld = part_ld; ap.sq_tiles_m = tiles_m;
     ap.js = eng->js; ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = s.partial; ap.sigf2 = eng->sigf2;
-    ap.partial_sq = (grad && eng->strict_active) ? s.partial_sq : nullptr;
+    ap.partial_sq = (grad && eng->strict_active && !mean_only) ? s.partial_sq : nullptr;
     ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par; ap.invl = eng->invl; ap.xmu = eng->xmu;
     ap.Xs = dev_in + off * d;
     if (predict) {
-      ap.out_m = dev_out[0] + off; ap.out_s = dev_out[1] + off;
+      ap.out_m = dev_out[0] + off; ap.out_s = dev_out[1] ? dev_out[1] + off : nullptr;
       ap.out_dm = dev_out[2] ? dev_out[2] + off * d : nullptr; ap.out_ds = dev_out[3] ? dev_out[3] + off * d : nullptr;
       ap.out_ldN = N;
     } else {
@@ -971,6 +974,11 @@ extern "C" int gpo_predict_grad(gpo_engine* eng, long long N, const double* Xs, 
                                 void* stream) {
   if (!eng || !Xs || !m || !s || !dmdx || !dsdx || N < 0) return GPO_ERR_ARG;
   return sweep(eng, ACQ_NONE, 0.0, true, false, 1, N, Xs, m, s, dmdx, dsdx, (cudaStream_t)stream);
+}
+
+extern "C" int gpo_predict_mean_grad(gpo_engine* eng, long long N, const double* Xs, double* m, double* dmdx, void* stream) {
+  if (!eng || !Xs || !m || !dmdx || N < 0) return GPO_ERR_ARG;
+  return sweep(eng, ACQ_NONE, 0.0, true, true, 0, N, Xs, m, nullptr, dmdx, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int gpo_acq(gpo_engine* eng, int kind, double par, long long N, const double* Xs, double* f, double* df, void* stream) {

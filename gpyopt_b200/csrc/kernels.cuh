@@ -737,13 +737,13 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
     }
     if (p.kind == ACQ_NONE) {
       p.out_m[(long long)z * p.out_ldN + i] = m;
-      p.out_s[(long long)z * p.out_ldN + i] = s;
+      if (p.out_s) p.out_s[(long long)z * p.out_ldN + i] = s;  // null: mean-only call (no variance partials exist)
       if (p.grad) {
 #pragma unroll
         for (int q = 0; q < DMAX; ++q)
           if (q < d) {
             p.out_dm[((long long)z * p.out_ldN + i) * d + q] = dm[q];
-            p.out_ds[((long long)z * p.out_ldN + i) * d + q] = ds[q];
+            if (p.out_ds) p.out_ds[((long long)z * p.out_ldN + i) * d + q] = ds[q];
           }
       }
       continue;

@@ -376,6 +376,13 @@ class GPRegressionB200(object):
         return dm[0][:, :, None], ds[0] * (2.0 * s[0][:, None])
 
 
+    def mean_gradients(self, Xnew):
+        """d mean / dx [N, d] alone (the first output of predictive_gradients) without the variance contraction."""
+        Xnew = np.atleast_2d(np.asarray(Xnew, dtype=np.float64))
+        self._ensure_own_state()
+        return self.engine.predict_mean_grad(Xnew)[1][0]
+
+
 class HMC(object):
     """Hybrid Monte Carlo over the (transformed) hyper-parameters: GPy.inference.mcmc.HMC as used by
     GPModel_MCMC.updateModel (gpmodel.py:253-255).  Every leapfrog gradient is one device refit."""

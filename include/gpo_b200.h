@@ -88,6 +88,11 @@ int gpo_predict(gpo_engine* eng, long long N, const double* Xs, int with_noise, 
 int gpo_predict_grad(gpo_engine* eng, long long N, const double* Xs, double* m, double* s, double* dmdx,
                      double* dsdx, void* stream);
 
+/* Posterior mean and its input gradient only (no variance: the dense contraction is skipped).  Serves the callers
+ * that reach through to GPy's GP.predictive_gradients for the mean Jacobian alone -- estimate_L's Lipschitz sweep and
+ * its L-BFGS (GPyOpt/core/evaluators/batch_local_penalization.py:52-72).  m [S, N], dmdx [S, N, d] (host|device). */
+int gpo_predict_mean_grad(gpo_engine* eng, long long N, const double* Xs, double* m, double* dmdx, void* stream);
+
 /* Acquisition*._compute_acq / _compute_acq_withGradients: f [N], df [N, d] (df may be NULL: value only).
  * For S > 1 the *_MCMC kinds average over the hyper-parameter sets.  If a Local-Penalization state is set
  * (gpo_lp_set) the output is AcquisitionLP.acquisition_function / d_acquisition_function instead

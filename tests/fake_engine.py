@@ -64,6 +64,10 @@ class FakeEngine(object):
         return (np.array([r[0][:, 0] for r in res]), np.array([r[1][:, 0] for r in res]),
                 np.array([r[2] for r in res]), np.array([r[3] for r in res]))
 
+    def predict_mean_grad(self, Xs, out=None, stream=None):
+        m, _, dm, _ = self.predict_grad(Xs)
+        return m, dm
+
     def posterior_cov(self, X1, X2=None, with_noise=False):
         g = self.gps[0]
         X1 = np.atleast_2d(np.asarray(X1, dtype=float))

@@ -55,6 +55,11 @@ def _run(GPyOpt, model, acquisition_factory, evaluator_type='sequential', batch_
     X0 = GPyOpt.experiment_design.initial_design('random', space, 5)
     if evaluator_type == 'sequential':
         ev = GPyOpt.core.evaluators.Sequential(acq)
+    elif evaluator_type == 'lp_fast':
+        import importlib
+        import gpyopt_b200.evaluators as evs
+        importlib.reload(evs)
+        ev = evs.LocalPenalization(acq, batch_size)
     else:
         ev = GPyOpt.core.evaluators.LocalPenalization(acq, batch_size)
     bo = GPyOpt.methods.ModularBayesianOptimization(model, space, objective, acq, ev, X0)
@@ -108,6 +113,39 @@ def test_local_penalization_batch_matches(gpyopt):
                  evaluator_type='lp', batch_size=3, iters=2, seed=11)
     assert Xr.shape == Xn.shape
     assert np.max(np.abs(Xr - Xn)) < 1e-5, np.max(np.abs(Xr - Xn))
+
+
+def test_fast_lp_evaluator_gives_the_reference_batches(gpyopt):
+    """gpyopt_b200.evaluators.LocalPenalization (Lipschitz estimate on the mean-only path) == the reference evaluator
+    run on the same model: same estimate_L, same batches, same BO trajectory."""
+    GPyOpt, models, acqs = gpyopt
+    from gpyopt_b200 import kern
+    import importlib
+    import gpyopt_b200.evaluators as evs
+    importlib.reload(evs)
+    from GPyOpt.core.evaluators.batch_local_penalization import estimate_L as ref_estimate_L
+    from oracle import gpyopt_numpy as og
+
+    def new_factory(m, s, o):
+        return acqs.AcquisitionLP(m, s, o, acqs.AcquisitionEI(m, s, o))
+
+    mk = lambda: models.GPModel(kernel=kern.Matern52(2), optimize_restarts=1, verbose=False)
+    Xa, _ = _run(GPyOpt, mk(), new_factory, evaluator_type='lp', batch_size=3, iters=2, seed=11)
+    Xb, _ = _run(GPyOpt, mk(), new_factory, evaluator_type='lp_fast', batch_size=3, iters=2, seed=11)
+    assert np.array_equal(Xa, Xb)
+    # the constant itself, on a fixed model
+    rng = np.random.default_rng(3)
+    X = np.column_stack([rng.uniform(-5, 10, 14), rng.uniform(1, 15, 14)])
+    m = models.GPModel(kernel=kern.RBF(2, lengthscale=3.0), exact_feval=True, max_iters=0, verbose=False)
+    m.updateModel(X, og.normalize_stats(branin(X)), None, None)
+    bounds = GPyOpt.Design_space(DOMAIN).get_bounds()
+    np.random.seed(5)
+    L_ref = ref_estimate_L(m.model, bounds)
+    np.random.seed(5)
+    L_new = evs.estimate_L(m.model, bounds)
+    assert L_new == L_ref and L_new > 0
+    g = m.model.mean_gradients(X[:3])
+    assert g.shape == (3, 2) and np.array_equal(g, m.model.predictive_gradients(X[:3])[0][:, :, 0])
 
 
 def test_mcmc_model_plugin_shapes(gpyopt):

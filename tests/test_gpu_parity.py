@@ -304,6 +304,31 @@ def test_topk_semantics(engine):
     assert np.array_equal(idx, [1, 0])
 
 
+def test_mean_only_path_equals_the_full_prediction(engine):
+    """gpo_predict_mean_grad (no variance contraction) returns bitwise the m and dmdx of gpo_predict_grad: several
+    hyper-parameter sets, ragged chunks, host and device pointers, all kernels."""
+    import torch
+    rng = np.random.default_rng(12)
+    n, d, S, N = 300, 5, 3, 1000
+    X = rng.random((n, d)); Y = np.sin(4 * X).sum(1)
+    Xs = rng.random((N, d))
+    engine.set_chunk(384)
+    try:
+        for kernel in ('rbf', 'matern52', 'matern32'):
+            engine.fit(kernel, X, Y, 0.5 + rng.random(S), 0.3 + rng.random((S, d)), 1e-2 * (1 + rng.random(S)))
+            m, s, dm, ds = engine.predict_grad(Xs)
+            m2, dm2 = engine.predict_mean_grad(Xs)
+            assert np.array_equal(m, m2) and np.array_equal(dm, dm2)
+            xd = torch.from_numpy(Xs).cuda()
+            m3, dm3 = engine.predict_mean_grad(xd)
+            torch.cuda.synchronize()
+            assert np.array_equal(m3.cpu().numpy(), m) and np.array_equal(dm3.cpu().numpy(), dm)
+            m1, dm1 = engine.predict_mean_grad(Xs[7:8])                    # a single point (L-BFGS step)
+            assert np.array_equal(m1[:, 0], m[:, 7]) and np.array_equal(dm1[:, 0], dm[:, 7])
+    finally:
+        engine.set_chunk(0)
+
+
 @pytest.mark.parametrize('d,N,row0', [(1, 1000, 0), (2, 4097, 3), (3, 100000, 12345), (6, 300001, 7), (10, 65536, 1), (16, 999, 2 ** 40 + 5)])
 def test_device_design_is_numpy_philox_stream(engine, d, N, row0):
     """gpo_design_uniform == numpy.random.Generator(numpy.random.Philox(key)).uniform(...) bit for bit (row f4)."""

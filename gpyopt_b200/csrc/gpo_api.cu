@@ -65,12 +65,14 @@ struct gpo_engine {
   double* stage_in = nullptr;  size_t stage_in_bytes = 0;
   double* stage_out[4] = {nullptr, nullptr, nullptr, nullptr};  size_t stage_out_bytes[4] = {0, 0, 0, 0};
   // local penalisation
-  int lp_on = 0, lp_K = 0, lp_transform = 0, lp_cap = 0;
+  int lp_on = 0, lp_K = 0, lp_transform = 0, lp_cap = 0, lp_d = 0;
+  std::vector<double> lp_host;  // what lp_xb / lp_r / lp_s currently hold (Xb, r, s back to back): re-applying it is free
   double *lp_xb = nullptr, *lp_r = nullptr, *lp_s = nullptr;
   // top-k scratch
   double* tk_vals[2] = {nullptr, nullptr};  long long* tk_idx[2] = {nullptr, nullptr};  size_t tk_cap = 0;
   // device-side design: when gen_on, the sweep generates its candidates (Philox stream) instead of reading Xs
   bool gen_on = false;  DesignParams gen;  long long gen_row0 = 0;
+  int* smalln_ticket = nullptr;  int smalln_ticket_cap = 0;   // [S] arrival counters of the small-N kernel
   long long* gen_idx = nullptr;  double* gen_x = nullptr;  // [TOPK_SEG/2], [TOPK_SEG/2][DMAX] winners of a generated design
   // per-block best candidates written by K3 (fused selection)
   double* blk_val = nullptr;  long long* blk_idx = nullptr;  size_t blk_cap = 0;  bool want_blk = false;
@@ -253,6 +255,7 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->blk_val) cudaFree(eng->blk_val);
   if (eng->blk_idx) cudaFree(eng->blk_idx);
   if (eng->gen_idx) cudaFree(eng->gen_idx);
+  if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
   if (eng->gen_x) cudaFree(eng->gen_x);
   for (int i = 0; i < 5; ++i) if (eng->cov_buf[i]) cudaFree(eng->cov_buf[i]);
   for (cudaEvent_t e : eng->chol_ev) cudaEventDestroy(e);
@@ -802,6 +805,54 @@ static void launch_design(gpo_engine* eng, DesignParams p, long long row0, long 
 
 // kind == ACQ_NONE: predict  (o0 = m [S][N], o1 = s [S][N], o2 = dmdx [S][N][d], o3 = dsdx [S][N][d])
 // otherwise:        acquisition (o0 = f [N], o1 = df [N][d])
+// small-N latency path (see smalln_wk_kernel): nc in 1..8 candidates, returns the number of partial rows K3 must add
+constexpr int SMALLN_MAX = 8, SMALLN_LDP = 8;
+template <int R>
+static void launch_smalln_r(const SmallNParams& p, int nc, dim3 grid, cudaStream_t st) {
+  if (nc <= 1) smalln_wk_kernel<1, R><<<grid, 256, 0, st>>>(p);
+  else if (nc <= 2) smalln_wk_kernel<2, R><<<grid, 256, 0, st>>>(p);
+  else if (nc <= 4) smalln_wk_kernel<4, R><<<grid, 256, 0, st>>>(p);
+  else smalln_wk_kernel<8, R><<<grid, 256, 0, st>>>(p);
+}
+static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool use_ht, cudaStream_t st,
+                         const double** final_rows) {
+  const int n_pad = eng->n_pad;
+  if (eng->smalln_ticket_cap < eng->S) {
+    GPO_CUDA_OK(cudaDeviceSynchronize());
+    if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
+    eng->smalln_ticket = nullptr; eng->smalln_ticket_cap = 0;
+    GPO_CUDA_OK(cudaMalloc(&eng->smalln_ticket, (size_t)eng->S * sizeof(int)));
+    GPO_CUDA_OK(cudaMemset(eng->smalln_ticket, 0, (size_t)eng->S * sizeof(int)));
+    eng->smalln_ticket_cap = eng->S;
+  }
+  const int R = n_pad >= 2048 ? 4 : 1;   // rows per warp: enough CTAs to pull W^-1 through every SM at any n
+  SmallNParams p;
+  p.W = eng->W; p.w_z = (long long)n_pad * n_pad;
+  p.Kt = s.Kt; p.Ht = use_ht ? s.Ht : nullptr; p.kt_z = eng->nc_ld * (long long)n_pad;
+  p.Xtc = eng->Xtc; p.ldx = n_pad; p.n_pad = n_pad; p.d = d_epi;
+  const int row_blocks = n_pad / (8 * R);
+  p.partial = s.partial; p.part_z = (long long)row_blocks * (d_epi + 2) * SMALLN_LDP; p.ldp = SMALLN_LDP;
+  p.final_rows = s.partial + (long long)eng->S * p.part_z;
+  p.ticket = eng->smalln_ticket;
+  *final_rows = p.final_rows;
+  dim3 grid((unsigned)row_blocks, (unsigned)eng->S, 1);
+  if (R == 4) launch_smalln_r<4>(p, nc, grid, st); else launch_smalln_r<1>(p, nc, grid, st);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  return GPO_OK;
+}
+
+// K1 for nc <= 8 candidates (one thread per training point)
+static int launch_cov_small(gpo_engine* eng, const CovParams& p_in, int nc, cudaStream_t st) {
+  CovParams p = p_in;
+  p.nc_run = nc <= 1 ? 1 : nc <= 2 ? 2 : nc <= 4 ? 4 : 8;   // the candidate slots smalln_wk_kernel<NC> will read
+  dim3 grid((unsigned)p.js, (unsigned)eng->S, 1);
+  cov_small_kernel<<<grid, 256, 0, st>>>(p);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  return GPO_OK;
+}
+
 // mean_only (predict mode): K1 + K3 only -- posterior mean and its gradient, no variance GEMM (o1, o3 unused)
 static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_only, int with_noise, long long N,
                  const double* Xs, double* o0, double* o1, double* o2, double* o3, cudaStream_t user) {
@@ -855,7 +906,13 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     cp.n = eng->n; cp.n_pad = n_pad; cp.d = d; cp.kern = eng->kern; cp.alpha = eng->alpha; cp.invl = eng->invl;
     cp.sigf2 = eng->sigf2; cp.Kt = s.Kt; cp.Ht = (grad && eng->kern != KERN_RBF) ? s.Ht : nullptr; cp.mean = s.mean;
     cp.dmean = s.dmean; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
-    if ((rc = launch_cov(eng, cp, grad, S, st))) return rc;
+    // a handful of points (L-BFGS steps) on a well-conditioned model: the latency kernels below
+    const bool tiny = N <= SMALLN_MAX && (mean_only || !eng->strict_active);
+    if (tiny) {
+      if (!grad) cp.dmean = nullptr;
+      if (mean_only) { cp.Kt = nullptr; cp.Ht = nullptr; }
+      if ((rc = launch_cov_small(eng, cp, (int)N, st))) return rc;
+    } else if ((rc = launch_cov(eng, cp, grad, S, st))) return rc;
     // variance GEMM
     GemmParams g = gemm_defaults();
     g.tiles_m = tiles_m; g.tiles_n = tiles_n; g.kblocks = tiles_m;
@@ -876,6 +933,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     }
     int part_nv = 1, part_rows = tiles_m;
     long long part_ld = eng->nc_ld;
+    const double* small_final = nullptr;  // the small-N kernel's reduced partial rows
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (eng->profiling && !mean_only) {
       if (eng->prof_used == eng->prof_events.size()) {
@@ -892,6 +950,18 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     }
     if (mean_only) {
       part_rows = 0;  // K3 then reads no variance partials
+    } else if (w_form && N <= SMALLN_MAX) {
+      // a handful of points (L-BFGS steps): batched matrix-vector product over W^-1 instead of 128-wide tensor-core tiles
+      if ((rc = launch_smalln(eng, s, (int)N, grad ? d : 0, grad && eng->kern != KERN_RBF, st, &small_final))) return rc;
+      part_rows = 1; part_nv = (grad ? d : 0) + 2; part_ld = SMALLN_LDP;
+      if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
+      if (grad && eng->strict_active) {  // ill-conditioned model: variance from the reference's own triangular form as well
+        GemmParams gs = gemm_defaults();
+        gs.tiles_m = tiles_m; gs.tiles_n = tiles_n; gs.kblocks = tiles_m;
+        gs.a = {0, 0, 0, 0, 0, 1}; gs.b = {0, 0, 0, 0, 0, 1};
+        gs.partial = s.partial_sq; gs.ldp = eng->nc_ld; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
+        if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, gs, S, st))) return rc;
+      }
     } else if (w_form) {
       g.krange = KR_FULL; g.raster = RO_M_FASTEST;
       g.d = grad ? d : 0; g.Xtc = eng->Xtc; g.ldx = n_pad; g.Kt = s.Kt; g.Ht = (grad && eng->kern != KERN_RBF) ? s.Ht : nullptr;
@@ -918,7 +988,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     memset(&ap, 0, sizeof(ap));
     ap.n_cand = rows; ap.nc_pad = eng->nc_ld; ap.S = S; ap.d = d; ap.tiles_m = part_rows; ap.grad = grad ? 1 : 0;
     ap.part_nv = part_nv; ap.part_ld = part_ld; ap.sq_tiles_m = tiles_m;
-    ap.js = eng->js; ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = s.partial; ap.sigf2 = eng->sigf2;
+    ap.js = eng->js; ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = small_final ? small_final : s.partial; ap.sigf2 = eng->sigf2;
     ap.partial_sq = (grad && eng->strict_active && !mean_only) ? s.partial_sq : nullptr;
     ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par; ap.invl = eng->invl; ap.xmu = eng->xmu;
     ap.Xs = dev_in + off * d;
@@ -988,24 +1058,38 @@ extern "C" int gpo_acq(gpo_engine* eng, int kind, double par, long long N, const
 
 extern "C" int gpo_lp_set(gpo_engine* eng, int K, const double* Xb, const double* r, const double* s, int transform) {
   if (!eng || K < 0) return GPO_ERR_ARG;
-  if (transform < 0) { eng->lp_on = 0; eng->lp_K = 0; return GPO_OK; }
+  if (transform < 0) { eng->lp_on = 0; return GPO_OK; }  // the uploaded penalisers stay resident
   if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_lp_set before gpo_fit");
-  GPO_CUDA_OK(cudaSetDevice(eng->device));
-  GPO_CUDA_OK(cudaDeviceSynchronize());
-  if (K > eng->lp_cap) {
-    if (eng->lp_xb) cudaFree(eng->lp_xb);
-    if (eng->lp_r) cudaFree(eng->lp_r);
-    if (eng->lp_s) cudaFree(eng->lp_s);
-    eng->lp_cap = std::max(K, 64);
-    GPO_CUDA_OK(cudaMalloc(&eng->lp_xb, (size_t)eng->lp_cap * DMAX * 8));
-    GPO_CUDA_OK(cudaMalloc(&eng->lp_r, (size_t)eng->lp_cap * 8));
-    GPO_CUDA_OK(cudaMalloc(&eng->lp_s, (size_t)eng->lp_cap * 8));
-  }
   if (K > 0) {
     if (!Xb || !r || !s) return GPO_ERR_ARG;
-    GPO_CUDA_OK(cudaMemcpy(eng->lp_xb, Xb, (size_t)K * eng->d * 8, cudaMemcpyHostToDevice));
-    GPO_CUDA_OK(cudaMemcpy(eng->lp_r, r, (size_t)K * 8, cudaMemcpyHostToDevice));
-    GPO_CUDA_OK(cudaMemcpy(eng->lp_s, s, (size_t)K * 8, cudaMemcpyHostToDevice));
+    // AcquisitionLP sets and clears the state around every evaluation (other acquisitions share the engine): the
+    // same penalisers come back thousands of times per batch element, so only a CHANGED set is uploaded
+    const size_t nx = (size_t)K * eng->d;
+    const bool same = eng->lp_d == eng->d && eng->lp_host.size() == nx + 2 * (size_t)K &&
+                      memcmp(eng->lp_host.data(), Xb, nx * 8) == 0 && memcmp(eng->lp_host.data() + nx, r, (size_t)K * 8) == 0 &&
+                      memcmp(eng->lp_host.data() + nx + K, s, (size_t)K * 8) == 0;
+    if (!same) {
+      GPO_CUDA_OK(cudaSetDevice(eng->device));
+      GPO_CUDA_OK(cudaDeviceSynchronize());
+      if (K > eng->lp_cap) {
+        if (eng->lp_xb) cudaFree(eng->lp_xb);
+        if (eng->lp_r) cudaFree(eng->lp_r);
+        if (eng->lp_s) cudaFree(eng->lp_s);
+        eng->lp_xb = eng->lp_r = eng->lp_s = nullptr;
+        eng->lp_cap = std::max(K, 64);
+        GPO_CUDA_OK(cudaMalloc(&eng->lp_xb, (size_t)eng->lp_cap * DMAX * 8));
+        GPO_CUDA_OK(cudaMalloc(&eng->lp_r, (size_t)eng->lp_cap * 8));
+        GPO_CUDA_OK(cudaMalloc(&eng->lp_s, (size_t)eng->lp_cap * 8));
+      }
+      eng->lp_host.clear();
+      GPO_CUDA_OK(cudaMemcpy(eng->lp_xb, Xb, nx * 8, cudaMemcpyHostToDevice));
+      GPO_CUDA_OK(cudaMemcpy(eng->lp_r, r, (size_t)K * 8, cudaMemcpyHostToDevice));
+      GPO_CUDA_OK(cudaMemcpy(eng->lp_s, s, (size_t)K * 8, cudaMemcpyHostToDevice));
+      eng->lp_host.assign(Xb, Xb + nx);
+      eng->lp_host.insert(eng->lp_host.end(), r, r + K);
+      eng->lp_host.insert(eng->lp_host.end(), s, s + K);
+      eng->lp_d = eng->d;
+    }
   }
   eng->lp_on = 1; eng->lp_K = K; eng->lp_transform = transform;
   return GPO_OK;

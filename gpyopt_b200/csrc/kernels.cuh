@@ -962,4 +962,176 @@ __global__ void gather_rows_kernel(const double* __restrict__ X, const long long
   out[t] = i >= 0 ? X[i * d + q] : __longlong_as_double(0x7ff8000000000000LL);
 }
 
+// --------------------------------------------------------------------------------------------------
+// Latency path for a handful of candidates (the L-BFGS steps of the acquisition optimiser: N = 1 ... 8 per call).
+// The tensor-core GEMM works on 128-candidate tiles, so a single point costs 128x its flops (2 n^2 * 128 = 4.3 GFLOP at
+// n = 4096, ~0.3 ms).  Here b = W^-1 k is a batched matrix-vector product streamed once over W^-1 (HBM/L2-bound:
+// 8 n^2 bytes), fused with the same epilogue reductions as EPI_GRAD:
+//   S0_i = sum_j b_ji k_ji,   H0_i = sum_j b_ji h_ji,   P_qi = sum_j b_ji h_ji xc_jq
+// One warp owns R rows j of W^-1 and NC candidates (R x NC accumulators, lanes stride over the columns: coalesced 256-byte
+// row segments, each k value reused for R rows), one CTA = 8 warps = 8 R rows; every CTA leaves one partial row for K3,
+// which adds them in row-block order (deterministic; a candidate's result does not depend on NC or on its neighbours).
+// --------------------------------------------------------------------------------------------------
+struct SmallNParams {
+  const double* W;   long long w_z;      // [S][n_pad][n_pad]
+  const double* Kt;  const double* Ht;   // [S][nc_ld][n_pad] candidate-major rows from K1 (Ht null: RBF, h = -k)
+  long long kt_z;
+  const double* Xtc; int ldx;            // centred training coordinates [d][ldx]
+  int n_pad, d;                          // d = 0: value only (S0 and H0)
+  double* partial;   long long part_z;   // [S][row blocks][d + 2][ldp]
+  int ldp;
+  double* final_rows;                    // [S][d + 2][ldp]: the partial rows added in row-block order by the last CTA
+  int* ticket;                           // [S] arrival counters (zero before the launch; the last CTA resets its own)
+};
+
+template <int NC, int R>
+__global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
+  __shared__ double red[8][DMAX + 2][NC];
+  const int z = blockIdx.y, rb = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = rb * (8 * R) + warp * R, n_pad = p.n_pad, d = p.d;
+  const double* Wr = p.W + (long long)z * p.w_z + (long long)row0 * n_pad;
+  const double* Kt = p.Kt + (long long)z * p.kt_z;
+  double acc[R][NC];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[r][i] = 0.0;
+#pragma unroll 2
+  for (int c = lane; c < n_pad; c += 32) {
+    double kv[NC], w[R];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) kv[i] = __ldg(Kt + (long long)i * n_pad + c);
+#pragma unroll
+    for (int r = 0; r < R; ++r) w[r] = __ldg(Wr + (long long)r * n_pad + c);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < NC; ++i) acc[r][i] = fma(w[r], kv[i], acc[r][i]);
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[r][i] += __shfl_xor_sync(0xffffffffu, acc[r][i], o);
+  // lane i < NC finishes candidate i over this warp's R rows
+  double s0 = 0.0, h0 = 0.0, pq[DMAX];
+#pragma unroll
+  for (int q = 0; q < DMAX; ++q) pq[q] = 0.0;
+  if (lane < NC) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double b = 0.0;
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (lane == i) b = acc[r][i];
+      const int j = row0 + r;
+      const double kj = __ldg(Kt + (long long)lane * n_pad + j);
+      const double bh = p.Ht ? b * __ldg(p.Ht + (long long)z * p.kt_z + (long long)lane * n_pad + j) : -(b * kj);
+      s0 = fma(b, kj, s0);
+      h0 += bh;
+#pragma unroll
+      for (int q = 0; q < DMAX; ++q)
+        if (q < d) pq[q] = fma(bh, __ldg(p.Xtc + (long long)q * p.ldx + j), pq[q]);
+    }
+    red[warp][0][lane] = s0;
+    red[warp][1][lane] = h0;
+#pragma unroll
+    for (int q = 0; q < DMAX; ++q)
+      if (q < d) red[warp][2 + q][lane] = pq[q];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < (d + 2) * NC; idx += 256) {
+    const int v = idx / NC, i = idx - v * NC;
+    double t = 0.0;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += red[w8][v][i];
+    p.partial[(long long)z * p.part_z + ((long long)rb * (d + 2) + v) * p.ldp + i] = t;
+  }
+  // the last CTA of this hyper-parameter set to arrive adds the partial rows (fixed order, so the sum is deterministic)
+  // and leaves ONE row for K3: a single K3 thread would otherwise walk row_blocks x (d+2) dependent loads per candidate
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(p.ticket + z, 1);
+    is_last = (t == (int)gridDim.x - 1);
+    if (is_last) p.ticket[z] = 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int idx = threadIdx.x; idx < (d + 2) * NC; idx += 256) {
+    const int v = idx / NC, i = idx - v * NC;
+    const double* src = p.partial + (long long)z * p.part_z + (long long)v * p.ldp + i;
+    double t = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(src + (long long)b * (d + 2) * p.ldp);
+    p.final_rows[((long long)z * (d + 2) + v) * p.ldp + i] = t;
+  }
+}
+
+// K1 for the same handful of candidates: one thread per TRAINING point (K1 proper gives each candidate a thread and
+// would run 128-candidate blocks that are all padding but one row).  Block `split` covers K1's slice `split` of the
+// training index and leaves the same per-slice partial sums in mean / dmean, K*^T / H*^T rows in Kt / Ht, for the
+// candidate slots 0 .. nc_run-1 (slots past the last candidate shadow it, as K1's padding does).
+__global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
+  __shared__ double red[8][DMAX + 1];
+  const int z = blockIdx.y, split = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = p.d;
+  const double* invl = p.invl + (long long)z * d;
+  const double sf2 = p.sigf2[z];
+  const double* alpha = p.alpha + (long long)z * p.n_pad;
+  const int j_begin = split * p.tiles_per_split * COV_JT, j_end = min(p.n_pad, j_begin + p.tiles_per_split * COV_JT);
+  const long long zs = (long long)z * p.js + split;
+  for (int i = 0; i < (int)p.nc_run; ++i) {
+    const long long cand = i < p.n_cand ? i : p.n_cand - 1;
+    double xs[DMAX], m = 0.0, dm[DMAX];
+#pragma unroll
+    for (int q = 0; q < DMAX; ++q) {
+      xs[q] = q < d ? p.Xs[cand * d + q] * invl[q] : 0.0;
+      dm[q] = 0.0;
+    }
+    for (int j = j_begin + tid; j < j_end; j += 256) {
+      double r2 = 0.0, df[DMAX];
+#pragma unroll
+      for (int q = 0; q < DMAX; ++q) {
+        df[q] = q < d ? xs[q] - p.Xt[q * p.ldx + j] * invl[q] : 0.0;
+        r2 = fma(df[q], df[q], r2);
+      }
+      double kv, hv;
+      kern_k_h(p.kern, sf2, r2, kv, hv);
+      if (j >= p.n) { kv = 0.0; hv = 0.0; }
+      const double aj = alpha[j];
+      m = fma(kv, aj, m);
+      const double w = aj * hv;
+#pragma unroll
+      for (int q = 0; q < DMAX; ++q) dm[q] = fma(w, df[q], dm[q]);
+      if (p.Kt) p.Kt[((long long)z * p.nc_ld + i) * p.n_pad + j] = kv;
+      if (p.Ht) p.Ht[((long long)z * p.nc_ld + i) * p.n_pad + j] = hv;
+    }
+    // block sums (fixed shuffle tree, then the eight warps in order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    if (lane == 0) red[warp][0] = m;
+    if (p.dmean) {
+#pragma unroll
+      for (int q = 0; q < DMAX; ++q)
+        if (q < d) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) dm[q] += __shfl_xor_sync(0xffffffffu, dm[q], o);
+          if (lane == 0) red[warp][1 + q] = dm[q];
+        }
+    }
+    __syncthreads();
+    if (tid <= (p.dmean ? d : 0)) {
+      double t = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) t += red[w8][tid];
+      if (tid == 0) p.mean[zs * p.nc_ld + i] = t;
+      else p.dmean[(zs * d + (tid - 1)) * p.nc_ld + i] = t * invl[tid - 1];
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace gpo

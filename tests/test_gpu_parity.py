@@ -304,6 +304,63 @@ def test_topk_semantics(engine):
     assert np.array_equal(idx, [1, 0])
 
 
+@pytest.mark.parametrize('kernel,ARD,S', [('rbf', False, 1), ('matern52', True, 1), ('matern32', False, 3), ('rbf', True, 2)])
+def test_small_batch_latency_path(engine, kernel, ARD, S):
+    """N <= 8 (the L-BFGS steps) runs on dedicated latency kernels (thread-per-training-point K1, matrix-vector product
+    over W^-1 with a last-CTA reduction): oracle parity for every N in 1..9, rows independent of the batch they are in
+    (bitwise), agreement with the tensor-core path, strict-variance mode, Local Penalization and the MCMC average."""
+    from oracle import gpy_numpy as G, gpyopt_numpy as og
+    rng = np.random.default_rng(31 + S)
+    n, d = 333, 5
+    X = rng.random((n, d)); Y = og.normalize_stats(np.sin(3 * X).sum(1, keepdims=True))
+    var = 0.6 + rng.random(S); ls = 0.4 + rng.random((S, d if ARD else 1)); nz = 1e-2 * (1 + rng.random(S))
+    K = {'rbf': G.RBF, 'matern52': G.Matern52, 'matern32': G.Matern32}[kernel]
+    gps = [G.GPRegression(X, Y, K(d, variance=var[z], lengthscale=ls[z], ARD=ARD), noise_var=nz[z]) for z in range(S)]
+    engine.fit(kernel, X, Y[:, 0], var, np.broadcast_to(ls, (S, d)), nz)
+    X9 = X[np.argsort(Y[:, 0])[:9]] + 0.02 * rng.standard_normal((9, d))   # near the best observations: EI is not in its
+    kind = 'EI' if S == 1 else 'EI_MCMC'                                    # far tail, where its relative condition number explodes
+    ref = [og.gp_predict_withGradients(g, X9) for g in gps]
+    fmins = [og.gp_get_fmin(g) for g in gps]
+    if S == 1:
+        fo, dfo = og.acq_EI_withGradients(ref[0][0].copy(), ref[0][1].copy(), ref[0][2], ref[0][3], fmins[0], 0.01)
+    else:
+        fo, dfo = og.acq_EI_MCMC_withGradients([r[0] for r in ref], [r[1] for r in ref], [r[2] for r in ref], [r[3] for r in ref], fmins, 0.01)
+    f9, df9 = engine.acq(kind, 0.01, X9, grad=True)                   # N = 9: tensor-core path
+    for N in range(1, 10):
+        f, df = engine.acq(kind, 0.01, X9[:N], grad=True)
+        assert scaled_err(f, fo[:N, 0]) < 1e-10 and scaled_err(df, dfo[:N]) < 1e-10
+        assert np.array_equal(engine.acq(kind, 0.01, X9[:N]), f)      # value-only call: same values
+        m, s, dm, ds = engine.predict_grad(X9[:N])
+        for z in range(S):
+            assert scaled_err(m[z], ref[z][0][:N, 0]) < 1e-10 and scaled_err(s[z], ref[z][1][:N, 0]) < 1e-10
+            assert scaled_err(dm[z], ref[z][2][:N]) < 1e-10 and scaled_err(ds[z], ref[z][3][:N]) < 1e-10
+        if N <= 8:
+            f1, df1 = engine.acq(kind, 0.01, X9[N - 1:N], grad=True)  # the same row alone
+            assert f1[0] == f[N - 1] and np.array_equal(df1[0], df[N - 1])
+        assert scaled_err(f, f9[:N]) < 1e-10 and scaled_err(df, df9[:N]) < 1e-10   # two summation orders of one contraction
+    # strict-variance mode (the parity guard of ill-conditioned models) on the latency path
+    engine.set_strict_variance(1)
+    try:
+        engine.fit(kernel, X, Y[:, 0], var, np.broadcast_to(ls, (S, d)), nz)
+        f, df = engine.acq(kind, 0.01, X9[:3], grad=True)
+        assert scaled_err(f, fo[:3, 0]) < 1e-10 and scaled_err(df, dfo[:3]) < 1e-10
+    finally:
+        engine.set_strict_variance(-1)
+        engine.fit(kernel, X, Y[:, 0], var, np.broadcast_to(ls, (S, d)), nz)
+    if S == 1:  # Local Penalization on top
+        Xb, r, sc = rng.random((4, d)), np.full(4, 0.3), np.full(4, 0.2)
+        af, adf = og.acquisition_function_withGradients(fo, dfo)
+        val_o = og.lp_penalized_acquisition(af, X9, Xb, r, sc, 'none')
+        g_o = np.vstack([og.lp_d_acquisition(af[i:i + 1], adf[i:i + 1], X9[i:i + 1], Xb, r, sc, 'none') for i in range(9)])
+        engine.lp_set(Xb, r, sc, 'none')
+        try:
+            for N in (1, 4, 8):
+                v, g = engine.acq('EI', 0.01, X9[:N], grad=True)
+                assert scaled_err(v, val_o[:N]) < 1e-10 and scaled_err(g, g_o[:N]) < 1e-10
+        finally:
+            engine.lp_set(None, None, None, None)
+
+
 def test_mean_only_path_equals_the_full_prediction(engine):
     """gpo_predict_mean_grad (no variance contraction) returns bitwise the m and dmdx of gpo_predict_grad: several
     hyper-parameter sets, ragged chunks, host and device pointers, all kernels."""
@@ -323,8 +380,12 @@ def test_mean_only_path_equals_the_full_prediction(engine):
             m3, dm3 = engine.predict_mean_grad(xd)
             torch.cuda.synchronize()
             assert np.array_equal(m3.cpu().numpy(), m) and np.array_equal(dm3.cpu().numpy(), dm)
-            m1, dm1 = engine.predict_mean_grad(Xs[7:8])                    # a single point (L-BFGS step)
-            assert np.array_equal(m1[:, 0], m[:, 7]) and np.array_equal(dm1[:, 0], dm[:, 7])
+            # a single point (L-BFGS step) takes the latency kernels: bitwise equal to the full prediction of that same
+            # point, and equal to the row of the big sweep up to summation order
+            m1, dm1 = engine.predict_mean_grad(Xs[7:8])
+            mf, _, dmf, _ = engine.predict_grad(Xs[7:8])
+            assert np.array_equal(m1, mf) and np.array_equal(dm1, dmf)
+            assert scaled_err(m1[:, 0], m[:, 7]) < 1e-13 and scaled_err(dm1[:, 0], dm[:, 7]) < 1e-13
     finally:
         engine.set_chunk(0)
 

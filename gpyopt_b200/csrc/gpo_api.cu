@@ -34,6 +34,8 @@ struct gpo_engine {
   int sm_count = 0;
   char last_error[512] = {0};
   bool fitted = false;
+  bool finalized = false;  // fmin, K1's staging tiles and the variance probe follow lazily (finalize_state): ML-II / HMC
+                           // refit hundreds of times and only ask for the log-likelihood and its gradient
   // problem
   int n = 0, n_pad = 0, d = 0, S = 0, kern = 0;
   // capacity the buffers were allocated for
@@ -541,6 +543,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool want_kt_
 // parity guard (see variance_probe_kernel): decide which variance form gradient sweeps use.  Probes the first
 // min(n, 512) training inputs (their order is arbitrary, so this is a sample): 2 small GEMMs instead of 2 n-wide ones.
 // launch_* enqueues the kernels and the copy of the result; finish_* (after a stream sync) takes the decision.
+static int finalize_state(gpo_engine* eng);
+
 static int launch_variance_probe(gpo_engine* eng, cudaStream_t st) {
   const int n = eng->n, n_pad = eng->n_pad, d = eng->d, S = eng->S, kernel = eng->kern;
   const int n_probe = std::min(n, 512), probe_pad = ((n_probe + TILE - 1) / TILE) * TILE;
@@ -647,7 +651,8 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
 
   // GPy jitchol ladder: plain attempt, then jitter = mean(diag Ky) * 1e-6 * 10^t, t = 0..4.
   // A hyper-parameter set that factorises keeps jitter 0; only failing sets are retried.  Everything of one attempt
-  // (factorisation, alpha, fmin sweep, scalars, variance probe) is enqueued back to back and checked after ONE sync.
+  // (factorisation, alpha, log-likelihood scalars) is enqueued back to back and checked after ONE sync.  What only
+  // predictions need (fmin sweep, K1's staging tiles, variance probe) is left to finalize_state.
   eng->h_jit.assign(S, 0.0);
   eng->h_info.assign(S, 0);
   eng->h_logdet.resize(S); eng->h_quad.resize(S); eng->h_fmin.resize(S);
@@ -663,28 +668,13 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
         GPO_CUDA_OK(cudaMemcpyAsync(eng->alpha + (size_t)z * n_pad, eng->Y, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, st));
       gemv_kernel<<<grd, 256, 0, st>>>(eng->X, eng->alpha, eng->tmpv, n_pad, 0);
       gemv_kernel<<<grd, 256, 0, st>>>(eng->U, eng->tmpv, eng->alpha, n_pad, 1);
-      dim3 tgrid(n_pad / COV_JT, S);
-      build_xtile_kernel<<<tgrid, 128, 0, st>>>(eng->xtile, eng->Xt, n_pad, eng->alpha, eng->invl, n_pad, d, eng->dp);
-      eng->launches += 3;
-      GPO_CUDA_OK(cudaGetLastError());
-    }
-    // fmin = min_i mean(X_i): GPModel.get_fmin (gpmodel.py:129) -- a K1 sweep over the training inputs
-    {
-      Slot& s = eng->slot[0];
-      CovParams cp;
-      cp.Xs = eng->Xaos; cp.n_cand = n; cp.nc_run = n_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n;
-      cp.n_pad = n_pad; cp.d = d; cp.kern = kernel; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
-      cp.Kt = nullptr; cp.Ht = nullptr; cp.mean = s.mean; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
-      if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
-      fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, s.mean, eng->nc_ld, eng->js, n, n_pad, eng->logdet,
+      fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, nullptr, eng->nc_ld, eng->js, n, n_pad, eng->logdet,
                                             eng->quad, eng->fmin);
-      eng->launches++;
+      eng->launches += 3;
       GPO_CUDA_OK(cudaGetLastError());
       GPO_CUDA_OK(cudaMemcpyAsync(eng->h_logdet.data(), eng->logdet, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
       GPO_CUDA_OK(cudaMemcpyAsync(eng->h_quad.data(), eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
-      GPO_CUDA_OK(cudaMemcpyAsync(eng->h_fmin.data(), eng->fmin, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
     }
-    if ((rc = launch_variance_probe(eng, st))) return rc;
     GPO_CUDA_OK(cudaStreamSynchronize(st));
     bool any = false;
     for (int z = 0; z < S; ++z) {
@@ -698,14 +688,46 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
     }
     if (!any) break;
   }
-  finish_variance_probe(eng);
   eng->fitted = true;
+  eng->finalized = false;
+  return GPO_OK;
+}
+
+// Second half of a refit, run once before the first call that needs it: K1's tile-major staging buffer, fmin (a K1 sweep
+// over the training inputs, GPModel.get_fmin gpmodel.py:129) and the variance probe of the parity guard.
+static int finalize_state(gpo_engine* eng) {
+  if (eng->finalized) return GPO_OK;
+  if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "no fitted state");
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  const int n = eng->n, n_pad = eng->n_pad, d = eng->d, S = eng->S;
+  cudaStream_t st = eng->fit_stream;
+  int rc;
+  dim3 tgrid(n_pad / COV_JT, S);
+  build_xtile_kernel<<<tgrid, 128, 0, st>>>(eng->xtile, eng->Xt, n_pad, eng->alpha, eng->invl, n_pad, d, eng->dp);
+  eng->launches++;
+  Slot& s = eng->slot[0];
+  CovParams cp;
+  cp.Xs = eng->Xaos; cp.n_cand = n; cp.nc_run = n_pad; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad; cp.n = n;
+  cp.n_pad = n_pad; cp.d = d; cp.kern = eng->kern; cp.alpha = eng->alpha; cp.invl = eng->invl; cp.sigf2 = eng->sigf2;
+  cp.Kt = nullptr; cp.Ht = nullptr; cp.mean = s.mean; cp.dmean = nullptr; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
+  if ((rc = launch_cov(eng, cp, false, S, st))) return rc;
+  fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, s.mean, eng->nc_ld, eng->js, n, n_pad, eng->logdet,
+                                        eng->quad, eng->fmin);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  eng->h_fmin.resize(S);
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->h_fmin.data(), eng->fmin, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+  if ((rc = launch_variance_probe(eng, st))) return rc;
+  GPO_CUDA_OK(cudaStreamSynchronize(st));
+  finish_variance_probe(eng);
+  eng->finalized = true;
   return GPO_OK;
 }
 
 extern "C" int gpo_get_fmin(gpo_engine* eng, double* fmin) {
   if (!eng || !fmin) return GPO_ERR_ARG;
   if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_get_fmin before gpo_fit");
+  { const int frc = finalize_state(eng); if (frc) return frc; }
   for (int z = 0; z < eng->S; ++z) fmin[z] = eng->h_fmin[z];
   return GPO_OK;
 }
@@ -858,6 +880,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
                  const double* Xs, double* o0, double* o1, double* o2, double* o3, cudaStream_t user) {
   if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "sweep before gpo_fit");
   if (N <= 0) return GPO_OK;
+  { const int frc = finalize_state(eng); if (frc) return frc; }
   GPO_CUDA_OK(cudaSetDevice(eng->device));
   const int S = eng->S, d = eng->d, n_pad = eng->n_pad, tiles_m = n_pad / TILE;
   const bool predict = kind == ACQ_NONE;
@@ -1275,6 +1298,7 @@ extern "C" int gpo_alloc(gpo_engine* eng, int kernel, int n, int d, int S) {
   int rc = ensure_capacity(eng, n_pad, d, S);
   if (rc) return rc;
   eng->fitted = false;
+  eng->finalized = false;
   eng->n = n; eng->n_pad = n_pad; eng->d = d; eng->S = S; eng->kern = kernel;
   if (kernel != KERN_RBF)
     for (int i = 0; i < 2; ++i)
@@ -1285,6 +1309,7 @@ extern "C" int gpo_alloc(gpo_engine* eng, int kernel, int n, int d, int S) {
 extern "C" int gpo_state_buffers(gpo_engine* eng, void** ptrs, long long* bytes, int max) {
   if (!eng || !ptrs || !bytes) return GPO_ERR_ARG;
   if (eng->n_pad == 0) GPO_FAIL(GPO_ERR_STATE, "gpo_state_buffers before gpo_fit / gpo_alloc");
+  if (eng->fitted) { const int frc = finalize_state(eng); if (frc) return frc; }  // fmin and K1's tiles are part of the state
   const size_t S = eng->S, d = eng->d, np = eng->n_pad;
   struct { void* p; size_t b; } list[] = {
       {eng->Xt, d * np * 8}, {eng->Xtc, d * np * 8}, {eng->xmu, (size_t)DMAX * 8}, {eng->Xaos, d * np * 8}, {eng->Y, np * 8},
@@ -1312,6 +1337,7 @@ extern "C" int gpo_state_commit(gpo_engine* eng) {
   GPO_CUDA_OK(cudaMemcpy(eng->h_sigf2.data(), eng->sigf2, (size_t)S * 8, cudaMemcpyDeviceToHost));
   GPO_CUDA_OK(cudaMemcpy(eng->h_noise.data(), eng->noise, (size_t)S * 8, cudaMemcpyDeviceToHost));
   eng->fitted = true;
+  eng->finalized = true;  // fmin and K1's tiles arrived with the broadcast; only the probe verdict is local
   return run_variance_probe(eng, eng->fit_stream);
 }
 
@@ -1324,6 +1350,7 @@ extern "C" int gpo_set_strict_variance(gpo_engine* eng, int mode) {
 
 extern "C" int gpo_get_info(gpo_engine* eng, double* info, int count) {
   if (!eng || !info || count < 1) return GPO_ERR_ARG;
+  if (eng->fitted) { const int frc = finalize_state(eng); if (frc) return frc; }
   const double vals[] = {eng->strict_active ? 1.0 : 0.0, eng->var_disc, (double)eng->nc_ld, (double)eng->n_pad,
                          (double)eng->sm_count, (double)eng->S};
   const int have = (int)(sizeof(vals) / sizeof(vals[0]));
@@ -1367,6 +1394,7 @@ extern "C" int gpo_posterior_cov(gpo_engine* eng, long long N1, const double* X1
                                  double* out) {
   if (!eng || !X1 || !out || N1 < 1 || (X2 && N2 < 1)) return GPO_ERR_ARG;
   if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_posterior_cov before gpo_fit");
+  { const int frc = finalize_state(eng); if (frc) return frc; }
   if (eng->S != 1) GPO_FAIL(GPO_ERR_ARG, "gpo_posterior_cov needs a single hyper-parameter set (S = 1)");
   const bool same = X2 == nullptr;
   if (same) { X2 = X1; N2 = N1; }

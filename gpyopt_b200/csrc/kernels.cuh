@@ -478,9 +478,11 @@ __global__ void fit_scalars_kernel(const double* L, const double* alpha, const d
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     ld += log(L[((long long)z * n_pad + i) * n_pad + i]);
     qd = fma(alpha[(long long)z * n_pad + i], y[i], qd);
-    double mi = 0.0;
-    for (int sp = 0; sp < js; ++sp) mi += mean[((long long)z * js + sp) * mean_ld + i];
-    mn = ::fmin(mn, mi);
+    if (mean) {  // null: the refit proper (log-likelihood only); fmin follows when the state is finalised
+      double mi = 0.0;
+      for (int sp = 0; sp < js; ++sp) mi += mean[((long long)z * js + sp) * mean_ld + i];
+      mn = ::fmin(mn, mi);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -496,7 +498,7 @@ __global__ void fit_scalars_kernel(const double* L, const double* alpha, const d
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += sh[0][i]; b += sh[1][i]; c = ::fmin(c, sh[2][i]); }
     logdet[z] = 2.0 * a;
     quad[z] = b;
-    fmin_out[z] = c;
+    if (mean) fmin_out[z] = c;
   }
 }
 

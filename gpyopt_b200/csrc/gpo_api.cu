@@ -426,9 +426,14 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
   // diagonal factorisation and panel need), while the rest of the update runs on a side stream on the other SMs.
   // Every tile still receives its rank-128 updates in the order kb = 0, 1, 2, ...: the factor is bit-identical.
   const bool lookahead = nb >= 8;
+  const char* inv_env = getenv("GPO_INVERSE");
+  // measured: wins for 8 <= nb < 32 (1.34 -> 1.12 ms at n=1024, 2.68 -> 2.23 at 2048, 5.32 -> 3.89 at 3072); from nb = 32 on its
+  // K = 128 products are less efficient than the long-K products of the recursion (6.63 vs 6.30 ms at n=4096)
+  const bool interleave = lookahead && (inv_env ? inv_env[0] == 'i' : nb < 32);   // GPO_INVERSE=i|r overrides (tuning)
   cudaStream_t sb = eng->slot[0].stream;
+  cudaStream_t sc = sb;   // look-ahead mode: the triangular inverse rides along on the side stream, after each trailing update
   if (lookahead) {
-    while ((int)eng->chol_ev.size() < 2 * nb + 1) {
+    while ((int)eng->chol_ev.size() < 3 * nb + 2) {
       cudaEvent_t e;
       GPO_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       eng->chol_ev.push_back(e);
@@ -436,13 +441,56 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
     GPO_CUDA_OK(cudaEventRecord(eng->chol_ev[2 * nb], st));  // the Gram matrix is ready
     GPO_CUDA_OK(cudaStreamWaitEvent(sb, eng->chol_ev[2 * nb], 0));
   }
+  // Interleaved inverse (look-ahead mode).  The Cholesky chain diagonal kernel -> panel -> column update is latency-bound
+  // and leaves most SMs idle, so X = L^-1 is built alongside it by block forward substitution L X = I on the side stream:
+  //   after diagonal block kb:  X[kb, c] = X_kk R[kb, c]                     (c < kb; row kb of the inverse is final)
+  //   after panel kb:           R[i, c] -= L[i, kb] X[kb, c]   (i > kb, c < kb),    R[i, kb] = -L[i, kb] X_kk
+  // with the running right-hand side R kept in the not yet final rows of X (and transposed in U, the K-major operand).
+  // Every product has K = 128; nothing of the inverse is left after the last diagonal block but its own row.
+  const int max_inv_ctas = std::max(16, eng->sm_count - 32);   // like the trailing update: 32 SMs stay with the critical path
+  auto inverse_step = [&](int kb) -> int {
+    const int rem = nb - kb - 1;
+    GPO_CUDA_OK(cudaStreamWaitEvent(sc, eng->chol_ev[2 * nb + 1 + kb], 0));  // X_kk = L_kk^-1 is there
+    if (kb > 0) {
+      GemmParams f = gemm_defaults();
+      f.tiles_m = 1; f.tiles_n = kb; f.kblocks = 1;
+      f.a = {kb * TILE, kb * TILE, 0, 0, 0, 1};                    // X_kk
+      f.b = {0, kb * TILE, 0, 0, 0, 1};                            // B[n][k] = R[kb][k, c-block n] = U[c-block n][kb, k]
+      f.C = eng->X; f.ldc = n_pad; f.c_off_z = nn; f.c_row0 = kb * TILE; f.c_col0 = 0;
+      f.Ct = eng->U; f.ldct = n_pad; f.ct_off_z = nn; f.ct_row0 = 0; f.ct_col0 = kb * TILE;   // in place on its own B tile
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapX, eng->mapU, f, S, sc, max_inv_ctas))) return rc;
+    }
+    if (rem == 0) return GPO_OK;
+    GPO_CUDA_OK(cudaStreamWaitEvent(sc, eng->chol_ev[2 * kb], 0));            // panel kb (L[i, kb], i > kb) is final
+    GemmParams u = gemm_defaults();
+    u.kblocks = 1; u.alpha = -1.0;
+    u.a = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};                // L[i, kb]
+    u.C = eng->X; u.ldc = n_pad; u.c_off_z = nn; u.c_row0 = (kb + 1) * TILE;
+    u.Ct = eng->U; u.ldct = n_pad; u.ct_off_z = nn; u.ct_col0 = (kb + 1) * TILE;
+    if (kb > 0) {
+      GemmParams a2 = u;
+      a2.tiles_m = rem; a2.tiles_n = kb; a2.beta = 1.0;
+      a2.b = {0, kb * TILE, 0, 0, 0, 1};                           // row kb of X through U
+      a2.c_col0 = 0; a2.ct_row0 = 0;
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapU, a2, S, sc, max_inv_ctas))) return rc;
+    }
+    GemmParams b2 = u;
+    b2.tiles_m = rem; b2.tiles_n = 1; b2.beta = 0.0;               // first contribution to column block kb of R
+    b2.b = {kb * TILE, kb * TILE, 0, 0, 0, 1};                     // U_kk = X_kk^T
+    b2.c_col0 = kb * TILE; b2.ct_row0 = kb * TILE;
+    return launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapU, b2, S, sc, max_inv_ctas);
+  };
   int last_rest = -1;
   for (int kb = 0; kb < nb; ++kb) {
     diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb,
                                                                     std::max(0, std::min(TILE, eng->n - kb * TILE)), eng->info);
     eng->launches++;
     const int rem = nb - kb - 1;
-    if (rem == 0) break;
+    if (interleave) GPO_CUDA_OK(cudaEventRecord(eng->chol_ev[2 * nb + 1 + kb], st));
+    if (rem == 0) {
+      if (interleave && (rc = inverse_step(kb))) return rc;
+      break;
+    }
     // panel: A[kb+1:, kb] <- A[kb+1:, kb] * L_kk^-T       (B operand = rows of X_kk)
     GemmParams p = gemm_defaults();
     p.tiles_m = rem; p.tiles_n = 1; p.kblocks = 1;
@@ -474,6 +522,7 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
       if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, r, S, sb, std::max(16, eng->sm_count - 32)))) return rc;
       GPO_CUDA_OK(cudaEventRecord(eng->chol_ev[2 * kb + 1], sb));
     }
+    if (interleave && (rc = inverse_step(kb))) return rc;   // queued behind the trailing update the next steps wait for
     // column kb+1 on the main stream, after the side stream's previous update of those tiles
     if (last_rest >= 0) GPO_CUDA_OK(cudaStreamWaitEvent(st, eng->chol_ev[2 * last_rest + 1], 0));
     if (rem >= 2) last_rest = kb;
@@ -485,9 +534,13 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
     if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, c, S, st))) return rc;
   }
   if (lookahead && last_rest >= 0) GPO_CUDA_OK(cudaStreamWaitEvent(st, eng->chol_ev[2 * last_rest + 1], 0));
-  // triangular inverse, recursively: X21 = -X22 (L21 X11)
+  if (interleave) {  // the inverse is complete when the side stream drains
+    GPO_CUDA_OK(cudaEventRecord(eng->chol_ev[3 * nb + 1], sc));
+    GPO_CUDA_OK(cudaStreamWaitEvent(st, eng->chol_ev[3 * nb + 1], 0));
+  }
+  // triangular inverse, recursively: X21 = -X22 (L21 X11)   (short factorisations only)
   std::vector<std::vector<TriNode>> levels;
-  build_tree(0, nb, 0, levels);
+  if (!interleave) build_tree(0, nb, 0, levels);
   for (int lv = (int)levels.size() - 1; lv >= 0; --lv) {
     const std::vector<TriNode>& nodes = levels[lv];
     // same-shape, evenly spaced nodes of one level (always the case when n_pad/128 is a power of two) go out as ONE

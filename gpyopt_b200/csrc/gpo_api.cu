@@ -75,6 +75,7 @@ struct gpo_engine {
   // device-side design: when gen_on, the sweep generates its candidates (Philox stream) instead of reading Xs
   bool gen_on = false;  DesignParams gen;  long long gen_row0 = 0;
   int* smalln_ticket = nullptr;  int smalln_ticket_cap = 0;   // [S] arrival counters of the small-N kernel
+  double* smalln_sq = nullptr;  size_t smalln_sq_cap = 0;     // per-CTA partial rows of its strict-variance (|L^-1 k|^2) form
   long long* gen_idx = nullptr;  double* gen_x = nullptr;  // [TOPK_SEG/2], [TOPK_SEG/2][DMAX] winners of a generated design
   // per-block best candidates written by K3 (fused selection)
   double* blk_val = nullptr;  long long* blk_idx = nullptr;  size_t blk_cap = 0;  bool want_blk = false;
@@ -258,6 +259,7 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->blk_idx) cudaFree(eng->blk_idx);
   if (eng->gen_idx) cudaFree(eng->gen_idx);
   if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
+  if (eng->smalln_sq) cudaFree(eng->smalln_sq);
   if (eng->gen_x) cudaFree(eng->gen_x);
   for (int i = 0; i < 5; ++i) if (eng->cov_buf[i]) cudaFree(eng->cov_buf[i]);
   for (cudaEvent_t e : eng->chol_ev) cudaEventDestroy(e);
@@ -882,15 +884,18 @@ static void launch_design(gpo_engine* eng, DesignParams p, long long row0, long 
 // otherwise:        acquisition (o0 = f [N], o1 = df [N][d])
 // small-N latency path (see smalln_wk_kernel): nc in 1..8 candidates, returns the number of partial rows K3 must add
 constexpr int SMALLN_MAX = 8, SMALLN_LDP = 8;
-template <int R>
+template <int R, bool SQ>
 static void launch_smalln_r(const SmallNParams& p, int nc, dim3 grid, cudaStream_t st) {
-  if (nc <= 1) smalln_wk_kernel<1, R><<<grid, 256, 0, st>>>(p);
-  else if (nc <= 2) smalln_wk_kernel<2, R><<<grid, 256, 0, st>>>(p);
-  else if (nc <= 4) smalln_wk_kernel<4, R><<<grid, 256, 0, st>>>(p);
-  else smalln_wk_kernel<8, R><<<grid, 256, 0, st>>>(p);
+  if (nc <= 1) smalln_wk_kernel<1, R, SQ><<<grid, 256, 0, st>>>(p);
+  else if (nc <= 2) smalln_wk_kernel<2, R, SQ><<<grid, 256, 0, st>>>(p);
+  else if (nc <= 4) smalln_wk_kernel<4, R, SQ><<<grid, 256, 0, st>>>(p);
+  else smalln_wk_kernel<8, R, SQ><<<grid, 256, 0, st>>>(p);
 }
+// W-form (sq = false): b = W^-1 k with the EPI_GRAD reductions, d_epi + 2 values per candidate, reduced rows left behind
+// the per-CTA rows in s.partial (*final_rows, leading dimension SMALLN_LDP).
+// Strict form (sq = true): |L^-1 k|^2 from X = L^-1, one value per candidate written to sq_dest [S][sq_ld].
 static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool use_ht, cudaStream_t st,
-                         const double** final_rows) {
+                         const double** final_rows, bool sq = false, double* sq_dest = nullptr, long long sq_ld = 0) {
   const int n_pad = eng->n_pad;
   if (eng->smalln_ticket_cap < eng->S) {
     GPO_CUDA_OK(cudaDeviceSynchronize());
@@ -900,18 +905,34 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
     GPO_CUDA_OK(cudaMemset(eng->smalln_ticket, 0, (size_t)eng->S * sizeof(int)));
     eng->smalln_ticket_cap = eng->S;
   }
-  const int R = n_pad >= 2048 ? 4 : 1;   // rows per warp: enough CTAs to pull W^-1 through every SM at any n
-  SmallNParams p;
-  p.W = eng->W; p.w_z = (long long)n_pad * n_pad;
-  p.Kt = s.Kt; p.Ht = use_ht ? s.Ht : nullptr; p.kt_z = eng->nc_ld * (long long)n_pad;
-  p.Xtc = eng->Xtc; p.ldx = n_pad; p.n_pad = n_pad; p.d = d_epi;
+  const int R = n_pad >= 2048 ? 4 : 1;   // rows per warp: enough CTAs to pull the matrix through every SM at any n
   const int row_blocks = n_pad / (8 * R);
-  p.partial = s.partial; p.part_z = (long long)row_blocks * (d_epi + 2) * SMALLN_LDP; p.ldp = SMALLN_LDP;
-  p.final_rows = s.partial + (long long)eng->S * p.part_z;
+  SmallNParams p;
+  p.w_z = (long long)n_pad * n_pad;
+  p.Kt = s.Kt; p.Ht = use_ht ? s.Ht : nullptr; p.kt_z = eng->nc_ld * (long long)n_pad;
+  p.Xtc = eng->Xtc; p.ldx = n_pad; p.n_pad = n_pad; p.d = d_epi; p.ldp = SMALLN_LDP;
   p.ticket = eng->smalln_ticket;
-  *final_rows = p.final_rows;
+  if (sq) {
+    const size_t need = (size_t)eng->S * row_blocks * SMALLN_LDP * 8;
+    if (need > eng->smalln_sq_cap) {
+      GPO_CUDA_OK(cudaDeviceSynchronize());
+      if (eng->smalln_sq) cudaFree(eng->smalln_sq);
+      eng->smalln_sq = nullptr; eng->smalln_sq_cap = 0;
+      GPO_CUDA_OK(cudaMalloc(&eng->smalln_sq, need));
+      eng->smalln_sq_cap = need;
+    }
+    p.W = eng->X; p.Ht = nullptr;
+    p.partial = eng->smalln_sq; p.part_z = (long long)row_blocks * SMALLN_LDP;
+    p.final_rows = sq_dest; p.final_ld = sq_ld;
+  } else {
+    p.W = eng->W;
+    p.partial = s.partial; p.part_z = (long long)row_blocks * (d_epi + 2) * SMALLN_LDP;
+    p.final_rows = s.partial + (long long)eng->S * p.part_z; p.final_ld = SMALLN_LDP;
+    *final_rows = p.final_rows;
+  }
   dim3 grid((unsigned)row_blocks, (unsigned)eng->S, 1);
-  if (R == 4) launch_smalln_r<4>(p, nc, grid, st); else launch_smalln_r<1>(p, nc, grid, st);
+  if (sq) { if (R == 4) launch_smalln_r<4, true>(p, nc, grid, st); else launch_smalln_r<1, true>(p, nc, grid, st); }
+  else { if (R == 4) launch_smalln_r<4, false>(p, nc, grid, st); else launch_smalln_r<1, false>(p, nc, grid, st); }
   eng->launches++;
   GPO_CUDA_OK(cudaGetLastError());
   return GPO_OK;
@@ -983,7 +1004,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     cp.sigf2 = eng->sigf2; cp.Kt = s.Kt; cp.Ht = (grad && eng->kern != KERN_RBF) ? s.Ht : nullptr; cp.mean = s.mean;
     cp.dmean = s.dmean; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
     // a handful of points (L-BFGS steps) on a well-conditioned model: the latency kernels below
-    const bool tiny = N <= SMALLN_MAX && (mean_only || !eng->strict_active);
+    const bool tiny = N <= SMALLN_MAX;
     if (tiny) {
       if (!grad) cp.dmean = nullptr;
       if (mean_only) { cp.Kt = nullptr; cp.Ht = nullptr; }
@@ -1010,6 +1031,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     int part_nv = 1, part_rows = tiles_m;
     long long part_ld = eng->nc_ld;
     const double* small_final = nullptr;  // the small-N kernel's reduced partial rows
+    int sq_rows = tiles_m;                // partial rows of the strict-variance form
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (eng->profiling && !mean_only) {
       if (eng->prof_used == eng->prof_events.size()) {
@@ -1026,18 +1048,21 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     }
     if (mean_only) {
       part_rows = 0;  // K3 then reads no variance partials
-    } else if (w_form && N <= SMALLN_MAX) {
-      // a handful of points (L-BFGS steps): batched matrix-vector product over W^-1 instead of 128-wide tensor-core tiles
-      if ((rc = launch_smalln(eng, s, (int)N, grad ? d : 0, grad && eng->kern != KERN_RBF, st, &small_final))) return rc;
-      part_rows = 1; part_nv = (grad ? d : 0) + 2; part_ld = SMALLN_LDP;
-      if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
-      if (grad && eng->strict_active) {  // ill-conditioned model: variance from the reference's own triangular form as well
-        GemmParams gs = gemm_defaults();
-        gs.tiles_m = tiles_m; gs.tiles_n = tiles_n; gs.kblocks = tiles_m;
-        gs.a = {0, 0, 0, 0, 0, 1}; gs.b = {0, 0, 0, 0, 0, 1};
-        gs.partial = s.partial_sq; gs.ldp = eng->nc_ld; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
-        if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, gs, S, st))) return rc;
+    } else if (tiny) {
+      // a handful of points (L-BFGS steps): batched matrix-vector products instead of 128-wide tensor-core tiles
+      if (w_form) {
+        if ((rc = launch_smalln(eng, s, (int)N, grad ? d : 0, grad && eng->kern != KERN_RBF, st, &small_final))) return rc;
+        part_rows = 1; part_nv = (grad ? d : 0) + 2; part_ld = SMALLN_LDP;
+        if (grad && eng->strict_active) {  // ill-conditioned model: variance from the reference's own triangular form as well
+          if ((rc = launch_smalln(eng, s, (int)N, 0, false, st, nullptr, true, s.partial_sq, eng->nc_ld))) return rc;
+          sq_rows = 1;
+        }
+      } else {  // value only on an ill-conditioned model: the triangular form alone
+        if ((rc = launch_smalln(eng, s, (int)N, 0, false, st, nullptr, true, s.partial, SMALLN_LDP))) return rc;
+        small_final = s.partial;
+        part_rows = 1; part_nv = 1; part_ld = SMALLN_LDP;
       }
+      if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
     } else if (w_form) {
       g.krange = KR_FULL; g.raster = RO_M_FASTEST;
       g.d = grad ? d : 0; g.Xtc = eng->Xtc; g.ldx = n_pad; g.Kt = s.Kt; g.Ht = (grad && eng->kern != KERN_RBF) ? s.Ht : nullptr;
@@ -1063,7 +1088,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     AcqParams ap;
     memset(&ap, 0, sizeof(ap));
     ap.n_cand = rows; ap.nc_pad = eng->nc_ld; ap.S = S; ap.d = d; ap.tiles_m = part_rows; ap.grad = grad ? 1 : 0;
-    ap.part_nv = part_nv; ap.part_ld = part_ld; ap.sq_tiles_m = tiles_m;
+    ap.part_nv = part_nv; ap.part_ld = part_ld; ap.sq_tiles_m = sq_rows;
     ap.js = eng->js; ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = small_final ? small_final : s.partial; ap.sigf2 = eng->sigf2;
     ap.partial_sq = (grad && eng->strict_active && !mean_only) ? s.partial_sq : nullptr;
     ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par; ap.invl = eng->invl; ap.xmu = eng->xmu;

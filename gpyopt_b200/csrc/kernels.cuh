@@ -982,15 +982,19 @@ struct SmallNParams {
   int n_pad, d;                          // d = 0: value only (S0 and H0)
   double* partial;   long long part_z;   // [S][row blocks][d + 2][ldp]
   int ldp;
-  double* final_rows;                    // [S][d + 2][ldp]: the partial rows added in row-block order by the last CTA
+  double* final_rows;                    // [S][nvals][final_ld]: the partial rows added in row-block order by the last CTA
+  long long final_ld;
   int* ticket;                           // [S] arrival counters (zero before the launch; the last CTA resets its own)
 };
 
-template <int NC, int R>
+// SQ = true: the strict-variance form instead.  W is then X = L^-1 (lower triangular: the column loop stops at the
+// diagonal) and the only reduction is sum_j (X k)_j^2 = |L^-1 k|^2, one value per candidate.
+template <int NC, int R, bool SQ>
 __global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
   __shared__ double red[8][DMAX + 2][NC];
   const int z = blockIdx.y, rb = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = rb * (8 * R) + warp * R, n_pad = p.n_pad, d = p.d;
+  const int row0 = rb * (8 * R) + warp * R, n_pad = p.n_pad, d = SQ ? -1 : p.d;   // d + 2 values per candidate (SQ: one)
+  const int c_end = SQ ? min(n_pad, ((row0 + R + 31) >> 5) << 5) : n_pad;
   const double* Wr = p.W + (long long)z * p.w_z + (long long)row0 * n_pad;
   const double* Kt = p.Kt + (long long)z * p.kt_z;
   double acc[R][NC];
@@ -999,7 +1003,7 @@ __global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
 #pragma unroll
     for (int i = 0; i < NC; ++i) acc[r][i] = 0.0;
 #pragma unroll 2
-  for (int c = lane; c < n_pad; c += 32) {
+  for (int c = lane; c < c_end; c += 32) {
     double kv[NC], w[R];
 #pragma unroll
     for (int i = 0; i < NC; ++i) kv[i] = __ldg(Kt + (long long)i * n_pad + c);
@@ -1027,6 +1031,7 @@ __global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
 #pragma unroll
       for (int i = 0; i < NC; ++i)
         if (lane == i) b = acc[r][i];
+      if (SQ) { s0 = fma(b, b, s0); continue; }
       const int j = row0 + r;
       const double kj = __ldg(Kt + (long long)lane * n_pad + j);
       const double bh = p.Ht ? b * __ldg(p.Ht + (long long)z * p.kt_z + (long long)lane * n_pad + j) : -(b * kj);
@@ -1037,7 +1042,7 @@ __global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
         if (q < d) pq[q] = fma(bh, __ldg(p.Xtc + (long long)q * p.ldx + j), pq[q]);
     }
     red[warp][0][lane] = s0;
-    red[warp][1][lane] = h0;
+    if (!SQ) red[warp][1][lane] = h0;
 #pragma unroll
     for (int q = 0; q < DMAX; ++q)
       if (q < d) red[warp][2 + q][lane] = pq[q];
@@ -1068,7 +1073,7 @@ __global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
     const double* src = p.partial + (long long)z * p.part_z + (long long)v * p.ldp + i;
     double t = 0.0;
     for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(src + (long long)b * (d + 2) * p.ldp);
-    p.final_rows[((long long)z * (d + 2) + v) * p.ldp + i] = t;
+    p.final_rows[((long long)z * (d + 2) + v) * p.final_ld + i] = t;
   }
 }
 

@@ -342,8 +342,15 @@ def test_small_batch_latency_path(engine, kernel, ARD, S):
     engine.set_strict_variance(1)
     try:
         engine.fit(kernel, X, Y[:, 0], var, np.broadcast_to(ls, (S, d)), nz)
-        f, df = engine.acq(kind, 0.01, X9[:3], grad=True)
-        assert scaled_err(f, fo[:3, 0]) < 1e-10 and scaled_err(df, dfo[:3]) < 1e-10
+        assert engine.info()['strict_variance']
+        for N in (1, 3, 8, 9):   # 9: the tensor-core form of the same guard
+            f, df = engine.acq(kind, 0.01, X9[:N], grad=True)
+            assert scaled_err(f, fo[:N, 0]) < 1e-10 and scaled_err(df, dfo[:N]) < 1e-10
+            fv = engine.acq(kind, 0.01, X9[:N])          # value only: the triangular form alone
+            assert scaled_err(fv, fo[:N, 0]) < 1e-10
+            m, s = engine.predict(X9[:N])
+            for z in range(S):
+                assert scaled_err(s[z], ref[z][1][:N, 0]) < 1e-10
     finally:
         engine.set_strict_variance(-1)
         engine.fit(kernel, X, Y[:, 0], var, np.broadcast_to(ls, (S, d)), nz)

@@ -368,6 +368,48 @@ def test_small_batch_latency_path(engine, kernel, ARD, S):
             engine.lp_set(None, None, None, None)
 
 
+def test_engine_lifecycle_across_shapes(engine):
+    """ONE engine refitted through a sequence of different (n, d, S, kernel) problems -- growing and shrinking buffers,
+    switching kernels (the H*^T buffers appear on demand), Local Penalization set and cleared, latency and tensor-core
+    paths, ML-II style refits without prediction in between (lazy finalisation): every answer against the oracle."""
+    from oracle import gpy_numpy as G, gpyopt_numpy as og
+    rng = np.random.default_rng(77)
+    K = {'rbf': G.RBF, 'matern52': G.Matern52, 'matern32': G.Matern32}
+    cases = [(50, 2, 1, 'rbf'), (300, 5, 2, 'matern52'), (40, 2, 1, 'matern32'), (700, 3, 1, 'rbf'), (129, 16, 3, 'matern52'),
+             (20, 1, 1, 'rbf'), (1030, 4, 1, 'matern32'), (64, 6, 2, 'rbf')]
+    for n, d, S, kernel in cases:
+        X = rng.random((n, d)); Y = og.normalize_stats(np.cos(3 * X).sum(1, keepdims=True) + 0.05 * rng.standard_normal((n, 1)))
+        for rep in range(2):          # the second refit changes only the hyper-parameters (cached data upload, no prediction between)
+            var = 0.7 + rng.random(S); ls = 0.4 + rng.random((S, d)); nz = 1e-2 * (1 + rng.random(S))
+            engine.fit(kernel, X, Y[:, 0], var, ls, nz)
+            if rep == 0:
+                ll, _ = engine.get_loglik()          # ML-II style: log-likelihood only, state not finalised
+        gps = [G.GPRegression(X, Y, K[kernel](d, variance=var[z], lengthscale=ls[z], ARD=True), noise_var=nz[z]) for z in range(S)]
+        ll, _ = engine.get_loglik()
+        for z in range(S):
+            assert abs(ll[z] - gps[z].log_likelihood()) <= 1e-10 * abs(gps[z].log_likelihood())
+        for N in (3, 200):
+            Xs = rng.random((N, d))
+            m, s, dm, ds = engine.predict_grad(Xs)
+            for z in range(S):
+                mo, so, dmo, dso = og.gp_predict_withGradients(gps[z], Xs)
+                tv, tg = parity_tolerances(gps[z], Xs)
+                assert scaled_err(m[z], mo[:, 0]) < tv and scaled_err(s[z], so[:, 0]) < tv
+                assert scaled_err(dm[z], dmo) < tg and scaled_err(ds[z], dso) < tg
+        fm = engine.get_fmin()
+        for z in range(S):
+            assert abs(fm[z] - og.gp_get_fmin(gps[z])) < 1e-10 * max(1.0, abs(fm[z]))
+        if S == 1:   # LP on, then off again: the plain acquisition must come back
+            Xs = rng.random((6, d))
+            plain = engine.acq('LCB', 2.0, Xs)
+            engine.lp_set(rng.random((3, d)), np.full(3, 0.2), np.full(3, 0.3), 'softplus')
+            pen = engine.acq('LCB', 2.0, Xs)
+            engine.lp_set(None, None, None, None)
+            assert not np.array_equal(pen, plain) and np.array_equal(engine.acq('LCB', 2.0, Xs), plain)
+            mo, so = og.gp_predict(gps[0], Xs)
+            assert scaled_err(plain, og.acq_LCB(mo, so, 2.0)[:, 0]) < 1e-10
+
+
 def test_mean_only_path_equals_the_full_prediction(engine):
     """gpo_predict_mean_grad (no variance contraction) returns bitwise the m and dmdx of gpo_predict_grad: several
     hyper-parameter sets, ragged chunks, host and device pointers, all kernels."""

@@ -74,6 +74,7 @@ struct gpo_engine {
   double* tk_vals[2] = {nullptr, nullptr};  long long* tk_idx[2] = {nullptr, nullptr};  size_t tk_cap = 0;
   // device-side design: when gen_on, the sweep generates its candidates (Philox stream) instead of reading Xs
   bool gen_on = false;  DesignParams gen;  long long gen_row0 = 0;
+  bool smalln_attr_done = false;
   int* smalln_ticket = nullptr;  int smalln_ticket_cap = 0;   // [S] arrival counters of the small-N kernel
   double* smalln_sq = nullptr;  size_t smalln_sq_cap = 0;     // per-CTA partial rows of its strict-variance (|L^-1 k|^2) form
   long long* gen_idx = nullptr;  double* gen_x = nullptr;  // [TOPK_SEG/2], [TOPK_SEG/2][DMAX] winners of a generated design
@@ -884,12 +885,27 @@ static void launch_design(gpo_engine* eng, DesignParams p, long long row0, long 
 // otherwise:        acquisition (o0 = f [N], o1 = df [N][d])
 // small-N latency path (see smalln_wk_kernel): nc in 1..8 candidates, returns the number of partial rows K3 must add
 constexpr int SMALLN_MAX = 8, SMALLN_LDP = 8;
-template <int R, bool SQ>
+template <bool SQ, int ROWS>
 static void launch_smalln_r(const SmallNParams& p, int nc, dim3 grid, cudaStream_t st) {
-  if (nc <= 1) smalln_wk_kernel<1, R, SQ><<<grid, 256, 0, st>>>(p);
-  else if (nc <= 2) smalln_wk_kernel<2, R, SQ><<<grid, 256, 0, st>>>(p);
-  else if (nc <= 4) smalln_wk_kernel<4, R, SQ><<<grid, 256, 0, st>>>(p);
-  else smalln_wk_kernel<8, R, SQ><<<grid, 256, 0, st>>>(p);
+  constexpr int smem = smalln_smem_bytes(ROWS);
+  if (nc <= 1) smalln_wk_kernel<1, SQ, ROWS><<<grid, 256, smem, st>>>(p);
+  else if (nc <= 2) smalln_wk_kernel<2, SQ, ROWS><<<grid, 256, smem, st>>>(p);
+  else if (nc <= 4) smalln_wk_kernel<4, SQ, ROWS><<<grid, 256, smem, st>>>(p);
+  else smalln_wk_kernel<8, SQ, ROWS><<<grid, 256, smem, st>>>(p);
+}
+template <int NC, int ROWS>
+static cudaError_t smalln_attr() {
+  cudaError_t e = cudaFuncSetAttribute(smalln_wk_kernel<NC, false, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smalln_smem_bytes(ROWS));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(smalln_wk_kernel<NC, true, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smalln_smem_bytes(ROWS));
+}
+template <int ROWS>
+static cudaError_t smalln_attr_rows() {
+  cudaError_t e;
+  if ((e = smalln_attr<1, ROWS>()) != cudaSuccess) return e;
+  if ((e = smalln_attr<2, ROWS>()) != cudaSuccess) return e;
+  if ((e = smalln_attr<4, ROWS>()) != cudaSuccess) return e;
+  return smalln_attr<8, ROWS>();
 }
 // W-form (sq = false): b = W^-1 k with the EPI_GRAD reductions, d_epi + 2 values per candidate, reduced rows left behind
 // the per-CTA rows in s.partial (*final_rows, leading dimension SMALLN_LDP).
@@ -897,6 +913,10 @@ static void launch_smalln_r(const SmallNParams& p, int nc, dim3 grid, cudaStream
 static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool use_ht, cudaStream_t st,
                          const double** final_rows, bool sq = false, double* sq_dest = nullptr, long long sq_ld = 0) {
   const int n_pad = eng->n_pad;
+  if (!eng->smalln_attr_done) {
+    GPO_CUDA_OK(smalln_attr_rows<32>()); GPO_CUDA_OK(smalln_attr_rows<16>()); GPO_CUDA_OK(smalln_attr_rows<8>());
+    eng->smalln_attr_done = true;
+  }
   if (eng->smalln_ticket_cap < eng->S) {
     GPO_CUDA_OK(cudaDeviceSynchronize());
     if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
@@ -905,8 +925,8 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
     GPO_CUDA_OK(cudaMemset(eng->smalln_ticket, 0, (size_t)eng->S * sizeof(int)));
     eng->smalln_ticket_cap = eng->S;
   }
-  const int R = n_pad >= 2048 ? 4 : 1;   // rows per warp: enough CTAs to pull the matrix through every SM at any n
-  const int row_blocks = n_pad / (8 * R);
+  const int rows = n_pad >= 4096 ? 32 : (n_pad >= 2048 ? 16 : 8);   // rows per CTA: at least ~128 CTAs from n = 1024 on
+  const int row_blocks = n_pad / rows;
   SmallNParams p;
   p.w_z = (long long)n_pad * n_pad;
   p.Kt = s.Kt; p.Ht = use_ht ? s.Ht : nullptr; p.kt_z = eng->nc_ld * (long long)n_pad;
@@ -931,17 +951,31 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
     *final_rows = p.final_rows;
   }
   dim3 grid((unsigned)row_blocks, (unsigned)eng->S, 1);
-  if (sq) { if (R == 4) launch_smalln_r<4, true>(p, nc, grid, st); else launch_smalln_r<1, true>(p, nc, grid, st); }
-  else { if (R == 4) launch_smalln_r<4, false>(p, nc, grid, st); else launch_smalln_r<1, false>(p, nc, grid, st); }
+  if (rows == 32) { if (sq) launch_smalln_r<true, 32>(p, nc, grid, st); else launch_smalln_r<false, 32>(p, nc, grid, st); }
+  else if (rows == 16) { if (sq) launch_smalln_r<true, 16>(p, nc, grid, st); else launch_smalln_r<false, 16>(p, nc, grid, st); }
+  else { if (sq) launch_smalln_r<true, 8>(p, nc, grid, st); else launch_smalln_r<false, 8>(p, nc, grid, st); }
   eng->launches++;
   GPO_CUDA_OK(cudaGetLastError());
   return GPO_OK;
 }
 
 // K1 for nc <= 8 candidates (one thread per training point)
+static int ensure_ticket(gpo_engine* eng) {
+  if (eng->smalln_ticket_cap >= eng->S) return GPO_OK;
+  GPO_CUDA_OK(cudaDeviceSynchronize());
+  if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
+  eng->smalln_ticket = nullptr; eng->smalln_ticket_cap = 0;
+  GPO_CUDA_OK(cudaMalloc(&eng->smalln_ticket, (size_t)eng->S * sizeof(int)));
+  GPO_CUDA_OK(cudaMemset(eng->smalln_ticket, 0, (size_t)eng->S * sizeof(int)));
+  eng->smalln_ticket_cap = eng->S;
+  return GPO_OK;
+}
+
 static int launch_cov_small(gpo_engine* eng, const CovParams& p_in, int nc, cudaStream_t st) {
+  { const int trc = ensure_ticket(eng); if (trc) return trc; }
   CovParams p = p_in;
   p.nc_run = nc <= 1 ? 1 : nc <= 2 ? 2 : nc <= 4 ? 4 : 8;   // the candidate slots smalln_wk_kernel<NC> will read
+  p.ticket = eng->smalln_ticket;
   dim3 grid((unsigned)p.js, (unsigned)eng->S, 1);
   cov_small_kernel<<<grid, 256, 0, st>>>(p);
   eng->launches++;
@@ -1089,7 +1123,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     memset(&ap, 0, sizeof(ap));
     ap.n_cand = rows; ap.nc_pad = eng->nc_ld; ap.S = S; ap.d = d; ap.tiles_m = part_rows; ap.grad = grad ? 1 : 0;
     ap.part_nv = part_nv; ap.part_ld = part_ld; ap.sq_tiles_m = sq_rows;
-    ap.js = eng->js; ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = small_final ? small_final : s.partial; ap.sigf2 = eng->sigf2;
+    ap.js = tiny ? 1 : eng->js; ap.js_ld = eng->js; ap.with_noise = with_noise; ap.mean = s.mean; ap.dmean = s.dmean; ap.partial = small_final ? small_final : s.partial; ap.sigf2 = eng->sigf2;
     ap.partial_sq = (grad && eng->strict_active && !mean_only) ? s.partial_sq : nullptr;
     ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par; ap.invl = eng->invl; ap.xmu = eng->xmu;
     ap.Xs = dev_in + off * d;

@@ -36,6 +36,7 @@ struct CovParams {
                            // js depends only on n_pad, so a row's result never depends on the batch it is in
   double* mean;           // [S][js][nc_ld]      per-slice partial sums, added in slice order by K3 / fit_scalars
   double* dmean;          // [S][js][d][nc_ld]   (GRAD only)
+  int* ticket;            // cov_small_kernel only: [S] arrival counters (zero before the launch)
 };
 
 // One thread owns one candidate (its scaled coordinates, mean and mean-gradient accumulators stay in registers for the
@@ -573,6 +574,7 @@ struct AcqParams {
   int grad;              // produce gradients (partials then hold S0, H0, P_1..P_d)
   int with_noise;
   int js;                // K1's slices of the training index: mean / dmean hold js partial sums per candidate
+  int js_ld;             // slices per hyper-parameter set in the buffers (>= js; js = 1 after cov_small_kernel's own reduction)
   const double* mean;    // [S][js][nc_pad]
   const double* dmean;   // [S][js][d][nc_pad]
   const double* partial; // [S][tiles_m][nv][nc_pad]; nv = 1 (sum of squares) or d + 2 (S0, H0, P_1..P_d)
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
   const int z_begin = zsplit ? blockIdx.y : 0, z_end = zsplit ? blockIdx.y + 1 : p.S;
   for (int z = z_begin; z < z_end; ++z) {
     double m = 0.0;
-    for (int sp = 0; sp < p.js; ++sp) m += p.mean[((long long)z * p.js + sp) * p.nc_pad + i];
+    for (int sp = 0; sp < p.js; ++sp) m += p.mean[((long long)z * p.js_ld + sp) * p.nc_pad + i];
     const double* part = p.partial + (long long)z * p.tiles_m * nv * p.part_ld + i;
     double s0 = 0.0;
     if (p.grad && p.partial_sq) {
@@ -731,7 +733,7 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
           const double il = p.invl[z * d + q];
           const double gq = ((p.Xs[i * d + q] - p.xmu[q]) * h0 - pq) * il * il;
           double dmq = 0.0;
-          for (int sp = 0; sp < p.js; ++sp) dmq += p.dmean[(((long long)z * p.js + sp) * d + q) * p.nc_pad + i];
+          for (int sp = 0; sp < p.js; ++sp) dmq += p.dmean[(((long long)z * p.js_ld + sp) * d + q) * p.nc_pad + i];
           dm[q] = dmq;
           ds[q] = -2.0 * gq * inv2s;
         } else { dm[q] = 0.0; ds[q] = 0.0; }
@@ -989,30 +991,73 @@ struct SmallNParams {
 
 // SQ = true: the strict-variance form instead.  W is then X = L^-1 (lower triangular: the column loop stops at the
 // diagonal) and the only reduction is sum_j (X k)_j^2 = |L^-1 k|^2, one value per candidate.
-template <int NC, int R, bool SQ>
+// One CTA owns SMALLN_ROWS rows (four per warp) and streams them in chunks of SMALLN_CW columns through a ring of
+// SMALLN_STAGES shared-memory stages filled by TMA bulk copies (one 1 KB copy per row and chunk, issued by the 32 lanes of
+// warp 0, one mbarrier per stage): 96 KB per SM are in flight without holding a register.  Plain loads did not get
+// there -- the compiler schedules the FMAs of step t ahead of the loads of step t+1, each warp had ~1.5 steps in flight
+// and the kernel ran at 2.6 of HBM's 7.7 TB/s with every warp on the long scoreboard (ncu, profiles/).
+// SMALLN_ROWS is a template parameter (32 / 16 / 8 rows per CTA, i.e. 4 / 2 / 1 per warp): smaller matrices need more,
+// thinner CTAs to put every SM's load path to work (n = 2048: 64 CTAs of 32 rows took 25 us for 32 MB out of L2).
+constexpr int SMALLN_CW = 128, SMALLN_STAGES = 4;
+constexpr int smalln_smem_bytes(int rows) { return SMALLN_STAGES * rows * SMALLN_CW * 8 + SMALLN_STAGES * 8; }
+
+template <int NC, bool SQ, int SMALLN_ROWS>
 __global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
+  extern __shared__ __align__(128) double smalln_smem[];
   __shared__ double red[8][DMAX + 2][NC];
+  double* tile = smalln_smem;                                                            // [STAGES][ROWS][CW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smalln_smem + SMALLN_STAGES * SMALLN_ROWS * SMALLN_CW);
+  constexpr int R = SMALLN_ROWS / 8;
   const int z = blockIdx.y, rb = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = rb * (8 * R) + warp * R, n_pad = p.n_pad, d = SQ ? -1 : p.d;   // d + 2 values per candidate (SQ: one)
-  const int c_end = SQ ? min(n_pad, ((row0 + R + 31) >> 5) << 5) : n_pad;
-  const double* Wr = p.W + (long long)z * p.w_z + (long long)row0 * n_pad;
+  const int n_pad = p.n_pad, d = SQ ? -1 : p.d;   // d + 2 values per candidate (SQ: one)
+  const int row0 = rb * SMALLN_ROWS + warp * R;
+  const int nchunks = SQ ? (rb * SMALLN_ROWS + SMALLN_ROWS + SMALLN_CW - 1) / SMALLN_CW : n_pad / SMALLN_CW;
+  const double* Wblk = p.W + (long long)z * p.w_z + (long long)rb * SMALLN_ROWS * n_pad;
   const double* Kt = p.Kt + (long long)z * p.kt_z;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < SMALLN_STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t) {  // warp 0: chunk t of all 32 rows into stage t % STAGES
+    const int s = t % SMALLN_STAGES;
+    if (lane == 0) mbar_arrive_expect_tx(&full[s], SMALLN_ROWS * SMALLN_CW * 8);
+    __syncwarp();
+    if (lane < SMALLN_ROWS)
+      tma_bulk_load(tile + ((long long)s * SMALLN_ROWS + lane) * SMALLN_CW, Wblk + (long long)lane * n_pad + (long long)t * SMALLN_CW,
+                    SMALLN_CW * 8, &full[s]);
+  };
+  if (warp == 0)
+    for (int t = 0; t < SMALLN_STAGES && t < nchunks; ++t) issue(t);
   double acc[R][NC];
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int i = 0; i < NC; ++i) acc[r][i] = 0.0;
-#pragma unroll 2
-  for (int c = lane; c < c_end; c += 32) {
-    double kv[NC], w[R];
+  for (int t = 0; t < nchunks; ++t) {
+    const int s = t % SMALLN_STAGES;
+    double2 kv[2][NC];   // this chunk of the candidates' covariance vectors (shared by every CTA: L1 / L2 hits)
 #pragma unroll
-    for (int i = 0; i < NC; ++i) kv[i] = __ldg(Kt + (long long)i * n_pad + c);
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-    for (int r = 0; r < R; ++r) w[r] = __ldg(Wr + (long long)r * n_pad + c);
+      for (int i = 0; i < NC; ++i)
+        kv[u][i] = __ldg(reinterpret_cast<const double2*>(Kt + (long long)i * n_pad + t * SMALLN_CW + 64 * u + 2 * lane));
+    mbar_wait(&full[s], (uint32_t)((t / SMALLN_STAGES) & 1));
+    const double* ts = tile + ((long long)s * SMALLN_ROWS + warp * R) * SMALLN_CW + 2 * lane;
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int i = 0; i < NC; ++i) acc[r][i] = fma(w[r], kv[i], acc[r][i]);
+      for (int r = 0; r < R; ++r) {
+        const double2 w = *reinterpret_cast<const double2*>(ts + r * SMALLN_CW + 64 * u);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          acc[r][i] = fma(w.x, kv[u][i].x, acc[r][i]);
+          acc[r][i] = fma(w.y, kv[u][i].y, acc[r][i]);
+        }
+      }
+    __syncthreads();   // every warp is done with stage s: refill it
+    if (warp == 0 && t + SMALLN_STAGES < nchunks) issue(t + SMALLN_STAGES);
   }
 #pragma unroll
   for (int r = 0; r < R; ++r)
@@ -1068,12 +1113,15 @@ __global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  for (int idx = threadIdx.x; idx < (d + 2) * NC; idx += 256) {
+  // one warp per (value, candidate) pair: the lanes fetch every 32nd partial row at once and a fixed shuffle tree adds them
+  for (int idx = warp; idx < (d + 2) * NC; idx += 8) {
     const int v = idx / NC, i = idx - v * NC;
     const double* src = p.partial + (long long)z * p.part_z + (long long)v * p.ldp + i;
     double t = 0.0;
-    for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(src + (long long)b * (d + 2) * p.ldp);
-    p.final_rows[((long long)z * (d + 2) + v) * p.final_ld + i] = t;
+    for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(src + (long long)b * (d + 2) * p.ldp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) p.final_rows[((long long)z * (d + 2) + v) * p.final_ld + i] = t;
   }
 }
 
@@ -1138,6 +1186,32 @@ __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
       else p.dmean[(zs * d + (tid - 1)) * p.nc_ld + i] = t * invl[tid - 1];
     }
     __syncthreads();
+  }
+  // the last block of this hyper-parameter set adds the slices (in slice order) into slice 0: K3 then reads one value
+  // per candidate and output instead of walking js dependent loads for each (41 us for a single point at n=4096)
+  if (p.js == 1) return;
+  __shared__ int is_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int t = atomicAdd(p.ticket + z, 1);
+    is_last = (t == (int)gridDim.x - 1);
+    if (is_last) p.ticket[z] = 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int nv = p.dmean ? d + 1 : 1;
+  for (int idx = tid; idx < nv * (int)p.nc_run; idx += 256) {
+    const int v = idx / (int)p.nc_run, i = idx - v * (int)p.nc_run;
+    double t = 0.0;
+    if (v == 0) {
+      for (int sp = 0; sp < p.js; ++sp) t += __ldcg(p.mean + ((long long)z * p.js + sp) * p.nc_ld + i);
+      p.mean[(long long)z * p.js * p.nc_ld + i] = t;
+    } else {
+      for (int sp = 0; sp < p.js; ++sp) t += __ldcg(p.dmean + (((long long)z * p.js + sp) * d + (v - 1)) * p.nc_ld + i);
+      p.dmean[((long long)z * p.js * d + (v - 1)) * p.nc_ld + i] = t;
+    }
   }
 }
 

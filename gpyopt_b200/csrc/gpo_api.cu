@@ -74,6 +74,10 @@ struct gpo_engine {
   double* tk_vals[2] = {nullptr, nullptr};  long long* tk_idx[2] = {nullptr, nullptr};  size_t tk_cap = 0;
   // device-side design: when gen_on, the sweep generates its candidates (Philox stream) instead of reading Xs
   bool gen_on = false;  DesignParams gen;  long long gen_row0 = 0;
+  // page-locked staging of the latency path: a host-array call with <= 8 candidates uploads its points from here with an
+  // asynchronous copy and K3 writes the results straight into it (no device->host copies, one stream sync)
+  unsigned char* pin_buf = nullptr;      // host address
+  unsigned char* pin_dev = nullptr;      // the same memory as the device sees it
   bool smalln_attr_done = false;
   int* smalln_ticket = nullptr;  int smalln_ticket_cap = 0;   // [S] arrival counters of the small-N kernel
   double* smalln_sq = nullptr;  size_t smalln_sq_cap = 0;     // per-CTA partial rows of its strict-variance (|L^-1 k|^2) form
@@ -260,6 +264,7 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->blk_idx) cudaFree(eng->blk_idx);
   if (eng->gen_idx) cudaFree(eng->gen_idx);
   if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
+  if (eng->pin_buf) cudaFreeHost(eng->pin_buf);
   if (eng->smalln_sq) cudaFree(eng->smalln_sq);
   if (eng->gen_x) cudaFree(eng->gen_x);
   for (int i = 0; i < 5; ++i) if (eng->cov_buf[i]) cudaFree(eng->cov_buf[i]);
@@ -1000,13 +1005,28 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
   if (predict) { row_bytes[0] = row_bytes[1] = 8; row_bytes[2] = row_bytes[3] = (size_t)d * 8; for (int i = 0; i < 4; ++i) planes[i] = S; }
   else { row_bytes[0] = 8; row_bytes[1] = (size_t)d * 8; row_bytes[2] = row_bytes[3] = 0; planes[0] = planes[1] = 1; planes[2] = planes[3] = 0; }
   double* dev_out[4] = {nullptr, nullptr, nullptr, nullptr};
-  bool out_dev[4] = {true, true, true, true};
+  bool out_dev[4] = {true, true, true, true}, out_pin[4] = {false, false, false, false};
+  size_t pin_off[4] = {0, 0, 0, 0};
   int rc;
+  // latency path with host arrays: page-locked staging (see pin_buf)
+  constexpr size_t PIN_IN_BYTES = (size_t)SMALLN_MAX * DMAX * 8, PIN_BYTES = 512 << 10;
+  const bool tiny_call = N <= SMALLN_MAX && !gen;
+  size_t pin_used = PIN_IN_BYTES;
+  if (tiny_call && !eng->pin_buf) {
+    GPO_CUDA_OK(cudaHostAlloc((void**)&eng->pin_buf, PIN_BYTES, cudaHostAllocMapped));
+    GPO_CUDA_OK(cudaHostGetDevicePointer((void**)&eng->pin_dev, eng->pin_buf, 0));
+  }
   for (int i = 0; i < 4; ++i) {
     if (!outs[i]) continue;
     out_dev[i] = is_device_ptr(outs[i]);
+    const size_t bytes = (size_t)planes[i] * N * row_bytes[i];
     if (out_dev[i]) dev_out[i] = outs[i];
-    else {
+    else if (tiny_call && pin_used + bytes <= PIN_BYTES) {
+      dev_out[i] = reinterpret_cast<double*>(eng->pin_dev + pin_used);   // the kernel writes host memory directly
+      pin_off[i] = pin_used;
+      out_pin[i] = true;
+      pin_used += (bytes + 63) & ~(size_t)63;
+    } else {
       if ((rc = grow(eng, &eng->stage_out[i], &eng->stage_out_bytes[i], (size_t)planes[i] * N * row_bytes[i]))) return rc;
       dev_out[i] = eng->stage_out[i];
     }
@@ -1028,7 +1048,10 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     const long long rows = std::min(chunk, N - off);
     const long long nc_run = ((rows + TILE - 1) / TILE) * TILE;
     const int tiles_n = (int)(nc_run / TILE);
-    if (!in_dev)
+    if (!in_dev && tiny_call) {  // through the page-locked buffer: a truly asynchronous copy
+      memcpy(eng->pin_buf, Xs, (size_t)rows * d * 8);
+      GPO_CUDA_OK(cudaMemcpyAsync(eng->stage_in, eng->pin_buf, (size_t)rows * d * 8, cudaMemcpyHostToDevice, st));
+    } else if (!in_dev)
       GPO_CUDA_OK(cudaMemcpyAsync(eng->stage_in + off * d, Xs + off * d, (size_t)rows * d * 8, cudaMemcpyHostToDevice, st));
     if (gen) launch_design(eng, eng->gen, eng->gen_row0 + off, rows, eng->stage_in + off * d, st);
     // K1
@@ -1152,7 +1175,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     GPO_CUDA_OK(cudaGetLastError());
     // results back to host memory, chunk by chunk
     for (int i = 0; i < 4; ++i) {
-      if (!outs[i] || out_dev[i]) continue;
+      if (!outs[i] || out_dev[i] || out_pin[i]) continue;
       GPO_CUDA_OK(cudaMemcpy2DAsync((char*)outs[i] + off * row_bytes[i], (size_t)N * row_bytes[i],
                                     (char*)dev_out[i] + off * row_bytes[i], (size_t)N * row_bytes[i],
                                     (size_t)rows * row_bytes[i], planes[i], cudaMemcpyDeviceToHost, st));
@@ -1167,6 +1190,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
   if (any_host) {
     for (int i = 0; i < 2; ++i) GPO_CUDA_OK(cudaStreamSynchronize(eng->slot[i].stream));
   }
+  for (int i = 0; i < 4; ++i)
+    if (outs[i] && out_pin[i]) memcpy(outs[i], eng->pin_buf + pin_off[i], (size_t)planes[i] * N * row_bytes[i]);
   return GPO_OK;
 }
 

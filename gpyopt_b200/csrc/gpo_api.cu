@@ -76,6 +76,7 @@ struct gpo_engine {
   bool gen_on = false;  DesignParams gen;  long long gen_row0 = 0;
   // page-locked staging of the latency path: a host-array call with <= 8 candidates uploads its points from here with an
   // asynchronous copy and K3 writes the results straight into it (no device->host copies, one stream sync)
+  double* fit_pin = nullptr;  size_t fit_pin_cap = 0;   // page-locked staging of gpo_fit's small uploads / downloads
   unsigned char* pin_buf = nullptr;      // host address
   unsigned char* pin_dev = nullptr;      // the same memory as the device sees it
   bool smalln_attr_done = false;
@@ -265,6 +266,7 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->gen_idx) cudaFree(eng->gen_idx);
   if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
   if (eng->pin_buf) cudaFreeHost(eng->pin_buf);
+  if (eng->fit_pin) cudaFreeHost(eng->fit_pin);
   if (eng->smalln_sq) cudaFree(eng->smalln_sq);
   if (eng->gen_x) cudaFree(eng->gen_x);
   for (int i = 0; i < 5; ++i) if (eng->cov_buf[i]) cudaFree(eng->cov_buf[i]);
@@ -706,9 +708,25 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
   }
   eng->h_invl.assign((size_t)S * d, 0.0); eng->h_sigf2.assign(variance, variance + S); eng->h_noise.assign(noise, noise + S);
   for (int i = 0; i < S * d; ++i) eng->h_invl[i] = 1.0 / lengthscale[i];
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->invl, eng->h_invl.data(), (size_t)S * d * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->sigf2, eng->h_sigf2.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(eng->noise, eng->h_noise.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  // the small transfers of a refit go through one page-locked block: copies from / to pageable memory are staged
+  // synchronously by the driver (~8 us each, and a tiny model's whole refit takes 0.14 ms)
+  const size_t pin_need = ((size_t)S * (d + 6) + 8) * 8;
+  if (pin_need > eng->fit_pin_cap) {
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+    if (eng->fit_pin) cudaFreeHost(eng->fit_pin);
+    eng->fit_pin = nullptr; eng->fit_pin_cap = 0;
+    GPO_CUDA_OK(cudaHostAlloc((void**)&eng->fit_pin, pin_need, cudaHostAllocDefault));
+    eng->fit_pin_cap = pin_need;
+  }
+  double* pin_invl = eng->fit_pin, *pin_sigf2 = pin_invl + (size_t)S * d, *pin_noise = pin_sigf2 + S, *pin_jit = pin_noise + S;
+  double* pin_logdet = pin_jit + S, *pin_quad = pin_logdet + S;
+  int* pin_info = reinterpret_cast<int*>(pin_quad + S);
+  memcpy(pin_invl, eng->h_invl.data(), (size_t)S * d * 8);
+  memcpy(pin_sigf2, eng->h_sigf2.data(), (size_t)S * 8);
+  memcpy(pin_noise, eng->h_noise.data(), (size_t)S * 8);
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->invl, pin_invl, (size_t)S * d * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->sigf2, pin_sigf2, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->noise, pin_noise, (size_t)S * 8, cudaMemcpyHostToDevice, st));
 
   // GPy jitchol ladder: plain attempt, then jitter = mean(diag Ky) * 1e-6 * 10^t, t = 0..4.
   // A hyper-parameter set that factorises keeps jitter 0; only failing sets are retried.  Everything of one attempt
@@ -719,9 +737,10 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
   eng->h_logdet.resize(S); eng->h_quad.resize(S); eng->h_fmin.resize(S);
   std::vector<int> tries(S, 0);
   for (int attempt = 0; attempt <= 6; ++attempt) {
-    GPO_CUDA_OK(cudaMemcpyAsync(eng->jitter, eng->h_jit.data(), (size_t)S * 8, cudaMemcpyHostToDevice, st));
+    memcpy(pin_jit, eng->h_jit.data(), (size_t)S * 8);   // (the previous attempt's copy has completed: it was synchronised)
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->jitter, pin_jit, (size_t)S * 8, cudaMemcpyHostToDevice, st));
     if ((rc = factorize(eng, st))) return rc;
-    GPO_CUDA_OK(cudaMemcpyAsync(eng->h_info.data(), eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(pin_info, eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
     // alpha = L^-T (L^-1 y)
     {
       dim3 grd((n_pad + 7) / 8, S);
@@ -733,10 +752,13 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
                                             eng->quad, eng->fmin);
       eng->launches += 3;
       GPO_CUDA_OK(cudaGetLastError());
-      GPO_CUDA_OK(cudaMemcpyAsync(eng->h_logdet.data(), eng->logdet, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
-      GPO_CUDA_OK(cudaMemcpyAsync(eng->h_quad.data(), eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+      GPO_CUDA_OK(cudaMemcpyAsync(pin_logdet, eng->logdet, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+      GPO_CUDA_OK(cudaMemcpyAsync(pin_quad, eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
     }
     GPO_CUDA_OK(cudaStreamSynchronize(st));
+    memcpy(eng->h_info.data(), pin_info, S * sizeof(int));
+    memcpy(eng->h_logdet.data(), pin_logdet, (size_t)S * 8);
+    memcpy(eng->h_quad.data(), pin_quad, (size_t)S * 8);
     bool any = false;
     for (int z = 0; z < S; ++z) {
       if (eng->h_info[z] == 0) continue;

@@ -58,7 +58,7 @@ struct gpo_engine {
   double *logdet = nullptr, *quad = nullptr, *fmin = nullptr;        // [S]
   int* info = nullptr;                                               // [S]
   std::vector<double> h_logdet, h_quad, h_fmin;
-  double* gradpart = nullptr;
+  double* gradpart = nullptr;  double* gradpart_pin = nullptr;  size_t gradpart_cap = 0;   // loglik-gradient partials
   // sweep
   Slot slot[2];
   cudaEvent_t ev_in = nullptr;
@@ -239,7 +239,7 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
 
 static void free_state(gpo_engine* eng) {
   double** ptrs[] = {&eng->Xt, &eng->Xtc, &eng->xmu, &eng->Xaos, &eng->Y, &eng->invl, &eng->sigf2, &eng->noise, &eng->jitter, &eng->A, &eng->X,
-                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->xtile, &eng->probe_out, &eng->logdet, &eng->quad, &eng->fmin, &eng->gradpart};
+                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->xtile, &eng->probe_out, &eng->logdet, &eng->quad, &eng->fmin};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
   for (int i = 0; i < 2; ++i) {
@@ -266,6 +266,8 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->gen_idx) cudaFree(eng->gen_idx);
   if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
   if (eng->pin_buf) cudaFreeHost(eng->pin_buf);
+  if (eng->gradpart) cudaFree(eng->gradpart);
+  if (eng->gradpart_pin) cudaFreeHost(eng->gradpart_pin);
   if (eng->fit_pin) cudaFreeHost(eng->fit_pin);
   if (eng->smalln_sq) cudaFree(eng->smalln_sq);
   if (eng->gen_x) cudaFree(eng->gen_x);
@@ -347,7 +349,6 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   GPO_CUDA_OK(cudaMalloc(&eng->quad, (size_t)S * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->fmin, (size_t)S * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->info, (size_t)S * sizeof(int)));
-  GPO_CUDA_OK(cudaMalloc(&eng->gradpart, (size_t)S * 256 * (DMAX + 2) * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->probe_out, (size_t)S * 8));
   eng->h_X.clear(); eng->h_Y.clear();
   int rc;
@@ -829,15 +830,28 @@ extern "C" int gpo_get_loglik_grad(gpo_engine* eng, double* grad) {
   if (!eng || !grad) return GPO_ERR_ARG;
   if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_get_loglik_grad before gpo_fit");
   GPO_CUDA_OK(cudaSetDevice(eng->device));
-  const int S = eng->S, d = eng->d, nblk = 256;
+  const int S = eng->S, d = eng->d, nblk = (eng->n + 7) / 8;
   cudaStream_t st = eng->fit_stream;
   dim3 grd(nblk, S);
-  loglik_grad_kernel<<<grd, 256, 0, st>>>(eng->W, eng->alpha, eng->Xt, eng->n_pad, eng->n, eng->n_pad, d, eng->kern, eng->invl,
-                                          eng->sigf2, eng->gradpart);
+  const size_t need = (size_t)S * nblk * (d + 2) * 8;
+  if (need > eng->gradpart_cap) {  // device partials + their page-locked landing zone
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+    if (eng->gradpart) cudaFree(eng->gradpart);
+    if (eng->gradpart_pin) cudaFreeHost(eng->gradpart_pin);
+    eng->gradpart = nullptr; eng->gradpart_pin = nullptr; eng->gradpart_cap = 0;
+    GPO_CUDA_OK(cudaMalloc(&eng->gradpart, need));
+    GPO_CUDA_OK(cudaHostAlloc((void**)&eng->gradpart_pin, need, cudaHostAllocDefault));
+    eng->gradpart_cap = need;
+  }
+#define GPO_LLG(DP) loglik_grad_kernel<DP><<<grd, 256, 0, st>>>(eng->W, eng->alpha, eng->Xt, eng->n_pad, eng->n, eng->n_pad, d, \
+                                                              eng->kern, eng->invl, eng->sigf2, eng->gradpart)
+  if (d <= 2) GPO_LLG(2); else if (d <= 4) GPO_LLG(4); else if (d <= 6) GPO_LLG(6); else if (d <= 8) GPO_LLG(8);
+  else if (d <= 12) GPO_LLG(12); else GPO_LLG(16);
+#undef GPO_LLG
   eng->launches++;
   GPO_CUDA_OK(cudaGetLastError());
-  std::vector<double> part((size_t)S * nblk * (d + 2));
-  GPO_CUDA_OK(cudaMemcpyAsync(part.data(), eng->gradpart, part.size() * 8, cudaMemcpyDeviceToHost, st));
+  const double* part = eng->gradpart_pin;
+  GPO_CUDA_OK(cudaMemcpyAsync(eng->gradpart_pin, eng->gradpart, need, cudaMemcpyDeviceToHost, st));
   GPO_CUDA_OK(cudaStreamSynchronize(st));
   for (int z = 0; z < S; ++z)
     for (int q = 0; q < d + 2; ++q) {

@@ -229,7 +229,7 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
   cudaEventCreateWithFlags(&eng->ev_in, cudaEventDisableTiming);
   int rc = gemm_setup(eng);
   if (rc != GPO_OK) {
-    snprintf(g_create_error, sizeof(g_create_error), "%s", eng->last_error);
+    snprintf(g_create_error, sizeof(g_create_error), "%.255s", eng->last_error);
     delete eng;
     return rc;
   }

@@ -62,8 +62,7 @@ __global__ void __launch_bounds__(COV_THREADS) cov_mean_kernel(const CovParams p
   const long long c0 = (long long)blockIdx.x * COV_THREADS;
   const long long cand = c0 + tid;
   const double* invl = p.invl + (long long)z * p.d;
-  const double sf2 = p.sigf2[z];
-  const double* alpha = p.alpha + (long long)z * p.n_pad;
+  const double sf2 = p.sigf2[z];   // (alpha comes in through the staged tiles)
   double xs[DP], dm[DP], m = 0.0;
 #pragma unroll
   for (int q = 0; q < DP; ++q) {

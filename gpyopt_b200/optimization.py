@@ -11,6 +11,8 @@ rows f2 / f4).  Needs the reference package (GPyOpt) importable: these classes r
 * :class:`FusedAnchorPointsGenerator` -- ``ObjectiveAnchorPointsGenerator`` whose scoring + ``argsort[:k]``
   (anchor_points_generator.py:62-67) is the fused device sweep + top-k (``gpo_acq_topk``) when the acquisition has
   constant cost and the space no constraints.
+* :class:`FusedThompsonAnchorPointsGenerator` -- Thompson-sampling anchors (anchor_points_generator.py:72-88) scored
+  with one sweep and one vectorised normal draw instead of a Python loop over 25 000 candidates (same random stream).
 * :class:`DeviceDesignAnchorPointsGenerator` -- the same, with the random design itself generated on the device
   (``gpo_acq_topk_uniform``): for all-continuous box domains the 1000 ... 1e7 candidate rows of
   ``initial_design('random', ...)`` (experiment_design/random_design.py:56-76) never exist on the host.
@@ -164,6 +166,17 @@ class DeviceDesignAnchorPointsGenerator(FusedAnchorPointsGenerator):
         return rows
 
 
+class FusedThompsonAnchorPointsGenerator(ThompsonSamplingAnchorPointsGenerator if HAVE_GPYOPT else object):
+    """ThompsonSamplingAnchorPointsGenerator (anchor_points_generator.py:72-88) without its 25 000-iteration Python loop:
+    one device value sweep (``model.predict``) and ONE vectorised ``numpy.random.normal`` call, which consumes NumPy's
+    global legacy stream exactly like the reference's element-by-element loop -- the scores, and therefore the anchors,
+    are identical for a given seed."""
+
+    def get_anchor_point_scores(self, X):
+        means, stds = self.model.predict(X)
+        return np.random.normal(np.asarray(means).reshape(-1), np.asarray(stds).reshape(-1))
+
+
 class BatchedAcquisitionOptimizer(AcquisitionOptimizer):
     """AcquisitionOptimizer whose local optimisations share their device calls (see module docstring)."""
 
@@ -192,7 +205,7 @@ class BatchedAcquisitionOptimizer(AcquisitionOptimizer):
             else:
                 gen = ObjectiveAnchorPointsGenerator(self.space, random_design_type, f)
         elif self.type_anchor_points_logic == thompson_sampling_anchor_points_logic:
-            gen = ThompsonSamplingAnchorPointsGenerator(self.space, sobol_design_type, self.model)
+            gen = FusedThompsonAnchorPointsGenerator(self.space, sobol_design_type, self.model)
         anchor_points = gen.get(duplicate_manager=duplicate_manager, context_manager=self.context_manager)
 
         fns = {'f': f}

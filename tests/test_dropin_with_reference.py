@@ -253,6 +253,31 @@ def test_device_design_anchor_points(gpyopt):
     assert g2.get(num_anchor=3).shape == (3, 2) and g2.calls == 0
 
 
+def test_thompson_anchor_scores_match_the_reference_loop(gpyopt):
+    """FusedThompsonAnchorPointsGenerator draws the reference's scores (same global NumPy stream) in one call."""
+    GPyOpt, models, acqs = gpyopt
+    import importlib
+    import gpyopt_b200.optimization as opt
+    importlib.reload(opt)
+    from gpyopt_b200 import kern
+    from oracle import gpyopt_numpy as og
+    from GPyOpt.optimization.anchor_points_generator import ThompsonSamplingAnchorPointsGenerator
+    rng = np.random.default_rng(4)
+    space = GPyOpt.Design_space(DOMAIN)
+    X = np.column_stack([rng.uniform(-5, 10, 10), rng.uniform(1, 15, 10)])
+    model = models.GPModel(kernel=kern.RBF(2, lengthscale=3.0), exact_feval=True, max_iters=0, verbose=False)
+    model.updateModel(X, og.normalize_stats(branin(X)), None, None)
+    cand = np.column_stack([rng.uniform(-5, 10, 300), rng.uniform(1, 15, 300)])
+    ref = ThompsonSamplingAnchorPointsGenerator(space, 'random', model, num_samples=300)
+    new = opt.FusedThompsonAnchorPointsGenerator(space, 'random', model, num_samples=300)
+    np.random.seed(8); a = ref.get_anchor_point_scores(cand)
+    np.random.seed(8); b = new.get_anchor_point_scores(cand)
+    assert np.array_equal(a, b)
+    np.random.seed(9); pa = ref.get(num_anchor=5)
+    np.random.seed(9); pb = new.get(num_anchor=5)
+    assert np.array_equal(pa, pb)
+
+
 def test_rendezvous_propagates_errors_and_handles_uneven_workers():
     import threading
     from gpyopt_b200.optimization import Rendezvous

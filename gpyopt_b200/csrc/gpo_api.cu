@@ -645,7 +645,9 @@ static void finish_variance_probe(gpo_engine* eng) {
   for (int z = 0; z < eng->S; ++z) {
     const double scale = std::sqrt(std::max(eng->h_sigf2[z] + eng->h_noise[z], 1e-300));
     eng->var_disc = std::max(eng->var_disc, eng->h_disc[z] / scale);
-    if (!(eng->h_disc[z] <= 2e-11 * scale)) need = true;
+    // 7e-12: over ~350 random models the error of s at candidate points (relative to their own largest s) stayed below
+    // ~13x this training-point discrepancy, so the fast form is kept only where it is good for the 1e-10 parity bar
+    if (!(eng->h_disc[z] <= 7e-12 * scale)) need = true;
   }
   eng->strict_active = eng->strict_mode == 1 || (eng->strict_mode < 0 && need);
 }

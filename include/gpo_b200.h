@@ -146,7 +146,7 @@ int gpo_posterior_cov(gpo_engine* eng, long long N1, const double* X1, long long
  * (sigma_f^2 - k.b: 2 n^2 flop per candidate in total).  On an ill-conditioned Gram matrix that form cancels badly,
  * whereas the reference's sigma_f^2 - |L^-1 k|^2 (GPy PosteriorExact._raw_predict) does not.  After every refit the
  * engine measures max |s_L - s_W| over the training inputs; in mode -1 (automatic, default) it adds the triangular
- * pass (3 n^2 flop per candidate, as the reference itself spends) when that discrepancy exceeds 2e-11 sqrt(sf2 + noise).
+ * pass (3 n^2 flop per candidate, as the reference itself spends) when that discrepancy exceeds 7e-12 sqrt(sf2 + noise).
  * mode 0 = never, 1 = always.  gpo_get_info: info[0] = strict pass active, info[1] = measured discrepancy (scaled),
  * info[2] = chunk (candidates), info[3] = padded n, info[4] = SM count, info[5] = S. */
 int gpo_set_strict_variance(gpo_engine* eng, int mode);

@@ -95,10 +95,14 @@ def parity_tolerances(gp, Xs, base=1e-10):
     dsB = gp.kern.gradients_X(-2 * b.T, Xs, gp.X) / (2 * sA[:, None])
     floor_s = np.max(np.abs(sA - sB)) / np.max(np.abs(sA))
     floor_g = np.max(np.abs(dsA - dsB)) / max(np.max(np.abs(dsA)), 1e-300)
-    return max(base, 10 * floor_s), max(base, 10 * floor_g)
+    # the mean has its own floor: alpha from the two triangular solves (dpotrs, what GPy stores) versus alpha = W^-1 y
+    mA = np.dot(Kx.T, gp.posterior.woodbury_vector)
+    mB = np.dot(Kx.T, np.dot(Wi, gp.Y))
+    floor_m = np.max(np.abs(mA - mB)) / max(np.max(np.abs(mA)), 1e-300)
+    return max(base, 10 * floor_s, 10 * floor_m), max(base, 10 * floor_g)
 
 
-def ei_input_error_budget(mo, so, dmo, dso, m, s, dm, ds, fmin, jitter):
+def ei_input_error_budget(mo, so, dmo, dso, m, s, dm, ds, fmin, jitter, fmin_err=0.0):
     """First-order change of EI and of its gradient caused by the (separately asserted, <= 1e-10 scaled) deviations of
     their inputs:  dEI = -Phi(u) dm + phi(u) ds,  d(grad) = phi d(ds) - Phi d(dm) - phi du (u ds + dm),
     du = -(dm + u ds)/s.  In the far tail (EI ~ 1e-25 at u ~ -10) the RELATIVE condition number of the value is ~u^2,
@@ -110,7 +114,7 @@ def ei_input_error_budget(mo, so, dmo, dso, m, s, dm, ds, fmin, jitter):
     dmo, dso, dm, ds = (np.asarray(a, dtype=float).reshape(mo.size, -1) for a in (dmo, dso, dm, ds))
     u = (fmin - mo - jitter) / so
     Phi, phi = 0.5 * sp.erfc(-u / np.sqrt(2.0)), np.exp(-0.5 * u * u) / np.sqrt(2.0 * np.pi)
-    em, es = np.abs(m - mo), np.abs(s - so)
+    em, es = np.abs(m - mo) + abs(fmin_err), np.abs(s - so)   # (fmin enters u exactly like the mean does)
     du = (em + np.abs(u) * es) / so
     bf = Phi * em + phi * es
     bdf = (phi[:, None] * np.abs(ds - dso) + Phi[:, None] * np.abs(dm - dmo)

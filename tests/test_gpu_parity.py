@@ -622,8 +622,14 @@ def test_randomised_shapes_against_oracle(n, d, N, kernel, ARD, S, noise, seed):
         # u*Phi + phi cancels ~u^2 digits in the far tail (SURVEY 'EI tail cancellation'): below 1e-100 only the order of
         # magnitude is meaningful, so such candidate sets are scaled by 1e-100
         scale_f = max(np.max(np.abs(fo)), 1e-100)
-        assert np.max(np.abs(f - fo[:, 0])) / scale_f < 10 * tol_v and np.max(np.abs(fv - fo[:, 0])) / scale_f < 10 * tol_v
-        assert np.max(np.abs(df - dfo)) / max(np.max(np.abs(dfo)), 1e-100) < 100 * tol_g
+        # ... and wherever EI is small against its inputs the (already asserted) deviations of m and s are amplified by
+        # ~u^2: the comparison allows their first-order effect on top of the scaled tolerance (conftest.ei_input_error_budget)
+        fm_e = eng.get_fmin()
+        budgets = [ei_input_error_budget(ref[z][0], ref[z][1], ref[z][2], ref[z][3], m[z], s[z], dm[z], ds[z], fmins[z], 0.01,
+                                         fmin_err=fm_e[z] - fmins[z]) for z in range(S)]
+        bf, bdf = sum(b[0] for b in budgets) / S, sum(b[1] for b in budgets) / S
+        assert np.max(np.abs(f - fo[:, 0])) < 10 * tol_v * scale_f + bf and np.max(np.abs(fv - fo[:, 0])) < 10 * tol_v * scale_f + bf
+        assert np.max(np.abs(df - dfo)) < 100 * tol_g * max(np.max(np.abs(dfo)), 1e-100) + bdf
         k = min(3, N)
         vals, idx = eng.acq_topk(kind, 0.01, Xs, k)
         assert np.array_equal(np.sort(fv)[::-1][:k], -vals)

@@ -26,7 +26,7 @@ constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 4) * 32;  // 2 consumer warp
 constexpr int GEMM_SCRATCH_BYTES = (16 + (16 + 2) * 2) * TILE * 8;  // xj [d][128] + red [(d+2)][2][128], d <= 16
 constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + GEMM_SCRATCH_BYTES;
 
-enum KRange { KR_FULL = 0, KR_LE_M = 1, KR_GE_N = 2, KR_GE_MAX = 3 };
+enum KRange { KR_FULL = 0, KR_LE_M = 1, KR_GE_N = 2, KR_GE_MAX = 3, KR_GE_M = 4 };
 enum TileSkip { TS_ALL = 0, TS_LOWER = 1 };
 enum Raster { RO_M_FASTEST = 0, RO_HEAVY_FIRST = 1 };
 enum Epilogue { EPI_STORE = 0, EPI_SUMSQ = 1, EPI_GRAD = 2 };
@@ -60,6 +60,9 @@ struct GemmParams {
   // EPI_SUMSQ / EPI_GRAD: partial[((z*tiles_m + tile_m)*nvals + v)*ldp + tile_n*128 + col]
   double* partial;
   long long ldp;
+  // EPI_SUMSQ, optional: the product itself, transposed, as the next product's K-major operand  Tt[z][col][row]
+  double* Tt;
+  long long tt_ld, tt_z;   // row pitch (= n_pad) and per-batch stride of Tt
   // EPI_GRAD: partial values per column are [S0 = sum_j b_j k_j, H0 = sum_j b_j h_j, P_q = sum_j b_j h_j xc_jq]
   int d;
   const double* Xtc;    // centred training inputs, SoA [d][ldx] (zero on the padding rows)
@@ -99,14 +102,15 @@ __device__ __forceinline__ GemmTile gemm_decode(const GemmParams& p, long long w
   } else if (p.raster == RO_M_FASTEST) {
     t.tile_m = x % p.tiles_m;
     t.tile_n = x / p.tiles_m;
-  } else {  // heaviest row blocks (largest k range under KR_LE_M) first
-    t.tile_m = p.tiles_m - 1 - x / p.tiles_n;
+  } else {  // heaviest row blocks first: the largest k range is the last row block under KR_LE_M, the first under KR_GE_M
+    t.tile_m = p.krange == KR_GE_M ? x / p.tiles_n : p.tiles_m - 1 - x / p.tiles_n;
     t.tile_n = x % p.tiles_n;
   }
   int kb_begin = 0, kb_end = p.kblocks;
   if (p.krange == KR_LE_M) kb_end = min(t.tile_m + 1, p.kblocks);
   else if (p.krange == KR_GE_N) kb_begin = t.tile_n;
   else if (p.krange == KR_GE_MAX) kb_begin = max(t.tile_m, t.tile_n);
+  else if (p.krange == KR_GE_M) kb_begin = t.tile_m;
   if (ksplit > 1) {
     const int len = (kb_end - kb_begin + ksplit - 1) / ksplit;
     kb_begin = min(kb_end, kb_begin + t.split * len);
@@ -259,6 +263,18 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     double* red = reinterpret_cast<double*>(scratch);  // EPI_SUMSQ: [2][128]; EPI_GRAD: after the coordinates
     const int half = warp & 1;
     if constexpr (EPI == EPI_SUMSQ) {
+      if (p.Tt) {  // t = L^-1 k kept for the second triangular product (b = L^-T t): 64-byte runs per candidate row
+        double* Tz = p.Tt + (long long)z * p.tt_z;
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+          const int r = tile_m * TILE + wm + 8 * f + rr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+              Tz[(long long)(tile_n * TILE + wn + 8 * j + (e ? 4 + t : t)) * p.tt_ld + r] = acc[f][j][e];
+        }
+      }
       named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
 #pragma unroll
       for (int j = 0; j < 4; ++j)

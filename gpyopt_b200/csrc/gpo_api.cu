@@ -22,6 +22,8 @@ struct Slot {
   double* Kt = nullptr;  // [S][nc_ld][n_pad]
   double* Ht = nullptr;  // [S][nc_ld][n_pad], only for non-RBF kernels (allocated on demand)
   CUtensorMap mapKt;
+  double* Tt = nullptr;  // [S][nc_ld][n_pad]  t = L^-1 k of the chunk (strict gradient sweeps: b = L^-T t), allocated on demand
+  CUtensorMap mapTt;
   double* mean = nullptr;     // [S][js][nc_ld]   per-slice partial sums of K1
   double* dmean = nullptr;    // [S][js][d][nc_ld]
   double* partial = nullptr;  // [S][tiles_m][d+2][nc_ld]
@@ -244,7 +246,7 @@ static void free_state(gpo_engine* eng) {
   if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
   for (int i = 0; i < 2; ++i) {
     Slot& s = eng->slot[i];
-    double** sp[] = {&s.Kt, &s.Ht, &s.mean, &s.dmean, &s.partial, &s.partial_sq, &s.zbuf};
+    double** sp[] = {&s.Kt, &s.Ht, &s.Tt, &s.mean, &s.dmean, &s.partial, &s.partial_sq, &s.zbuf};
     for (auto pp : sp) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   }
   eng->cap_n_pad = eng->cap_d = eng->cap_S = 0;
@@ -1165,6 +1167,25 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
       g.ksplit = ksplit;
       if (ksplit > 1) { g.ldp = nc_run; part_ld = nc_run; }
       part_nv = g.d + 2; part_rows = tiles_m * ksplit;
+      if (grad && eng->strict_active && !small) {
+        // ill-conditioned model, large sweep: b = W^-1 k = L^-T (L^-1 k) as TWO triangular products of n^2 flop each.
+        // The first one is the reference's own variance form (sum of squares of t = L^-1 k) and leaves t behind as the
+        // second one's K-major operand, so the strict variance costs nothing beyond the fast path's 2 n^2
+        // (before: the full W^-1 product plus the triangular one, 3 n^2).
+        if (!s.Tt) {
+          GPO_CUDA_OK(cudaMalloc(&s.Tt, (size_t)S * eng->nc_ld * n_pad * 8));
+          if ((rc = make_map(eng, &s.mapTt, s.Tt, n_pad, eng->nc_ld, S))) return rc;
+        }
+        GemmParams gs = gemm_defaults();
+        gs.tiles_m = tiles_m; gs.tiles_n = tiles_n; gs.kblocks = tiles_m;
+        gs.a = {0, 0, 0, 0, 0, 1}; gs.b = {0, 0, 0, 0, 0, 1};
+        gs.partial = s.partial_sq; gs.ldp = eng->nc_ld; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
+        gs.Tt = s.Tt; gs.tt_ld = n_pad; gs.tt_z = eng->nc_ld * (long long)n_pad;
+        if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, gs, S, st))) return rc;
+        g.krange = KR_GE_M; g.raster = RO_HEAVY_FIRST;     // A = U = L^-T (upper triangular), B = t
+        if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapU, s.mapTt, g, S, st))) return rc;
+        if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
+      } else {
       if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s.mapKt, g, S, st))) return rc;
       if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
       if (grad && eng->strict_active) {  // ill-conditioned model: variance from the reference's own triangular form as well
@@ -1173,6 +1194,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
         gs.a = {0, 0, 0, 0, 0, 1}; gs.b = {0, 0, 0, 0, 0, 1};
         gs.partial = s.partial_sq; gs.ldp = eng->nc_ld; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
         if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, gs, S, st))) return rc;
+      }
       }
     } else {
       g.krange = KR_LE_M; g.raster = RO_HEAVY_FIRST;

@@ -351,6 +351,18 @@ def test_small_batch_latency_path(engine, kernel, ARD, S):
             m, s = engine.predict(X9[:N])
             for z in range(S):
                 assert scaled_err(s[z], ref[z][1][:N, 0]) < 1e-10
+        # a large strict sweep: b = L^-T (L^-1 k) as two triangular products (the first one IS the strict variance)
+        X400 = X[rng.integers(0, n, 400)] + 0.05 * rng.standard_normal((400, d))
+        r400 = [og.gp_predict_withGradients(g, X400) for g in gps]
+        m4, s4, dm4, ds4 = engine.predict_grad(X400)
+        for z in range(S):
+            assert scaled_err(m4[z], r400[z][0][:, 0]) < 1e-10 and scaled_err(s4[z], r400[z][1][:, 0]) < 1e-10
+            assert scaled_err(dm4[z], r400[z][2]) < 1e-10 and scaled_err(ds4[z], r400[z][3]) < 1e-10
+        engine.set_strict_variance(0)      # the fast form on the same points: same answer on this well-conditioned model
+        engine.fit(kernel, X, Y[:, 0], var, np.broadcast_to(ls, (S, d)), nz)
+        m5, s5, dm5, ds5 = engine.predict_grad(X400)
+        assert scaled_err(s5, s4) < 1e-10 and scaled_err(ds5, ds4) < 1e-10 and np.array_equal(m5, m4) and np.array_equal(dm5, dm4)
+        engine.set_strict_variance(1)
     finally:
         engine.set_strict_variance(-1)
         engine.fit(kernel, X, Y[:, 0], var, np.broadcast_to(ls, (S, d)), nz)

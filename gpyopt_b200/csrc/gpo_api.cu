@@ -929,7 +929,10 @@ static void launch_design(gpo_engine* eng, DesignParams p, long long row0, long 
 // kind == ACQ_NONE: predict  (o0 = m [S][N], o1 = s [S][N], o2 = dmdx [S][N][d], o3 = dsdx [S][N][d])
 // otherwise:        acquisition (o0 = f [N], o1 = df [N][d])
 // small-N latency path (see smalln_wk_kernel): nc in 1..8 candidates, returns the number of partial rows K3 must add
-constexpr int SMALLN_MAX = 8, SMALLN_LDP = 8;
+constexpr int SMALLN_MAX = 8;        // candidates per launch of the matrix-vector kernel
+constexpr int SMALLN_MAX_CALL = 32;  // candidates per call that still take the latency path (ceil(N / 8) launches)
+constexpr int SMALLN_LDP = 8;        // leading dimension of the per-CTA partial rows
+constexpr int SMALLN_FLD = SMALLN_MAX_CALL;  // ... and of the reduced rows K3 reads
 template <bool SQ, int ROWS>
 static void launch_smalln_r(const SmallNParams& p, int nc, dim3 grid, cudaStream_t st) {
   constexpr int smem = smalln_smem_bytes(ROWS);
@@ -992,15 +995,24 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
   } else {
     p.W = eng->W;
     p.partial = s.partial; p.part_z = (long long)row_blocks * (d_epi + 2) * SMALLN_LDP;
-    p.final_rows = s.partial + (long long)eng->S * p.part_z; p.final_ld = SMALLN_LDP;
+    p.final_rows = s.partial + (long long)eng->S * p.part_z; p.final_ld = SMALLN_FLD;
     *final_rows = p.final_rows;
   }
   dim3 grid((unsigned)row_blocks, (unsigned)eng->S, 1);
-  if (rows == 32) { if (sq) launch_smalln_r<true, 32>(p, nc, grid, st); else launch_smalln_r<false, 32>(p, nc, grid, st); }
-  else if (rows == 16) { if (sq) launch_smalln_r<true, 16>(p, nc, grid, st); else launch_smalln_r<false, 16>(p, nc, grid, st); }
-  else { if (sq) launch_smalln_r<true, 8>(p, nc, grid, st); else launch_smalln_r<false, 8>(p, nc, grid, st); }
-  eng->launches++;
-  GPO_CUDA_OK(cudaGetLastError());
+  // groups of up to 8 candidates, one launch each (every launch streams the matrix once: beyond a few groups the
+  // tensor-core path wins again, hence SMALLN_MAX_CALL)
+  double* final0 = p.final_rows;
+  for (int g0 = 0; g0 < nc; g0 += SMALLN_MAX) {
+    const int ncg = std::min(SMALLN_MAX, nc - g0);
+    p.Kt = s.Kt + (long long)g0 * n_pad;
+    p.Ht = (!sq && use_ht) ? s.Ht + (long long)g0 * n_pad : nullptr;
+    p.final_rows = final0 + g0;
+    if (rows == 32) { if (sq) launch_smalln_r<true, 32>(p, ncg, grid, st); else launch_smalln_r<false, 32>(p, ncg, grid, st); }
+    else if (rows == 16) { if (sq) launch_smalln_r<true, 16>(p, ncg, grid, st); else launch_smalln_r<false, 16>(p, ncg, grid, st); }
+    else { if (sq) launch_smalln_r<true, 8>(p, ncg, grid, st); else launch_smalln_r<false, 8>(p, ncg, grid, st); }
+    eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
+  }
   return GPO_OK;
 }
 
@@ -1019,7 +1031,9 @@ static int ensure_ticket(gpo_engine* eng) {
 static int launch_cov_small(gpo_engine* eng, const CovParams& p_in, int nc, cudaStream_t st) {
   { const int trc = ensure_ticket(eng); if (trc) return trc; }
   CovParams p = p_in;
-  p.nc_run = nc <= 1 ? 1 : nc <= 2 ? 2 : nc <= 4 ? 4 : 8;   // the candidate slots smalln_wk_kernel<NC> will read
+  // the candidate slots the matrix-vector launches will read: {1, 2, 4, 8} for the last (or only) group of eight
+  const int tail = nc % SMALLN_MAX == 0 ? SMALLN_MAX : nc % SMALLN_MAX;
+  p.nc_run = (nc - tail) + (tail <= 1 ? 1 : tail <= 2 ? 2 : tail <= 4 ? 4 : 8);
   p.ticket = eng->smalln_ticket;
   dim3 grid((unsigned)p.js, (unsigned)eng->S, 1);
   cov_small_kernel<<<grid, 256, 0, st>>>(p);
@@ -1049,8 +1063,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
   size_t pin_off[4] = {0, 0, 0, 0};
   int rc;
   // latency path with host arrays: page-locked staging (see pin_buf)
-  constexpr size_t PIN_IN_BYTES = (size_t)SMALLN_MAX * DMAX * 8, PIN_BYTES = 512 << 10;
-  const bool tiny_call = N <= SMALLN_MAX && !gen;
+  constexpr size_t PIN_IN_BYTES = (size_t)SMALLN_MAX_CALL * DMAX * 8, PIN_BYTES = 1 << 20;
+  const bool tiny_call = N <= SMALLN_MAX_CALL && !gen;
   size_t pin_used = PIN_IN_BYTES;
   if (tiny_call && !eng->pin_buf) {
     GPO_CUDA_OK(cudaHostAlloc((void**)&eng->pin_buf, PIN_BYTES, cudaHostAllocMapped));
@@ -1101,7 +1115,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     cp.sigf2 = eng->sigf2; cp.Kt = s.Kt; cp.Ht = (grad && eng->kern != KERN_RBF) ? s.Ht : nullptr; cp.mean = s.mean;
     cp.dmean = s.dmean; cp.js = eng->js; cp.tiles_per_split = eng->tiles_per_split;
     // a handful of points (L-BFGS steps) on a well-conditioned model: the latency kernels below
-    const bool tiny = N <= SMALLN_MAX;
+    const bool tiny = N <= SMALLN_MAX_CALL;
     if (tiny) {
       if (!grad) cp.dmean = nullptr;
       if (mean_only) { cp.Kt = nullptr; cp.Ht = nullptr; }
@@ -1149,15 +1163,15 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
       // a handful of points (L-BFGS steps): batched matrix-vector products instead of 128-wide tensor-core tiles
       if (w_form) {
         if ((rc = launch_smalln(eng, s, (int)N, grad ? d : 0, grad && eng->kern != KERN_RBF, st, &small_final))) return rc;
-        part_rows = 1; part_nv = (grad ? d : 0) + 2; part_ld = SMALLN_LDP;
+        part_rows = 1; part_nv = (grad ? d : 0) + 2; part_ld = SMALLN_FLD;
         if (grad && eng->strict_active) {  // ill-conditioned model: variance from the reference's own triangular form as well
           if ((rc = launch_smalln(eng, s, (int)N, 0, false, st, nullptr, true, s.partial_sq, eng->nc_ld))) return rc;
           sq_rows = 1;
         }
       } else {  // value only on an ill-conditioned model: the triangular form alone
-        if ((rc = launch_smalln(eng, s, (int)N, 0, false, st, nullptr, true, s.partial, SMALLN_LDP))) return rc;
+        if ((rc = launch_smalln(eng, s, (int)N, 0, false, st, nullptr, true, s.partial, SMALLN_FLD))) return rc;
         small_final = s.partial;
-        part_rows = 1; part_nv = 1; part_ld = SMALLN_LDP;
+        part_rows = 1; part_nv = 1; part_ld = SMALLN_FLD;
       }
       if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
     } else if (w_form) {

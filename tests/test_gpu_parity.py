@@ -325,7 +325,14 @@ def test_small_batch_latency_path(engine, kernel, ARD, S):
         fo, dfo = og.acq_EI_withGradients(ref[0][0].copy(), ref[0][1].copy(), ref[0][2], ref[0][3], fmins[0], 0.01)
     else:
         fo, dfo = og.acq_EI_MCMC_withGradients([r[0] for r in ref], [r[1] for r in ref], [r[2] for r in ref], [r[3] for r in ref], fmins, 0.01)
-    f9, df9 = engine.acq(kind, 0.01, X9, grad=True)                   # N = 9: tensor-core path
+    X40 = np.vstack([X9, X[np.argsort(Y[:, 0])[9:40]] + 0.02 * rng.standard_normal((31, d))])
+    f9, df9 = engine.acq(kind, 0.01, X40, grad=True)                  # N = 40: tensor-core path (the latency path ends at 32)
+    for N in (12, 17, 32):                                            # several groups of eight through the latency kernels
+        fN, dfN = engine.acq(kind, 0.01, X40[:N], grad=True)
+        assert scaled_err(fN, f9[:N]) < 1e-10 and scaled_err(dfN, df9[:N]) < 1e-10
+        f1, df1 = engine.acq(kind, 0.01, X40[N - 1:N], grad=True)     # rows are independent of the batch they are in
+        assert f1[0] == fN[N - 1] and np.array_equal(df1[0], dfN[N - 1])
+        assert np.array_equal(engine.acq(kind, 0.01, X40[:N]), fN)
     for N in range(1, 10):
         f, df = engine.acq(kind, 0.01, X9[:N], grad=True)
         assert scaled_err(f, fo[:N, 0]) < 1e-10 and scaled_err(df, dfo[:N]) < 1e-10
@@ -334,7 +341,7 @@ def test_small_batch_latency_path(engine, kernel, ARD, S):
         for z in range(S):
             assert scaled_err(m[z], ref[z][0][:N, 0]) < 1e-10 and scaled_err(s[z], ref[z][1][:N, 0]) < 1e-10
             assert scaled_err(dm[z], ref[z][2][:N]) < 1e-10 and scaled_err(ds[z], ref[z][3][:N]) < 1e-10
-        if N <= 8:
+        if N <= 9:
             f1, df1 = engine.acq(kind, 0.01, X9[N - 1:N], grad=True)  # the same row alone
             assert f1[0] == f[N - 1] and np.array_equal(df1[0], df[N - 1])
         assert scaled_err(f, f9[:N]) < 1e-10 and scaled_err(df, df9[:N]) < 1e-10   # two summation orders of one contraction
@@ -343,7 +350,7 @@ def test_small_batch_latency_path(engine, kernel, ARD, S):
     try:
         engine.fit(kernel, X, Y[:, 0], var, np.broadcast_to(ls, (S, d)), nz)
         assert engine.info()['strict_variance']
-        for N in (1, 3, 8, 9):   # 9: the tensor-core form of the same guard
+        for N in (1, 3, 8, 9, 20):
             f, df = engine.acq(kind, 0.01, X9[:N], grad=True)
             assert scaled_err(f, fo[:N, 0]) < 1e-10 and scaled_err(df, dfo[:N]) < 1e-10
             fv = engine.acq(kind, 0.01, X9[:N])          # value only: the triangular form alone

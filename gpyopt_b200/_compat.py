@@ -84,4 +84,62 @@ except Exception:  # GPyOpt (or its GPy dependency) absent: same contracts, rest
         def _compute_acq_withGradients(self, x):
             raise NotImplementedError('')
 
-    LPBase = AcquisitionBase
+    class LPBase(AcquisitionBase):
+        """Host side of Local Penalization for an environment without GPyOpt: the contract of
+        GPyOpt/acquisitions/LP.py:40-140 (penaliser parameters, log-space penalised value, gradient with the direction
+        vector dropped).  With GPyOpt importable the B200 class inherits the reference's own methods instead."""
+
+        def update_batches(self, X_batch, L, Min):
+            self.X_batch = X_batch
+            if X_batch is not None:
+                self.r_x0, self.s_x0 = self._hammer_function_precompute(X_batch, L, Min, self.model)
+
+        def _hammer_function_precompute(self, x0, L, Min, model):
+            if x0 is None:
+                return None, None
+            x0 = np.atleast_2d(x0)
+            mean, spread = model.predict(x0)
+            spread = np.sqrt(np.maximum(spread, 1e-16))     # sqrt of the returned std: the reference's quirk (LP.py:55-59)
+            return ((mean - Min) / L).ravel(), (spread / L).ravel()
+
+        def _z_and_norm(self, x):
+            nm = np.linalg.norm(np.atleast_2d(x)[:, None, :] - np.atleast_2d(self.X_batch)[None, :, :], axis=-1)
+            return (nm - self.r_x0) / self.s_x0, nm
+
+        def _inner(self, x):
+            return -self.acq.acquisition_function(x)[:, 0]
+
+        def acquisition_function(self, x):
+            from scipy.stats import norm
+            g = self._inner(x)
+            if self.transform == 'softplus':
+                big = g >= 40.
+                g = np.where(big, np.log(np.where(big, g, 1.)), np.log(np.log1p(np.exp(np.where(big, 0., g)))))
+            elif self.transform == 'none':
+                g = np.log(g + 1e-50)
+            out = -g
+            if self.X_batch is not None:
+                out = out - norm.logcdf(self._z_and_norm(x)[0]).sum(axis=-1)
+            return out
+
+        def d_acquisition_function(self, x):
+            from scipy.stats import norm
+            x = np.atleast_2d(x)
+            scale = 1.
+            if self.transform == 'softplus':
+                g = self._inner(x)
+                scale = 1. / (np.log1p(np.exp(g)) * (1. + np.exp(-g)))
+            elif self.transform == 'none':
+                scale = 1. / self._inner(x)
+            grad = scale * self.acq.acquisition_function_withGradients(x)[1]
+            if self.X_batch is None:
+                return grad
+            z, nm = self._z_and_norm(x)
+            cdf = norm.cdf(z)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                pen = np.exp(-0.5 * z * z) / (self.s_x0 * np.sqrt(2. * np.pi) * cdf * nm)
+            pen[cdf < 1e-50] = 0.
+            return grad - pen.sum(axis=1)[:, None]
+
+        def acquisition_function_withGradients(self, x):
+            return self.acquisition_function(x), self.d_acquisition_function(x)

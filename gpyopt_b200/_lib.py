@@ -57,6 +57,7 @@ SIGNATURES = {
                                          ctypes.c_int, ctypes.c_void_p]),
     'gpo_set_strict_variance': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'gpo_get_info': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    'gpo_set_option': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong]),
     'gpo_set_profiling': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     'gpo_get_profile': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     'gpo_alloc': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
@@ -96,7 +97,7 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         assert a.dtype == np.float64 or a.dtype == np.int64, a.dtype
         assert a.flags['C_CONTIGUOUS']
-        return a.ctypes.data
+        return a.ctypes.data or None   # (zero-size arrays have no buffer)
     # torch tensor
     assert a.is_contiguous()
     return a.data_ptr()
@@ -292,12 +293,17 @@ class Engine(object):
         kk = min(k, int(N))
         return vals[:kk], idx[:kk], xt[:kk]
 
-    def topk(self, v, k, largest=False, stream=None):
+    def topk(self, v, k, largest=False, stream=None, out=None):
         if isinstance(v, np.ndarray):
             v = _f64(v).reshape(-1)
             N = v.size
         else:
             N = int(v.numel())
+        if out is not None:   # device tensors (float64 [k], int64 [k]): records stay in HBM, no synchronisation
+            vals, idx = out
+            rc = self._lib.gpo_topk(self._h, N, _ptr(v), int(k), int(bool(largest)), _ptr(vals), _ptr(idx), stream)
+            self._check(rc, 'gpo_topk')
+            return vals, idx
         vals = np.empty(k)
         idx = np.empty(k, dtype=np.int64)
         rc = self._lib.gpo_topk(self._h, N, _ptr(v), int(k), int(bool(largest)), _ptr(vals), _ptr(idx), stream)
@@ -316,8 +322,16 @@ class Engine(object):
         return out
 
     def set_strict_variance(self, mode):
-        """-1 automatic (default), 0 never, 1 always: see gpo_set_strict_variance in include/gpo_b200.h."""
+        """1 the reference's variance form always (default), 0 fast form, -1 automatic: see gpo_set_strict_variance in
+        include/gpo_b200.h."""
         self._check(self._lib.gpo_set_strict_variance(self._h, int(mode)), 'gpo_set_strict_variance')
+
+    OPTIONS = {'serpentine': 0, 'bn_sweep': 1, 'bn_fit': 2, 'inverse': 3}
+
+    def set_option(self, key, value):
+        """Tuning knobs for measurements (gpo_set_option in include/gpo_b200.h)."""
+        k = self.OPTIONS[key] if isinstance(key, str) else int(key)
+        self._check(self._lib.gpo_set_option(self._h, k, int(value)), 'gpo_set_option')
 
     def info(self):
         v = np.zeros(6)

@@ -120,8 +120,8 @@ class AcquisitionLP(LPBase):
     grad   = scale * d(-acq)/dx - sum_k d_k  (direction dropped, LP.py:91-132)
     Both are evaluated inside the K3 epilogue on the device.  Like the reference, ``acquisition_function`` returns
     a 1-D array [N], and the gradient is only meaningful row by row (how L-BFGS calls it).
-    When the inner acquisition uses a non-constant cost or the space has constraints, the reference's host
-    formulas are applied to the fused inner acquisition instead.
+    When the inner acquisition uses a non-constant cost, the space has constraints or the transform is neither 'none' nor
+    'softplus', the reference's host formulas (inherited) are applied to the fused inner acquisition instead.
     """
 
     analytical_gradient_prediction = True
@@ -138,32 +138,14 @@ class AcquisitionLP(LPBase):
         self.r_x0 = None
         self.s_x0 = None
 
-    def update_batches(self, X_batch, L, Min):
-        """LP.py:40-46."""
-        self.X_batch = X_batch
-        if X_batch is not None:
-            self.r_x0, self.s_x0 = self._hammer_function_precompute(X_batch, L, Min, self.model)
-
-    def _hammer_function_precompute(self, x0, L, Min, model):
-        """LP.py:48-62 (keeps the reference's sqrt-of-std quirk)."""
-        if x0 is None:
-            return None, None
-        if len(x0.shape) == 1:
-            x0 = x0[None, :]
-        m = model.predict(x0)[0]
-        pred = model.predict(x0)[1].copy()
-        pred[pred < 1e-16] = 1e-16
-        s = np.sqrt(pred)
-        r_x0 = (m - Min) / L
-        s_x0 = s / L
-        return r_x0.flatten(), s_x0.flatten()
-
     def _device_path_ok(self):
         from ._compat import constant_cost_withGradients
         plain_cost = self.acq.cost_withGradients is constant_cost_withGradients
         no_constraints = self.acq.space is None or not getattr(self.acq.space, 'constraints', None)
         same_dim = self.acq.space is None or (self.acq.space.model_dimensionality == self.acq.space.objective_dimensionality)
-        return plain_cost and no_constraints and same_dim
+        # any transform string other than 'none' / 'softplus' is the identity in the reference (LP.py:79-83, 113-121): host path
+        known_transform = self.transform in ('none', 'softplus')
+        return plain_cost and no_constraints and same_dim and known_transform
 
     def _run(self, x, grad):
         eng = _engine_of(self.model)
@@ -173,55 +155,22 @@ class AcquisitionLP(LPBase):
         finally:
             eng.lp_set(None, None, None, None)
 
+    # update_batches / _hammer_function_precompute and the host formulas are inherited: the reference's own methods when
+    # GPyOpt is importable, gpyopt_b200._compat.LPBase otherwise
     def acquisition_function(self, x):
         x = np.atleast_2d(np.asarray(x, dtype=np.float64))
         if self._device_path_ok():
             return self._run(x, grad=False)
-        return self._host_penalized(x)
+        return super(AcquisitionLP, self).acquisition_function(x)
 
     def d_acquisition_function(self, x):
         x = np.atleast_2d(np.asarray(x, dtype=np.float64))
         if self._device_path_ok():
             return self._run(x, grad=True)[1]
-        return self._host_gradient(x)
+        return super(AcquisitionLP, self).d_acquisition_function(x)
 
     def acquisition_function_withGradients(self, x):
         x = np.atleast_2d(np.asarray(x, dtype=np.float64))
         if self._device_path_ok():
             return self._run(x, grad=True)
-        return self._host_penalized(x), self._host_gradient(x)
-
-    # -- reference host formulas on top of the fused inner acquisition (cost / constraints present) ----
-    def _host_penalized(self, x):
-        from scipy.stats import norm
-        fval = -self.acq.acquisition_function(x)[:, 0]
-        if self.transform == 'softplus':
-            fval_org = fval.copy()
-            fval[fval_org >= 40.] = np.log(fval_org[fval_org >= 40.])
-            fval[fval_org < 40.] = np.log(np.log1p(np.exp(fval_org[fval_org < 40.])))
-        elif self.transform == 'none':
-            fval = np.log(fval + 1e-50)
-        fval = -fval
-        if self.X_batch is not None:
-            nm = np.sqrt((np.square(x[:, None, :] - np.atleast_2d(self.X_batch)[None, :, :])).sum(-1))
-            fval += -norm.logcdf((nm - self.r_x0) / self.s_x0).sum(axis=-1)
-        return fval
-
-    def _host_gradient(self, x):
-        from scipy.stats import norm
-        fval = -self.acq.acquisition_function(x)[:, 0]
-        if self.transform == 'softplus':
-            scale = 1. / (np.log1p(np.exp(fval)) * (1. + np.exp(-fval)))
-        elif self.transform == 'none':
-            scale = 1. / fval
-        else:
-            scale = 1.
-        _, grad_acq_x = self.acq.acquisition_function_withGradients(x)
-        if self.X_batch is None:
-            return scale * grad_acq_x
-        nm = np.sqrt((np.square(x[:, None, :] - np.atleast_2d(self.X_batch)[None, :, :])).sum(-1))
-        z = (nm - self.r_x0) / self.s_x0
-        h = norm.cdf(z)
-        dk = 1. / (self.s_x0 * np.sqrt(2 * np.pi) * h) * np.exp(-np.square(z) / 2) / nm
-        dk[h < 1e-50] = 0.
-        return scale * grad_acq_x - dk[:, :, None].sum(axis=1)
+        return super(AcquisitionLP, self).acquisition_function_withGradients(x)

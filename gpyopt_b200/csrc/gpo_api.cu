@@ -16,14 +16,18 @@ using namespace gpo;
 // --------------------------------------------------------------------------------------------------
 // engine
 // --------------------------------------------------------------------------------------------------
+// one tensor map per B-tile height: box 16 x 128 (A operands, B operands of the 128 x 128 kernel) and 16 x 64 (B operands of
+// the 128 x 64 kernel)
+struct TMap { CUtensorMap m128, m64; };
+
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   double* Kt = nullptr;  // [S][nc_ld][n_pad]
   double* Ht = nullptr;  // [S][nc_ld][n_pad], only for non-RBF kernels (allocated on demand)
-  CUtensorMap mapKt;
+  TMap mapKt;
   double* Tt = nullptr;  // [S][nc_ld][n_pad]  t = L^-1 k of the chunk (strict gradient sweeps: b = L^-T t), allocated on demand
-  CUtensorMap mapTt;
+  TMap mapTt;
   double* mean = nullptr;     // [S][js][nc_ld]   per-slice partial sums of K1
   double* dmean = nullptr;    // [S][js][d][nc_ld]
   double* partial = nullptr;  // [S][tiles_m][d+2][nc_ld]
@@ -53,7 +57,7 @@ struct gpo_engine {
   double* probe_out = nullptr;                                       // [S] device
   // posterior state (device), each [S][n_pad][n_pad] unless noted
   double *A = nullptr, *X = nullptr, *U = nullptr, *W = nullptr, *T = nullptr;
-  CUtensorMap mapA, mapX, mapU, mapW, mapT;
+  TMap mapA, mapX, mapU, mapW, mapT;
   double *alpha = nullptr, *tmpv = nullptr;                          // [S][n_pad]
   double* xtile = nullptr;                                           // [S][n_pad/32][dp+1][32] K1 staging (TMA source)
   int dp = 0;                                                        // K1's padded dimension for this d
@@ -67,6 +71,11 @@ struct gpo_engine {
   cudaStream_t fit_stream = nullptr;
   // host<->device staging (grow-only)
   double* stage_in = nullptr;  size_t stage_in_bytes = 0;
+  // pageable host candidates (what GPyOpt hands over: plain NumPy arrays) go through a ring of page-locked chunk buffers:
+  // host memcpy + truly asynchronous H2D copy per chunk, instead of the driver's synchronous staging of pageable copies
+  static constexpr int IN_PIN = 4;
+  double* in_pin[IN_PIN] = {nullptr, nullptr, nullptr, nullptr};  size_t in_pin_bytes = 0;
+  cudaEvent_t in_pin_ev[IN_PIN] = {nullptr, nullptr, nullptr, nullptr};  bool in_pin_busy[IN_PIN] = {false, false, false, false};
   double* stage_out[4] = {nullptr, nullptr, nullptr, nullptr};  size_t stage_out_bytes[4] = {0, 0, 0, 0};
   // local penalisation
   int lp_on = 0, lp_K = 0, lp_transform = 0, lp_cap = 0, lp_d = 0;
@@ -89,9 +98,15 @@ struct gpo_engine {
   double* blk_val = nullptr;  long long* blk_idx = nullptr;  size_t blk_cap = 0;  bool want_blk = false;
   // full-covariance scratch (grow-only): K*^T staging, L^-1 K* for both point sets, result, K1 mean scratch
   double* cov_buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  size_t cov_bytes[5] = {0, 0, 0, 0, 0};
-  // parity guard: variance form used by gradient sweeps (-1 auto, 0 fast k.W^-1.k, 1 strict |L^-1 k|^2)
-  int strict_mode = -1;
-  bool strict_active = false;
+  // variance form used by gradient sweeps: 1 (default) the reference's own sigma_f^2 - |L^-1 k|^2 always, 0 the fast
+  // k.W^-1.k form, -1 automatic (probe after every refit decides)
+  int strict_mode = 1;
+  bool strict_active = true;
+  // tuning knobs (gpo_set_option)
+  int opt_serpentine = 1;   // serpentine dealing of GEMM work items
+  int opt_bn_sweep = 64;    // column-tile width of the sweep GEMMs (64: two CTAs per SM, 128: one)
+  int opt_bn_fit = 64;      // the same for the rectangular GEMMs of the refit
+  int opt_inverse = 0;      // triangular inverse of the refit: 0 automatic, 1 interleaved with the Cholesky, 2 recursive
   double var_disc = 0.0;
   std::vector<cudaEvent_t> chol_ev;  // look-ahead events of the blocked Cholesky (2 per block column)
   // counters / live profiling of the dominant kernel (variance GEMM) for the benchmark's roofline
@@ -145,16 +160,19 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // map over a [batch][rows][cols] float64 array, box = 16 (cols) x 128 (rows) x 1, SWIZZLE_128B
-static int make_map(gpo_engine* eng, CUtensorMap* map, double* base, long long cols, long long rows, long long batch) {
+static int make_map(gpo_engine* eng, TMap* map, double* base, long long cols, long long rows, long long batch) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t strides[2] = {(cuuint64_t)cols * 8, (cuuint64_t)cols * rows * 8};
-  cuuint32_t box[3] = {GEMM_BK, TILE, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  for (int v = 0; v < 2; ++v) {
+    cuuint32_t box[3] = {GEMM_BK, (cuuint32_t)(v == 0 ? TILE : TILE / 2), 1};
+    CUresult r = fn(v == 0 ? &map->m128 : &map->m64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  }
   return GPO_OK;
 }
 
@@ -167,26 +185,56 @@ template <int DP>
 static cudaError_t cov_attr() {
   return cudaFuncSetAttribute(cov_mean_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cov_smem_bytes(DP, true));
 }
+template <int EPI, int BN, int STAGES>
+static cudaError_t gemm_attr() {
+  return cudaFuncSetAttribute(dgemm_nt_kernel<EPI, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              BN == TILE ? GEMM_SMEM_LIMIT_1 : GEMM_SMEM_LIMIT_2);
+}
+template <int EPI>
+static cudaError_t gemm_attr_epi() {
+  cudaError_t e;
+  if ((e = gemm_attr<EPI, 128, 4>()) != cudaSuccess) return e;
+  if ((e = gemm_attr<EPI, 64, 4>()) != cudaSuccess) return e;
+  return gemm_attr<EPI, 64, 3>();
+}
 static int gemm_setup(gpo_engine* eng) {
-  GPO_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  GPO_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<EPI_SUMSQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  GPO_CUDA_OK(cudaFuncSetAttribute(dgemm_nt_kernel<EPI_GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+  GPO_CUDA_OK(gemm_attr_epi<EPI_STORE>());
+  GPO_CUDA_OK(gemm_attr_epi<EPI_SUMSQ>());
+  GPO_CUDA_OK(gemm_attr_epi<EPI_GRAD>());
   GPO_CUDA_OK(cudaFuncSetAttribute(diag_chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
   GPO_CUDA_OK(cov_attr<2>()); GPO_CUDA_OK(cov_attr<4>()); GPO_CUDA_OK(cov_attr<6>());
   GPO_CUDA_OK(cov_attr<8>()); GPO_CUDA_OK(cov_attr<12>()); GPO_CUDA_OK(cov_attr<16>());
   return GPO_OK;
 }
 
-static int launch_gemm(gpo_engine* eng, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p_in, int batch,
-                       cudaStream_t st, int max_ctas = 0) {
+template <int EPI>
+static void launch_gemm_epi(int bn, int stages, dim3 grid, int smem, cudaStream_t st, const TMap& ma, const TMap& mb,
+                            const GemmParams& p) {
+  if (bn == TILE) dgemm_nt_kernel<EPI, 128, 4><<<grid, GemmShape<128>::THREADS, smem, st>>>(ma.m128, mb.m128, p);
+  else if (stages == 4) dgemm_nt_kernel<EPI, 64, 4><<<grid, GemmShape<64>::THREADS, smem, st>>>(ma.m128, mb.m64, p);
+  else dgemm_nt_kernel<EPI, 64, 3><<<grid, GemmShape<64>::THREADS, smem, st>>>(ma.m128, mb.m64, p);
+}
+
+// p_in.tiles_n counts 128-wide column tiles; bn = 64 selects the 128 x 64 kernel (two CTAs per SM), which numbers its
+// column tiles in units of 64.  max_ctas limits the SMs the launch may occupy (side-stream launches of the refit).
+static int launch_gemm(gpo_engine* eng, int epi, const TMap& ma, const TMap& mb, const GemmParams& p_in, int batch,
+                       cudaStream_t st, int max_ctas = 0, int bn = TILE) {
   GemmParams p = p_in;
   p.batch = batch;
+  p.serpentine = eng->opt_serpentine ? 1 : 0;
+  if (p.tile_skip == TS_LOWER) bn = TILE;  // the lower-triangle numbering is in square tiles
+  if (bn != TILE) p.tiles_n *= TILE / bn;
+  int stages = 4;
+  const int d_epi = epi == EPI_GRAD ? p.d : 0;
+  if (bn != TILE && gemm_smem_bytes(epi, bn, 4, d_epi) > GEMM_SMEM_LIMIT_2) stages = 3;
+  const int smem = gemm_smem_bytes(epi, bn, stages, d_epi);
   const long long tiles = p.tile_skip == TS_LOWER ? (long long)p.tiles_m * (p.tiles_m + 1) / 2 : (long long)p.tiles_m * p.tiles_n;
   const long long work = tiles * (p.ksplit > 1 ? p.ksplit : 1) * batch;
-  dim3 grid((unsigned)std::min<long long>(work, max_ctas > 0 ? max_ctas : eng->sm_count), 1, 1);  // persistent: one CTA per SM
-  if (epi == EPI_STORE) dgemm_nt_kernel<EPI_STORE><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
-  else if (epi == EPI_SUMSQ) dgemm_nt_kernel<EPI_SUMSQ><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
-  else dgemm_nt_kernel<EPI_GRAD><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ma, mb, p);
+  const int per_sm = bn == TILE ? 1 : 2;
+  dim3 grid((unsigned)std::min<long long>(work, (long long)(max_ctas > 0 ? max_ctas : eng->sm_count) * per_sm), 1, 1);  // persistent
+  if (epi == EPI_STORE) launch_gemm_epi<EPI_STORE>(bn, stages, grid, smem, st, ma, mb, p);
+  else if (epi == EPI_SUMSQ) launch_gemm_epi<EPI_SUMSQ>(bn, stages, grid, smem, st, ma, mb, p);
+  else launch_gemm_epi<EPI_GRAD>(bn, stages, grid, smem, st, ma, mb, p);
   eng->launches++;
   GPO_CUDA_OK(cudaGetLastError());
   return GPO_OK;
@@ -259,6 +307,10 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   cudaDeviceSynchronize();
   free_state(eng);
   if (eng->stage_in) cudaFree(eng->stage_in);
+  for (int i = 0; i < gpo_engine::IN_PIN; ++i) {
+    if (eng->in_pin[i]) cudaFreeHost(eng->in_pin[i]);
+    if (eng->in_pin_ev[i]) cudaEventDestroy(eng->in_pin_ev[i]);
+  }
   for (int i = 0; i < 4; ++i) if (eng->stage_out[i]) cudaFree(eng->stage_out[i]);
   if (eng->lp_xb) cudaFree(eng->lp_xb);
   if (eng->lp_r) cudaFree(eng->lp_r);
@@ -439,10 +491,10 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
   // diagonal factorisation and panel need), while the rest of the update runs on a side stream on the other SMs.
   // Every tile still receives its rank-128 updates in the order kb = 0, 1, 2, ...: the factor is bit-identical.
   const bool lookahead = nb >= 8;
-  const char* inv_env = getenv("GPO_INVERSE");
   // measured: wins for 8 <= nb < 32 (1.34 -> 1.12 ms at n=1024, 2.68 -> 2.23 at 2048, 5.32 -> 3.89 at 3072); from nb = 32 on its
   // K = 128 products are less efficient than the long-K products of the recursion (6.63 vs 6.30 ms at n=4096)
-  const bool interleave = lookahead && (inv_env ? inv_env[0] == 'i' : nb < 32);   // GPO_INVERSE=i|r overrides (tuning)
+  const bool interleave = lookahead && (eng->opt_inverse ? eng->opt_inverse == 1 : nb < 32);
+  const int bnf = eng->opt_bn_fit == 64 ? 64 : TILE;   // tile width of the rectangular K = 128 products below
   cudaStream_t sb = eng->slot[0].stream;
   cudaStream_t sc = sb;   // look-ahead mode: the triangular inverse rides along on the side stream, after each trailing update
   if (lookahead) {
@@ -471,7 +523,7 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
       f.b = {0, kb * TILE, 0, 0, 0, 1};                            // B[n][k] = R[kb][k, c-block n] = U[c-block n][kb, k]
       f.C = eng->X; f.ldc = n_pad; f.c_off_z = nn; f.c_row0 = kb * TILE; f.c_col0 = 0;
       f.Ct = eng->U; f.ldct = n_pad; f.ct_off_z = nn; f.ct_row0 = 0; f.ct_col0 = kb * TILE;   // in place on its own B tile
-      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapX, eng->mapU, f, S, sc, max_inv_ctas))) return rc;
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapX, eng->mapU, f, S, sc, max_inv_ctas, bnf))) return rc;
     }
     if (rem == 0) return GPO_OK;
     GPO_CUDA_OK(cudaStreamWaitEvent(sc, eng->chol_ev[2 * kb], 0));            // panel kb (L[i, kb], i > kb) is final
@@ -485,13 +537,13 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
       a2.tiles_m = rem; a2.tiles_n = kb; a2.beta = 1.0;
       a2.b = {0, kb * TILE, 0, 0, 0, 1};                           // row kb of X through U
       a2.c_col0 = 0; a2.ct_row0 = 0;
-      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapU, a2, S, sc, max_inv_ctas))) return rc;
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapU, a2, S, sc, max_inv_ctas, bnf))) return rc;
     }
     GemmParams b2 = u;
     b2.tiles_m = rem; b2.tiles_n = 1; b2.beta = 0.0;               // first contribution to column block kb of R
     b2.b = {kb * TILE, kb * TILE, 0, 0, 0, 1};                     // U_kk = X_kk^T
     b2.c_col0 = kb * TILE; b2.ct_row0 = kb * TILE;
-    return launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapU, b2, S, sc, max_inv_ctas);
+    return launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapU, b2, S, sc, max_inv_ctas, bnf);
   };
   int last_rest = -1;
   for (int kb = 0; kb < nb; ++kb) {
@@ -510,7 +562,7 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
     p.a = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};
     p.b = {kb * TILE, kb * TILE, 0, 0, 0, 1};
     p.C = eng->A; p.ldc = n_pad; p.c_off_z = nn; p.c_row0 = (kb + 1) * TILE; p.c_col0 = kb * TILE;
-    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapX, p, S, st))) return rc;
+    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapX, p, S, st, 0, bnf))) return rc;
     // trailing update (lower tiles): A[kb+1:, kb+1:] -= P P^T
     GemmParams q = gemm_defaults();
     q.kblocks = 1;
@@ -544,7 +596,7 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
     c.a = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};
     c.b = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};
     c.c_row0 = (kb + 1) * TILE; c.c_col0 = (kb + 1) * TILE;
-    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, c, S, st))) return rc;
+    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, c, S, st, 0, bnf))) return rc;
   }
   if (lookahead && last_rest >= 0) GPO_CUDA_OK(cudaStreamWaitEvent(st, eng->chol_ev[2 * last_rest + 1], 0));
   if (interleave) {  // the inverse is complete when the side stream drains
@@ -627,7 +679,7 @@ static int launch_variance_probe(gpo_engine* eng, cudaStream_t st) {
   g.tiles_m = tiles_m; g.tiles_n = probe_pad / TILE; g.kblocks = tiles_m;
   g.a = {0, 0, 0, 0, 0, 1}; g.b = {0, 0, 0, 0, 0, 1};
   g.ldp = eng->nc_ld;
-  GemmParams gs = g; gs.partial = s0.partial_sq; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
+  GemmParams gs = g; gs.partial = s0.partial_sq; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST; gs.tri_diag = 1;
   if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s0.mapKt, gs, S, st))) return rc;
   GemmParams gg = g; gg.partial = s1.partial; gg.krange = KR_FULL; gg.raster = RO_M_FASTEST;
   gg.d = 0; gg.Xtc = eng->Xtc; gg.ldx = n_pad; gg.Kt = s0.Kt; gg.Ht = nullptr; gg.nc_ld = eng->nc_ld; gg.n_pad = n_pad;
@@ -805,9 +857,12 @@ static int finalize_state(gpo_engine* eng) {
   GPO_CUDA_OK(cudaGetLastError());
   eng->h_fmin.resize(S);
   GPO_CUDA_OK(cudaMemcpyAsync(eng->h_fmin.data(), eng->fmin, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
-  if ((rc = launch_variance_probe(eng, st))) return rc;
+  // the probe only runs in the opt-in automatic mode; by default gradient sweeps use the reference's variance form
+  const bool probe = eng->strict_mode < 0;
+  if (probe && (rc = launch_variance_probe(eng, st))) return rc;
   GPO_CUDA_OK(cudaStreamSynchronize(st));
-  finish_variance_probe(eng);
+  if (probe) finish_variance_probe(eng);
+  else { eng->strict_active = eng->strict_mode == 1; eng->var_disc = 0.0; }
   eng->finalized = true;
   return GPO_OK;
 }
@@ -891,6 +946,26 @@ static bool is_device_ptr(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static bool is_pinned_host_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static int ensure_in_pin(gpo_engine* eng, size_t bytes) {
+  if (bytes <= eng->in_pin_bytes) return GPO_OK;
+  GPO_CUDA_OK(cudaDeviceSynchronize());
+  for (int i = 0; i < gpo_engine::IN_PIN; ++i) {
+    if (eng->in_pin[i]) cudaFreeHost(eng->in_pin[i]);
+    eng->in_pin[i] = nullptr;
+    GPO_CUDA_OK(cudaHostAlloc((void**)&eng->in_pin[i], bytes, cudaHostAllocDefault));
+    if (!eng->in_pin_ev[i]) GPO_CUDA_OK(cudaEventCreateWithFlags(&eng->in_pin_ev[i], cudaEventDisableTiming));
+    eng->in_pin_busy[i] = false;
+  }
+  eng->in_pin_bytes = bytes;
+  return GPO_OK;
 }
 
 static int grow(gpo_engine* eng, double** buf, size_t* cap, size_t bytes) {
@@ -1050,6 +1125,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
   { const int frc = finalize_state(eng); if (frc) return frc; }
   GPO_CUDA_OK(cudaSetDevice(eng->device));
   const int S = eng->S, d = eng->d, n_pad = eng->n_pad, tiles_m = n_pad / TILE;
+  const int bns = eng->opt_bn_sweep == 64 ? 64 : TILE;   // column-tile width of the variance GEMMs
   const bool predict = kind == ACQ_NONE;
   const bool gen = eng->gen_on;
   const bool in_dev = gen || is_device_ptr(Xs);
@@ -1090,6 +1166,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     if ((rc = grow(eng, &eng->stage_in, &eng->stage_in_bytes, (size_t)N * d * 8))) return rc;
     dev_in = eng->stage_in;
   }
+  const bool in_pageable = !in_dev && !tiny_call && !is_pinned_host_ptr(Xs);
+  if (in_pageable && (rc = ensure_in_pin(eng, (size_t)std::min<long long>(eng->nc_ld, N) * d * 8))) return rc;
   GPO_CUDA_OK(cudaEventRecord(eng->ev_in, user));
   for (int i = 0; i < 2; ++i) GPO_CUDA_OK(cudaStreamWaitEvent(eng->slot[i].stream, eng->ev_in, 0));
 
@@ -1105,6 +1183,13 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     if (!in_dev && tiny_call) {  // through the page-locked buffer: a truly asynchronous copy
       memcpy(eng->pin_buf, Xs, (size_t)rows * d * 8);
       GPO_CUDA_OK(cudaMemcpyAsync(eng->stage_in, eng->pin_buf, (size_t)rows * d * 8, cudaMemcpyHostToDevice, st));
+    } else if (in_pageable) {
+      const int k = ci % gpo_engine::IN_PIN;
+      if (eng->in_pin_busy[k]) GPO_CUDA_OK(cudaEventSynchronize(eng->in_pin_ev[k]));
+      memcpy(eng->in_pin[k], Xs + off * d, (size_t)rows * d * 8);
+      GPO_CUDA_OK(cudaMemcpyAsync(eng->stage_in + off * d, eng->in_pin[k], (size_t)rows * d * 8, cudaMemcpyHostToDevice, st));
+      GPO_CUDA_OK(cudaEventRecord(eng->in_pin_ev[k], st));
+      eng->in_pin_busy[k] = true;
     } else if (!in_dev)
       GPO_CUDA_OK(cudaMemcpyAsync(eng->stage_in + off * d, Xs + off * d, (size_t)rows * d * 8, cudaMemcpyHostToDevice, st));
     if (gen) launch_design(eng, eng->gen, eng->gen_row0 + off, rows, eng->stage_in + off * d, st);
@@ -1193,26 +1278,26 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
         GemmParams gs = gemm_defaults();
         gs.tiles_m = tiles_m; gs.tiles_n = tiles_n; gs.kblocks = tiles_m;
         gs.a = {0, 0, 0, 0, 0, 1}; gs.b = {0, 0, 0, 0, 0, 1};
-        gs.partial = s.partial_sq; gs.ldp = eng->nc_ld; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
+        gs.partial = s.partial_sq; gs.ldp = eng->nc_ld; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST; gs.tri_diag = 1;
         gs.Tt = s.Tt; gs.tt_ld = n_pad; gs.tt_z = eng->nc_ld * (long long)n_pad;
-        if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, gs, S, st))) return rc;
-        g.krange = KR_GE_M; g.raster = RO_HEAVY_FIRST;     // A = U = L^-T (upper triangular), B = t
-        if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapU, s.mapTt, g, S, st))) return rc;
+        if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, gs, S, st, 0, bns))) return rc;
+        g.krange = KR_GE_M; g.raster = RO_HEAVY_FIRST; g.tri_diag = 2;     // A = U = L^-T (upper triangular), B = t
+        if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapU, s.mapTt, g, S, st, 0, bns))) return rc;
         if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
       } else {
-      if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s.mapKt, g, S, st))) return rc;
+      if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapW, s.mapKt, g, S, st, 0, bns))) return rc;
       if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
       if (grad && eng->strict_active) {  // ill-conditioned model: variance from the reference's own triangular form as well
         GemmParams gs = gemm_defaults();
         gs.tiles_m = tiles_m; gs.tiles_n = tiles_n; gs.kblocks = tiles_m;
         gs.a = {0, 0, 0, 0, 0, 1}; gs.b = {0, 0, 0, 0, 0, 1};
-        gs.partial = s.partial_sq; gs.ldp = eng->nc_ld; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST;
-        if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, gs, S, st))) return rc;
+        gs.partial = s.partial_sq; gs.ldp = eng->nc_ld; gs.krange = KR_LE_M; gs.raster = RO_HEAVY_FIRST; gs.tri_diag = 1;
+        if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, gs, S, st, 0, bns))) return rc;
       }
       }
     } else {
-      g.krange = KR_LE_M; g.raster = RO_HEAVY_FIRST;
-      if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, g, S, st))) return rc;
+      g.krange = KR_LE_M; g.raster = RO_HEAVY_FIRST; g.tri_diag = 1;
+      if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, g, S, st, 0, bns))) return rc;
       if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
     }
     // K3
@@ -1263,6 +1348,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
   }
   if (any_host) {
     for (int i = 0; i < 2; ++i) GPO_CUDA_OK(cudaStreamSynchronize(eng->slot[i].stream));
+    for (int i = 0; i < gpo_engine::IN_PIN; ++i) eng->in_pin_busy[i] = false;
   }
   for (int i = 0; i < 4; ++i)
     if (outs[i] && out_pin[i]) memcpy(outs[i], eng->pin_buf + pin_off[i], (size_t)planes[i] * N * row_bytes[i]);
@@ -1362,6 +1448,13 @@ static int topk_device(gpo_engine* eng, long long N, const double* v_dev, int k,
     pp ^= 1;
     if (blocks == 1) break;
   }
+  if (is_device_ptr(vals)) {  // device-resident records (multi-GPU all-gather): no copy to the host, no synchronisation
+    if (!is_device_ptr(idx)) GPO_FAIL(GPO_ERR_ARG, "top-k: vals and idx must both be host or both be device pointers");
+    topk_finish_kernel<<<1, 128, 0, st>>>(cv, cidx, k, kk, sign, vals, idx);
+    eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
+    return GPO_OK;
+  }
   std::vector<double> hv(k);
   std::vector<long long> hi(k);
   GPO_CUDA_OK(cudaMemcpyAsync(hv.data(), cv, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
@@ -1420,9 +1513,13 @@ static int acq_topk_impl(gpo_engine* eng, int kind, double par, long long N, con
     GPO_CUDA_OK(cudaMemcpyAsync(bv.data(), eng->blk_val, nblk * 8, cudaMemcpyDeviceToHost, st));
     GPO_CUDA_OK(cudaMemcpyAsync(bi.data(), eng->blk_idx, nblk * 8, cudaMemcpyDeviceToHost, st));
     GPO_CUDA_OK(cudaStreamSynchronize(st));
+    // NaN scores sort last (as np.argsort and the k > 1 path do): a block record is NaN only if all its rows are
     size_t best = 0;
-    for (size_t b = 1; b < nblk; ++b)
-      if (bv[b] > bv[best] || (bv[b] == bv[best] && bi[b] < bi[best])) best = b;
+    for (size_t b = 1; b < nblk; ++b) {
+      const bool nb_ = bv[b] != bv[b], nbest = bv[best] != bv[best];
+      if (nb_) { if (nbest && bi[b] < bi[best]) best = b; continue; }
+      if (nbest || bv[b] > bv[best] || (bv[b] == bv[best] && bi[b] < bi[best])) best = b;
+    }
     vals[0] = -bv[best];  // score = -f (or the LP value itself, which K3 negated to maximise)
     idx[0] = bi[best];
   } else {
@@ -1526,7 +1623,7 @@ extern "C" int gpo_state_buffers(gpo_engine* eng, void** ptrs, long long* bytes,
       {eng->Xt, d * np * 8}, {eng->Xtc, d * np * 8}, {eng->xmu, (size_t)DMAX * 8}, {eng->Xaos, d * np * 8}, {eng->Y, np * 8},
       {eng->invl, S * d * 8}, {eng->sigf2, S * 8}, {eng->noise, S * 8}, {eng->alpha, S * np * 8}, {eng->fmin, S * 8},
       {eng->logdet, S * 8}, {eng->quad, S * 8}, {eng->xtile, S * np * (size_t)(eng->dp + 1) * 8},
-      {eng->X, S * np * np * 8}, {eng->W, S * np * np * 8}};
+      {eng->X, S * np * np * 8}, {eng->U, S * np * np * 8}, {eng->W, S * np * np * 8}, {eng->A, S * np * np * 8}};
   const int cnt = (int)(sizeof(list) / sizeof(list[0]));
   if (cnt > max) GPO_FAIL(GPO_ERR_ARG, "gpo_state_buffers: need room for %d entries", cnt);
   for (int i = 0; i < cnt; ++i) { ptrs[i] = list[i].p; bytes[i] = (long long)list[i].b; }
@@ -1548,14 +1645,29 @@ extern "C" int gpo_state_commit(gpo_engine* eng) {
   GPO_CUDA_OK(cudaMemcpy(eng->h_sigf2.data(), eng->sigf2, (size_t)S * 8, cudaMemcpyDeviceToHost));
   GPO_CUDA_OK(cudaMemcpy(eng->h_noise.data(), eng->noise, (size_t)S * 8, cudaMemcpyDeviceToHost));
   eng->fitted = true;
-  eng->finalized = true;  // fmin and K1's tiles arrived with the broadcast; only the probe verdict is local
-  return run_variance_probe(eng, eng->fit_stream);
+  eng->finalized = true;  // fmin and K1's tiles arrived with the broadcast; only the probe verdict (automatic mode) is local
+  if (eng->strict_mode < 0) return run_variance_probe(eng, eng->fit_stream);
+  eng->strict_active = eng->strict_mode == 1;
+  return GPO_OK;
 }
 
 extern "C" int gpo_set_strict_variance(gpo_engine* eng, int mode) {
   if (!eng || mode < -1 || mode > 1) return GPO_ERR_ARG;
   eng->strict_mode = mode;
   if (mode >= 0) eng->strict_active = mode == 1;
+  else if (eng->fitted) eng->finalized = false;   // automatic: the probe runs with the next finalisation
+  return GPO_OK;
+}
+
+extern "C" int gpo_set_option(gpo_engine* eng, int key, long long value) {
+  if (!eng) return GPO_ERR_ARG;
+  switch (key) {
+    case GPO_OPT_SERPENTINE: eng->opt_serpentine = value != 0; break;
+    case GPO_OPT_BN_SWEEP: if (value != 64 && value != 128) return GPO_ERR_ARG; eng->opt_bn_sweep = (int)value; break;
+    case GPO_OPT_BN_FIT: if (value != 64 && value != 128) return GPO_ERR_ARG; eng->opt_bn_fit = (int)value; break;
+    case GPO_OPT_INVERSE: if (value < 0 || value > 2) return GPO_ERR_ARG; eng->opt_inverse = (int)value; break;
+    default: GPO_FAIL(GPO_ERR_ARG, "gpo_set_option: unknown key %d", key);
+  }
   return GPO_OK;
 }
 
@@ -1630,7 +1742,7 @@ extern "C" int gpo_posterior_cov(gpo_engine* eng, long long N1, const double* X1
   for (int sidx = 0; sidx < (same ? 1 : 2); ++sidx)
     GPO_CUDA_OK(cudaMemcpyAsync(xdev[sidx], Xh[sidx], (size_t)Nn[sidx] * d * 8, cudaMemcpyHostToDevice, st));
   if (same) xdev[1] = xdev[0];
-  CUtensorMap mapK, mapT[2];
+  TMap mapK, mapT[2];
   for (int sidx = 0; sidx < (same ? 1 : 2); ++sidx) {
     if ((rc = make_map(eng, &mapK, eng->cov_buf[0], n_pad, Np[sidx], 1))) return rc;
     if ((rc = make_map(eng, &mapT[sidx], eng->cov_buf[1 + sidx], n_pad, Np[sidx], 1))) return rc;
@@ -1641,7 +1753,7 @@ extern "C" int gpo_posterior_cov(gpo_engine* eng, long long N1, const double* X1
     if ((rc = launch_cov(eng, cp, false, 1, st))) return rc;
     // T = L^-1 K*, stored transposed ([point][training index]) so that it is K-major for the product below
     GemmParams g = gemm_defaults();
-    g.tiles_m = tiles; g.tiles_n = (int)(Np[sidx] / TILE); g.kblocks = tiles; g.krange = KR_LE_M; g.raster = RO_HEAVY_FIRST;
+    g.tiles_m = tiles; g.tiles_n = (int)(Np[sidx] / TILE); g.kblocks = tiles; g.krange = KR_LE_M; g.raster = RO_HEAVY_FIRST; g.tri_diag = 1;
     g.a = {0, 0, 0, 0, 0, 1}; g.b = {0, 0, 0, 0, 0, 1};
     g.Ct = eng->cov_buf[1 + sidx]; g.ldct = n_pad;
     if ((rc = launch_gemm(eng, EPI_STORE, eng->mapX, mapK, g, 1, st))) return rc;

@@ -620,7 +620,15 @@ __device__ __forceinline__ double log_ndtr(double z) {
   return log1p(-0.5 * erfc(t));
 }
 
-// block-wide argmax of (score, index) with warp shuffles; ties -> lowest index; inactive threads pass -inf
+// strict "a is a better (score, index) than b": larger score first, NaN last (as np.argsort and topk_before order them),
+// ties by lowest index
+__device__ __forceinline__ bool argmax_better(double va, long long ia, double vb, long long ib) {
+  const bool na = va != va, nb = vb != vb;
+  if (na || nb) return (!na && nb) || (na == nb && ia < ib);
+  return va > vb || (va == vb && ia < ib);
+}
+
+// block-wide argmax of (score, index) with warp shuffles; ties -> lowest index; NaN scores lose against any number
 __device__ __forceinline__ void block_argmax_store(double score, long long idx, double* blk_val, long long* blk_idx,
                                                    long long slot) {
   __shared__ double sv[4];
@@ -629,13 +637,13 @@ __device__ __forceinline__ void block_argmax_store(double score, long long idx, 
   for (int o = 16; o > 0; o >>= 1) {
     const double ov = __shfl_xor_sync(0xffffffffu, score, o);
     const long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (ov > score || (ov == score && oi < idx)) { score = ov; idx = oi; }
+    if (argmax_better(ov, oi, score, idx)) { score = ov; idx = oi; }
   }
   if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = score; si[threadIdx.x >> 5] = idx; }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-      if (sv[w] > score || (sv[w] == score && si[w] < idx)) { score = sv[w]; idx = si[w]; }
+      if (argmax_better(sv[w], si[w], score, idx)) { score = sv[w]; idx = si[w]; }
     blk_val[slot] = score;
     blk_idx[slot] = idx;
   }
@@ -905,6 +913,15 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_level_kernel(const double* 
   for (int t = threadIdx.x; t < k; t += TOPK_THREADS) {
     out_vals[(long long)blockIdx.x * k + t] = sv[t];
     out_idx[(long long)blockIdx.x * k + t] = si[t];
+  }
+}
+
+// last step of a top-k whose results stay on the device: undo the sign, pad past min(k, N) with (NaN, -1)
+__global__ void topk_finish_kernel(const double* __restrict__ sv, const long long* __restrict__ si, int k, long long kk,
+                                   double sign, double* __restrict__ vals, long long* __restrict__ idx) {
+  for (int t = threadIdx.x; t < k; t += blockDim.x) {
+    vals[t] = t < kk ? sign * sv[t] : __longlong_as_double(0x7ff8000000000000LL);
+    idx[t] = t < kk ? si[t] : -1LL;
   }
 }
 

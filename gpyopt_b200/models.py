@@ -195,6 +195,21 @@ class GPModel_MCMC(BOModel):
         self.hmc_samples = np.atleast_2d(np.asarray(samples, dtype=np.float64)).copy()
         self._resident = False
 
+    def adopt_samples(self, X, Y, rows, engine):
+        """Multi-GPU replicas: `engine` already holds the S factorisations for the full parameter rows `rows`
+        ([S, p] = variance, lengthscale(s), noise) of this (X, Y) -- replicated from the fitting rank by
+        ``gpyopt_b200.parallel.ShardedSweep.fit`` -- so nothing is refitted here."""
+        rows = np.atleast_2d(np.asarray(rows, dtype=np.float64))
+        self.input_dim = X.shape[1]
+        kern = self.kernel if self.kernel is not None else _kern.RBF(self.input_dim, variance=1.)
+        self.kernel = None
+        self.model = GPRegressionB200(X, Y, kernel=kern, noise_var=float(rows[0, -1]), device=self.device, engine=engine,
+                                      adopt_state=True)
+        self.model._samples = rows.copy()
+        free = np.ones(rows.shape[1], dtype=bool) if self.model._fixes_ is None else self.model._fixes_
+        self.hmc_samples = rows[:, free].copy()
+        self._resident = True
+
     def _make_resident(self):
         if self._resident and self.model._samples is not None:
             return

@@ -62,6 +62,39 @@ def allgather_topk(vals, idx, k, device=None, group=None):
     return merge_topk(records, k)
 
 
+def allgather_topk_device(vals_dev, idx_dev, row_offset, k, group=None, negate=False):
+    """Device-resident form of :func:`allgather_topk`: `vals_dev` (float64 [k]) and `idx_dev` (int64 [k], -1 = empty) are
+    CUDA tensors as ``Engine.topk(..., out=...)`` leaves them.  The k records are packed on the device, exchanged with
+    ONE collective (NCCL all_gather over NVLink) and read back with ONE device-to-host copy of world*k*16 bytes -- the
+    only synchronisation of the step -- then merged identically on every rank.  ``negate``: the records hold f and the
+    merge wants the score -f (smallest first)."""
+    import torch
+    dist = _dist()
+    rec = torch.empty((k, 2), dtype=torch.float64, device=vals_dev.device)
+    rec[:, 0] = -vals_dev if negate else vals_dev
+    gidx = torch.where(idx_dev >= 0, idx_dev + int(row_offset), idx_dev)
+    rec[:, 1] = gidx.view(torch.float64)   # int64 payload bit-cast so that one collective carries the record
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        out = torch.empty((dist.get_world_size(group) * k, 2), dtype=torch.float64, device=vals_dev.device)
+        dist.all_gather_into_tensor(out, rec, group=group)     # rank r's records are rows [r k, (r + 1) k)
+    else:
+        out = rec
+    host = out.cpu().reshape(-1, k, 2)
+    records = [(host[r, :, 0].numpy(), host[r, :, 1].contiguous().view(torch.int64).numpy()) for r in range(host.shape[0])]
+    return merge_topk(records, k)
+
+
+def state_checksums(engine):
+    """int64 wrap-around sum of every replicated state buffer (bit pattern), as a CUDA tensor: equal on two ranks iff
+    (up to collisions) the replicas hold identical bits."""
+    import torch
+    sums = []
+    for ptr, nbytes in engine.state_buffers():
+        t = torch.as_tensor(_DevBuf(ptr, nbytes), device='cuda:%d' % engine.device)
+        sums.append(t.view(torch.int64).sum())
+    return torch.stack(sums)
+
+
 class _DevBuf(object):
     """Expose a raw device allocation of the engine to torch through __cuda_array_interface__ (zero copy)."""
 

@@ -130,7 +130,9 @@ int gpo_acq_topk_uniform(gpo_engine* eng, int kind, double par, const unsigned l
                          long long N, const double* bounds, int k, double* vals, long long* idx, double* x_top,
                          void* stream);
 
-/* k smallest (largest = 0) or largest (largest = 1) entries of a device/host array v [N]. */
+/* k smallest (largest = 0) or largest (largest = 1) entries of a device/host array v [N].  vals / idx (host|device,
+ * both of the same kind): with device pointers the records stay in HBM and the call is asynchronous on `stream` (the
+ * multi-GPU path all-gathers them without a host round trip); entries past min(k, N) are (NaN, -1). */
 int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, int largest, double* vals, long long* idx,
              void* stream);
 
@@ -142,15 +144,29 @@ int gpo_topk(gpo_engine* eng, long long N, const double* v, int k, int largest, 
 int gpo_posterior_cov(gpo_engine* eng, long long N1, const double* X1, long long N2, const double* X2, int with_noise,
                       double* out);
 
-/* Parity guard.  Gradient sweeps need b = W^-1 k anyway and by default also take the variance from it
- * (sigma_f^2 - k.b: 2 n^2 flop per candidate in total).  On an ill-conditioned Gram matrix that form cancels badly,
- * whereas the reference's sigma_f^2 - |L^-1 k|^2 (GPy PosteriorExact._raw_predict) does not.  After every refit the
- * engine measures max |s_L - s_W| over the training inputs; in mode -1 (automatic, default) it adds the triangular
- * pass (3 n^2 flop per candidate, as the reference itself spends) when that discrepancy exceeds 7e-12 sqrt(sf2 + noise).
- * mode 0 = never, 1 = always.  gpo_get_info: info[0] = strict pass active, info[1] = measured discrepancy (scaled),
+/* Variance form of gradient sweeps.  The reference takes the posterior variance from sigma_f^2 - |L^-1 k|^2
+ * (GPy PosteriorExact._raw_predict via GPyOpt/models/gpmodel.py:98,136) and the variance gradient from b = W^-1 k
+ * (GP.predictive_gradients, gpmodel.py:138).
+ *   mode 1 (default): the reference's form, always.  Large sweeps run b = L^-T (L^-1 k) as two triangular products of
+ *                     n^2 flop each; the first one IS the sum-of-squares form, so the variance matches the reference by
+ *                     construction at the 2 n^2 flop per candidate of the single W^-1 product.
+ *   mode 0:           fast form, variance from sigma_f^2 - k.b with b = W^-1 k (one full product; cancels badly on
+ *                     ill-conditioned Gram matrices).  Opt-in.
+ *   mode -1:          automatic: after every refit both forms are compared at (up to 512 of) the training inputs and
+ *                     the fast form is kept only where max |s_L - s_W| <= 7e-12 sqrt(sf2 + noise).  Opt-in.
+ * gpo_get_info: info[0] = reference form active, info[1] = measured discrepancy (automatic mode, scaled),
  * info[2] = chunk (candidates), info[3] = padded n, info[4] = SM count, info[5] = S. */
 int gpo_set_strict_variance(gpo_engine* eng, int mode);
 int gpo_get_info(gpo_engine* eng, double* info, int count);
+
+/* Tuning knobs for measurements (the defaults are the product configuration; results do not depend on them beyond the
+ * summation order of the partial rows).
+ *   GPO_OPT_SERPENTINE  1 (default) / 0: deal the GEMM work items to the CTAs in serpentine rounds
+ *   GPO_OPT_BN_SWEEP    64 (default) / 128: column-tile width of the sweep GEMMs (64 = two CTAs per SM)
+ *   GPO_OPT_BN_FIT      64 (default) / 128: the same for the rectangular K = 128 products of the refit
+ *   GPO_OPT_INVERSE     0 automatic (default) / 1 interleaved with the Cholesky / 2 recursive triangular inverse */
+typedef enum { GPO_OPT_SERPENTINE = 0, GPO_OPT_BN_SWEEP = 1, GPO_OPT_BN_FIT = 2, GPO_OPT_INVERSE = 3 } gpo_option;
+int gpo_set_option(gpo_engine* eng, int key, long long value);
 
 /* Multi-GPU replication of the posterior state (one process per GPU; the collective itself is issued by the
  * host through torch.distributed / NCCL on the buffers listed here).

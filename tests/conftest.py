@@ -27,8 +27,12 @@ def scaled_err(a, ref):
     return float(np.max(np.abs(a - ref)) / (den if den > 0 else 1.0)) if ref.size else 0.0
 
 
+# ill-conditioned Gram matrices (cond 1e6 ... 1e9): GPyOpt's default flow, exact_feval=True (noise 1e-6) after the reference's
+# own ML-II (tests/golden/make_golden.py, mlii=True), plus one fixed long-lengthscale case
+ILL_CASES = ['ill_branin_rbf_exact_n40_mlii', 'ill_alpine2_rbf_ard_exact_n300_mlii', 'ill_branin_rbf_exact_n150_fixed',
+             'ill_branin_mat52_exact_n70_mlii']
 GP_CASES = ['c3_rbf_alpine2_n256', 'c3_rbf_ard_exact_n200', 'c3_mat52_alpine2_n192', 'c3_mat32_ard_n130',
-            'c1_branin_rbf_n20', 'c2_camel_mat52_n55', 'c1_1d_rbf_n7', 'c5_lp_gsobol_n128_gp']
+            'c1_branin_rbf_n20', 'c2_camel_mat52_n55', 'c1_1d_rbf_n7', 'c5_lp_gsobol_n128_gp'] + ILL_CASES
 MCMC_CASES = ['c4_mcmc_n64_S8', 'c4_mcmc_exact_n48_S4']
 
 
@@ -66,10 +70,10 @@ def grad_err(a, ref):
     return (float(np.max(np.abs(a[keep] - ref[keep])) / den), float(np.max(np.abs(a[~keep] - ref[~keep])) / den))
 
 
-def assert_grad_close(a, ref, tol=1e-10, tol_near_dup=1e-5):
+def assert_grad_close(a, ref, tol=1e-10, tol_near_dup=1e-7):
     e_all, e_dup = grad_err(a, ref)
     assert e_all < tol, e_all
-    assert e_dup < tol_near_dup, e_dup
+    assert e_dup < max(tol, tol_near_dup), e_dup
 
 
 def parity_tolerances(gp, Xs, base=1e-10):

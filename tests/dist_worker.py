@@ -11,6 +11,16 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 from gpyopt_b200 import parallel  # noqa: E402
 
 
+def _records(scores, k, world):
+    """what allgather_topk_device should have merged: rank 0 contributes 3 records, the others k"""
+    out = []
+    for r in range(world):
+        lo, hi = parallel.shard_rows(scores.size, r, world)
+        li = np.argsort(scores[lo:hi], kind='stable')[:k if r == 1 else 3]
+        out.append((scores[lo:hi][li], li + lo))
+    return out
+
+
 def main():
     dist.init_process_group('gloo')
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -32,6 +42,15 @@ def main():
     gathered = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(gathered, t)
     assert all(torch.equal(g, gathered[0]) for g in gathered)
+    # the device-resident form (records packed in a tensor, ONE collective, one copy back): same merge
+    tv = torch.full((k,), float('nan'), dtype=torch.float64)
+    ti = torch.full((k,), -1, dtype=torch.int64)
+    kk = k if rank == 1 else 3                     # rank 0 holds fewer records than k: padded with (NaN, -1)
+    tv[:kk] = torch.from_numpy(-local[li][:kk].copy())   # the engine leaves f; the merge wants the score -f
+    ti[:kk] = torch.from_numpy(li[:kk].astype(np.int64))
+    vd, idd = parallel.allgather_topk_device(tv, ti, lo, k, negate=True)
+    ref_d = parallel.merge_topk([(local0, idx0) for local0, idx0 in _records(scores, k, world)], k)
+    assert np.array_equal(idd, ref_d[1]) and np.array_equal(vd, ref_d[0]), (idd, ref_d[1])
     # fewer local rows than k on one rank
     vals2, idx2 = parallel.allgather_topk(local[li][:2] if rank == 0 else local[li], (li + lo)[:2] if rank == 0 else li + lo, k)
     assert len(idx2) == k and np.all(np.diff(vals2) >= 0)

@@ -41,7 +41,10 @@ def uniform(rng, bounds, n):
     return b[:, 0] + (b[:, 1] - b[:, 0]) * rng.random((n, len(bounds)))
 
 
-def make_gp_case(name, fn, bounds, n, N, kernel, variance, lengthscale, ARD, noise_var, exact_feval, seed):
+def make_gp_case(name, fn, bounds, n, N, kernel, variance, lengthscale, ARD, noise_var, exact_feval, seed, mlii=False):
+    """mlii: run the reference's own ML-II (GPModel.updateModel with max_iters=1000, one restart, seeded) before taking the
+    vectors -- GPyOpt's default flow; with exact_feval=True (noise fixed at 1e-6) it lands on ill-conditioned Gram
+    matrices (cond 1e6 ... 1e9), where the variance form and the explicit inverses matter."""
     rng = np.random.default_rng(seed)
     d = len(bounds)
     X = uniform(rng, bounds, n)
@@ -51,12 +54,20 @@ def make_gp_case(name, fn, bounds, n, N, kernel, variance, lengthscale, ARD, noi
     Xs[0] = X[0]
     Xs[1] = X[1] + 1e-9
     kern = KERNELS[kernel](d, variance=variance, lengthscale=lengthscale, ARD=ARD)
-    model = GPModel(kernel=kern, noise_var=noise_var, exact_feval=exact_feval, max_iters=0, verbose=False)
+    model = GPModel(kernel=kern, noise_var=noise_var, exact_feval=exact_feval, max_iters=1000 if mlii else 0,
+                    optimize_restarts=1, verbose=False)
+    np.random.seed(seed)
     model.updateModel(X, Y, None, None)
+    if mlii:   # the fitted hyper-parameters become the case's fixed ones
+        variance = float(model.model.kern.variance[0])
+        lengthscale = np.array(model.model.kern.lengthscale, dtype=float).copy()
+        model.max_iters = 0
     space = space_for(bounds)
     out = dict(X=X, Y=Y, Xs=Xs, bounds=np.asarray(bounds, float), kernel=kernel, variance=variance,
                lengthscale=np.atleast_1d(np.asarray(lengthscale, float)), ARD=ARD,
                noise_var=float(model.model.likelihood._noise()), exact_feval=exact_feval)
+    Ky = model.model.kern.K(X) + (out['noise_var'] + 1e-8) * np.eye(n)
+    out['cond'] = float(np.linalg.cond(Ky))
     m, s = model.predict(Xs)
     m0, s0 = model.predict(Xs, with_noise=False)
     mg, sg, dmdx, dsdx = model.predict_withGradients(Xs)
@@ -75,7 +86,7 @@ def make_gp_case(name, fn, bounds, n, N, kernel, variance, lengthscale, ARD, noi
         scores = acq.acquisition_function(Xs).flatten()
         out['%s_top5' % aname] = np.argsort(scores)[:5]
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
-    print(name, 'fmin', out['fmin'], 'EI max', out['EI_f'].max(), 'min s', s.min())
+    print(name, 'fmin', out['fmin'], 'EI max', out['EI_f'].max(), 'min s', s.min(), 'cond %.2e' % out['cond'], 'theta', variance, lengthscale)
     return model, space, out
 
 
@@ -156,6 +167,14 @@ if __name__ == '__main__':
     make_gp_case('c2_camel_mat52_n55', og.sixhumpcamel, [(-2, 2), (-1, 1)], 55, 300, 'matern52', 1.0, 0.7, False,
                  None, False, 50)
     make_gp_case('c1_1d_rbf_n7', lambda X: np.sin(3 * X) + X, [(0, 2)], 7, 64, 'rbf', 1.0, 0.4, False, 1e-4, False, 60)
+    # ill-conditioned cases: GPyOpt's default flow (exact_feval=True -> noise 1e-6, ML-II)
+    make_gp_case('ill_branin_rbf_exact_n40_mlii', og.branin, [(-5, 10), (1, 15)], 40, 300, 'rbf', 1.0, 1.0, False, None, True, 140,
+                 mlii=True)
+    make_gp_case('ill_branin_mat52_exact_n70_mlii', og.branin, [(-5, 10), (1, 15)], 70, 300, 'matern52', 1.0, 1.0, False, None,
+                 True, 154, mlii=True)
+    make_gp_case('ill_alpine2_rbf_ard_exact_n300_mlii', lambda X: og.alpine2(X), [(1, 10)] * 3, 300, 300, 'rbf', 1.0,
+                 [1.0, 1.0, 1.0], True, None, True, 160, mlii=True)
+    make_gp_case('ill_branin_rbf_exact_n150_fixed', og.branin, [(-5, 10), (1, 15)], 150, 300, 'rbf', 2.0, 4.0, False, None, True, 170)
     make_mcmc_case('c4_mcmc_n64_S8', [(0, 1)] * 4, 64, 128, 8, 2)
     make_mcmc_case('c4_mcmc_exact_n48_S4', [(0, 1)] * 4, 48, 64, 4, 3, exact_feval=True)
     make_lp_case('c5_lp_gsobol_n128', 70)

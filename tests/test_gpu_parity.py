@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from conftest import (load_golden, scaled_err, assert_grad_close, parity_tolerances, oracle_gp_from_golden, ei_input_error_budget,
-                      GP_CASES, MCMC_CASES)
+                      GP_CASES, MCMC_CASES, ILL_CASES)
 
 pytestmark = pytest.mark.gpu
 
@@ -370,8 +370,14 @@ def test_small_batch_latency_path(engine, kernel, ARD, S):
         m5, s5, dm5, ds5 = engine.predict_grad(X400)
         assert scaled_err(s5, s4) < 1e-10 and scaled_err(ds5, ds4) < 1e-10 and np.array_equal(m5, m4) and np.array_equal(dm5, dm4)
         engine.set_strict_variance(1)
+        engine.set_strict_variance(-1)     # automatic (opt-in): the probe decides; this model is well conditioned -> fast form
+        engine.fit(kernel, X, Y[:, 0], var, np.broadcast_to(ls, (S, d)), nz)
+        info = engine.info()
+        assert not info['strict_variance'] and 0.0 <= info['variance_discrepancy'] < 7e-12
+        m6, s6, dm6, ds6 = engine.predict_grad(X400)
+        assert np.array_equal(s6, s5) and np.array_equal(ds6, ds5)
     finally:
-        engine.set_strict_variance(-1)
+        engine.set_strict_variance(1)      # the default: the reference's variance form
         engine.fit(kernel, X, Y[:, 0], var, np.broadcast_to(ls, (S, d)), nz)
     if S == 1:  # Local Penalization on top
         Xb, r, sc = rng.random((4, d)), np.full(4, 0.3), np.full(4, 0.2)
@@ -507,6 +513,148 @@ def _oracle_gp(X, Y, d):
 
 
 # ------------------------------------------------------------------------------------------------------
+# (2b) the HEADLINE configuration against the oracle at its own size (BASELINE config 3: n = 2048, d = 6)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('kernel,ARD,noise', [('rbf', False, 1e-2),        # bench.py's synthetic_problem()
+                                              ('matern52', False, 1e-2),   # GPyOpt's default kernel
+                                              ('rbf', True, 1e-2),         # the ARD variant of SURVEY 8(d)
+                                              ('rbf', False, 1e-6)])       # exact_feval noise (cond ~ 1e6)
+def test_headline_config_matches_oracle_at_full_size(engine, kernel, ARD, noise):
+    """n = 2048, d = 6, alpine2, 4096 candidates: m, s, dm, ds, EI, dEI within 1e-10 (scaled) of the oracle, identical
+    top-5, through the default (reference) variance form and the large-sweep kernels bench.py times."""
+    from oracle import gpy_numpy as G, gpyopt_numpy as og
+    n, d, N = 2048, 6, 4096
+    rng = np.random.default_rng(0)
+    X = 1 + 9 * rng.random((n, d))
+    Y = og.normalize_stats(og.alpine2(X))
+    Xs = 1 + 9 * np.random.default_rng(1).random((N, d))
+    ls = np.linspace(1.5, 3.0, d) if ARD else np.array([2.0])
+    K = {'rbf': G.RBF, 'matern52': G.Matern52}[kernel]
+    gp = G.GPRegression(X, Y, K(d, variance=1.0, lengthscale=ls, ARD=ARD), noise_var=noise)
+    engine.fit(kernel, X, Y[:, 0], [1.0], np.broadcast_to(ls, (d,))[None, :], [noise])
+    assert engine.info()['strict_variance']          # the default is the reference's variance form
+    tol_v, tol_g = parity_tolerances(gp, Xs[:512])
+    if noise >= 1e-3:
+        assert tol_v == TOL and tol_g == TOL         # well conditioned: the stated 1e-10 applies as is
+    mo, so, dmo, dso = og.gp_predict_withGradients(gp, Xs)
+    fmin = og.gp_get_fmin(gp)
+    fo, dfo = og.acq_EI_withGradients(mo.copy(), so.copy(), dmo, dso, fmin, 0.01)
+    m, s, dm, ds = engine.predict_grad(Xs)
+    errs = dict(m=scaled_err(m[0], mo[:, 0]), s=scaled_err(s[0], so[:, 0]), dm=scaled_err(dm[0], dmo), ds=scaled_err(ds[0], dso))
+    assert errs['m'] < tol_v and errs['s'] < tol_v and errs['dm'] < tol_g and errs['ds'] < tol_g, errs
+    assert abs(engine.get_fmin()[0] - fmin) <= tol_v * abs(fmin)
+    f, df = engine.acq('EI', 0.01, Xs, grad=True)
+    fv = engine.acq('EI', 0.01, Xs)
+    bf, bdf = ei_input_error_budget(mo, so, dmo, dso, m[0], s[0], dm[0], ds[0], fmin, 0.01, fmin_err=engine.get_fmin()[0] - fmin)
+    ef, edf = np.max(np.abs(f - fo[:, 0])), np.max(np.abs(df - dfo))
+    assert ef <= tol_v * np.max(np.abs(fo)) + bf and np.max(np.abs(fv - fo[:, 0])) <= tol_v * np.max(np.abs(fo)) + bf, (ef, bf)
+    assert edf <= tol_g * np.max(np.abs(dfo)) + bdf, (edf, bdf)
+    _, idx = engine.acq_topk('EI', 0.01, Xs, 5)
+    assert np.array_equal(idx, og.anchor_topk(-fo[:, 0], 5))
+    # the opt-in fast form (variance from k.W^-1.k) gives the same answer on the well-conditioned models
+    if noise >= 1e-3:
+        engine.set_strict_variance(0)
+        try:
+            m2, s2, dm2, ds2 = engine.predict_grad(Xs)
+            assert scaled_err(s2[0], so[:, 0]) < TOL and scaled_err(ds2[0], dso) < TOL and np.array_equal(m2, m)
+        finally:
+            engine.set_strict_variance(1)
+
+
+@pytest.mark.parametrize('case', ILL_CASES)
+def test_ill_conditioned_goldens_keep_a_meaningful_tolerance(engine, case):
+    """cond(Ky) = 1e6 ... 1e9 (exact_feval noise 1e-6 after ML-II).  The comparison tolerance of the golden tests is the
+    reference arithmetic's own reproducibility floor (conftest.parity_tolerances); here it is checked to be of the order
+    eps * cond -- not vacuous -- and the engine's values are held to it on the sweep path, the latency path (N <= 32) and
+    the k-split path (N <= 256)."""
+    g = load_golden(case)
+    cond = float(g['cond'])
+    assert 1e6 <= cond <= 2e9
+    fit_from_golden(engine, g)
+    assert engine.info()['strict_variance']
+    Xs = g['Xs']
+    tol_v, tol_g = parity_tolerances(oracle_gp_from_golden(g), Xs)
+    assert tol_v <= max(TOL, 2.3e-16 * cond), (tol_v, cond)
+    for N in (1, 7, 32, 200, Xs.shape[0]):
+        m, s, dm, ds = engine.predict_grad(Xs[:N])
+        assert scaled_err(m[0], g['mg'][:N, 0]) < tol_v * max(1.0, np.max(np.abs(g['mg'])) / np.max(np.abs(g['mg'][:N])))
+        assert np.max(np.abs(s[0] - g['sg'][:N, 0])) < tol_v * np.max(np.abs(g['sg']))
+        mv, sv = engine.predict(Xs[:N])
+        assert np.max(np.abs(sv[0] - g['s'][:N, 0])) < tol_v * np.max(np.abs(g['s']))
+
+
+def test_fused_argmax_sorts_nan_last(engine):
+    """k = 1 selection (per-block warp-shuffle argmax in K3 + host merge) must treat NaN scores like np.argsort and the
+    k > 1 bitonic path: last.  LP with transform 'none' turns a tiny negative EI into log(negative) = NaN."""
+    g = load_golden('c3_rbf_alpine2_n256')
+    fit_from_golden(engine, g)
+    Xs = np.tile(g['Xs'], (3, 1))
+    try:
+        engine.lp_set(None, None, None, 'none')
+        f = engine.acq('MPI', 5.0, Xs)              # -log(Phi + 1e-50) values, all finite
+        assert np.all(np.isfinite(f))
+        v1, i1 = engine.acq_topk('MPI', 5.0, Xs, 1)
+        assert i1[0] == int(np.argmin(f)) and v1[0] == f.min()
+    finally:
+        engine.lp_set(None, None, None, None)
+    # gpo_topk on values containing NaN, k = 1 and k = 3, both directions (device-resident outputs too)
+    import torch
+    v = np.array([np.nan, 2.0, np.nan, 5.0, -1.0, 5.0] * 50)
+    for largest in (False, True):
+        vals, idx = engine.topk(v, 1, largest=largest)
+        want = int(np.nanargmax(v)) if largest else int(np.nanargmin(v))
+        assert idx[0] == want and vals[0] == v[want]
+        dv, di = torch.empty(3, dtype=torch.float64, device='cuda'), torch.empty(3, dtype=torch.int64, device='cuda')
+        engine.topk(torch.from_numpy(v).cuda(), 3, largest=largest, out=(dv, di))
+        torch.cuda.synchronize()
+        hv, hi = engine.topk(v, 3, largest=largest)
+        assert np.array_equal(di.cpu().numpy(), hi) and np.array_equal(dv.cpu().numpy(), hv)
+    dv, di = torch.empty(5, dtype=torch.float64, device='cuda'), torch.empty(5, dtype=torch.int64, device='cuda')
+    engine.topk(torch.tensor([3.0, 1.0], dtype=torch.float64, device='cuda'), 5, out=(dv, di))   # fewer values than k
+    torch.cuda.synchronize()
+    assert di.cpu().tolist() == [1, 0, -1, -1, -1] and np.isnan(dv.cpu().numpy()[2:]).all()
+
+
+@pytest.mark.parametrize('bn_sweep,serp', [(128, 0), (128, 1), (64, 0), (64, 1)])
+def test_gemm_shapes_and_schedules_agree(engine, bn_sweep, serp):
+    """The 128 x 128 and 128 x 64 (two CTAs per SM) GEMM shapes, with and without serpentine scheduling, give bitwise the
+    same sweep results: the tile width and the order in which CTAs pick work items never enter the arithmetic (every
+    output element is one accumulator chain over k in a fixed order; partial rows are added in row-block order by K3)."""
+    from oracle import gpyopt_numpy as og
+    rng = np.random.default_rng(3)
+    n, d, N = 700, 5, 3000
+    X = rng.random((n, d)); Y = og.normalize_stats(np.sin(3 * X).sum(1, keepdims=True))[:, 0]
+    Xs = rng.random((N, d))
+    engine.fit('matern52', X, Y, [1.1], np.full((1, d), 0.6), [1e-2])
+    ref = engine.predict_grad(Xs)
+    fref = engine.acq('EI', 0.01, Xs)
+    try:
+        engine.set_option('bn_sweep', bn_sweep)
+        engine.set_option('serpentine', serp)
+        out = engine.predict_grad(Xs)
+        for a, b in zip(out, ref):
+            assert np.array_equal(a, b)
+        assert np.array_equal(engine.acq('EI', 0.01, Xs), fref)
+        engine.set_strict_variance(0)
+        m0, s0, dm0, ds0 = engine.predict_grad(Xs)
+        assert scaled_err(s0, ref[1]) < TOL and scaled_err(ds0, ref[3]) < TOL
+    finally:
+        engine.set_strict_variance(1)
+        engine.set_option('bn_sweep', 64)
+        engine.set_option('serpentine', 1)
+    # the refit with either tile width of its rectangular products: identical factor, inverse and W^-1
+    from gpyopt_b200 import Engine
+    e2 = Engine(0)
+    try:
+        e2.set_option('bn_fit', 128 if bn_sweep == 64 else 64)
+        e2.fit('matern52', X, Y, [1.1], np.full((1, d), 0.6), [1e-2])
+        for a, b in zip(e2.get_state(), engine.get_state()):
+            assert np.array_equal(a, b)
+    finally:
+        e2.close()
+
+
+# ------------------------------------------------------------------------------------------------------
 # (3) properties at the full BASELINE sizes (n = 2048, d = 6; the oracle is too slow / too big there)
 # ------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope='module')
@@ -626,7 +774,7 @@ def test_randomised_shapes_against_oracle(n, d, N, kernel, ARD, S, noise, seed):
             assert scaled_err(dm[z], ref[z][2]) < tol_g
             # dsdx against the natural scale prior_std / lengthscale (tiny-|dsdx| candidate sets, see above)
             nat = np.sqrt(var[z] + nz[z]) / float(np.min(ls[z]))
-            assert np.max(np.abs(ds[z] - ref[z][3])) / max(nat, np.max(np.abs(ref[z][3]))) < 10 * tol_g
+            assert np.max(np.abs(ds[z] - ref[z][3])) / max(nat, np.max(np.abs(ref[z][3]))) < tol_g
         fmins = [og.gp_get_fmin(g) for g in gps]
         assert scaled_err(eng.get_fmin(), np.array(fmins)) < tol_v
         means, stds = [r[0] for r in ref], [r[1].copy() for r in ref]
@@ -647,8 +795,10 @@ def test_randomised_shapes_against_oracle(n, d, N, kernel, ARD, S, noise, seed):
         budgets = [ei_input_error_budget(ref[z][0], ref[z][1], ref[z][2], ref[z][3], m[z], s[z], dm[z], ds[z], fmins[z], 0.01,
                                          fmin_err=fm_e[z] - fmins[z]) for z in range(S)]
         bf, bdf = sum(b[0] for b in budgets) / S, sum(b[1] for b in budgets) / S
-        assert np.max(np.abs(f - fo[:, 0])) < 10 * tol_v * scale_f + bf and np.max(np.abs(fv - fo[:, 0])) < 10 * tol_v * scale_f + bf
-        assert np.max(np.abs(df - dfo)) < 100 * tol_g * max(np.max(np.abs(dfo)), 1e-100) + bdf
+        ef, efv = np.max(np.abs(f - fo[:, 0])), np.max(np.abs(fv - fo[:, 0]))
+        assert ef < tol_v * scale_f + bf and efv < tol_v * scale_f + bf, (ef, efv, tol_v * scale_f, bf)
+        edf = np.max(np.abs(df - dfo))
+        assert edf < tol_g * max(np.max(np.abs(dfo)), 1e-100) + bdf, (edf, tol_g * np.max(np.abs(dfo)), bdf)
         k = min(3, N)
         vals, idx = eng.acq_topk(kind, 0.01, Xs, k)
         assert np.array_equal(np.sort(fv)[::-1][:k], -vals)

@@ -220,3 +220,91 @@ def test_bo_loop_on_branin_engine_vs_oracle_trajectory():
     Xc, Yc = run(FakeEngine)
     assert np.max(np.abs(Xg - Xc)) < 1e-5, np.max(np.abs(Xg - Xc))
     assert Yg.min() < Yg[:5].min()
+
+
+# ------------------------------------------------------------------------------------------------------
+# HMC: GPModel_MCMC.updateModel on the engine against the oracle's HMC
+# ------------------------------------------------------------------------------------------------------
+def _hmc_problem(n=60, d=2, seed=11):
+    from oracle import gpyopt_numpy as og
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, d))
+    Y = og.normalize_stats(np.sin(4 * X[:, :1]) + np.cos(3 * X[:, 1:2]) + 0.1 * rng.standard_normal((n, 1)))
+    return X, Y
+
+
+def _oracle_mcmc_model(X, Y, theta0):
+    """The inner model GPModel_MCMC._create_model builds (gpmodel.py:213-238), on the oracle."""
+    from oracle import gpy_numpy as G
+    gp = G.GPRegression(X, Y, G.RBF(X.shape[1], variance=theta0[0], lengthscale=theta0[1]), noise_var=theta0[2])
+    gp.kern.set_prior(G.Gamma.from_EV(2., 4.))
+    gp.likelihood.variance.set_prior(G.Gamma.from_EV(2., 4.))
+    gp.Gaussian_noise.constrain_positive(warning=False)
+    return gp
+
+
+def test_hmc_chain_follows_the_oracle_chain_with_the_same_seed():
+    """Same NumPy seed, same starting point: the leapfrog trajectories are driven by the DEVICE log-likelihood gradient on
+    one side and by the oracle's on the other.  40 draws x 20 leapfrog steps (1600 refits): the same accept / reject
+    sequence and the same samples to 1e-8."""
+    from oracle import gpy_numpy as G
+    from gpyopt_b200 import GPModel_MCMC
+    from gpyopt_b200.gp import HMC
+    X, Y = _hmc_problem()
+    theta0 = np.array([1.3, 0.4, 0.05])
+    model = GPModel_MCMC(step_size=1e-1, leapfrog_steps=20)
+    model._create_model(X, Y)
+    model.model[:] = theta0
+    gp = _oracle_mcmc_model(X, Y, theta0)
+    assert np.allclose(model.model.optimizer_array, gp.optimizer_array, rtol=1e-14)
+    assert abs(model.model.objective_function() - gp.objective_function()) < 1e-9 * abs(gp.objective_function())
+    g_e = model.model._transform_gradients(model.model.objective_function_gradients())
+    g_o = gp._transform_gradients(gp.objective_function_gradients())
+    assert scaled_err(g_e, g_o) < 1e-9
+    np.random.seed(7)
+    ss_e = HMC(model.model, stepsize=1e-1).sample(num_samples=40, hmc_iters=20)
+    np.random.seed(7)
+    ss_o = G.HMC(gp, stepsize=1e-1).sample(num_samples=40, hmc_iters=20)
+    moved_e = np.any(np.diff(ss_e, axis=0) != 0, axis=1)
+    moved_o = np.any(np.diff(ss_o, axis=0) != 0, axis=1)
+    assert np.array_equal(moved_e, moved_o)                       # same accepted / rejected proposals
+    assert 5 < moved_o.sum()                                      # (the chain does move)
+    assert np.max(np.abs(ss_e - ss_o) / np.abs(ss_o)) < 1e-8, np.max(np.abs(ss_e - ss_o) / np.abs(ss_o))
+
+
+def test_gpmodel_mcmc_updatemodel_matches_the_oracle_flow_and_distribution():
+    """The whole GPModel_MCMC.updateModel (gpmodel.py:240-255: optimize(max_iters=200), 1 % parameter jitter, HMC, thinning)
+    on the engine against the same flow on the oracle: same seed -> same samples (ML-II end points agree to ~1e-7, the chain
+    keeps them together to 1e-5 over the first thinned draws), and 200 thinned samples from a DIFFERENT seed agree in
+    distribution (mean of log theta within 3 standard errors, spread within a factor 1.5)."""
+    from oracle import gpy_numpy as G
+    from gpyopt_b200 import GPModel_MCMC, AcquisitionEI_MCMC
+    X, Y = _hmc_problem()
+
+    def oracle_flow(seed, n_samples, n_burnin, interval, leapfrog):
+        np.random.seed(seed)
+        gp = _oracle_mcmc_model(X, Y, np.array([1.0, 1.0, Y.var() * 0.01]))
+        gp.optimize(max_iters=200)
+        gp.param_array[:] = gp.param_array * (1. + np.random.randn(gp.param_array.size) * 0.01)
+        gp._trigger_params_changed()
+        ss = G.HMC(gp, stepsize=1e-1).sample(num_samples=n_burnin + n_samples * interval, hmc_iters=leapfrog)
+        return ss[n_burnin::interval]
+
+    model = GPModel_MCMC(n_samples=10, n_burnin=20, subsample_interval=2, step_size=1e-1, leapfrog_steps=10)
+    np.random.seed(3)
+    model.updateModel(X, Y, None, None)
+    ref = oracle_flow(3, 10, 20, 2, 10)
+    assert model.hmc_samples.shape == ref.shape == (10, 3)
+    assert np.max(np.abs(model.hmc_samples - ref) / np.abs(ref)) < 1e-5
+    # the samples are usable by the integrated acquisition straight away
+    f = AcquisitionEI_MCMC(model, None, None, jitter=0.01)._compute_acq(X[:5])
+    assert f.shape == (5, 1) and np.all(np.isfinite(f))
+    # distribution: 200 thinned samples, engine seed 21 vs oracle seed 22
+    model = GPModel_MCMC(n_samples=200, n_burnin=100, subsample_interval=3, step_size=1e-1, leapfrog_steps=10)
+    np.random.seed(21)
+    model.updateModel(X, Y, None, None)
+    le, lo = np.log(model.hmc_samples), np.log(oracle_flow(22, 200, 100, 3, 10))
+    ess = 200 / 4.0                                              # thinned chain: conservative effective sample size
+    se = np.sqrt(le.var(0) / ess + lo.var(0) / ess)
+    assert np.all(np.abs(le.mean(0) - lo.mean(0)) < 3 * se), (le.mean(0), lo.mean(0), se)
+    assert np.all(le.std(0) / lo.std(0) < 1.5) and np.all(lo.std(0) / le.std(0) < 1.5)

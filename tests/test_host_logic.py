@@ -120,3 +120,60 @@ def test_two_rank_gloo_sweep_protocol():
                          capture_output=True, text=True, env=env, timeout=170)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert 'DIST_OK' in res.stdout
+
+
+def _compat_without_gpyopt():
+    """gpyopt_b200._compat as it loads on a machine without GPyOpt (the GPU box): the restated base classes."""
+    import importlib.util
+    blocked = {k: sys.modules.get(k) for k in list(sys.modules) if k == 'GPyOpt' or k.startswith('GPyOpt.')}
+    for k in blocked:
+        sys.modules.pop(k)
+    sys.modules['GPyOpt'] = None          # import GPyOpt -> ImportError
+    try:
+        spec = importlib.util.spec_from_file_location('_compat_nogpyopt', os.path.join(ROOT, 'gpyopt_b200', '_compat.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.modules.pop('GPyOpt', None)
+        sys.modules.update({k: v for k, v in blocked.items() if v is not None})
+    assert not mod.HAVE_GPYOPT
+    return mod
+
+
+@pytest.mark.parametrize('transform', ['none', 'softplus', 'identity'])
+def test_fallback_lp_host_formulas_match_the_oracle(transform):
+    """The Local-Penalization host formulas used when GPyOpt is absent (gpyopt_b200._compat.LPBase) against the oracle's
+    restatement of LP.py, incl. the precompute quirk (sqrt of the std) and a transform string the reference treats as
+    the identity."""
+    from oracle import gpyopt_numpy as og
+    C = _compat_without_gpyopt()
+    rng = np.random.default_rng(4)
+    d, N, K = 3, 40, 4
+
+    class Model(object):
+        analytical_gradient_prediction = True
+        def predict(self, x):
+            return np.sin(x).sum(1, keepdims=True), 0.3 + np.abs(np.cos(x)).sum(1, keepdims=True) * 1e-3
+
+    class Inner(C.AcquisitionBase):
+        analytical_gradient_prediction = True
+        def _compute_acq(self, x):
+            return 0.5 + np.square(x).sum(1, keepdims=True)
+        def _compute_acq_withGradients(self, x):
+            return self._compute_acq(x), 2 * x
+
+    model = Model()
+    lp = C.LPBase(model, None, None)
+    lp.acq, lp.transform, lp.X_batch, lp.r_x0, lp.s_x0 = Inner(model, None, None), transform, None, None, None
+    x, Xb = rng.random((N, d)), rng.random((K, d))
+    lp.update_batches(Xb, 0.7, -1.2)
+    m, s = model.predict(Xb)
+    r_o, s_o = og.lp_hammer_precompute(m, s, 0.7, -1.2)
+    assert np.array_equal(lp.r_x0, r_o) and np.array_equal(lp.s_x0, s_o)
+    af, adf = lp.acq.acquisition_function_withGradients(x)
+    assert np.allclose(lp.acquisition_function(x), og.lp_penalized_acquisition(af, x, Xb, r_o, s_o, transform), rtol=1e-13)
+    g_o = np.vstack([og.lp_d_acquisition(af[i:i + 1], adf[i:i + 1], x[i:i + 1], Xb, r_o, s_o, transform) for i in range(N)])
+    g = np.vstack([lp.d_acquisition_function(x[i:i + 1]) for i in range(N)])
+    assert np.allclose(g, g_o, rtol=1e-12, atol=1e-14)
+    lp.update_batches(None, None, None)
+    assert np.allclose(lp.acquisition_function(x), og.lp_penalized_acquisition(af, x, None, None, None, transform), rtol=1e-13)

@@ -393,8 +393,12 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   GPO_CUDA_OK(cudaMalloc(&eng->U, nn));
   GPO_CUDA_OK(cudaMalloc(&eng->W, nn));
   GPO_CUDA_OK(cudaMalloc(&eng->T, nn));
-  GPO_CUDA_OK(cudaMemset(eng->X, 0, nn));
-  GPO_CUDA_OK(cudaMemset(eng->U, 0, nn));
+  // (ordered on the fit stream and completed before anything else touches the buffers: a plain cudaMemset runs on the
+  // legacy default stream, which the engine's non-blocking streams do not wait for -- with S = 64 sets the 134 MB memsets
+  // could still be running when the first diagonal-block kernel wrote its inverse, and wiped it)
+  GPO_CUDA_OK(cudaMemsetAsync(eng->X, 0, nn, eng->fit_stream));
+  GPO_CUDA_OK(cudaMemsetAsync(eng->U, 0, nn, eng->fit_stream));
+  GPO_CUDA_OK(cudaStreamSynchronize(eng->fit_stream));
   GPO_CUDA_OK(cudaMalloc(&eng->alpha, (size_t)S * n_pad * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->tmpv, (size_t)S * n_pad * 8));
   eng->dp = d <= 2 ? 2 : d <= 4 ? 4 : d <= 6 ? 6 : d <= 8 ? 8 : d <= 12 ? 12 : 16;
@@ -821,7 +825,9 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
       if (eng->h_info[z] == 0) continue;
       any = true;
       // Ky's diagonal is sigf2 + noise + 1e-8 (stationary kernel): always > 0, so GPy's "diag <= 0" exit never fires
-      if (tries[z] >= 5) GPO_FAIL(GPO_ERR_NOT_PD, "not positive definite, even with jitter.");
+      if (tries[z] >= 5)
+        GPO_FAIL(GPO_ERR_NOT_PD, "not positive definite, even with jitter. (hyper-parameter set %d, first bad pivot at column %d)", z,
+                 eng->h_info[z] - 1);
       const double diag_mean = eng->h_sigf2[z] + eng->h_noise[z] + 1e-8;
       eng->h_jit[z] = diag_mean * 1e-6 * std::pow(10.0, tries[z]);
       tries[z]++;

@@ -55,25 +55,50 @@ def engine():
 
 # Row 1 of every golden GP candidate set is `X[1] + 1e-9` (tests/golden/make_golden.py): a candidate 1e-9 away from
 # a training point.  There GPy's distance formula |a|^2 + |b|^2 - 2 a.b cancels catastrophically, r is rounded to
-# exactly 0 and GPy's `1/r := 0` rule DROPS that training point's term from both gradients (an O(1e-9) artefact of
-# the reference's arithmetic).  The engine uses direct differences and keeps the (correct) term, so on that single row
-# gradients are compared at 1e-7 instead of 1e-10; every value (m, s, f) still holds 1e-10 there.
+# exactly 0 and GPy's `1/r := 0` rule DROPS that training point's term from both gradients -- an artefact of the
+# reference's arithmetic whose size is known in closed form:
+#     mean gradient:      alpha_1 h (x_q - X_1q) / l_q^2          |h| <= c sigma_f^2  (c = 1 RBF, 5/3 Matern52, 3 Matern32)
+#     variance gradient:  2 b_1 h (x_q - X_1q) / l_q^2,           b_1 = (W^-1 k)_1 = 1 - (noise + 1e-8) W^-1_11 at x = X_1
+# i.e. ~1e-9 |alpha_1| sigma_f^2 / l^2 and ~1e-9 sigma_f^2 / (l^2 s) for ds/dx = dv/dx / (2 s): 1e-13 on the well-conditioned
+# goldens, up to 2e-6 on the exact_feval ones (s ~ 1e-3, |alpha| ~ 1e3).  The engine uses direct differences and keeps the
+# (correct) term, so on that single row gradients are compared with this budget added (near_dup_budgets); every value
+# (m, s, f) still holds 1e-10 there.  Where the budget cannot be formed (Local Penalization: the row's gradient is
+# multiplied by 1 / acquisition value) the row is held to 1e-5; measured there: 1.7e-7.
 NEAR_DUP_ROW = 1
+NEAR_DUP_DELTA = 1e-9
+
+
+def near_dup_budgets(gp, g):
+    """Absolute size (with a factor 2 for the neglected change of the other terms) of the gradient terms the reference drops
+    on the near-duplicate row: (budget for dm/dx, budget for ds/dx)."""
+    c = {'rbf': 1.0, 'matern52': 5.0 / 3.0, 'matern32': 3.0}[str(g['kernel'])]
+    sf2 = float(g['variance'])
+    lmin = float(np.min(g['lengthscale']))
+    alpha1 = abs(float(gp.posterior.woodbury_vector[NEAR_DUP_ROW, 0]))
+    noise = float(g['noise_var']) + 1e-8
+    b1 = abs(1.0 - noise * float(gp.posterior.woodbury_inv[NEAR_DUP_ROW, NEAR_DUP_ROW]))
+    s_row = float(g['sg'][NEAR_DUP_ROW, 0])
+    dm = 2.0 * c * sf2 * alpha1 * NEAR_DUP_DELTA / lmin ** 2
+    ds = 2.0 * c * sf2 * max(b1, 1e-3) * NEAR_DUP_DELTA / (lmin ** 2 * s_row)
+    return dm, ds
 
 
 def grad_err(a, ref):
-    """(scaled error over all rows but the near-duplicate one, scaled error on that row alone)."""
+    """(scaled error over all rows but the near-duplicate one, ABSOLUTE error on that row alone, max|ref|)."""
     a, ref = np.asarray(a, dtype=np.float64), np.asarray(ref, dtype=np.float64)
     den = np.max(np.abs(ref))
     keep = np.ones(ref.shape[0], dtype=bool)
     keep[NEAR_DUP_ROW] = False
-    return (float(np.max(np.abs(a[keep] - ref[keep])) / den), float(np.max(np.abs(a[~keep] - ref[~keep])) / den))
+    return float(np.max(np.abs(a[keep] - ref[keep])) / den), float(np.max(np.abs(a[~keep] - ref[~keep]))), float(den)
 
 
-def assert_grad_close(a, ref, tol=1e-10, tol_near_dup=1e-7):
-    e_all, e_dup = grad_err(a, ref)
+def assert_grad_close(a, ref, tol=1e-10, near_dup_abs=None, tol_near_dup=1e-5):
+    e_all, e_dup, den = grad_err(a, ref)
     assert e_all < tol, e_all
-    assert e_dup < max(tol, tol_near_dup), e_dup
+    if near_dup_abs is not None:
+        assert e_dup <= tol * den + near_dup_abs, (e_dup, tol * den, near_dup_abs)
+    else:
+        assert e_dup < max(tol, tol_near_dup) * den, (e_dup / den)
 
 
 def parity_tolerances(gp, Xs, base=1e-10):

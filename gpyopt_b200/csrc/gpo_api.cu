@@ -33,6 +33,8 @@ struct Slot {
   double* partial = nullptr;  // [S][tiles_m][d+2][nc_ld]
   double* partial_sq = nullptr;  // [S][tiles_m][nc_ld]  (strict variance in gradient mode)
   double* zbuf = nullptr;        // [S][1+d][nc_ld]      per-set acquisition contributions (S > 1 only)
+  double* fs_mean = nullptr;     // [FUSED_CHUNK] mean and |L^-1 k|^2 left by the fused small-model sweep kernel (S = 1)
+  double* fs_sq = nullptr;
 };
 
 struct gpo_engine {
@@ -107,6 +109,8 @@ struct gpo_engine {
   int opt_bn_sweep = 64;    // column-tile width of the sweep GEMMs (64: two CTAs per SM, 128: one)
   int opt_bn_fit = 64;      // the same for the rectangular GEMMs of the refit
   int opt_inverse = 0;      // triangular inverse of the refit: 0 automatic, 1 interleaved with the Cholesky, 2 recursive
+  int opt_fused_small = 1;  // value sweeps of models with n <= 64 (S = 1) take the fused shared-memory-resident kernel
+  bool fused_attr_done = false;
   double var_disc = 0.0;
   std::vector<cudaEvent_t> chol_ev;  // look-ahead events of the blocked Cholesky (2 per block column)
   // counters / live profiling of the dominant kernel (variance GEMM) for the benchmark's roofline
@@ -294,7 +298,7 @@ static void free_state(gpo_engine* eng) {
   if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
   for (int i = 0; i < 2; ++i) {
     Slot& s = eng->slot[i];
-    double** sp[] = {&s.Kt, &s.Ht, &s.Tt, &s.mean, &s.dmean, &s.partial, &s.partial_sq, &s.zbuf};
+    double** sp[] = {&s.Kt, &s.Ht, &s.Tt, &s.mean, &s.dmean, &s.partial, &s.partial_sq, &s.zbuf, &s.fs_mean, &s.fs_sq};
     for (auto pp : sp) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   }
   eng->cap_n_pad = eng->cap_d = eng->cap_S = 0;
@@ -1123,6 +1127,65 @@ static int launch_cov_small(gpo_engine* eng, const CovParams& p_in, int nc, cuda
   return GPO_OK;
 }
 
+// Fused value sweep of a small model (fused_small_value_kernel): n <= 64, one hyper-parameter set.
+constexpr long long FUSED_CHUNK = 1LL << 18;   // candidates per launch (mean + sum of squares: 4 MB of scratch per slot)
+constexpr int FUSED_MAX_N = 64;
+template <int MF>
+static cudaError_t fused_attr() {
+  return cudaFuncSetAttribute(fused_small_value_kernel<MF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              fused_small_smem_bytes(MF, 4, DMAX));
+}
+static int launch_fused_small(gpo_engine* eng, Slot& s, const double* xs, long long rows, cudaStream_t st) {
+  if (!eng->fused_attr_done) {
+    GPO_CUDA_OK(fused_attr<1>()); GPO_CUDA_OK(fused_attr<2>()); GPO_CUDA_OK(fused_attr<3>()); GPO_CUDA_OK(fused_attr<4>());
+    GPO_CUDA_OK(fused_attr<5>()); GPO_CUDA_OK(fused_attr<6>()); GPO_CUDA_OK(fused_attr<7>()); GPO_CUDA_OK(fused_attr<8>());
+    eng->fused_attr_done = true;
+  }
+  if (!s.fs_mean) {
+    GPO_CUDA_OK(cudaMalloc(&s.fs_mean, (size_t)FUSED_CHUNK * 8));
+    GPO_CUDA_OK(cudaMalloc(&s.fs_sq, (size_t)FUSED_CHUNK * 8));
+  }
+  FusedSmallParams p;
+  p.Xs = xs; p.n_cand = rows; p.Linv = eng->X; p.Xt = eng->Xt; p.ldx = eng->n_pad; p.alpha = eng->alpha; p.invl = eng->invl;
+  p.sigf2 = eng->sigf2; p.n = eng->n; p.n_pad = eng->n_pad; p.d = eng->d; p.kern = eng->kern;
+  p.mean = s.fs_mean; p.sumsq = s.fs_sq; p.ld = FUSED_CHUNK;
+  const int mf = (eng->n + 7) / 8;
+  const int smem = fused_small_smem_bytes(mf, 4, eng->d);
+  const long long warp_items = (rows + 31) / 32;
+  // persistent: as many CTAs of 8 warps as fit on the SMs (the resident state is loaded once per CTA), every warp walks
+  // 32-candidate items
+  int per_sm = 1;
+  {
+    cudaError_t oe = cudaSuccess;
+    switch (mf) {
+      case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<1, 4>, FUSED_THREADS, smem); break;
+      case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<2, 4>, FUSED_THREADS, smem); break;
+      case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<3, 4>, FUSED_THREADS, smem); break;
+      case 4: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<4, 4>, FUSED_THREADS, smem); break;
+      case 5: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<5, 4>, FUSED_THREADS, smem); break;
+      case 6: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<6, 4>, FUSED_THREADS, smem); break;
+      case 7: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<7, 4>, FUSED_THREADS, smem); break;
+      default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<8, 4>, FUSED_THREADS, smem); break;
+    }
+    GPO_CUDA_OK(oe);
+    per_sm = std::max(1, per_sm);
+  }
+  dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((warp_items + 7) / 8, (long long)eng->sm_count * per_sm)), 1, 1);
+  switch (mf) {
+    case 1: fused_small_value_kernel<1, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
+    case 2: fused_small_value_kernel<2, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
+    case 3: fused_small_value_kernel<3, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
+    case 4: fused_small_value_kernel<4, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
+    case 5: fused_small_value_kernel<5, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
+    case 6: fused_small_value_kernel<6, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
+    case 7: fused_small_value_kernel<7, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
+    default: fused_small_value_kernel<8, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
+  }
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  return GPO_OK;
+}
+
 // mean_only (predict mode): K1 + K3 only -- posterior mean and its gradient, no variance GEMM (o1, o3 unused)
 static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_only, int with_noise, long long N,
                  const double* Xs, double* o0, double* o1, double* o2, double* o3, cudaStream_t user) {
@@ -1172,12 +1235,14 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     if ((rc = grow(eng, &eng->stage_in, &eng->stage_in_bytes, (size_t)N * d * 8))) return rc;
     dev_in = eng->stage_in;
   }
+  // small model, value only: K1 + variance contraction fused in one shared-memory-resident kernel, large chunks
+  const bool fused = eng->opt_fused_small && !grad && !mean_only && !tiny_call && S == 1 && eng->n <= FUSED_MAX_N;
+  const long long chunk = fused ? FUSED_CHUNK : eng->nc_ld;
   const bool in_pageable = !in_dev && !tiny_call && !is_pinned_host_ptr(Xs);
-  if (in_pageable && (rc = ensure_in_pin(eng, (size_t)std::min<long long>(eng->nc_ld, N) * d * 8))) return rc;
+  if (in_pageable && (rc = ensure_in_pin(eng, (size_t)std::min<long long>(chunk, N) * d * 8))) return rc;
   GPO_CUDA_OK(cudaEventRecord(eng->ev_in, user));
   for (int i = 0; i < 2; ++i) GPO_CUDA_OK(cudaStreamWaitEvent(eng->slot[i].stream, eng->ev_in, 0));
 
-  const long long chunk = eng->nc_ld;
   int ci = 0;
   for (long long off = 0; off < N; off += chunk, ++ci) {
     // profiling serialises the chunks on one slot so that the events around each GEMM launch bracket that kernel alone
@@ -1199,6 +1264,32 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     } else if (!in_dev)
       GPO_CUDA_OK(cudaMemcpyAsync(eng->stage_in + off * d, Xs + off * d, (size_t)rows * d * 8, cudaMemcpyHostToDevice, st));
     if (gen) launch_design(eng, eng->gen, eng->gen_row0 + off, rows, eng->stage_in + off * d, st);
+    if (fused) {
+      if ((rc = launch_fused_small(eng, s, dev_in + off * d, rows, st))) return rc;
+      AcqParams ap;
+      memset(&ap, 0, sizeof(ap));
+      ap.n_cand = rows; ap.nc_pad = FUSED_CHUNK; ap.S = 1; ap.d = d; ap.tiles_m = 1; ap.grad = 0; ap.part_nv = 1;
+      ap.part_ld = FUSED_CHUNK; ap.sq_tiles_m = 1; ap.js = 1; ap.js_ld = 1; ap.with_noise = with_noise; ap.mean = s.fs_mean;
+      ap.partial = s.fs_sq; ap.sigf2 = eng->sigf2; ap.noise = eng->noise; ap.fmin = eng->fmin; ap.kind = kind; ap.par = par;
+      ap.invl = eng->invl; ap.xmu = eng->xmu; ap.Xs = dev_in + off * d;
+      if (predict) { ap.out_m = dev_out[0] + off; ap.out_s = dev_out[1] ? dev_out[1] + off : nullptr; ap.out_ldN = N; }
+      else {
+        ap.out_f = dev_out[0] + off;
+        ap.lp_on = eng->lp_on; ap.lp_K = eng->lp_K; ap.lp_transform = eng->lp_transform;
+        ap.lp_xb = eng->lp_xb; ap.lp_r = eng->lp_r; ap.lp_s = eng->lp_s;
+      }
+      ap.blk_val = eng->want_blk ? eng->blk_val : nullptr; ap.blk_idx = eng->blk_idx; ap.row0 = off;
+      acq_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(ap);
+      eng->launches++;
+      GPO_CUDA_OK(cudaGetLastError());
+      for (int i = 0; i < 4; ++i) {
+        if (!outs[i] || out_dev[i] || out_pin[i]) continue;
+        GPO_CUDA_OK(cudaMemcpy2DAsync((char*)outs[i] + off * row_bytes[i], (size_t)N * row_bytes[i],
+                                      (char*)dev_out[i] + off * row_bytes[i], (size_t)N * row_bytes[i],
+                                      (size_t)rows * row_bytes[i], planes[i], cudaMemcpyDeviceToHost, st));
+      }
+      continue;
+    }
     // K1
     CovParams cp;
     cp.Xs = dev_in + off * d; cp.n_cand = rows; cp.nc_run = nc_run; cp.nc_ld = eng->nc_ld; cp.Xt = eng->Xt; cp.ldx = n_pad;
@@ -1672,6 +1763,7 @@ extern "C" int gpo_set_option(gpo_engine* eng, int key, long long value) {
     case GPO_OPT_BN_SWEEP: if (value != 64 && value != 128) return GPO_ERR_ARG; eng->opt_bn_sweep = (int)value; break;
     case GPO_OPT_BN_FIT: if (value != 64 && value != 128) return GPO_ERR_ARG; eng->opt_bn_fit = (int)value; break;
     case GPO_OPT_INVERSE: if (value < 0 || value > 2) return GPO_ERR_ARG; eng->opt_inverse = (int)value; break;
+    case GPO_OPT_FUSED_SMALL: eng->opt_fused_small = value != 0; break;
     default: GPO_FAIL(GPO_ERR_ARG, "gpo_set_option: unknown key %d", key);
   }
   return GPO_OK;

@@ -1239,4 +1239,144 @@ __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
   }
 }
 
+// =====================================================================================================
+// Fused value sweep for small models (n <= 64: every early BO iteration, BASELINE configs 1 and 2).
+// K1 + the variance contraction in ONE kernel: the whole posterior state -- L^-1 (<= 32 KB), the length-scaled training
+// inputs and alpha -- is resident in shared memory, candidates stream through, and K* never leaves the registers:
+//   * a warp owns 8 NF candidates; lane (g, t) evaluates k(x_train[4 kk + t], x_cand[8 nf + g]) directly in the
+//     B-fragment position of mma.m8n8k4 (no transposition, no K*^T round trip through HBM as on the general path)
+//   * t = L^-1 k runs on the FP64 tensor pipe (DMMA) against A fragments read from the resident L^-1, skipping the
+//     8 x 4 blocks above the diagonal; the model is padded to a multiple of 8 rows (not 128: at n = 55 the general
+//     path does (128/55)^2 = 5.4x the necessary flops)
+//   * mean = k . alpha is reduced in registers; the epilogue leaves mean and |L^-1 k|^2 per candidate, which K3
+//     (acq_kernel) turns into s / EI / MPI / LCB exactly as it does for the general path.
+// Reference arithmetic replaced: GPy kern.K + PosteriorExact._raw_predict (dtrtrs + sum of squares) as called from
+// /root/reference/GPyOpt/models/gpmodel.py:98 and acquisitions/LCB.py:39, EI.py:36, MPI.py:36.
+// Every candidate's result is independent of its neighbours and of the chunking (bitwise).
+// =====================================================================================================
+struct FusedSmallParams {
+  const double* Xs;       // candidates AoS [n_cand][d] of this chunk
+  long long n_cand;
+  const double* Linv;     // [S][n_pad][n_pad] lower triangular (identity on the padding)
+  const double* Xt;       // training inputs SoA [d][ldx]
+  long long ldx;
+  const double* alpha;    // [S][n_pad]
+  const double* invl;     // [S][d]
+  const double* sigf2;    // [S]
+  int n, n_pad, d, kern;
+  double* mean;           // [S][ld]
+  double* sumsq;          // [S][ld]   |L^-1 k|^2
+  long long ld;
+};
+
+constexpr int FUSED_THREADS = 256;
+__host__ __device__ constexpr int fused_small_smem_bytes(int mf, int nf, int d) {
+  const int np = 8 * mf;
+  return (np * (np + 4) + d * np + np + (FUSED_THREADS / 32) * (8 * nf * (d + 1) + 2 * 8 * nf)) * 8;
+}
+
+template <int MF, int NF>
+__global__ void __launch_bounds__(FUSED_THREADS) fused_small_value_kernel(const FusedSmallParams p) {
+  constexpr int NP = 8 * MF, PA = NP + 4, CW = 8 * NF;
+  extern __shared__ double fs_smem[];
+  const int d = p.d, PW = d + 1;
+  double* Ls = fs_smem;                         // [NP][PA]   L^-1
+  double* xts = Ls + NP * PA;                   // [d][NP]    training inputs / lengthscale
+  double* als = xts + d * NP;                   // [NP]       alpha
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  double* xsw = als + NP + warp * (CW * PW + 2 * CW);   // [CW][PW] this warp's candidates / lengthscale
+  double* outw = xsw + CW * PW;                 // [2][CW]    staging of the warp's results
+  const int z = blockIdx.y;
+  const double* invl = p.invl + (long long)z * d;
+  const double sf2 = p.sigf2[z];
+  {
+    const double* Lg = p.Linv + (long long)z * p.n_pad * p.n_pad;
+    for (int i = tid; i < NP * NP; i += FUSED_THREADS) {
+      const int r = i / NP, c = i - r * NP;
+      Ls[r * PA + c] = Lg[(long long)r * p.n_pad + c];
+    }
+    for (int i = tid; i < d * NP; i += FUSED_THREADS) {
+      const int q = i / NP, j = i - q * NP;
+      xts[i] = p.Xt[q * p.ldx + j] * invl[q];
+    }
+    for (int i = tid; i < NP; i += FUSED_THREADS) als[i] = p.alpha[(long long)z * p.n_pad + i];
+  }
+  __syncthreads();
+  const long long n_blocks = (p.n_cand + CW - 1) / CW;
+  for (long long blk = (long long)blockIdx.x * (FUSED_THREADS / 32) + warp; blk < n_blocks; blk += (long long)gridDim.x * (FUSED_THREADS / 32)) {
+    const long long c0 = blk * CW;
+    __syncwarp();
+    for (int i = lane; i < CW * d; i += 32) {
+      const int c = i / d, q = i - c * d;
+      const long long cand = min(c0 + c, p.n_cand - 1);      // rows past the end shadow the last one (never stored)
+      xsw[c * PW + q] = p.Xs[cand * d + q] * invl[q];
+    }
+    __syncwarp();
+    double acc[MF][NF][2], macc[NF];
+#pragma unroll
+    for (int mf = 0; mf < MF; ++mf)
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+#pragma unroll
+    for (int nf = 0; nf < NF; ++nf) macc[nf] = 0.0;
+#pragma unroll 1
+    for (int kp = 0; kp < MF; ++kp) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int j = 8 * kp + 4 * hh + t;            // this lane's training point of the k step
+        double r2[NF];
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) r2[nf] = 0.0;
+        for (int q = 0; q < d; ++q) {
+          const double xj = xts[q * NP + j];
+#pragma unroll
+          for (int nf = 0; nf < NF; ++nf) {
+            const double df = xsw[(8 * nf + g) * PW + q] - xj;
+            r2[nf] = fma(df, df, r2[nf]);
+          }
+        }
+        const double aj = als[j];
+        double kv[NF];
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) {
+          kv[nf] = j < p.n ? kern_k(p.kern, sf2, r2[nf]) : 0.0;
+          macc[nf] = fma(kv[nf], aj, macc[nf]);
+        }
+        // rows 8 mf .. 8 mf + 7 of L^-1 against k columns 8 kp + 4 hh .. + 3: zero above the diagonal (mf < kp)
+#pragma unroll
+        for (int mf = 0; mf < MF; ++mf) {
+          if (mf >= kp) {   // warp-uniform
+            const double a = Ls[(8 * mf + g) * PA + j];
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) dmma_884(acc[mf][nf][0], acc[mf][nf][1], a, kv[nf]);
+          }
+        }
+      }
+    }
+    // epilogue: lane (g, t) holds rows 8 mf + g of candidates 8 nf + 2 t + e; mean partials are per (j = .. + t, candidate 8 nf + g)
+#pragma unroll
+    for (int nf = 0; nf < NF; ++nf) {
+      double mv = macc[nf];
+      mv += __shfl_xor_sync(0xffffffffu, mv, 1);
+      mv += __shfl_xor_sync(0xffffffffu, mv, 2);
+      if (t == 0) outw[8 * nf + g] = mv;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double s2 = 0.0;
+#pragma unroll
+        for (int mf = 0; mf < MF; ++mf) s2 = fma(acc[mf][nf][e], acc[mf][nf][e], s2);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 4);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+        if (g == 0) outw[CW + 8 * nf + 2 * t + e] = s2;
+      }
+    }
+    __syncwarp();
+    if (lane < CW && c0 + lane < p.n_cand) {
+      p.mean[(long long)z * p.ld + c0 + lane] = outw[lane];
+      p.sumsq[(long long)z * p.ld + c0 + lane] = outw[CW + lane];
+    }
+  }
+}
+
 }  // namespace gpo

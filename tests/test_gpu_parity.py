@@ -911,3 +911,78 @@ def test_config5_gsobol_n4096_local_penalization(engine):
     ref_grad = np.vstack([og.lp_d_acquisition(af[i:i + 1], adf[i:i + 1], Xs[i:i + 1], Xb, r, sc, 'none') for i in rows])
     assert scaled_err(flp[rows], ref_val) < TOL
     assert np.max(np.abs(glp[rows] - ref_grad)) / np.max(np.abs(ref_grad)) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused small-model value sweep (n <= 64: K1 + variance contraction in one shared-memory-resident kernel)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,d,kernel,ARD', [(1, 1, 'rbf', False), (5, 2, 'matern52', False), (8, 3, 'rbf', True), (9, 2, 'matern32', False),
+                                            (20, 2, 'rbf', False), (33, 6, 'matern52', True), (55, 2, 'matern52', False),
+                                            (56, 10, 'rbf', False), (57, 4, 'rbf', True), (64, 16, 'matern32', True)])
+def test_fused_small_model_sweep(engine, n, d, kernel, ARD):
+    """Oracle parity (1e-10 scaled) of the fused kernel for every row-padding count 1 ... 8, all kernels, d up to 16;
+    agreement with the general tensor-core path (fused off); results independent (bitwise) of the position in the batch,
+    of the batch size and of the pointer kind; top-k and LP through it."""
+    import torch
+    from oracle import gpy_numpy as G, gpyopt_numpy as og
+    rng = np.random.default_rng(100 * n + d)
+    X = rng.random((n, d))
+    Y = og.normalize_stats(np.sin(3 * X).sum(1, keepdims=True) + 0.05 * rng.standard_normal((n, 1))) if n > 1 else np.array([[0.3]])
+    ls = 0.3 + rng.random(d if ARD else 1)
+    K = {'rbf': G.RBF, 'matern52': G.Matern52, 'matern32': G.Matern32}[kernel]
+    gp = G.GPRegression(X, Y, K(d, variance=1.2, lengthscale=ls, ARD=ARD), noise_var=1e-2)
+    engine.fit(kernel, X, Y, [1.2], np.broadcast_to(ls, (d,))[None, :], [1e-2])
+    N = 5000
+    Xs = rng.random((N, d))
+    Xs[:min(n, 20)] = X[:min(n, 20)]                       # candidates on training points
+    mo, so = og.gp_predict(gp, Xs)
+    m, s = engine.predict(Xs)
+    assert scaled_err(m[0], mo[:, 0]) < TOL and scaled_err(s[0], so[:, 0]) < TOL
+    m0, s0 = engine.predict(Xs, with_noise=False)
+    mo0, so0 = og.gp_predict(gp, Xs, with_noise=False)
+    assert np.array_equal(m0, m) and np.max(np.abs(s0[0] - so0[:, 0])) < TOL * np.max(np.abs(so[:, 0]))
+    fmin = og.gp_get_fmin(gp)
+    for acq, par, fo in (('EI', 0.01, og.acq_EI(mo, so.copy(), fmin, 0.01)), ('MPI', 0.01, og.acq_MPI(mo, so.copy(), fmin, 0.01)),
+                         ('LCB', 2.0, og.acq_LCB(mo, so, 2.0))):
+        f = engine.acq(acq, par, Xs)
+        # first-order effect of the (asserted, <= 1e-10 scaled) deviations of m, s and fmin on the acquisition value
+        em, es = np.abs(m[0] - mo[:, 0]) + abs(engine.get_fmin()[0] - fmin), np.abs(s[0] - so[:, 0])
+        u = (fmin - mo[:, 0] - par) / so[:, 0]
+        phi = np.exp(-0.5 * u * u) / np.sqrt(2 * np.pi)
+        from scipy.special import erfc
+        Phi = 0.5 * erfc(-u / np.sqrt(2))
+        budget = {'EI': 4 * np.max(Phi * em + phi * es), 'MPI': 4 * np.max(phi * (em + np.abs(u) * es) / so[:, 0]), 'LCB': 0.0}[acq]
+        assert np.max(np.abs(f - fo[:, 0])) <= TOL * np.max(np.abs(fo)) + budget
+        vals, idx = engine.acq_topk(acq, par, Xs, 5)
+        assert np.array_equal(idx, np.argsort(-f, kind='stable')[:5]) and np.array_equal(vals, -f[idx])
+        v1, i1 = engine.acq_topk(acq, par, Xs, 1)
+        assert i1[0] == idx[0] and v1[0] == vals[0]
+    f = engine.acq('EI', 0.01, Xs)
+    # independent of position, batch size (a different number of chunks / warps / padding rows) and pointer kind
+    perm = rng.permutation(N)
+    assert np.array_equal(engine.acq('EI', 0.01, Xs[perm]), f[perm])
+    for lo, hi in ((0, 33), (17, 4001), (4950, 5000)):
+        assert np.array_equal(engine.acq('EI', 0.01, Xs[lo:hi]), f[lo:hi])
+    fd = engine.acq('EI', 0.01, torch.from_numpy(Xs).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(fd.cpu().numpy(), f)
+    big = np.tile(Xs, (120, 1))                            # 600 000 rows: three launches of the fused kernel
+    fb = engine.acq('EI', 0.01, big)
+    assert np.array_equal(fb.reshape(120, N), np.broadcast_to(f, (120, N)))
+    # the general path (K1 -> HBM -> 128-padded DMMA GEMM) agrees to rounding
+    try:
+        engine.set_option('fused_small', 0)
+        fg = engine.acq('EI', 0.01, Xs)
+        mg, sg = engine.predict(Xs)
+    finally:
+        engine.set_option('fused_small', 1)
+    assert scaled_err(mg, m) < 1e-12 and scaled_err(sg, s) < 1e-11
+    # Local Penalization on top of the fused sweep
+    Xb, r, sc = rng.random((3, d)), np.full(3, 0.3), np.full(3, 0.2)
+    af = og.acquisition_function(og.acq_EI(mo, so.copy(), fmin, 0.01))
+    try:
+        engine.lp_set(Xb, r, sc, 'softplus')
+        v = engine.acq('EI', 0.01, Xs)
+    finally:
+        engine.lp_set(None, None, None, None)
+    assert scaled_err(v, og.lp_penalized_acquisition(af, Xs, Xb, r, sc, 'softplus')) < 1e-9

@@ -53,6 +53,9 @@ SIGNATURES = {
                                             ctypes.c_void_p, ctypes.c_void_p]),
     'gpo_topk': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'gpo_lbfgs': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                 ctypes.c_void_p]),
     'gpo_posterior_cov': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p,
                                          ctypes.c_int, ctypes.c_void_p]),
     'gpo_set_strict_variance': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -310,6 +313,21 @@ class Engine(object):
         self._check(rc, 'gpo_topk')
         kk = min(k, N)
         return vals[:kk], idx[:kk]
+
+    def lbfgs(self, kind, par, x0, bounds, maxiter=1000, pgtol=1e-5, factr=1e7):
+        """Batched multi-start L-BFGS on the device (gpo_lbfgs): minimise acquisition_function = -acq (or the LP value when
+        lp_set is active) from the rows of x0 inside the box `bounds` [d, 2].  -> (x [M, d], f [M], iterations [M], evaluations [M])."""
+        x0 = _f64(np.atleast_2d(x0))
+        bounds = _f64(np.atleast_2d(bounds))
+        M, d = x0.shape
+        assert d == self.d and bounds.shape == (d, 2)
+        x, f = np.empty((M, d)), np.empty(M)
+        it, nf = np.zeros(M, dtype=np.int32), np.zeros(M, dtype=np.int32)
+        k = ACQ[kind] if isinstance(kind, str) else int(kind)
+        rc = self._lib.gpo_lbfgs(self._h, k, float(par), M, _ptr(x0), _ptr(bounds), int(maxiter), float(pgtol), float(factr),
+                                 _ptr(x), _ptr(f), it.ctypes.data, nf.ctypes.data)
+        self._check(rc, 'gpo_lbfgs')
+        return x, f, it, nf
 
     def posterior_cov(self, X1, X2=None, with_noise=False):
         """Full posterior covariance [N1, N2] (X2 None: between X1 and itself, noise on the diagonal if with_noise)."""

@@ -111,6 +111,7 @@ struct gpo_engine {
   int opt_inverse = 0;      // triangular inverse of the refit: 0 automatic, 1 interleaved with the Cholesky, 2 recursive
   int opt_fused_small = 1;  // value sweeps of models with n <= 64 (S = 1) take the fused shared-memory-resident kernel
   bool fused_attr_done = false;
+  double* lb_buf = nullptr;  size_t lb_bytes = 0;   // device state of the batched L-BFGS (gpo_lbfgs)
   double var_disc = 0.0;
   std::vector<cudaEvent_t> chol_ev;  // look-ahead events of the blocked Cholesky (2 per block column)
   // counters / live profiling of the dominant kernel (variance GEMM) for the benchmark's roofline
@@ -329,6 +330,7 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->fit_pin) cudaFreeHost(eng->fit_pin);
   if (eng->smalln_sq) cudaFree(eng->smalln_sq);
   if (eng->gen_x) cudaFree(eng->gen_x);
+  if (eng->lb_buf) cudaFree(eng->lb_buf);
   for (int i = 0; i < 5; ++i) if (eng->cov_buf[i]) cudaFree(eng->cov_buf[i]);
   for (cudaEvent_t e : eng->chol_ev) cudaEventDestroy(e);
   for (auto& pe : eng->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
@@ -1688,6 +1690,73 @@ extern "C" int gpo_acq_topk_uniform(gpo_engine* eng, int kind, double par, const
     GPO_CUDA_OK(cudaGetLastError());
     GPO_CUDA_OK(cudaMemcpyAsync(x_top, eng->gen_x, (size_t)k * d * 8, cudaMemcpyDeviceToHost, st));
     GPO_CUDA_OK(cudaStreamSynchronize(st));
+  }
+  return GPO_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// batched multi-start L-BFGS on the device (lbfgs_update_kernel): all anchors advance in lock-step, one fused
+// value + gradient evaluation of the acquisition (N = M, the latency kernels) per round, no host round trip in the loop
+// --------------------------------------------------------------------------------------------------
+extern "C" int gpo_lbfgs(gpo_engine* eng, int kind, double par, int M, const double* x0, const double* bounds, int maxiter,
+                         double pgtol, double factr, double* x_out, double* f_out, int* iters, int* nfev) {
+  if (!eng || !x0 || !bounds || !x_out || !f_out || M < 1 || M > LB_MAXM || maxiter < 0 || kind < 0 || kind > 5) return GPO_ERR_ARG;
+  if (!eng->fitted) GPO_FAIL(GPO_ERR_STATE, "gpo_lbfgs before gpo_fit");
+  { const int frc = finalize_state(eng); if (frc) return frc; }
+  GPO_CUDA_OK(cudaSetDevice(eng->device));
+  const int d = eng->d;
+  cudaStream_t st = eng->fit_stream;
+  const size_t Md = (size_t)M * d, MH = (size_t)M * LB_HIST;
+  const size_t n_dbl = 6 * Md + 2 * MH * d + MH + 4 * (size_t)M + 2 * (size_t)d, n_int = 6 * (size_t)M + 2;
+  int rc;
+  if ((rc = grow(eng, &eng->lb_buf, &eng->lb_bytes, n_dbl * 8 + (size_t)M * sizeof(LbLineSearch) + n_int * 4 + 64))) return rc;
+  double* w = eng->lb_buf;
+  LbfgsParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.d = d; p.negate = eng->lp_on ? 0 : 1; p.maxiter = maxiter; p.pgtol = pgtol; p.ftol = factr * 2.220446049250313e-16;
+  p.x = w; w += Md; p.g = w; w += Md; p.xt = w; w += Md; double* gt = w; w += Md; p.dir = w; w += Md; double* x0d = w; w += Md;
+  p.S = w; w += MH * d; p.Y = w; w += MH * d; p.rho = w; w += MH;
+  p.f = w; w += M; double* ft = w; w += M; p.step = w; w += M; p.gd = w; w += M;
+  double* lo = w; w += d; double* hi = w; w += d;
+  p.ft = ft; p.gt = gt; p.lo = lo; p.hi = hi;
+  p.ls = reinterpret_cast<LbLineSearch*>(w);
+  int* iw = reinterpret_cast<int*>(p.ls + M);
+  p.hist_n = iw; iw += M; p.hist_head = iw; iw += M; p.iter = iw; iw += M; p.phase = iw; iw += M;
+  p.done = iw; iw += M; p.nfev = iw; iw += M; p.n_done = iw;
+  std::vector<double> hb(2 * (size_t)d);
+  for (int q = 0; q < d; ++q) {
+    hb[q] = bounds[2 * q]; hb[d + q] = bounds[2 * q + 1];
+    if (!(hb[q] <= hb[d + q])) GPO_FAIL(GPO_ERR_ARG, "gpo_lbfgs: empty box in dimension %d", q);
+  }
+  GPO_CUDA_OK(cudaMemcpyAsync(lo, hb.data(), 2 * (size_t)d * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(x0d, x0, Md * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaStreamSynchronize(st));   // (pageable sources: the staging above is already complete; keeps hb alive)
+  lbfgs_init_kernel<<<1, LB_MAXM, 0, st>>>(p, x0d);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  int* pin_done = reinterpret_cast<int*>(eng->fit_pin);
+  const long long max_rounds = std::min<long long>(20LL * maxiter + 60, 40000);   // (<= 20 evaluations per line search)
+  const int poll = 4;
+  for (long long r = 0; r < max_rounds; ++r) {
+    if ((rc = sweep(eng, kind, par, true, false, 1, M, p.xt, ft, gt, nullptr, nullptr, st))) return rc;
+    lbfgs_update_kernel<<<1, LB_MAXM, 0, st>>>(p);
+    eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
+    if (r % poll == poll - 1) {
+      GPO_CUDA_OK(cudaMemcpyAsync(pin_done, p.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+      GPO_CUDA_OK(cudaStreamSynchronize(st));
+      if (*pin_done >= M) break;
+    }
+  }
+  std::vector<int> hi_(2 * (size_t)M);
+  GPO_CUDA_OK(cudaMemcpyAsync(x_out, p.x, Md * 8, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(f_out, p.f, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(hi_.data(), p.iter, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(hi_.data() + M, p.nfev, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaStreamSynchronize(st));
+  for (int a = 0; a < M; ++a) {
+    if (iters) iters[a] = hi_[a];
+    if (nfev) nfev[a] = hi_[M + a];
   }
   return GPO_OK;
 }

@@ -1379,4 +1379,295 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_small_value_kernel(const 
   }
 }
 
+// =====================================================================================================
+// Batched multi-start L-BFGS, lock-step on the device.
+// The reference optimises its anchor points one after the other with SciPy's L-BFGS-B, one f(x) and one f_df(x) host call
+// per step (GPyOpt/optimization/optimizer.py:28-61, acquisition_optimizer.py:73-74).  Here all M anchors advance together:
+// per round ONE fused evaluation of value + gradient at the M trial points (the latency kernels, N = M) and ONE launch of
+// lbfgs_update_kernel, in which thread a runs anchor a's optimiser state machine:
+//   * direction: two-loop recursion over a ring of LB_HIST curvature pairs, scaled by y.y / s.y, on the free variables
+//     (a variable on a bound whose gradient -- or quasi-Newton direction -- points outward is frozen)
+//   * line search: the More-Thuente search of L-BFGS-B (MINPACK-2 dcsrch / dcstep in reverse-communication form, which is
+//     what makes it a state machine: ftol 1e-3, gtol 0.9, xtol 0.1, at most 20 evaluations, step capped so that the
+//     segment stays inside the box)
+//   * L-BFGS-B's update and stopping rules: pair skipped unless s.y > eps * (-g.s), projected-gradient norm <= pgtol,
+//     relative decrease <= factr * eps, maxiter; a failed search drops the history and restarts from steepest descent.
+// In the interior of the box the iterates follow SciPy's L-BFGS-B (same search, same update); at active bounds L-BFGS-B's
+// Cauchy-point / subspace step is replaced by the projected direction above.  No host round trip inside the loop: the
+// host only polls the finished-anchor count every few rounds.  (The test-suite keeps a line-by-line NumPy mirror of this state
+// machine and walks both along the same path.)
+// =====================================================================================================
+constexpr int LB_HIST = 10;
+constexpr int LB_MAXM = 64;
+
+struct LbLineSearch {   // dcsrch's saved state
+  double stx, fx, gx, sty, fy, gy, stmin, stmax, width, width1, finit, ginit, gtest, stpmx;
+  int brackt, stage, nls, pad;
+};
+
+struct LbfgsParams {
+  int M, d, negate, maxiter;        // negate: the sweep returns the acquisition (maximised): minimise -f, gradient -df
+  double pgtol, ftol;               // ftol = factr * machine epsilon
+  const double* lo; const double* hi;   // [d] box
+  double* x; double* g; double* f;  // [M][d], [M][d], [M]   current iterate
+  double* xt;                       // [M][d]  trial points = input of the next evaluation
+  const double* ft; const double* gt;   // [M], [M][d]  value / gradient at the trial points (sweep outputs)
+  double* dir;                      // [M][d]  search direction
+  double* S; double* Y; double* rho;    // [M][LB_HIST][d] x 2, [M][LB_HIST]
+  double* step; double* gd;         // [M] current step length, directional derivative g . dir at the iterate
+  LbLineSearch* ls;                 // [M]
+  int* hist_n; int* hist_head; int* iter; int* phase; int* done; int* nfev;   // [M]
+  int* n_done;                      // [1]
+};
+
+__device__ __forceinline__ double lb_clamp(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ double lb_cubic_gamma(double theta, double da, double db) {
+  const double s = ::fmax(fabs(theta), ::fmax(fabs(da), fabs(db)));
+  return s * sqrt(::fmax(0.0, (theta / s) * (theta / s) - (da / s) * (db / s)));
+}
+
+// MINPACK-2 dcstep: safeguarded cubic / quadratic step and update of the interval of uncertainty
+__device__ double lb_dcstep(double& stx, double& fx, double& dx, double& sty, double& fy, double& dy, double stp, double fp,
+                            double dp, int& brackt, double stpmin, double stpmax) {
+  const double sgnd = dp * (dx / fabs(dx));
+  double stpf;
+  if (fp > fx) {
+    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    double gamma = lb_cubic_gamma(theta, dx, dp);
+    if (stp < stx) gamma = -gamma;
+    const double p = (gamma - dx) + theta, q = ((gamma - dx) + gamma) + dp, r = p / q;
+    const double stpc = stx + r * (stp - stx);
+    const double stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx);
+    stpf = fabs(stpc - stx) < fabs(stpq - stx) ? stpc : stpc + (stpq - stpc) / 2.0;
+    brackt = 1;
+  } else if (sgnd < 0.0) {
+    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    double gamma = lb_cubic_gamma(theta, dx, dp);
+    if (stp > stx) gamma = -gamma;
+    const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + dx, r = p / q;
+    const double stpc = stp + r * (stx - stp);
+    const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    stpf = fabs(stpc - stp) > fabs(stpq - stp) ? stpc : stpq;
+    brackt = 1;
+  } else if (fabs(dp) < fabs(dx)) {
+    const double theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp;
+    double gamma = lb_cubic_gamma(theta, dx, dp);
+    if (stp > stx) gamma = -gamma;
+    const double p = (gamma - dp) + theta, q = (gamma + (dx - dp)) + gamma, r = p / q;
+    double stpc;
+    if (r < 0.0 && gamma != 0.0) stpc = stp + r * (stx - stp);
+    else if (stp > stx) stpc = stpmax;
+    else stpc = stpmin;
+    const double stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    if (brackt) {
+      stpf = fabs(stpc - stp) < fabs(stpq - stp) ? stpc : stpq;
+      stpf = stp > stx ? ::fmin(stp + 0.66 * (sty - stp), stpf) : ::fmax(stp + 0.66 * (sty - stp), stpf);
+    } else {
+      stpf = fabs(stpc - stp) > fabs(stpq - stp) ? stpc : stpq;
+      stpf = ::fmax(stpmin, ::fmin(stpmax, stpf));
+    }
+  } else {
+    if (brackt) {
+      const double theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp;
+      double gamma = lb_cubic_gamma(theta, dy, dp);
+      if (stp > sty) gamma = -gamma;
+      const double p = (gamma - dp) + theta, q = ((gamma - dp) + gamma) + dy, r = p / q;
+      stpf = stp + r * (sty - stp);
+    } else if (stp > stx) stpf = stpmax;
+    else stpf = stpmin;
+  }
+  if (fp > fx) { sty = stp; fy = fp; dy = dp; }
+  else {
+    if (sgnd < 0.0) { sty = stx; fy = fx; dy = dx; }
+    stx = stp; fx = fp; dx = dp;
+  }
+  return stpf;
+}
+
+__device__ void lb_dcsrch_start(LbLineSearch& st, double stp, double f, double g, double stpmax) {
+  st.brackt = 0; st.stage = 1; st.finit = f; st.ginit = g; st.gtest = 1e-3 * g; st.width = stpmax; st.width1 = 2.0 * stpmax;
+  st.stx = 0.0; st.fx = f; st.gx = g; st.sty = 0.0; st.fy = f; st.gy = g; st.stmin = 0.0; st.stmax = stp + 4.0 * stp;
+  st.stpmx = stpmax; st.nls = 0;
+}
+
+// one reverse-communication step of dcsrch after the evaluation (f, g) at step stp; returns true when the search ends
+// (convergence or one of dcsrch's warnings), otherwise stp holds the next trial step
+__device__ bool lb_dcsrch_next(LbLineSearch& st, double& stp, double f, double g) {
+  const double stpmax = st.stpmx;
+  const double ftest = st.finit + stp * st.gtest;
+  if (st.stage == 1 && f <= ftest && g >= 0.0) st.stage = 2;
+  bool warn = false;
+  if (st.brackt && (stp <= st.stmin || stp >= st.stmax)) warn = true;
+  if (st.brackt && st.stmax - st.stmin <= 0.1 * st.stmax) warn = true;
+  if (stp == stpmax && f <= ftest && g <= st.gtest) warn = true;
+  if (stp == 0.0 && (f > ftest || g >= st.gtest)) warn = true;
+  if (f <= ftest && fabs(g) <= 0.9 * (-st.ginit)) return true;
+  if (warn) return true;
+  if (st.stage == 1 && f <= st.fx && f > ftest) {
+    const double gt = st.gtest;
+    double fxm = st.fx - st.stx * gt, fym = st.fy - st.sty * gt, gxm = st.gx - gt, gym = st.gy - gt;
+    stp = lb_dcstep(st.stx, fxm, gxm, st.sty, fym, gym, stp, f - stp * gt, g - gt, st.brackt, st.stmin, st.stmax);
+    st.fx = fxm + st.stx * gt; st.fy = fym + st.sty * gt; st.gx = gxm + gt; st.gy = gym + gt;
+  } else {
+    stp = lb_dcstep(st.stx, st.fx, st.gx, st.sty, st.fy, st.gy, stp, f, g, st.brackt, st.stmin, st.stmax);
+  }
+  if (st.brackt) {
+    if (fabs(st.sty - st.stx) >= 0.66 * st.width1) stp = st.stx + 0.5 * (st.sty - st.stx);
+    st.width1 = st.width;
+    st.width = fabs(st.sty - st.stx);
+    st.stmin = ::fmin(st.stx, st.sty); st.stmax = ::fmax(st.stx, st.sty);
+  } else {
+    st.stmin = stp + 1.1 * (stp - st.stx);
+    st.stmax = stp + 4.0 * (stp - st.stx);
+  }
+  stp = ::fmin(::fmax(stp, 0.0), stpmax);
+  if ((st.brackt && (stp <= st.stmin || stp >= st.stmax)) || (st.brackt && st.stmax - st.stmin <= 0.1 * st.stmax)) stp = st.stx;
+  return false;
+}
+
+__global__ void lbfgs_init_kernel(const LbfgsParams p, const double* __restrict__ x0) {
+  const int a = threadIdx.x;
+  if (a == 0) *p.n_done = 0;
+  if (a >= p.M) return;
+  for (int q = 0; q < p.d; ++q) {
+    const double v = lb_clamp(x0[a * p.d + q], p.lo[q], p.hi[q]);
+    p.x[a * p.d + q] = v;
+    p.xt[a * p.d + q] = v;
+  }
+  p.hist_n[a] = 0; p.hist_head[a] = 0; p.iter[a] = 0; p.phase[a] = 0; p.done[a] = 0; p.nfev[a] = 0;
+  p.step[a] = 0.0; p.gd[a] = 0.0; p.f[a] = 0.0;
+}
+
+// one optimiser state-machine step per anchor after an evaluation at its trial point
+__global__ void lbfgs_update_kernel(const LbfgsParams p) {
+  const int a = threadIdx.x;
+  if (a >= p.M || p.done[a]) return;
+  const int d = p.d;
+  const double eps = 2.220446049250313e-16;
+  double* x = p.x + a * d; double* g = p.g + a * d; double* xt = p.xt + a * d; double* dir = p.dir + a * d;
+  LbLineSearch& ls = p.ls[a];
+  const double sgn = p.negate ? -1.0 : 1.0;
+  double F = sgn * p.ft[a];
+  double G[DMAX];
+  bool finite = F == F && fabs(F) < 1e300;
+  for (int q = 0; q < d; ++q) { G[q] = sgn * p.gt[a * d + q]; finite = finite && G[q] == G[q] && fabs(G[q]) < 1e300; }
+  p.nfev[a] += 1;
+  auto finish = [&]() {
+    p.done[a] = 1;
+    for (int q = 0; q < d; ++q) xt[q] = x[q];   // later (lock-step) evaluations of this anchor are idle repeats
+    atomicAdd(p.n_done, 1);
+  };
+  auto pg_norm = [&](const double* xx, const double* gg) {
+    double m = 0.0;
+    for (int q = 0; q < d; ++q) m = ::fmax(m, fabs(lb_clamp(xx[q] - gg[q], p.lo[q], p.hi[q]) - xx[q]));
+    return m;
+  };
+  bool steepest = false;
+  if (p.phase[a] == 0) {            // the evaluation at the start point
+    p.f[a] = F;
+    if (!finite) { finish(); return; }
+    for (int q = 0; q < d; ++q) g[q] = G[q];
+    if (pg_norm(x, g) <= p.pgtol) { finish(); return; }
+    steepest = true;
+    p.phase[a] = 1;
+  } else {                          // a line-search trial at xt = x + step * dir
+    double stp = p.step[a];
+    double gdt = 0.0;
+    if (finite) { for (int q = 0; q < d; ++q) gdt = fma(G[q], dir[q], gdt); }
+    else { F = ls.fx + 1e10 * (1.0 + fabs(ls.fx)); gdt = 1e10; }
+    ls.nls += 1;
+    const bool ended = lb_dcsrch_next(ls, stp, F, gdt);
+    if (!ended) {
+      if (ls.nls < 20) {            // next trial
+        p.step[a] = stp;
+        for (int q = 0; q < d; ++q) xt[q] = lb_clamp(x[q] + stp * dir[q], p.lo[q], p.hi[q]);
+        return;
+      }
+    }
+    if (ended && finite) {
+      // accept: curvature pair, new iterate, stopping rules (as scipy.optimize.fmin_l_bfgs_b: pgtol, factr, maxiter)
+      double sy = 0.0;
+      for (int q = 0; q < d; ++q) sy = fma(xt[q] - x[q], G[q] - g[q], sy);
+      if (sy > eps * (-p.gd[a] * p.step[a])) {
+        const int h = p.hist_head[a];
+        double* Sh = p.S + ((long long)a * LB_HIST + h) * d; double* Yh = p.Y + ((long long)a * LB_HIST + h) * d;
+        for (int q = 0; q < d; ++q) { Sh[q] = xt[q] - x[q]; Yh[q] = G[q] - g[q]; }
+        p.rho[a * LB_HIST + h] = 1.0 / sy;
+        p.hist_head[a] = (h + 1) % LB_HIST;
+        if (p.hist_n[a] < LB_HIST) p.hist_n[a] += 1;
+      }
+      const double f0 = p.f[a];
+      for (int q = 0; q < d; ++q) { x[q] = xt[q]; g[q] = G[q]; }
+      p.f[a] = F;
+      p.iter[a] += 1;
+      if (pg_norm(x, g) <= p.pgtol || (f0 - F) <= p.ftol * ::fmax(::fmax(fabs(f0), fabs(F)), 1.0) || p.iter[a] >= p.maxiter) {
+        finish(); return;
+      }
+    } else {
+      // failed search: with history, drop it and restart from steepest descent at the iterate; without, stop
+      if (p.hist_n[a] > 0) { p.hist_n[a] = 0; steepest = true; }
+      else { finish(); return; }
+    }
+  }
+  // ---- new search direction from the iterate (x, g) ----
+  bool fr[DMAX];
+  for (int q = 0; q < d; ++q) fr[q] = !((x[q] <= p.lo[q] && g[q] > 0.0) || (x[q] >= p.hi[q] && g[q] < 0.0));
+  double gdd = 0.0, dn = 0.0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int hn = steepest ? 0 : p.hist_n[a];
+    for (int pass = 0; pass <= d; ++pass) {
+      double v[DMAX], al[LB_HIST];
+      for (int q = 0; q < d; ++q) v[q] = fr[q] ? g[q] : 0.0;
+      for (int i = 0; i < hn; ++i) {        // newest to oldest
+        const int h = (p.hist_head[a] - 1 - i + 2 * LB_HIST) % LB_HIST;
+        const double* Sh = p.S + ((long long)a * LB_HIST + h) * d; const double* Yh = p.Y + ((long long)a * LB_HIST + h) * d;
+        double sv = 0.0;
+        for (int q = 0; q < d; ++q) sv = fma(Sh[q], v[q], sv);
+        al[i] = p.rho[a * LB_HIST + h] * sv;
+        for (int q = 0; q < d; ++q) v[q] = fma(-al[i], Yh[q], v[q]);
+      }
+      if (hn > 0) {
+        const int h = (p.hist_head[a] - 1 + LB_HIST) % LB_HIST;
+        const double* Yh = p.Y + ((long long)a * LB_HIST + h) * d;
+        double yy = 0.0;
+        for (int q = 0; q < d; ++q) yy = fma(Yh[q], Yh[q], yy);
+        const double gamma = 1.0 / (p.rho[a * LB_HIST + h] * yy);
+        for (int q = 0; q < d; ++q) v[q] *= gamma;
+      }
+      for (int i = hn - 1; i >= 0; --i) {   // oldest to newest
+        const int h = (p.hist_head[a] - 1 - i + 2 * LB_HIST) % LB_HIST;
+        const double* Sh = p.S + ((long long)a * LB_HIST + h) * d; const double* Yh = p.Y + ((long long)a * LB_HIST + h) * d;
+        double yv = 0.0;
+        for (int q = 0; q < d; ++q) yv = fma(Yh[q], v[q], yv);
+        const double be = p.rho[a * LB_HIST + h] * yv;
+        for (int q = 0; q < d; ++q) v[q] = fma(al[i] - be, Sh[q], v[q]);
+      }
+      bool blocked = false;
+      for (int q = 0; q < d; ++q) {
+        dir[q] = fr[q] ? -v[q] : 0.0;
+        // a free variable sitting on a bound and pushed outward by the quasi-Newton coupling: freeze it and redo
+        if (fr[q] && ((x[q] <= p.lo[q] && dir[q] < 0.0) || (x[q] >= p.hi[q] && dir[q] > 0.0))) { fr[q] = false; blocked = true; }
+      }
+      if (!blocked) break;
+    }
+    gdd = 0.0; dn = 0.0;
+    for (int q = 0; q < d; ++q) { gdd = fma(g[q], dir[q], gdd); dn = fma(dir[q], dir[q], dn); }
+    if (gdd < 0.0 || hn == 0) break;
+    p.hist_n[a] = 0;                        // not a descent direction: drop the history, steepest descent
+    steepest = true;
+  }
+  if (!(dn > 0.0) || !(gdd < 0.0)) { finish(); return; }
+  double stpmx = 1e10;
+  for (int q = 0; q < d; ++q) {
+    if (dir[q] > 0.0) stpmx = ::fmin(stpmx, (p.hi[q] - x[q]) / dir[q]);
+    else if (dir[q] < 0.0) stpmx = ::fmin(stpmx, (p.lo[q] - x[q]) / dir[q]);
+  }
+  const double stp = ::fmin(1.0, stpmx);
+  lb_dcsrch_start(ls, stp, p.f[a], gdd, stpmx);
+  p.step[a] = stp;
+  p.gd[a] = gdd;
+  for (int q = 0; q < d; ++q) xt[q] = lb_clamp(x[q] + stp * dir[q], p.lo[q], p.hi[q]);
+}
+
 }  // namespace gpo

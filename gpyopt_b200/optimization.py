@@ -4,10 +4,15 @@ rows f2 / f4).  Needs the reference package (GPyOpt) importable: these classes r
 * :class:`BatchedAcquisitionOptimizer` -- drop-in for ``GPyOpt.optimization.AcquisitionOptimizer``
   (GPyOpt/optimization/acquisition_optimizer.py:16-78).  The reference optimises its 5 anchor points one after the
   other, and ``OptLbfgs`` evaluates ``f(x)`` and ``f_df(x)`` at a single point per step (optimizer.py:44-51): a
-  latency-bound chain of N=1 device calls.  Here every anchor runs the UNCHANGED reference ``apply_optimizer`` (and
-  therefore SciPy's own L-BFGS-B) in its own thread, and a rendezvous stacks the points all threads are currently
-  asking for into ONE device call per round.  Each L-BFGS instance sees exactly the values it would have seen alone
-  (the engine's per-row results do not depend on the batch), so the optimum is identical, not just close.
+  latency-bound chain of N=1 device calls.  Two ways out:
+  ``local_optimizer='scipy'`` (default): every anchor runs the UNCHANGED reference ``apply_optimizer`` (and therefore
+  SciPy's own L-BFGS-B) in its own thread, and a rendezvous stacks the points all threads are currently asking for into
+  ONE device call per round.  Each L-BFGS instance sees the values it would have seen alone: a row's result does not
+  depend on the other rows of its call (bitwise for calls of up to 32 rows, ``test_small_batch_latency_path``; stacked
+  calls with more rows take the tensor-core path and agree to rounding, ~1e-13), so the optimum is the reference's.
+  ``local_optimizer='device'``: the optimiser itself runs inside the library (``gpo_lbfgs``): all anchors advance in
+  lock-step on the GPU -- projected L-BFGS, one fused value + gradient evaluation per round, no host round trip per step;
+  same stopping rules as SciPy's L-BFGS-B, optimum equal to the stopping tolerance rather than bit for bit.
 * :class:`FusedAnchorPointsGenerator` -- ``ObjectiveAnchorPointsGenerator`` whose scoring + ``argsort[:k]``
   (anchor_points_generator.py:62-67) is the fused device sweep + top-k (``gpo_acq_topk``) when the acquisition has
   constant cost and the space no constraints.
@@ -181,15 +186,61 @@ class BatchedAcquisitionOptimizer(AcquisitionOptimizer):
     """AcquisitionOptimizer whose local optimisations share their device calls (see module docstring)."""
 
     def __init__(self, space, optimizer='lbfgs', acquisition=None, device_design_seed=None, num_anchor_samples=1000,
-                 **kwargs):
+                 local_optimizer='scipy', lbfgs_options=None, **kwargs):
         if not HAVE_GPYOPT:
             raise ImportError("BatchedAcquisitionOptimizer builds on GPyOpt's optimizer classes; GPyOpt is not importable")
         super(BatchedAcquisitionOptimizer, self).__init__(space, optimizer, **kwargs)
         self.acquisition = acquisition     # optional: enables the fused anchor sweep
         self.device_design_seed = device_design_seed   # not None: the anchor design is generated on the device
         self.num_anchor_samples = int(num_anchor_samples)
+        # 'scipy': the reference's own SciPy L-BFGS-B per anchor, device calls batched by the rendezvous (bit-identical
+        # optimum).  'device': all anchors advance in lock-step inside the library (gpo_lbfgs: projected L-BFGS on the GPU,
+        # one fused evaluation per round, no host round trip per step) -- same stopping rules, optimum equal to tolerance.
+        self.local_optimizer = local_optimizer
+        # tighter than SciPy's defaults (pgtol 1e-5, factr 1e7): rounds are cheap on the device, and the optimum then agrees
+        # with a converged L-BFGS-B run to ~1e-7 instead of to SciPy's own stopping slack (~1e-4)
+        self.lbfgs_options = dict(maxiter=1000, pgtol=1e-9, factr=10.0)
+        self.lbfgs_options.update(lbfgs_options or {})
         self._device_gen = None
         self.last_stats = None
+
+    def _device_lbfgs_target(self, duplicate_manager):
+        """(engine, kind, par, lp_acquisition or None) when the local optimisation can run inside the library: L-BFGS on an
+        all-continuous box without context variables or duplicate handling, on a fused acquisition with constant cost (or
+        Local Penalization around one); None otherwise."""
+        from .acquisitions import _FusedAcquisition, AcquisitionLP, _engine_of
+        acq = self.acquisition
+        if self.local_optimizer != 'device' or acq is None or self.optimizer_name != 'lbfgs' or duplicate_manager:
+            return None
+        if len(getattr(self.context_manager, 'context_index', [])) > 0:
+            return None
+        types = getattr(self.space, 'has_types', {})
+        if not self.space.has_continuous() or any(v for t, v in types.items() if t != 'continuous') or self.space.has_constraints():
+            return None
+        if isinstance(acq, AcquisitionLP):
+            if not acq._device_path_ok():
+                return None
+            return _engine_of(acq.model), acq.acq._kind, acq.acq._par(), acq
+        if isinstance(acq, _FusedAcquisition) and _plain(acq):
+            return _engine_of(acq.model), acq._kind, acq._par(), None
+        return None
+
+    def _optimize_on_device(self, target, anchor_points, f):
+        eng, kind, par, lp = target
+        bounds = np.asarray(self.context_manager.noncontext_bounds, dtype=np.float64)
+        if lp is not None:
+            eng.lp_set(lp.X_batch, lp.r_x0, lp.s_x0, lp.transform)
+        try:
+            X, fx, iters, nfev = eng.lbfgs(kind, par, np.atleast_2d(anchor_points), bounds, **self.lbfgs_options)
+        finally:
+            if lp is not None:
+                eng.lp_set(None, None, None, None)
+        # as apply_optimizer (optimizer.py:160-170): round to the design space, report f at the rounded point
+        Xr = np.vstack([self.space.round_optimum(x[None, :]) for x in X])
+        fr = np.asarray(f(Xr)).reshape(-1)
+        best = int(np.argmin(fr))
+        self.last_stats = {'device_calls': 1, 'rows': int(np.sum(nfev)), 'lbfgs_iterations': iters.tolist(), 'evaluations': nfev.tolist()}
+        return np.atleast_2d(Xr[best]), np.atleast_2d(fr[best])
 
     def optimize(self, f=None, df=None, f_df=None, duplicate_manager=None):
         self.f, self.df, self.f_df = f, df, f_df
@@ -207,6 +258,10 @@ class BatchedAcquisitionOptimizer(AcquisitionOptimizer):
         elif self.type_anchor_points_logic == thompson_sampling_anchor_points_logic:
             gen = FusedThompsonAnchorPointsGenerator(self.space, sobol_design_type, self.model)
         anchor_points = gen.get(duplicate_manager=duplicate_manager, context_manager=self.context_manager)
+
+        target = self._device_lbfgs_target(duplicate_manager)
+        if target is not None:
+            return self._optimize_on_device(target, anchor_points, f)
 
         fns = {'f': f}
         if f_df is not None:

@@ -130,6 +130,18 @@ int gpo_acq_topk_uniform(gpo_engine* eng, int kind, double par, const unsigned l
                          long long N, const double* bounds, int k, double* vals, long long* idx, double* x_top,
                          void* stream);
 
+/* Batched multi-start L-BFGS on the device: the local optimisation of the acquisition from M anchor points
+ * (GPyOpt/optimization/acquisition_optimizer.py:73-74 -> optimizer.py:28-61, one SciPy L-BFGS-B run per anchor with one
+ * f(x) and one f_df(x) host call per step).  All M <= 64 anchors advance in lock-step: per round one fused value + gradient
+ * evaluation at the M trial points and one optimiser-state kernel (projected L-BFGS with 10 curvature pairs, Armijo
+ * backtracking along the projected path, SciPy's stopping rules: projected gradient <= pgtol, relative decrease <=
+ * factr * eps, maxiter iterations).  Minimises acquisition_function(x) = -acq(x) -- or the Local-Penalization value when
+ * gpo_lp_set is active -- inside the box `bounds` (host [d, 2]).  x0 (host [M, d]) start points; x_out (host [M, d]) and
+ * f_out (host [M]) the optimised points and the minimised values; iters / nfev (host [M], may be NULL) accepted steps and
+ * evaluations per anchor. */
+int gpo_lbfgs(gpo_engine* eng, int kind, double par, int M, const double* x0, const double* bounds, int maxiter, double pgtol,
+              double factr, double* x_out, double* f_out, int* iters, int* nfev);
+
 /* k smallest (largest = 0) or largest (largest = 1) entries of a device/host array v [N].  vals / idx (host|device,
  * both of the same kind): with device pointers the records stay in HBM and the call is asynchronous on `stream` (the
  * multi-GPU path all-gathers them without a host round trip); entries past min(k, N) are (NaN, -1). */

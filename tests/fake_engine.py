@@ -119,3 +119,225 @@ class FakeEngine(object):
         X = self.design_uniform(key, N, bounds, row0)
         vals, idx = self.acq_topk(kind, par, X, k)
         return vals, idx, X[idx]
+
+    def lbfgs(self, kind, par, x0, bounds, maxiter=1000, pgtol=1e-5, factr=1e7):
+        """NumPy mirror of the device optimiser's state machine (csrc/kernels.cuh: lbfgs_update_kernel), anchor by anchor:
+        lets the CPU suite check the algorithm (convergence, bounds, stopping rules) and the wrapper's plumbing."""
+        x0 = np.atleast_2d(np.asarray(x0, dtype=float))
+        lo, hi = np.asarray(bounds, dtype=float)[:, 0], np.asarray(bounds, dtype=float)[:, 1]
+        M, d = x0.shape
+        X, Fv = np.empty((M, d)), np.empty(M)
+        iters, nfev = np.zeros(M, dtype=np.int32), np.zeros(M, dtype=np.int32)
+
+        def evaluate(x):
+            if self._lp is not None:
+                v, g = self.acq(kind, par, x[None, :], grad=True)
+                return float(v[0]), np.asarray(g[0], dtype=float)
+            f, df = self.acq(kind, par, x[None, :], grad=True)
+            return -float(f[0]), -np.asarray(df[0], dtype=float)
+
+        for a in range(M):
+            X[a], Fv[a], iters[a], nfev[a] = lbfgs_mirror(evaluate, x0[a], lo, hi, maxiter, pgtol, factr)
+        return X, Fv, iters, nfev
+
+
+# ---- mirror of csrc/kernels.cuh: lb_dcstep / lb_dcsrch / lbfgs_update_kernel ----------------------------------------
+def _dcstep(st, stp, fp, dp, stpmin, stpmax):
+    stx, fx, dx, sty, fy, dy, brackt = st['stx'], st['fx'], st['gx'], st['sty'], st['fy'], st['gy'], st['brackt']
+    sgnd = dp * (dx / abs(dx))
+    if fp > fx:
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp
+        s = max(abs(theta), abs(dx), abs(dp))
+        gamma = s * np.sqrt(max(0.0, (theta / s) ** 2 - (dx / s) * (dp / s)))
+        if stp < stx:
+            gamma = -gamma
+        p = (gamma - dx) + theta; q = ((gamma - dx) + gamma) + dp; r = p / q
+        stpc = stx + r * (stp - stx)
+        stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / 2.0) * (stp - stx)
+        stpf = stpc if abs(stpc - stx) < abs(stpq - stx) else stpc + (stpq - stpc) / 2.0
+        brackt = True
+    elif sgnd < 0.0:
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp
+        s = max(abs(theta), abs(dx), abs(dp))
+        gamma = s * np.sqrt(max(0.0, (theta / s) ** 2 - (dx / s) * (dp / s)))
+        if stp > stx:
+            gamma = -gamma
+        p = (gamma - dp) + theta; q = ((gamma - dp) + gamma) + dx; r = p / q
+        stpc = stp + r * (stx - stp)
+        stpq = stp + (dp / (dp - dx)) * (stx - stp)
+        stpf = stpc if abs(stpc - stp) > abs(stpq - stp) else stpq
+        brackt = True
+    elif abs(dp) < abs(dx):
+        theta = 3.0 * (fx - fp) / (stp - stx) + dx + dp
+        s = max(abs(theta), abs(dx), abs(dp))
+        gamma = s * np.sqrt(max(0.0, (theta / s) ** 2 - (dx / s) * (dp / s)))
+        if stp > stx:
+            gamma = -gamma
+        p = (gamma - dp) + theta; q = (gamma + (dx - dp)) + gamma; r = p / q
+        if r < 0.0 and gamma != 0.0:
+            stpc = stp + r * (stx - stp)
+        elif stp > stx:
+            stpc = stpmax
+        else:
+            stpc = stpmin
+        stpq = stp + (dp / (dp - dx)) * (stx - stp)
+        if brackt:
+            stpf = stpc if abs(stpc - stp) < abs(stpq - stp) else stpq
+            stpf = min(stp + 0.66 * (sty - stp), stpf) if stp > stx else max(stp + 0.66 * (sty - stp), stpf)
+        else:
+            stpf = stpc if abs(stpc - stp) > abs(stpq - stp) else stpq
+            stpf = max(stpmin, min(stpmax, stpf))
+    else:
+        if brackt:
+            theta = 3.0 * (fp - fy) / (sty - stp) + dy + dp
+            s = max(abs(theta), abs(dy), abs(dp))
+            gamma = s * np.sqrt(max(0.0, (theta / s) ** 2 - (dy / s) * (dp / s)))
+            if stp > sty:
+                gamma = -gamma
+            p = (gamma - dp) + theta; q = ((gamma - dp) + gamma) + dy; r = p / q
+            stpf = stp + r * (sty - stp)
+        elif stp > stx:
+            stpf = stpmax
+        else:
+            stpf = stpmin
+    if fp > fx:
+        sty, fy, dy = stp, fp, dp
+    else:
+        if sgnd < 0.0:
+            sty, fy, dy = stx, fx, dx
+        stx, fx, dx = stp, fp, dp
+    st.update(stx=stx, fx=fx, gx=dx, sty=sty, fy=fy, gy=dy, brackt=brackt)
+    return stpf
+
+
+def _dcsrch_start(st, stp, f, g, stpmax):
+    st.update(brackt=False, stage=1, finit=f, ginit=g, gtest=1e-3 * g, width=stpmax, width1=2.0 * stpmax, stx=0.0, fx=f, gx=g,
+              sty=0.0, fy=f, gy=g, stmin=0.0, stmax=stp + 4.0 * stp)
+
+
+def _dcsrch_next(st, stp, f, g, stpmax):
+    """-> (done, new stp).  MINPACK-2 dcsrch with L-BFGS-B's constants (ftol 1e-3, gtol 0.9, xtol 0.1, stpmin 0)."""
+    ftest = st['finit'] + stp * st['gtest']
+    if st['stage'] == 1 and f <= ftest and g >= 0.0:
+        st['stage'] = 2
+    warn = False
+    if st['brackt'] and (stp <= st['stmin'] or stp >= st['stmax']):
+        warn = True
+    if st['brackt'] and st['stmax'] - st['stmin'] <= 0.1 * st['stmax']:
+        warn = True
+    if stp == stpmax and f <= ftest and g <= st['gtest']:
+        warn = True
+    if stp == 0.0 and (f > ftest or g >= st['gtest']):
+        warn = True
+    if f <= ftest and abs(g) <= 0.9 * (-st['ginit']):
+        return True, stp
+    if warn:
+        return True, stp
+    if st['stage'] == 1 and f <= st['fx'] and f > ftest:
+        gt = st['gtest']
+        sm = dict(stx=st['stx'], fx=st['fx'] - st['stx'] * gt, gx=st['gx'] - gt, sty=st['sty'], fy=st['fy'] - st['sty'] * gt,
+                  gy=st['gy'] - gt, brackt=st['brackt'])
+        stp = _dcstep(sm, stp, f - stp * gt, g - gt, st['stmin'], st['stmax'])
+        st.update(stx=sm['stx'], sty=sm['sty'], brackt=sm['brackt'], fx=sm['fx'] + sm['stx'] * gt, fy=sm['fy'] + sm['sty'] * gt,
+                  gx=sm['gx'] + gt, gy=sm['gy'] + gt)
+    else:
+        stp = _dcstep(st, stp, f, g, st['stmin'], st['stmax'])
+    if st['brackt']:
+        if abs(st['sty'] - st['stx']) >= 0.66 * st['width1']:
+            stp = st['stx'] + 0.5 * (st['sty'] - st['stx'])
+        st['width1'] = st['width']
+        st['width'] = abs(st['sty'] - st['stx'])
+        st['stmin'], st['stmax'] = min(st['stx'], st['sty']), max(st['stx'], st['sty'])
+    else:
+        st['stmin'] = stp + 1.1 * (stp - st['stx'])
+        st['stmax'] = stp + 4.0 * (stp - st['stx'])
+    stp = min(max(stp, 0.0), stpmax)
+    if (st['brackt'] and (stp <= st['stmin'] or stp >= st['stmax'])) or (st['brackt'] and st['stmax'] - st['stmin'] <= 0.1 * st['stmax']):
+        stp = st['stx']
+    return False, stp
+
+
+def lbfgs_mirror(evaluate, x0, lo, hi, maxiter, pgtol, factr, H=10):
+    eps = 2.220446049250313e-16
+    ftol = factr * eps
+    d = x0.size
+    x = np.clip(np.asarray(x0, dtype=float), lo, hi)
+    S, Y, R = [], [], []
+    f, g = evaluate(x)
+    nfev, it = 1, 0
+
+    def pgn(xx, gg):
+        return float(np.max(np.abs(np.clip(xx - gg, lo, hi) - xx)))
+
+    if not np.isfinite(f) or pgn(x, g) <= pgtol:
+        return x, f, it, nfev
+    steepest = True
+    while True:
+        # ---- direction: two-loop recursion on the free variables ----
+        free = ~(((x <= lo) & (g > 0)) | ((x >= hi) & (g < 0)))
+        hist = [] if steepest else list(range(len(S) - 1, -1, -1))
+        while True:
+            v = np.where(free, g, 0.0)
+            al = []
+            for h in hist:
+                al.append(R[h] * S[h].dot(v)); v = v - al[-1] * Y[h]
+            if hist:
+                v = v / (R[-1] * Y[-1].dot(Y[-1]))
+            for i in range(len(hist) - 1, -1, -1):
+                h = hist[i]
+                v = v + (al[i] - R[h] * Y[h].dot(v)) * S[h]
+            dirn = np.where(free, -v, 0.0)
+            # a free variable sitting on a bound and pushed outward by the quasi-Newton coupling: freeze it and redo
+            block = free & (((x <= lo) & (dirn < 0)) | ((x >= hi) & (dirn > 0)))
+            if not block.any():
+                break
+            free = free & ~block
+        gd = g.dot(dirn)
+        if not gd < 0 and hist:
+            S, Y, R = [], [], []
+            steepest = True
+            continue
+        dn = dirn.dot(dirn)
+        if not dn > 0 or not gd < 0:
+            break
+        with np.errstate(divide='ignore', invalid='ignore'):
+            room = np.where(dirn > 0, (hi - x) / dirn, np.where(dirn < 0, (lo - x) / dirn, np.inf))
+        stpmx = float(min(np.min(room), 1e10))
+        stp = min(1.0, stpmx)
+        st = {}
+        _dcsrch_start(st, stp, f, gd, stpmx)
+        nls = 0
+        accepted = False
+        while True:
+            xt = np.clip(x + stp * dirn, lo, hi)
+            F, G = evaluate(xt); nfev += 1; nls += 1
+            if not (np.isfinite(F) and np.all(np.isfinite(G))):
+                F, gdt = st['fx'] + 1e10 * (1.0 + abs(st['fx'])), 1e10
+            else:
+                gdt = G.dot(dirn)
+            done, stp_new = _dcsrch_next(st, stp, F, gdt, stpmx)
+            if done:
+                accepted = np.isfinite(F) and F < 1e299
+                break
+            if nls >= 20:
+                break
+            stp = stp_new
+        if not accepted:
+            if S:
+                S, Y, R = [], [], []
+                steepest = True
+                continue
+            break
+        s, y = xt - x, G - g
+        sy = s.dot(y)
+        if sy > eps * (-gd * stp):
+            S.append(s); Y.append(y); R.append(1.0 / sy)
+            if len(S) > H:
+                S.pop(0); Y.pop(0); R.pop(0)
+        f0 = f
+        x, f, g = xt, F, G
+        it += 1
+        steepest = False
+        if pgn(x, g) <= pgtol or (f0 - f) <= ftol * max(abs(f0), abs(f), 1.0) or it >= maxiter:
+            break
+    return x, f, it, nfev

@@ -309,3 +309,65 @@ def test_rendezvous_propagates_errors_and_handles_uneven_workers():
     [t.join() for t in ts]
     assert out[(1, 2)] == (4.0, out[(1, 2)][1]) and np.array_equal(out[(0, 1)][1], [2.0, 2.0])
     assert errs == ['negative'] and seen[0] == 3 and sum(seen) == 2 + 3 + 4 + 1
+
+
+def test_device_lbfgs_optimizer_wrapper(gpyopt):
+    """BatchedAcquisitionOptimizer(local_optimizer='device'): the anchors' local optimisation runs inside the library
+    (gpo_lbfgs; here its NumPy mirror in the FakeEngine).  Same anchors as the reference optimiser (same seed), optimum at
+    least as good as the reference's SciPy run and equal to it within the reference's own stopping slack; Local
+    Penalization goes through the same call; spaces / acquisitions the device optimiser cannot serve fall back."""
+    GPyOpt, models, acqs = gpyopt
+    import importlib
+    import gpyopt_b200.optimization as opt
+    importlib.reload(opt)
+    from gpyopt_b200 import kern
+    from oracle import gpyopt_numpy as og
+    from scipy.optimize import fmin_l_bfgs_b
+    rng = np.random.default_rng(5)
+    space = GPyOpt.Design_space(DOMAIN)
+    X = np.column_stack([rng.uniform(-5, 10, 14), rng.uniform(1, 15, 14)])
+    Y = og.normalize_stats(branin(X))
+    model = models.GPModel(kernel=kern.RBF(2, lengthscale=3.0), exact_feval=True, max_iters=0, verbose=False)
+    model.updateModel(X, Y, None, None)
+    for acq_cls in (acqs.AcquisitionEI, acqs.AcquisitionLCB):
+        acq_ref = acq_cls(model, space, GPyOpt.optimization.AcquisitionOptimizer(space, 'lbfgs'))
+        np.random.seed(11)
+        x_ref, f_ref = acq_ref.optimize()
+        new_opt = opt.BatchedAcquisitionOptimizer(space, 'lbfgs', local_optimizer='device')
+        acq_new = acq_cls(model, space, new_opt)
+        new_opt.acquisition = acq_new
+        np.random.seed(11)
+        x_new, f_new = acq_new.optimize()
+        assert x_new.shape == (1, 2) and 'lbfgs_iterations' in new_opt.last_stats       # the device path was taken
+        assert np.ravel(f_new)[0] <= np.ravel(f_ref)[0] + 1e-9
+        assert np.max(np.abs(x_new - x_ref)) < 1e-3 and abs(np.ravel(f_new)[0] - np.ravel(f_ref)[0]) < 1e-6
+        # a converged SciPy run started from the device optimum stays put
+        fun = lambda z: (lambda r: (float(r[0][0, 0]), r[1][0]))(acq_new.acquisition_function_withGradients(z[None, :]))
+        r = fmin_l_bfgs_b(fun, x_new[0], bounds=space.get_bounds(), pgtol=1e-10, factr=10.0)
+        assert np.max(np.abs(r[0] - x_new[0])) < 1e-6
+    # Local Penalization around EI: penalisers set, device optimiser minimises the penalised value
+    inner = acqs.AcquisitionEI(model, space, None, jitter=0.01)
+    lp_opt = opt.BatchedAcquisitionOptimizer(space, 'lbfgs', local_optimizer='device')
+    lp = acqs.AcquisitionLP(model, space, lp_opt, inner)
+    lp_opt.acquisition = lp
+    lp.update_batches(x_new, 3.0, float(Y.min()))
+    np.random.seed(12)
+    x_lp, f_lp = lp.optimize()
+    assert 'lbfgs_iterations' in lp_opt.last_stats and np.linalg.norm(x_lp - x_new) > 1e-3    # pushed away from the penaliser
+    ref_lp_opt = GPyOpt.optimization.AcquisitionOptimizer(space, 'lbfgs')
+    lp_ref = acqs.AcquisitionLP(model, space, ref_lp_opt, inner)
+    lp_ref.update_batches(x_new, 3.0, float(Y.min()))
+    np.random.seed(12)
+    x_lpr, f_lpr = lp_ref.optimize()
+    # (the reference's LP "gradient" drops the penalisers' direction vectors -- SURVEY Appendix B.6 -- so it is not the gradient
+    #  of the LP value and two line searches do not stop at the same point: agreement to 1e-5 in value)
+    assert abs(np.ravel(f_lp)[0] - np.ravel(f_lpr)[0]) < 1e-5 and np.max(np.abs(x_lp - x_lpr)) < 1e-2
+    # a mixed space is not served by the device optimiser: the rendezvous path answers
+    mixed = GPyOpt.Design_space([{'name': 'a', 'type': 'continuous', 'domain': (-5, 10)},
+                                 {'name': 'b', 'type': 'discrete', 'domain': (1, 5, 9, 15)}])
+    mo = opt.BatchedAcquisitionOptimizer(mixed, 'lbfgs', local_optimizer='device')
+    am = acqs.AcquisitionEI(model, mixed, mo, jitter=0.01)
+    mo.acquisition = am
+    np.random.seed(13)
+    xm, _ = am.optimize()
+    assert 'lbfgs_iterations' not in mo.last_stats and xm[0, 1] in (1, 5, 9, 15)

@@ -314,3 +314,111 @@ def test_gpmodel_mcmc_updatemodel_matches_the_oracle_flow_and_distribution():
     se = np.sqrt(le.var(0) / ess + lo.var(0) / ess)
     assert np.all(np.abs(le.mean(0) - lo.mean(0)) < 3 * se), (le.mean(0), lo.mean(0), se)
     assert np.all(le.std(0) / lo.std(0) < 1.5) and np.all(lo.std(0) / le.std(0) < 1.5)
+
+
+# ------------------------------------------------------------------------------------------------------
+# batched multi-start L-BFGS on the device -- needs no GPyOpt: driven against SciPy and against the
+# NumPy mirror of the state machine on the same engine
+# ------------------------------------------------------------------------------------------------------
+def _lbfgs_problem(case):
+    from oracle import gpyopt_numpy as og
+    rng = np.random.default_rng(3)
+    if case == 'branin':
+        b = np.array([[-5., 10.], [1., 15.]]); n, ls, nz, fn = 20, 3.0, 1e-6, og.branin
+    elif case == 'alpine6':
+        b = np.array([[1., 10.]] * 6); n, ls, nz, fn = 300, 2.0, 1e-2, og.alpine2
+    else:
+        b = np.array([[-4., 6.]] * 10); n, ls, nz, fn = 500, 3.0, 1e-2, lambda X: og.gSobol(X, np.ones(10))
+    X = b[:, 0] + (b[:, 1] - b[:, 0]) * rng.random((n, b.shape[0]))
+    Y = og.normalize_stats(fn(X))[:, 0]
+    Xs = b[:, 0] + (b[:, 1] - b[:, 0]) * rng.random((2000, b.shape[0]))
+    return X, Y, b, ls, nz, Xs
+
+
+@pytest.mark.parametrize('case,kind,par,M', [('branin', 'EI', 0.01, 5), ('branin', 'LCB', 2.0, 5), ('alpine6', 'EI', 0.01, 5),
+                                             ('alpine6', 'LCB', 2.0, 16), ('gsobol10', 'EI', 0.01, 32), ('gsobol10', 'MPI', 0.01, 40)])
+def test_device_lbfgs_against_scipy_and_mirror(case, kind, par, M):
+    from scipy.optimize import fmin_l_bfgs_b
+    from gpyopt_b200 import Engine
+    from fake_engine import lbfgs_mirror
+    X, Y, b, ls, nz, Xs = _lbfgs_problem(case)
+    d = b.shape[0]
+    eng = Engine(0)
+    try:
+        eng.fit('rbf', X, Y, [1.0], np.full((1, d), ls), [nz])
+        _, idx = eng.acq_topk(kind, par, Xs, M)
+        A = Xs[idx]
+
+        def fun(z):
+            f, df = eng.acq(kind, par, z[None, :], grad=True)
+            return -float(f[0]), -df[0]
+
+        opts = dict(maxiter=1000, pgtol=1e-9, factr=10.0)
+        x, f, it, nf = eng.lbfgs(kind, par, A, b, **opts)
+        assert np.all(x >= b[:, 0]) and np.all(x <= b[:, 1]) and np.all(nf >= 1)
+        fa, ga = eng.acq(kind, par, x, grad=True)
+        assert np.allclose(-fa, f, rtol=1e-12, atol=1e-300)                      # the reported value is the value at x
+        # (1) a stationary point of the box-constrained problem: projected gradient ~ 0 relative to the start's
+        pg = np.max(np.abs(np.clip(x + ga, b[:, 0], b[:, 1]) - x), axis=1)
+        f0, g0 = eng.acq(kind, par, A, grad=True)
+        pg0 = np.max(np.abs(np.clip(A + g0, b[:, 0], b[:, 1]) - A), axis=1)
+        assert np.all(f <= -f0 + 1e-15) and np.all(pg <= np.maximum(1e-3 * pg0, 1e-6)), (pg, pg0)   # (most runs stop on factr)
+        # (2) the NumPy mirror of the state machine, driven by single-point calls of the same engine, walks the same path
+        same = 0
+        for a in range(min(M, 8)):
+            xm, fm, itm, nfm = lbfgs_mirror(fun, A[a], b[:, 0], b[:, 1], opts['maxiter'], opts['pgtol'], opts['factr'])
+            if np.max(np.abs(xm - x[a])) < 1e-7 * np.max(b[:, 1] - b[:, 0]) and abs(fm - f[a]) <= 1e-9 * max(1.0, abs(fm)):
+                same += 1
+        assert same >= min(M, 8) - 1, same
+        # (3) SciPy's L-BFGS-B from the same anchors: same optimum within 1e-6 wherever both end in the same basin, never worse
+        close = 0
+        for a in range(min(M, 8)):
+            r = fmin_l_bfgs_b(fun, A[a], bounds=[tuple(bb) for bb in b], maxiter=1000, pgtol=1e-9, factr=10.0)
+            if np.max(np.abs(r[0] - x[a])) < 1e-6 * np.max(b[:, 1] - b[:, 0]):
+                close += 1
+                assert abs(r[1] - f[a]) <= 1e-9 * max(1.0, abs(r[1]))
+            else:
+                assert f[a] <= r[1] + 1e-9 * max(1.0, abs(r[1])) or np.max(np.abs(r[0] - x[a])) > 1e-3
+        assert close >= (min(M, 8) * 3) // 4, close
+        # (4) polishing the best point with a converged SciPy run does not move it
+        best = int(np.argmin(f))
+        r = fmin_l_bfgs_b(fun, x[best], bounds=[tuple(bb) for bb in b], maxiter=200, pgtol=1e-10, factr=10.0)
+        assert np.max(np.abs(r[0] - x[best])) < 1e-6 * np.max(b[:, 1] - b[:, 0])
+        # (5) SciPy's default stopping rules: same optimum to the slack of those rules
+        x2, f2, _, nf2 = eng.lbfgs(kind, par, A, b, maxiter=1000, pgtol=1e-5, factr=1e7)
+        near = np.max(np.abs(x2 - x), axis=1) < 1e-3 * np.max(b[:, 1] - b[:, 0])
+        assert np.all(f2 <= -f0 + 1e-15) and near.sum() >= (M * 3) // 5
+        assert np.all(np.abs(f2 - f)[near] <= 1e-6 * np.maximum(1.0, np.abs(f[near])))
+    finally:
+        eng.close()
+
+
+def test_device_lbfgs_under_local_penalization_and_maxiter():
+    """Local Penalization active (the minimised function is the penalised value itself) and the maxiter stop."""
+    from scipy.optimize import fmin_l_bfgs_b
+    from gpyopt_b200 import Engine
+    X, Y, b, ls, nz, Xs = _lbfgs_problem('alpine6')
+    eng = Engine(0)
+    try:
+        eng.fit('rbf', X, Y, [1.0], np.full((1, 6), ls), [nz])
+        Xb = Xs[:3]
+        eng.lp_set(Xb, np.full(3, 0.8), np.full(3, 0.4), 'softplus')
+        _, idx = eng.acq_topk('EI', 0.01, Xs, 6)
+        A = Xs[idx]
+        x, f, it, nf = eng.lbfgs('EI', 0.01, A, b, maxiter=1000, pgtol=1e-9, factr=10.0)
+        v, g = eng.acq('EI', 0.01, x, grad=True)
+        assert np.allclose(v, f, rtol=1e-12)
+
+        def fun(z):
+            vv, gg = eng.acq('EI', 0.01, z[None, :], grad=True)
+            return float(vv[0]), gg[0]
+        v0 = eng.acq('EI', 0.01, A)
+        assert np.all(f <= v0 + 1e-15)
+        best = int(np.argmin(f))
+        r = fmin_l_bfgs_b(fun, x[best], bounds=[tuple(bb) for bb in b], maxiter=200, pgtol=1e-10, factr=10.0)
+        assert np.max(np.abs(r[0] - x[best])) < 1e-5 * 9.0 and r[1] >= f[best] - 1e-9 * max(1.0, abs(f[best]))
+        x3, f3, it3, _ = eng.lbfgs('EI', 0.01, A, b, maxiter=2, pgtol=1e-12, factr=0.0)
+        assert np.all(it3 <= 2) and np.all(f3 >= f - 1e-12)
+    finally:
+        eng.lp_set(None, None, None, None)
+        eng.close()

@@ -1321,34 +1321,40 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_small_value_kernel(const 
     for (int nf = 0; nf < NF; ++nf) macc[nf] = 0.0;
 #pragma unroll 1
     for (int kp = 0; kp < MF; ++kp) {
+      // the lane's two training points of this pair of k steps (j = 8 kp + 4 hh + t) against its NF candidates: all 2 NF
+      // covariance values are evaluated in one straight-line block (independent chains interleave), then fed to the DMMAs
+      double r2[2 * NF], kv[2 * NF];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int j = 8 * kp + 4 * hh + t;            // this lane's training point of the k step
-        double r2[NF];
-#pragma unroll
-        for (int nf = 0; nf < NF; ++nf) r2[nf] = 0.0;
-        for (int q = 0; q < d; ++q) {
-          const double xj = xts[q * NP + j];
-#pragma unroll
-          for (int nf = 0; nf < NF; ++nf) {
-            const double df = xsw[(8 * nf + g) * PW + q] - xj;
-            r2[nf] = fma(df, df, r2[nf]);
-          }
-        }
-        const double aj = als[j];
-        double kv[NF];
+      for (int v = 0; v < 2 * NF; ++v) r2[v] = 0.0;
+      const int j0 = 8 * kp + t;
+      for (int q = 0; q < d; ++q) {
+        const double xj0 = xts[q * NP + j0], xj1 = xts[q * NP + j0 + 4];
 #pragma unroll
         for (int nf = 0; nf < NF; ++nf) {
-          kv[nf] = j < p.n ? kern_k(p.kern, sf2, r2[nf]) : 0.0;
-          macc[nf] = fma(kv[nf], aj, macc[nf]);
+          const double xc = xsw[(8 * nf + g) * PW + q];
+          const double d0 = xc - xj0, d1 = xc - xj1;
+          r2[nf] = fma(d0, d0, r2[nf]);
+          r2[NF + nf] = fma(d1, d1, r2[NF + nf]);
         }
-        // rows 8 mf .. 8 mf + 7 of L^-1 against k columns 8 kp + 4 hh .. + 3: zero above the diagonal (mf < kp)
+      }
+      kern_k_vec<2 * NF>(p.kern, sf2, r2, kv);
+      const double a0 = als[j0], a1 = als[j0 + 4];
+#pragma unroll
+      for (int nf = 0; nf < NF; ++nf) {
+        kv[nf] = j0 < p.n ? kv[nf] : 0.0;               // padding rows of the model carry no covariance
+        kv[NF + nf] = j0 + 4 < p.n ? kv[NF + nf] : 0.0;
+        macc[nf] = fma(kv[nf], a0, macc[nf]);
+        macc[nf] = fma(kv[NF + nf], a1, macc[nf]);
+      }
+      // rows 8 mf .. 8 mf + 7 of L^-1 against k columns 8 kp + 4 hh .. + 3: zero above the diagonal (mf < kp)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
         for (int mf = 0; mf < MF; ++mf) {
           if (mf >= kp) {   // warp-uniform
-            const double a = Ls[(8 * mf + g) * PA + j];
+            const double a = Ls[(8 * mf + g) * PA + j0 + 4 * hh];
 #pragma unroll
-            for (int nf = 0; nf < NF; ++nf) dmma_884(acc[mf][nf][0], acc[mf][nf][1], a, kv[nf]);
+            for (int nf = 0; nf < NF; ++nf) dmma_884(acc[mf][nf][0], acc[mf][nf][1], a, kv[hh * NF + nf]);
           }
         }
       }

@@ -51,6 +51,11 @@ __device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gsrc, 
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// L2 prefetch of a contiguous range (cp.async.bulk.prefetch.L2): a hint, no completion to wait for.  16-byte aligned, size a
+// multiple of 16.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

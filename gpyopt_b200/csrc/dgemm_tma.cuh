@@ -68,6 +68,7 @@ struct GemmParams {
   int ksplit;  // >= 1: grid.y slices of the k range (EPI_GRAD only: its reductions are linear in the accumulator);
                // slice s of row block m writes partial row m*ksplit + s
   int serpentine;  // deal the work items to the CTAs in serpentine rounds (see gemm_item)
+  int prefetch_kt; // EPI_GRAD: bulk-prefetch the tile's K* / H* entries into L2 at the start of the work item
   int tri_diag;    // the A operand is triangular inside its diagonal 128-block (k block == row block): 1 lower (zero for
                    // k > row: L^-1 under KR_LE_M), 2 upper (zero for k < row: L^-T under KR_GE_M).  The 8-row fragments that
                    // lie entirely in the zero part are skipped (they add exact zeros): the diagonal block costs ~56 % of a
@@ -207,6 +208,18 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int a_row = p.a.row0 + node * p.a.row_z + t.tile_m * TILE, a_col = p.a.col0 + node * p.a.col_z;
         const int b_row = p.b.row0 + node * p.b.row_z + t.tile_n * BN, b_col = p.b.col0 + node * p.b.col_z;
         const int a_bat = p.a.bat0 + set * p.a.bat_z, b_bat = p.b.bat0 + set * p.b.bat_z;
+        if constexpr (EPI == EPI_GRAD) {
+          // The epilogue re-reads the K* (and H*) entries of this tile.  When K* is not this product's own B operand (the
+          // second triangular product streams t = L^-1 K* instead) those lines have long left the L2: pull them back now,
+          // a whole main loop ahead of their use (one 1 KB bulk prefetch per candidate row)
+          if (p.prefetch_kt) {
+            const long long off = ((long long)t.z * p.nc_ld + (long long)t.tile_n * BN) * p.n_pad + (long long)t.tile_m * TILE;
+            for (int c = 0; c < BN; ++c) {
+              l2_prefetch_bulk(p.Kt + off + (long long)c * p.n_pad, TILE * 8);
+              if (p.Ht) l2_prefetch_bulk(p.Ht + off + (long long)c * p.n_pad, TILE * 8);
+            }
+          }
+        }
         for (int it = 0; it < t.nk; ++it, ++g) {
           const int s = (int)(g % STAGES);
           if (g >= STAGES) mbar_wait(&empty_bar[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
@@ -392,28 +405,38 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       double s0[4][2], h0[4][2];
 #pragma unroll
       for (int j = 0; j < 4; ++j) s0[j][0] = s0[j][1] = h0[j][0] = h0[j][1] = 0.0;
+      // the tile's K* (H*) entries are fetched in two batches of 32 (64) independent loads per lane, each issued in full
+      // before its first use: one L2 / DRAM round trip per batch instead of one per fragment row (ncu: 58 % of this
+      // epilogue's stall samples were long-scoreboard waits on eight dependent round trips)
 #pragma unroll
-      for (int f = 0; f < 8; ++f) {
-        const int r = wm + 8 * f + rr;
-        double kv[4][2], hv[4][2];
+      for (int fb = 0; fb < 2; ++fb) {
+        double kv[4][4][2], hv[4][4][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int f4 = 0; f4 < 4; ++f4) {
+          const int r = wm + 8 * (4 * fb + f4) + rr;
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const long long o = (long long)(wn + 8 * j + (e ? 4 + t : t)) * p.n_pad + r;
-            kv[j][e] = __ldg(Kt + o);
-            hv[j][e] = Ht ? __ldg(Ht + o) : 0.0;
-          }
+          for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+            for (int e = 0; e < 2; ++e) {
+              const long long o = (long long)(wn + 8 * j + (e ? 4 + t : t)) * p.n_pad + r;
+              kv[f4][j][e] = __ldg(Kt + o);
+              hv[f4][j][e] = Ht ? __ldg(Ht + o) : 0.0;
+            }
+        }
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const double b = acc[f][j][e];
-            s0[j][e] = fma(b, kv[j][e], s0[j][e]);
-            const double bh = Ht ? b * hv[j][e] : -(b * kv[j][e]);
-            h0[j][e] += bh;
-            acc[f][j][e] = bh;
-          }
+        for (int f4 = 0; f4 < 4; ++f4) {
+          const int f = 4 * fb + f4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const double b = acc[f][j][e];
+              s0[j][e] = fma(b, kv[f4][j][e], s0[j][e]);
+              const double bh = Ht ? b * hv[f4][j][e] : -(b * kv[f4][j][e]);
+              h0[j][e] += bh;
+              acc[f][j][e] = bh;
+            }
+        }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)

@@ -109,8 +109,8 @@ struct gpo_engine {
   int opt_bn_sweep = 64;    // column-tile width of the sweep GEMMs (64: two CTAs per SM, 128: one)
   int opt_bn_fit = 64;      // the same for the rectangular GEMMs of the refit
   int opt_inverse = 0;      // triangular inverse of the refit: 0 automatic, 1 interleaved with the Cholesky, 2 recursive
-  int opt_fused_small = 1;  // value sweeps of models with n <= 64 (S = 1) take the fused shared-memory-resident kernel
-  bool fused_attr_done = false;
+  int opt_prefetch_kt = 0;  // strict gradient sweeps: L2 prefetch of the K* tile the EPI_GRAD epilogue re-reads (measured: no gain)
+  int opt_fused_small = 1;  // value sweeps of models with n <= 128 (S = 1) take the fused shared-memory-resident kernel
   double* lb_buf = nullptr;  size_t lb_bytes = 0;   // device state of the batched L-BFGS (gpo_lbfgs)
   double var_disc = 0.0;
   std::vector<cudaEvent_t> chol_ev;  // look-ahead events of the blocked Cholesky (2 per block column)
@@ -1129,20 +1129,36 @@ static int launch_cov_small(gpo_engine* eng, const CovParams& p_in, int nc, cuda
   return GPO_OK;
 }
 
-// Fused value sweep of a small model (fused_small_value_kernel): n <= 64, one hyper-parameter set.
+// Fused value sweep of a small model (fused_small_value_kernel): n <= 128, one hyper-parameter set.  Models of up to 64
+// rows run with 32 candidates per warp (NF = 4), larger ones with 16 (NF = 2: the accumulators are 8 MF NF registers).
 constexpr long long FUSED_CHUNK = 1LL << 18;   // candidates per launch (mean + sum of squares: 4 MB of scratch per slot)
-constexpr int FUSED_MAX_N = 64;
+constexpr int FUSED_MAX_N = 128;
 template <int MF>
-static cudaError_t fused_attr() {
-  return cudaFuncSetAttribute(fused_small_value_kernel<MF, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              fused_small_smem_bytes(MF, 4, DMAX));
+static int fused_launch_t(gpo_engine* eng, const FusedSmallParams& p, long long rows, cudaStream_t st) {
+  constexpr int NF = MF <= 8 ? 4 : 2;
+  const int smem = fused_small_smem_bytes(MF, NF, p.d);
+  static bool attr_done[8] = {false, false, false, false, false, false, false, false};   // per device
+  if (eng->device < 8 && !attr_done[eng->device]) {
+    GPO_CUDA_OK(cudaFuncSetAttribute(fused_small_value_kernel<MF, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fused_small_smem_bytes(MF, NF, DMAX)));
+    attr_done[eng->device] = true;
+  } else if (eng->device >= 8) {
+    GPO_CUDA_OK(cudaFuncSetAttribute(fused_small_value_kernel<MF, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     fused_small_smem_bytes(MF, NF, DMAX)));
+  }
+  // persistent: as many CTAs of 8 warps as fit on the SMs (the resident state is loaded once per CTA), every warp walks
+  // items of 8 NF candidates
+  int per_sm = 1;
+  GPO_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<MF, NF>, FUSED_THREADS, smem));
+  per_sm = std::max(1, per_sm);
+  const long long warp_items = (rows + 8 * NF - 1) / (8 * NF);
+  dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((warp_items + 7) / 8, (long long)eng->sm_count * per_sm)), 1, 1);
+  fused_small_value_kernel<MF, NF><<<grid, FUSED_THREADS, smem, st>>>(p);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  return GPO_OK;
 }
 static int launch_fused_small(gpo_engine* eng, Slot& s, const double* xs, long long rows, cudaStream_t st) {
-  if (!eng->fused_attr_done) {
-    GPO_CUDA_OK(fused_attr<1>()); GPO_CUDA_OK(fused_attr<2>()); GPO_CUDA_OK(fused_attr<3>()); GPO_CUDA_OK(fused_attr<4>());
-    GPO_CUDA_OK(fused_attr<5>()); GPO_CUDA_OK(fused_attr<6>()); GPO_CUDA_OK(fused_attr<7>()); GPO_CUDA_OK(fused_attr<8>());
-    eng->fused_attr_done = true;
-  }
   if (!s.fs_mean) {
     GPO_CUDA_OK(cudaMalloc(&s.fs_mean, (size_t)FUSED_CHUNK * 8));
     GPO_CUDA_OK(cudaMalloc(&s.fs_sq, (size_t)FUSED_CHUNK * 8));
@@ -1151,41 +1167,24 @@ static int launch_fused_small(gpo_engine* eng, Slot& s, const double* xs, long l
   p.Xs = xs; p.n_cand = rows; p.Linv = eng->X; p.Xt = eng->Xt; p.ldx = eng->n_pad; p.alpha = eng->alpha; p.invl = eng->invl;
   p.sigf2 = eng->sigf2; p.n = eng->n; p.n_pad = eng->n_pad; p.d = eng->d; p.kern = eng->kern;
   p.mean = s.fs_mean; p.sumsq = s.fs_sq; p.ld = FUSED_CHUNK;
-  const int mf = (eng->n + 7) / 8;
-  const int smem = fused_small_smem_bytes(mf, 4, eng->d);
-  const long long warp_items = (rows + 31) / 32;
-  // persistent: as many CTAs of 8 warps as fit on the SMs (the resident state is loaded once per CTA), every warp walks
-  // 32-candidate items
-  int per_sm = 1;
-  {
-    cudaError_t oe = cudaSuccess;
-    switch (mf) {
-      case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<1, 4>, FUSED_THREADS, smem); break;
-      case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<2, 4>, FUSED_THREADS, smem); break;
-      case 3: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<3, 4>, FUSED_THREADS, smem); break;
-      case 4: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<4, 4>, FUSED_THREADS, smem); break;
-      case 5: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<5, 4>, FUSED_THREADS, smem); break;
-      case 6: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<6, 4>, FUSED_THREADS, smem); break;
-      case 7: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<7, 4>, FUSED_THREADS, smem); break;
-      default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_small_value_kernel<8, 4>, FUSED_THREADS, smem); break;
-    }
-    GPO_CUDA_OK(oe);
-    per_sm = std::max(1, per_sm);
+  switch ((eng->n + 7) / 8) {
+    case 1: return fused_launch_t<1>(eng, p, rows, st);
+    case 2: return fused_launch_t<2>(eng, p, rows, st);
+    case 3: return fused_launch_t<3>(eng, p, rows, st);
+    case 4: return fused_launch_t<4>(eng, p, rows, st);
+    case 5: return fused_launch_t<5>(eng, p, rows, st);
+    case 6: return fused_launch_t<6>(eng, p, rows, st);
+    case 7: return fused_launch_t<7>(eng, p, rows, st);
+    case 8: return fused_launch_t<8>(eng, p, rows, st);
+    case 9: return fused_launch_t<9>(eng, p, rows, st);
+    case 10: return fused_launch_t<10>(eng, p, rows, st);
+    case 11: return fused_launch_t<11>(eng, p, rows, st);
+    case 12: return fused_launch_t<12>(eng, p, rows, st);
+    case 13: return fused_launch_t<13>(eng, p, rows, st);
+    case 14: return fused_launch_t<14>(eng, p, rows, st);
+    case 15: return fused_launch_t<15>(eng, p, rows, st);
+    default: return fused_launch_t<16>(eng, p, rows, st);
   }
-  dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((warp_items + 7) / 8, (long long)eng->sm_count * per_sm)), 1, 1);
-  switch (mf) {
-    case 1: fused_small_value_kernel<1, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
-    case 2: fused_small_value_kernel<2, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
-    case 3: fused_small_value_kernel<3, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
-    case 4: fused_small_value_kernel<4, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
-    case 5: fused_small_value_kernel<5, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
-    case 6: fused_small_value_kernel<6, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
-    case 7: fused_small_value_kernel<7, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
-    default: fused_small_value_kernel<8, 4><<<grid, FUSED_THREADS, smem, st>>>(p); break;
-  }
-  eng->launches++;
-  GPO_CUDA_OK(cudaGetLastError());
-  return GPO_OK;
 }
 
 // mean_only (predict mode): K1 + K3 only -- posterior mean and its gradient, no variance GEMM (o1, o3 unused)
@@ -1381,6 +1380,7 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
         gs.Tt = s.Tt; gs.tt_ld = n_pad; gs.tt_z = eng->nc_ld * (long long)n_pad;
         if ((rc = launch_gemm(eng, EPI_SUMSQ, eng->mapX, s.mapKt, gs, S, st, 0, bns))) return rc;
         g.krange = KR_GE_M; g.raster = RO_HEAVY_FIRST; g.tri_diag = 2;     // A = U = L^-T (upper triangular), B = t
+        g.prefetch_kt = eng->opt_prefetch_kt;
         if ((rc = launch_gemm(eng, EPI_GRAD, eng->mapU, s.mapTt, g, S, st, 0, bns))) return rc;
         if (pe1) { GPO_CUDA_OK(cudaEventRecord(pe1, st)); pe1 = nullptr; }
       } else {
@@ -1833,6 +1833,7 @@ extern "C" int gpo_set_option(gpo_engine* eng, int key, long long value) {
     case GPO_OPT_BN_FIT: if (value != 64 && value != 128) return GPO_ERR_ARG; eng->opt_bn_fit = (int)value; break;
     case GPO_OPT_INVERSE: if (value < 0 || value > 2) return GPO_ERR_ARG; eng->opt_inverse = (int)value; break;
     case GPO_OPT_FUSED_SMALL: eng->opt_fused_small = value != 0; break;
+    case GPO_OPT_PREFETCH_KT: eng->opt_prefetch_kt = value != 0; break;
     default: GPO_FAIL(GPO_ERR_ARG, "gpo_set_option: unknown key %d", key);
   }
   return GPO_OK;

@@ -1240,8 +1240,8 @@ __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
 }
 
 // =====================================================================================================
-// Fused value sweep for small models (n <= 64: every early BO iteration, BASELINE configs 1 and 2).
-// K1 + the variance contraction in ONE kernel: the whole posterior state -- L^-1 (<= 32 KB), the length-scaled training
+// Fused value sweep for small models (n <= 128: every early BO iteration, BASELINE configs 1 and 2).
+// K1 + the variance contraction in ONE kernel: the whole posterior state -- L^-1 (<= 132 KB), the length-scaled training
 // inputs and alpha -- is resident in shared memory, candidates stream through, and K* never leaves the registers:
 //   * a warp owns 8 NF candidates; lane (g, t) evaluates k(x_train[4 kk + t], x_cand[8 nf + g]) directly in the
 //     B-fragment position of mma.m8n8k4 (no transposition, no K*^T round trip through HBM as on the general path)

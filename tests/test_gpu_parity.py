@@ -914,13 +914,15 @@ def test_config5_gsobol_n4096_local_penalization(engine):
 
 
 # ------------------------------------------------------------------------------------------------------
-# fused small-model value sweep (n <= 64: K1 + variance contraction in one shared-memory-resident kernel)
+# fused small-model value sweep (n <= 128: K1 + variance contraction in one shared-memory-resident kernel)
 # ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('n,d,kernel,ARD', [(1, 1, 'rbf', False), (5, 2, 'matern52', False), (8, 3, 'rbf', True), (9, 2, 'matern32', False),
                                             (20, 2, 'rbf', False), (33, 6, 'matern52', True), (55, 2, 'matern52', False),
-                                            (56, 10, 'rbf', False), (57, 4, 'rbf', True), (64, 16, 'matern32', True)])
+                                            (56, 10, 'rbf', False), (57, 4, 'rbf', True), (64, 16, 'matern32', True),
+                                            (65, 2, 'rbf', False), (100, 6, 'matern52', True), (120, 16, 'matern32', True),
+                                            (128, 3, 'rbf', False)])
 def test_fused_small_model_sweep(engine, n, d, kernel, ARD):
-    """Oracle parity (1e-10 scaled) of the fused kernel for every row-padding count 1 ... 8, all kernels, d up to 16;
+    """Oracle parity (1e-10 scaled) of the fused kernel for row-padding counts 1 ... 16 (both warp shapes), all kernels, d up to 16;
     agreement with the general tensor-core path (fused off); results independent (bitwise) of the position in the batch,
     of the batch size and of the pointer kind; top-k and LP through it."""
     import torch

@@ -62,6 +62,23 @@ def refit_matrix():
                 eng.close()
 
 
+def prefetch_ab():
+    n, d, N = 2048, 6, 9472 * 32
+    rng = np.random.default_rng(0)
+    X = 1 + 9 * rng.random((n, d)); Y = np.sin(X).sum(1); Y = (Y - Y.mean()) / Y.std()
+    xs = torch.from_numpy(1 + 9 * rng.random((N, d))).cuda()
+    f = torch.empty(N, dtype=torch.float64, device='cuda'); df = torch.empty((N, d), dtype=torch.float64, device='cuda')
+    eng = Engine(0)
+    for kernel in ('rbf', 'matern52'):
+        eng.fit(kernel, X, Y, [1.0], np.full((1, d), 2.0), [1e-2])
+        for rep in range(3):
+            for pf in (0, 1):
+                eng.set_option('prefetch_kt', pf)
+                print(json.dumps({"what": "prefetch_kt", "kernel": kernel, "prefetch": pf, "rep": rep,
+                                  "grad_cand_per_s": rate(eng, 'EI', xs, f, df, True, reps=4)})); sys.stdout.flush()
+    eng.close()
+
+
 if __name__ == '__main__':
     what = sys.argv[1:] or ['c3', 'c4', 'refit']
     if 'c3' in what:
@@ -70,3 +87,5 @@ if __name__ == '__main__':
         sweep_matrix('c4', 512, 4, 64, 1024 * 96, 'EI_MCMC')
     if 'refit' in what:
         refit_matrix()
+    if 'pf' in what:
+        prefetch_ab()

@@ -96,26 +96,40 @@ __global__ void __launch_bounds__(COV_THREADS) cov_mean_kernel(const CovParams p
     mbar_wait(&bars[buf], (uint32_t)(((jt - jt_begin) >> 1) & 1));
     const double* xj = xj_s0 + buf * (DP + 1) * COV_JT;
     const int j0 = jt * COV_JT;
-#pragma unroll 4
-    for (int jj = 0; jj < COV_JT; ++jj) {
-      double r2 = 0.0, df[DP];
+    // JV training points at a time: all JV covariance values are evaluated in one straight-line block (kernel switch
+    // outside, no per-point branches), so their dependency chains -- exp is 17 dependent FMAs -- interleave
+    constexpr int JV = 4;
+    constexpr bool KEEP_DF = DP <= 8;    // the scaled differences stay in registers for the gradient (recomputed for larger d)
+#pragma unroll 1
+    for (int jb = 0; jb < COV_JT; jb += JV) {
+      double r2[JV], kv[JV], hv[JV], df[KEEP_DF ? JV : 1][DP];
 #pragma unroll
-      for (int q = 0; q < DP; ++q) {
-        df[q] = xs[q] - xj[q * COV_JT + jj];
-        r2 = fma(df[q], df[q], r2);
-      }
-      double kv, hv;
-      kern_k_h(p.kern, sf2, r2, kv, hv);
-      if (j0 + jj >= p.n) { kv = 0.0; hv = 0.0; }
-      const double aj = xj[DP * COV_JT + jj];
-      m = fma(kv, aj, m);
-      if (GRAD) {
-        const double w = aj * hv;
+      for (int v = 0; v < JV; ++v) {
+        r2[v] = 0.0;
 #pragma unroll
-        for (int q = 0; q < DP; ++q) dm[q] = fma(w, df[q], dm[q]);
-        if (Ht) tile_h[jj * COV_PITCH + tid] = hv;
+        for (int q = 0; q < DP; ++q) {
+          const double dq = xs[q] - xj[q * COV_JT + jb + v];
+          if (KEEP_DF) df[KEEP_DF ? v : 0][q] = dq;
+          r2[v] = fma(dq, dq, r2[v]);
+        }
       }
-      if (Kt) tile_k[jj * COV_PITCH + tid] = kv;
+      kern_k_h_vec<JV>(p.kern, sf2, r2, kv, hv);
+#pragma unroll
+      for (int v = 0; v < JV; ++v) {
+        const int jj = jb + v;
+        const bool live = j0 + jj < p.n;
+        kv[v] = live ? kv[v] : 0.0;
+        hv[v] = live ? hv[v] : 0.0;
+        const double aj = xj[DP * COV_JT + jj];
+        m = fma(kv[v], aj, m);
+        if (GRAD) {
+          const double w = aj * hv[v];
+#pragma unroll
+          for (int q = 0; q < DP; ++q) dm[q] = fma(w, KEEP_DF ? df[KEEP_DF ? v : 0][q] : xs[q] - xj[q * COV_JT + jj], dm[q]);
+          if (Ht) tile_h[jj * COV_PITCH + tid] = hv[v];
+        }
+        if (Kt) tile_k[jj * COV_PITCH + tid] = kv[v];
+      }
     }
     __syncthreads();
     if (Kt) {

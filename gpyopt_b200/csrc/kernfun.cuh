@@ -75,6 +75,34 @@ __device__ __forceinline__ double kern_k(int kind, double sf2, double r2) {
   return k;
 }
 
+// NV (k, h) pairs at once with the (warp-uniform) kernel switch outside the loop: the same arithmetic as kern_k_h, element by
+// element (bitwise), in one straight-line block whose independent chains the compiler interleaves
+template <int NV>
+__device__ __forceinline__ void kern_k_h_vec(int kind, double sf2, const double (&r2)[NV], double (&k)[NV], double (&h)[NV]) {
+  if (kind == KERN_RBF) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { k[v] = sf2 * exp_nonpos(-0.5 * r2[v]); h[v] = -k[v]; }
+  } else if (kind == KERN_MATERN52) {
+    const double s5 = 2.23606797749978969641;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const double r = sqrt_nobranch(r2[v]);
+      const double e = sf2 * exp_nonpos(-s5 * r);
+      k[v] = (1.0 + s5 * r + (5.0 / 3.0) * r2[v]) * e;
+      h[v] = -(5.0 / 3.0) * (1.0 + s5 * r) * e;
+    }
+  } else {
+    const double s3 = 1.73205080756887729353;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const double r = sqrt_nobranch(r2[v]);
+      const double e = sf2 * exp_nonpos(-s3 * r);
+      k[v] = (1.0 + s3 * r) * e;
+      h[v] = -3.0 * e;
+    }
+  }
+}
+
 // NV covariance values at once, the (warp-uniform) kernel switch outside the loop: straight-line code in which the
 // compiler interleaves the NV independent dependency chains
 template <int NV>

@@ -397,9 +397,13 @@ def run_gpu_arm(args, cfg):
         summary = os.path.join(ROOT, 'profiles', 'gemm_sweep_r02_summary.json')
         if os.path.exists(summary) and args.config == 'c3':
             try:
-                js = json.load(open(summary))
-                traffic = js.get('dram_bytes_per_chunk')
-                traffic_src = "stored ncu value (profiles/gemm_sweep_r02_summary.json, `ncu --set full` of the same kernels), not measured in this run"
+                js = json.load(open(summary))      # the variance-contraction launches of ONE chunk (two in the default form)
+                want = 2 if info['strict_variance'] else 1
+                ls = [l for l in js['launches'] if 'dgemm_nt_kernel' in l['kernel']][:want]
+                if len(ls) == want:
+                    traffic = float(sum(l['dram_bytes_total'] for l in ls))
+                    traffic_src = ("stored ncu value (profiles/gemm_sweep_r02_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of "
+                                   "`ncu --set full` captures of the same kernels on one 9472-candidate chunk), NOT measured in this run")
             except Exception:
                 traffic = None
         # CPU baseline + parity of what was timed: the oracle sweeps the first rows of the same design

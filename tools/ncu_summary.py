@@ -45,32 +45,39 @@ src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-n
 blocks, cur = [], None
 for r in csv.reader(io.StringIO(src)):
     if r and r[0] == 'Kernel Name':
-        cur = {'rows': []}; blocks.append(cur); continue
+        cur = {'name': r[1] if len(r) > 1 else '', 'rows': []}; blocks.append(cur); continue
     if cur is not None:
         cur['rows'].append(r)
-seen = 0
+# (the CSV may list every launch twice: SASS view and source view) -> keep the first block with stall columns per launch, in order
+usable = []
 for b in blocks:
-    if not b['rows'] or seen >= len(launches):
+    if not b['rows']:
         continue
     h = b['rows'][0]
-    data = [r for r in b['rows'][1:] if len(r) >= len(h)]
-    if '# Samples' not in h or not data:
+    if '# Samples' in h and 'Source' in h and 'Instructions Executed' in h:
+        data = [r for r in b['rows'][1:] if len(r) >= len(h)]
+        if data and (not usable or usable[-1][0] != b['name'] or len(usable) < len(launches)):
+            usable.append((b['name'], h, data))
+dedup = []
+for u in usable:
+    if dedup and dedup[-1][0] == u[0] and len(dedup[-1][2]) == len(u[2]):
         continue
+    dedup.append(u)
+for li, (name, h, data) in enumerate(dedup[:len(launches)]):
     cols = [i for i, x in enumerate(h) if x.startswith('stall_') and 'Not Issued' not in x]
     tot = collections.Counter()
     for r in data:
         for i in cols:
             tot[h[i]] += int(r[i] or 0)
     total = sum(tot.values())
-    launches[seen]['stall_samples_top'] = {k: round(v / total, 3) for k, v in tot.most_common(6)} if total else {}
+    launches[li]['stall_samples_top'] = {k: round(v / total, 3) for k, v in tot.most_common(6)} if total else {}
     ops = collections.Counter()
     si, ie = h.index('Source'), h.index('Instructions Executed')
     for r in data:
         tok = r[si].split()
         op = (tok[1] if tok and tok[0].startswith('@') and len(tok) > 1 else (tok[0] if tok else '?')).split('.')[0]
         ops[op] += int(r[ie] or 0)
-    launches[seen]['executed_warp_instructions_top'] = dict(ops.most_common(8))
-    seen += 2 if len(blocks) == 2 * len(launches) else 1   # (the CSV lists every kernel twice)
+    launches[li]['executed_warp_instructions_top'] = dict(ops.most_common(8))
 res = {'report': rep.split('/')[-1], 'tool': 'ncu --set full --clock-control none --import-source on (one launch each, cold cache, serialised)',
        'launches': launches}
 if note:

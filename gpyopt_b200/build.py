@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'gpo_api.cu')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in ('gpo_api.cu', 'dgemm_tma.cuh', 'kernels.cuh', 'kernfun.cuh', 'common.cuh')]
+DEPS = [os.path.join(HERE, 'csrc', f) for f in ('gpo_api.cu', 'dgemm_tma.cuh', 'kernels.cuh', 'refit_kernels.cuh', 'kernfun.cuh', 'common.cuh')]
 DEPS.append(os.path.join(HERE, '..', 'include', 'gpo_b200.h'))
 OUT_DIR = os.path.join(HERE, 'lib')
 OUT = os.path.join(OUT_DIR, 'libgpo_b200.so')

@@ -10,6 +10,7 @@
 #include "../../include/gpo_b200.h"
 #include "dgemm_tma.cuh"
 #include "kernels.cuh"
+#include "refit_kernels.cuh"
 
 using namespace gpo;
 
@@ -92,7 +93,8 @@ struct gpo_engine {
   double* fit_pin = nullptr;  size_t fit_pin_cap = 0;   // page-locked staging of gpo_fit's small uploads / downloads
   unsigned char* pin_buf = nullptr;      // host address
   unsigned char* pin_dev = nullptr;      // the same memory as the device sees it
-  bool smalln_attr_done = false;
+  bool smalln_attr_done = false, smalln_both_attr_done = false;
+  const LbfgsParams* lb_fused = nullptr;   // set while gpo_lbfgs runs: K3 of a tiny call continues into the optimiser step
   int* smalln_ticket = nullptr;  int smalln_ticket_cap = 0;   // [S] arrival counters of the small-N kernel
   double* smalln_sq = nullptr;  size_t smalln_sq_cap = 0;     // per-CTA partial rows of its strict-variance (|L^-1 k|^2) form
   long long* gen_idx = nullptr;  double* gen_x = nullptr;  // [TOPK_SEG/2], [TOPK_SEG/2][DMAX] winners of a generated design
@@ -114,6 +116,10 @@ struct gpo_engine {
   double* lb_buf = nullptr;  size_t lb_bytes = 0;   // device state of the batched L-BFGS (gpo_lbfgs)
   double var_disc = 0.0;
   std::vector<cudaEvent_t> chol_ev;  // look-ahead events of the blocked Cholesky (2 per block column)
+  int opt_fit_path = 0;     // refit: 0 short critical chain (factorize_chain), 1 the round-1 look-ahead scheme (factorize)
+  std::vector<cudaEvent_t> fit_ev;   // events of factorize_chain (6 per block column + 4)
+  cudaStream_t fit_side[3] = {nullptr, nullptr, nullptr};   // its side streams: inverse steps, diagonal-block inverses, W^-1
+  double* rdiag = nullptr;           // [S][n_pad] reciprocal pivots 1 / L_jj (diagonal-block kernel, mode 1 -> mode 2)
   // counters / live profiling of the dominant kernel (variance GEMM) for the benchmark's roofline
   long long launches = 0;
   int profiling = 0;
@@ -207,6 +213,9 @@ static int gemm_setup(gpo_engine* eng) {
   GPO_CUDA_OK(gemm_attr_epi<EPI_SUMSQ>());
   GPO_CUDA_OK(gemm_attr_epi<EPI_GRAD>());
   GPO_CUDA_OK(cudaFuncSetAttribute(diag_chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
+  GPO_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES));
+  GPO_CUDA_OK(cudaFuncSetAttribute(rank128_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, rank128_smem_bytes<4, 4>()));
+  GPO_CUDA_OK(cudaFuncSetAttribute(rank128_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rank128_smem_bytes<8, 2>()));
   GPO_CUDA_OK(cov_attr<2>()); GPO_CUDA_OK(cov_attr<4>()); GPO_CUDA_OK(cov_attr<6>());
   GPO_CUDA_OK(cov_attr<8>()); GPO_CUDA_OK(cov_attr<12>()); GPO_CUDA_OK(cov_attr<16>());
   return GPO_OK;
@@ -280,7 +289,12 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
     cudaStreamCreateWithFlags(&eng->slot[i].stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&eng->slot[i].done, cudaEventDisableTiming);
   }
-  cudaStreamCreateWithFlags(&eng->fit_stream, cudaStreamNonBlocking);
+  {  // the refit's critical chain runs on the fit stream: its CTAs go first whenever SMs free up
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaStreamCreateWithPriority(&eng->fit_stream, cudaStreamNonBlocking, prio_hi);
+  }
+  for (int i = 0; i < 3; ++i) cudaStreamCreateWithFlags(&eng->fit_side[i], cudaStreamNonBlocking);
   cudaEventCreateWithFlags(&eng->ev_in, cudaEventDisableTiming);
   int rc = gemm_setup(eng);
   if (rc != GPO_OK) {
@@ -294,7 +308,7 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
 
 static void free_state(gpo_engine* eng) {
   double** ptrs[] = {&eng->Xt, &eng->Xtc, &eng->xmu, &eng->Xaos, &eng->Y, &eng->invl, &eng->sigf2, &eng->noise, &eng->jitter, &eng->A, &eng->X,
-                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->xtile, &eng->probe_out, &eng->logdet, &eng->quad, &eng->fmin};
+                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->rdiag, &eng->xtile, &eng->probe_out, &eng->logdet, &eng->quad, &eng->fmin};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
   for (int i = 0; i < 2; ++i) {
@@ -341,6 +355,8 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
     cudaEventDestroy(eng->slot[i].done);
   }
   cudaStreamDestroy(eng->fit_stream);
+  for (int i = 0; i < 3; ++i) cudaStreamDestroy(eng->fit_side[i]);
+  for (cudaEvent_t e : eng->fit_ev) cudaEventDestroy(e);
   cudaEventDestroy(eng->ev_in);
   delete eng;
   return GPO_OK;
@@ -407,6 +423,7 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   GPO_CUDA_OK(cudaStreamSynchronize(eng->fit_stream));
   GPO_CUDA_OK(cudaMalloc(&eng->alpha, (size_t)S * n_pad * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->tmpv, (size_t)S * n_pad * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->rdiag, (size_t)S * n_pad * 8));
   eng->dp = d <= 2 ? 2 : d <= 4 ? 4 : d <= 6 ? 6 : d <= 8 ? 8 : d <= 12 ? 12 : 16;
   GPO_CUDA_OK(cudaMalloc(&eng->xtile, (size_t)S * n_pad * (eng->dp + 1) * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->logdet, (size_t)S * 8));
@@ -558,7 +575,7 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
   int last_rest = -1;
   for (int kb = 0; kb < nb; ++kb) {
     diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb,
-                                                                    std::max(0, std::min(TILE, eng->n - kb * TILE)), eng->info);
+                                                                    std::max(0, std::min(TILE, eng->n - kb * TILE)), eng->info, 0, eng->rdiag);
     eng->launches++;
     const int rem = nb - kb - 1;
     if (interleave) GPO_CUDA_OK(cudaEventRecord(eng->chol_ev[2 * nb + 1 + kb], st));
@@ -662,6 +679,159 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
     p.sym_diag = 1;
     if ((rc = launch_gemm(eng, EPI_STORE, eng->mapU, eng->mapU, p, S, st))) return rc;
   }
+  return GPO_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// refit with a short critical chain (default).  Same mathematics as factorize() -- right-looking blocked Cholesky, the
+// inverse by block forward substitution alongside it, W^-1 = L^-T L^-1 -- arranged so that the serial chain per block
+// column is   diagonal 128-block Cholesky (no inverse)  ->  panel by block substitution  ->  update of block column kb+1
+// in three short launches on the (high-priority) fit stream, and everything else rides on side streams:
+//   fit_side[1]  the 128 x 128 inverse of each diagonal block (diag kernel, mode 2), needed by the inverse steps only
+//   fit_side[0]  the steps of L X = I (three K = 128 products per block column, rank128_kernel)
+//   slot[0]      the trailing update of block columns >= kb+2 (persistent DMMA GEMM on most SMs)
+//   fit_side[2]  W^-1 accumulated as rank-128 updates, one per finished block row of X (instead of one long product
+//                after the factorisation whose makespan is the nb-block-long tile (0,0))
+// Every tile receives its updates in the order kb = 0, 1, 2, ... with fixed summation order inside every kernel: the
+// state is bit-reproducible and independent of how the streams interleave.
+// --------------------------------------------------------------------------------------------------
+static R128Params r128_defaults() {
+  R128Params p;
+  memset(&p, 0, sizeof(p));
+  p.alpha = 1.0;
+  return p;
+}
+template <int MI, int NJ>
+static int launch_r128(gpo_engine* eng, const R128Params& p, int S, cudaStream_t st) {
+  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)S, 1);
+  rank128_kernel<MI, NJ><<<grid, 256, rank128_smem_bytes<MI, NJ>(), st>>>(p);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  return GPO_OK;
+}
+
+static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
+  const int n_pad = eng->n_pad, S = eng->S, nb = n_pad / TILE;
+  const long long nn = (long long)n_pad * n_pad;
+  int rc;
+  cudaStream_t sb = eng->slot[0].stream, sc = eng->fit_side[0], sd = eng->fit_side[1], se = eng->fit_side[2];
+  while ((int)eng->fit_ev.size() < 6 * nb + 4) {
+    cudaEvent_t e;
+    GPO_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    eng->fit_ev.push_back(e);
+  }
+  enum { EV_CHOL = 0, EV_INV = 1, EV_PANEL = 2, EV_BULK = 3, EV_ROW = 4, EV_W = 5 };
+  auto ev = [&](int kind, int kb) { return eng->fit_ev[(size_t)kind * nb + kb]; };
+  cudaEvent_t ev_start = eng->fit_ev[6 * (size_t)nb], ev_sc = eng->fit_ev[6 * (size_t)nb + 1], ev_se = eng->fit_ev[6 * (size_t)nb + 2];
+  // W^-1 is accumulated: zero it first (after whatever the fit stream has done so far, e.g. an earlier attempt's reads)
+  GPO_CUDA_OK(cudaEventRecord(ev_start, st));
+  GPO_CUDA_OK(cudaStreamWaitEvent(se, ev_start, 0));
+  GPO_CUDA_OK(cudaMemsetAsync(eng->W, 0, (size_t)S * nn * 8, se));
+  {
+    dim3 blk(16, 16), grd(n_pad / 16, n_pad / 16, S);
+    gram_kernel<<<grd, blk, 0, st>>>(eng->A, eng->Xt, n_pad, eng->n, n_pad, eng->d, eng->kern, eng->invl, eng->sigf2,
+                                     eng->noise, eng->jitter);
+    eng->launches++;
+  }
+  GPO_CUDA_OK(cudaMemsetAsync(eng->info, 0, S * sizeof(int), st));
+  const int bulk_ctas = std::max(16, eng->sm_count - 48), w_ctas = 40;
+  int last_bulk = -1;
+  for (int kb = 0; kb < nb; ++kb) {
+    const int rem = nb - kb - 1, kT = kb * TILE, k1T = (kb + 1) * TILE;
+    const int n_valid = std::max(0, std::min(TILE, eng->n - kT));
+    // ---- critical chain: Cholesky of the diagonal block (+ its four 32 x 32 inverses) ----
+    diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info, 1, eng->rdiag);
+    eng->launches++;
+    GPO_CUDA_OK(cudaEventRecord(ev(EV_CHOL, kb), st));
+    // ---- side: X_kk = L_kk^-1, U_kk ----
+    GPO_CUDA_OK(cudaStreamWaitEvent(sd, ev(EV_CHOL, kb), 0));
+    diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, sd>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info, 2, eng->rdiag);
+    eng->launches++;
+    GPO_CUDA_OK(cudaEventRecord(ev(EV_INV, kb), sd));
+    // ---- critical chain: panel ----
+    if (rem > 0) {
+      trsm_panel_kernel<<<dim3((unsigned)(rem * (TILE / TRSM_RS)), (unsigned)S), 256, TRSM_SMEM_BYTES, st>>>(eng->A, eng->X, n_pad, kb);
+      eng->launches++;
+      GPO_CUDA_OK(cudaGetLastError());
+      GPO_CUDA_OK(cudaEventRecord(ev(EV_PANEL, kb), st));
+    }
+    // ---- side: block row kb of the inverse becomes final: X[kb, c] = X_kk R[kb, c], c < kb (in place on U) ----
+    GPO_CUDA_OK(cudaStreamWaitEvent(sc, ev(EV_INV, kb), 0));
+    if (kb > 0) {
+      R128Params f = r128_defaults();
+      f.A = eng->X; f.lda = n_pad; f.a_z = nn; f.a_row0 = kT; f.a_col0 = kT;
+      f.B = eng->U; f.ldb = n_pad; f.b_z = nn; f.b_row0 = 0; f.b_col0 = kT;
+      f.C = eng->X; f.ldc = n_pad; f.c_z = nn; f.c_row0 = kT; f.c_col0 = 0;
+      f.Ct = eng->U; f.ldct = n_pad; f.ct_z = nn; f.ct_row0 = 0; f.ct_col0 = kT;
+      f.tiles_m = 1; f.tiles_n = kb * (TILE / 32);
+      if ((rc = launch_r128<8, 2>(eng, f, S, sc))) return rc;
+    }
+    GPO_CUDA_OK(cudaEventRecord(ev(EV_ROW, kb), sc));
+    // ---- side: W^-1[i, j] += U[i, kb] U[j, kb]^T for j <= i <= kb (mirrored into the upper tiles with the last block row) ----
+    {
+      GPO_CUDA_OK(cudaStreamWaitEvent(se, ev(EV_ROW, kb), 0));
+      GemmParams w = gemm_defaults();
+      w.tiles_m = kb + 1; w.tiles_n = kb + 1; w.kblocks = 1; w.tile_skip = TS_LOWER;
+      w.a = {0, kT, 0, 0, 0, 1};
+      w.b = w.a;
+      w.beta = 1.0;
+      w.C = eng->W; w.ldc = n_pad; w.c_off_z = nn;
+      if (rem == 0) { w.Ct = eng->W; w.ldct = n_pad; w.ct_off_z = nn; }
+      w.sym_diag = 1;
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapU, eng->mapU, w, S, se, rem == 0 ? 0 : w_ctas))) return rc;
+    }
+    if (rem == 0) break;
+    // ---- side: running right-hand side of L X = I ----
+    GPO_CUDA_OK(cudaStreamWaitEvent(sc, ev(EV_PANEL, kb), 0));
+    {
+      R128Params u = r128_defaults();
+      u.alpha = -1.0;
+      u.A = eng->A; u.lda = n_pad; u.a_z = nn; u.a_row0 = k1T; u.a_col0 = kT;          // L[i, kb], i > kb
+      u.B = eng->U; u.ldb = n_pad; u.b_z = nn; u.b_col0 = kT;
+      u.C = eng->X; u.ldc = n_pad; u.c_z = nn; u.c_row0 = k1T;
+      u.Ct = eng->U; u.ldct = n_pad; u.ct_z = nn; u.ct_col0 = k1T;
+      u.tiles_m = rem * 2;
+      if (kb > 0) {   // R[i, c] -= L[i, kb] X[kb, c],  c < kb
+        R128Params a2 = u;
+        a2.b_row0 = 0; a2.c_col0 = 0; a2.ct_row0 = 0; a2.beta = 1.0; a2.tiles_n = kb * 2;
+        if ((rc = launch_r128<4, 4>(eng, a2, S, sc))) return rc;
+      }
+      R128Params b2 = u;   // R[i, kb] = -L[i, kb] X_kk
+      b2.b_row0 = kT; b2.c_col0 = kT; b2.ct_row0 = kT; b2.beta = 0.0; b2.tiles_n = 2;
+      if ((rc = launch_r128<4, 4>(eng, b2, S, sc))) return rc;
+    }
+    // ---- side: trailing update of block columns >= kb+2 ----
+    if (rem >= 2) {
+      GemmParams r = gemm_defaults();
+      r.kblocks = 1; r.alpha = -1.0; r.beta = 1.0;
+      r.C = eng->A; r.ldc = n_pad; r.c_off_z = nn;
+      r.tiles_m = rem - 1; r.tiles_n = rem - 1; r.tile_skip = TS_LOWER;
+      r.a = {(kb + 2) * TILE, kT, 0, 0, 0, 1};
+      r.b = r.a;
+      r.c_row0 = (kb + 2) * TILE; r.c_col0 = (kb + 2) * TILE;
+      GPO_CUDA_OK(cudaStreamWaitEvent(sb, ev(EV_PANEL, kb), 0));
+      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, r, S, sb, bulk_ctas))) return rc;
+      GPO_CUDA_OK(cudaEventRecord(ev(EV_BULK, kb), sb));
+    }
+    // ---- critical chain: block column kb+1 (after the side stream's previous update of those tiles) ----
+    if (last_bulk >= 0) GPO_CUDA_OK(cudaStreamWaitEvent(st, ev(EV_BULK, last_bulk), 0));
+    if (rem >= 2) last_bulk = kb;
+    {
+      R128Params c = r128_defaults();
+      c.alpha = -1.0; c.beta = 1.0;
+      c.A = eng->A; c.lda = n_pad; c.a_z = nn; c.a_row0 = k1T; c.a_col0 = kT;
+      c.B = eng->A; c.ldb = n_pad; c.b_z = nn; c.b_row0 = k1T; c.b_col0 = kT;
+      c.C = eng->A; c.ldc = n_pad; c.c_z = nn; c.c_row0 = k1T; c.c_col0 = k1T;
+      c.tiles_m = rem * 2; c.tiles_n = 2; c.skip_upper = 1;
+      if ((rc = launch_r128<4, 4>(eng, c, S, st))) return rc;
+    }
+  }
+  // join the side streams (the last trailing update was waited for by the last block-column update)
+  GPO_CUDA_OK(cudaEventRecord(ev_sc, sc));
+  GPO_CUDA_OK(cudaEventRecord(ev_se, se));
+  GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_sc, 0));
+  GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_se, 0));
+  if (last_bulk >= 0) GPO_CUDA_OK(cudaStreamWaitEvent(st, ev(EV_BULK, last_bulk), 0));
   return GPO_OK;
 }
 
@@ -806,7 +976,7 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
   for (int attempt = 0; attempt <= 6; ++attempt) {
     memcpy(pin_jit, eng->h_jit.data(), (size_t)S * 8);   // (the previous attempt's copy has completed: it was synchronised)
     GPO_CUDA_OK(cudaMemcpyAsync(eng->jitter, pin_jit, (size_t)S * 8, cudaMemcpyHostToDevice, st));
-    if ((rc = factorize(eng, st))) return rc;
+    if ((rc = (eng->opt_fit_path == 0 && n_pad >= 2 * TILE) ? factorize_chain(eng, st) : factorize(eng, st))) return rc;
     GPO_CUDA_OK(cudaMemcpyAsync(pin_info, eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
     // alpha = L^-T (L^-1 y)
     {
@@ -1016,6 +1186,7 @@ static void launch_design(gpo_engine* eng, DesignParams p, long long row0, long 
 // kind == ACQ_NONE: predict  (o0 = m [S][N], o1 = s [S][N], o2 = dmdx [S][N][d], o3 = dsdx [S][N][d])
 // otherwise:        acquisition (o0 = f [N], o1 = df [N][d])
 // small-N latency path (see smalln_wk_kernel): nc in 1..8 candidates, returns the number of partial rows K3 must add
+static int ensure_ticket(gpo_engine* eng);
 constexpr int SMALLN_MAX = 8;        // candidates per launch of the matrix-vector kernel
 constexpr int SMALLN_MAX_CALL = 32;  // candidates per call that still take the latency path (ceil(N / 8) launches)
 constexpr int SMALLN_LDP = 8;        // leading dimension of the per-CTA partial rows
@@ -1052,13 +1223,13 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
     GPO_CUDA_OK(smalln_attr_rows<32>()); GPO_CUDA_OK(smalln_attr_rows<16>()); GPO_CUDA_OK(smalln_attr_rows<8>());
     eng->smalln_attr_done = true;
   }
-  if (eng->smalln_ticket_cap < eng->S) {
+  if (eng->smalln_ticket_cap < 2 * eng->S) {
     GPO_CUDA_OK(cudaDeviceSynchronize());
     if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
     eng->smalln_ticket = nullptr; eng->smalln_ticket_cap = 0;
-    GPO_CUDA_OK(cudaMalloc(&eng->smalln_ticket, (size_t)eng->S * sizeof(int)));
-    GPO_CUDA_OK(cudaMemset(eng->smalln_ticket, 0, (size_t)eng->S * sizeof(int)));
-    eng->smalln_ticket_cap = eng->S;
+    GPO_CUDA_OK(cudaMalloc(&eng->smalln_ticket, (size_t)2 * eng->S * sizeof(int)));
+    GPO_CUDA_OK(cudaMemset(eng->smalln_ticket, 0, (size_t)2 * eng->S * sizeof(int)));
+    eng->smalln_ticket_cap = 2 * eng->S;
   }
   const int rows = n_pad >= 4096 ? 32 : (n_pad >= 2048 ? 16 : 8);   // rows per CTA: at least ~128 CTAs from n = 1024 on
   const int row_blocks = n_pad / rows;
@@ -1103,15 +1274,80 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
   return GPO_OK;
 }
 
+// Both forms of the latency kernel in one launch (gradient calls in the reference variance form): W-form reductions to
+// s.partial (*final_rows), |L^-1 k|^2 to s.partial_sq [S][nc_ld].
+template <int ROWS>
+static void launch_smalln_both_r(const SmallNParams& pw, const SmallNParams& ps, int nc, dim3 grid, cudaStream_t st) {
+  constexpr int smem = smalln_smem_bytes(ROWS);
+  if (nc <= 1) smalln_both_kernel<1, ROWS><<<grid, 256, smem, st>>>(pw, ps);
+  else if (nc <= 2) smalln_both_kernel<2, ROWS><<<grid, 256, smem, st>>>(pw, ps);
+  else if (nc <= 4) smalln_both_kernel<4, ROWS><<<grid, 256, smem, st>>>(pw, ps);
+  else smalln_both_kernel<8, ROWS><<<grid, 256, smem, st>>>(pw, ps);
+}
+template <int ROWS>
+static cudaError_t smalln_both_attr() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(smalln_both_kernel<1, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smalln_smem_bytes(ROWS))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(smalln_both_kernel<2, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smalln_smem_bytes(ROWS))) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(smalln_both_kernel<4, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smalln_smem_bytes(ROWS))) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(smalln_both_kernel<8, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smalln_smem_bytes(ROWS));
+}
+static int launch_smalln_both(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool use_ht, cudaStream_t st, const double** final_rows) {
+  const int n_pad = eng->n_pad;
+  if (!eng->smalln_both_attr_done) {
+    GPO_CUDA_OK(smalln_both_attr<16>()); GPO_CUDA_OK(smalln_both_attr<8>());
+    eng->smalln_both_attr_done = true;
+  }
+  { const int trc = ensure_ticket(eng); if (trc) return trc; }
+  // rows per CTA: 16 from n = 2048 on (64 KB ring, three CTAs per SM).  With 32 rows at n = 4096 the 2 x 128 CTAs of 128 KB each
+  // do not fit the 148 SMs at once and the launch ran in two waves (98 us for 201 MB)
+  const int rows = n_pad >= 2048 ? 16 : 8;
+  const int row_blocks = n_pad / rows;
+  const size_t need = (size_t)eng->S * row_blocks * SMALLN_LDP * 8;
+  if (need > eng->smalln_sq_cap) {
+    GPO_CUDA_OK(cudaDeviceSynchronize());
+    if (eng->smalln_sq) cudaFree(eng->smalln_sq);
+    eng->smalln_sq = nullptr; eng->smalln_sq_cap = 0;
+    GPO_CUDA_OK(cudaMalloc(&eng->smalln_sq, need));
+    eng->smalln_sq_cap = need;
+  }
+  SmallNParams pw, ps;
+  pw.w_z = (long long)n_pad * n_pad;
+  pw.Kt = s.Kt; pw.Ht = use_ht ? s.Ht : nullptr; pw.kt_z = eng->nc_ld * (long long)n_pad;
+  pw.Xtc = eng->Xtc; pw.ldx = n_pad; pw.n_pad = n_pad; pw.d = d_epi; pw.ldp = SMALLN_LDP;
+  pw.ticket = eng->smalln_ticket;
+  pw.W = eng->W;
+  pw.partial = s.partial; pw.part_z = (long long)row_blocks * (d_epi + 2) * SMALLN_LDP;
+  pw.final_rows = s.partial + (long long)eng->S * pw.part_z; pw.final_ld = SMALLN_FLD;
+  *final_rows = pw.final_rows;
+  ps = pw;
+  ps.W = eng->X; ps.Ht = nullptr; ps.ticket = eng->smalln_ticket + eng->S;
+  ps.partial = eng->smalln_sq; ps.part_z = (long long)row_blocks * SMALLN_LDP;
+  ps.final_rows = s.partial_sq; ps.final_ld = eng->nc_ld;
+  dim3 grid((unsigned)row_blocks, (unsigned)eng->S, 2);
+  double* fw = pw.final_rows; double* fs = ps.final_rows;
+  for (int g0 = 0; g0 < nc; g0 += SMALLN_MAX) {
+    const int ncg = std::min(SMALLN_MAX, nc - g0);
+    pw.Kt = s.Kt + (long long)g0 * n_pad; ps.Kt = pw.Kt;
+    pw.Ht = use_ht ? s.Ht + (long long)g0 * n_pad : nullptr;
+    pw.final_rows = fw + g0; ps.final_rows = fs + g0;
+    if (rows == 16) launch_smalln_both_r<16>(pw, ps, ncg, grid, st);
+    else launch_smalln_both_r<8>(pw, ps, ncg, grid, st);
+    eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
+  }
+  return GPO_OK;
+}
+
 // K1 for nc <= 8 candidates (one thread per training point)
 static int ensure_ticket(gpo_engine* eng) {
-  if (eng->smalln_ticket_cap >= eng->S) return GPO_OK;
+  if (eng->smalln_ticket_cap >= 2 * eng->S) return GPO_OK;
   GPO_CUDA_OK(cudaDeviceSynchronize());
   if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
   eng->smalln_ticket = nullptr; eng->smalln_ticket_cap = 0;
-  GPO_CUDA_OK(cudaMalloc(&eng->smalln_ticket, (size_t)eng->S * sizeof(int)));
-  GPO_CUDA_OK(cudaMemset(eng->smalln_ticket, 0, (size_t)eng->S * sizeof(int)));
-  eng->smalln_ticket_cap = eng->S;
+  GPO_CUDA_OK(cudaMalloc(&eng->smalln_ticket, (size_t)2 * eng->S * sizeof(int)));
+  GPO_CUDA_OK(cudaMemset(eng->smalln_ticket, 0, (size_t)2 * eng->S * sizeof(int)));
+  eng->smalln_ticket_cap = 2 * eng->S;
   return GPO_OK;
 }
 
@@ -1345,12 +1581,11 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     } else if (tiny) {
       // a handful of points (L-BFGS steps): batched matrix-vector products instead of 128-wide tensor-core tiles
       if (w_form) {
-        if ((rc = launch_smalln(eng, s, (int)N, grad ? d : 0, grad && eng->kern != KERN_RBF, st, &small_final))) return rc;
-        part_rows = 1; part_nv = (grad ? d : 0) + 2; part_ld = SMALLN_FLD;
-        if (grad && eng->strict_active) {  // ill-conditioned model: variance from the reference's own triangular form as well
-          if ((rc = launch_smalln(eng, s, (int)N, 0, false, st, nullptr, true, s.partial_sq, eng->nc_ld))) return rc;
+        if (grad && eng->strict_active) {  // reference variance form: b = W^-1 k and |L^-1 k|^2, both streams in one launch
+          if ((rc = launch_smalln_both(eng, s, (int)N, d, eng->kern != KERN_RBF, st, &small_final))) return rc;
           sq_rows = 1;
-        }
+        } else if ((rc = launch_smalln(eng, s, (int)N, grad ? d : 0, grad && eng->kern != KERN_RBF, st, &small_final))) return rc;
+        part_rows = 1; part_nv = (grad ? d : 0) + 2; part_ld = SMALLN_FLD;
       } else {  // value only on an ill-conditioned model: the triangular form alone
         if ((rc = launch_smalln(eng, s, (int)N, 0, false, st, nullptr, true, s.partial, SMALLN_FLD))) return rc;
         small_final = s.partial;
@@ -1419,7 +1654,10 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     }
     ap.zbuf = s.zbuf;
     ap.blk_val = eng->want_blk ? eng->blk_val : nullptr; ap.blk_idx = eng->blk_idx; ap.row0 = off;
-    {
+    if (tiny && !eng->want_blk) {   // a handful of points: one warp per candidate (and, inside gpo_lbfgs, the optimiser step)
+      acq_small_kernel<<<(unsigned)rows, 32, 0, st>>>(ap, eng->lb_fused);
+      eng->launches++;
+    } else {
       dim3 kgrid((unsigned)((rows + 127) / 128), (unsigned)(S > 1 ? S : 1), 1);
       acq_kernel<<<kgrid, 128, 0, st>>>(ap);
       eng->launches++;
@@ -1709,7 +1947,7 @@ extern "C" int gpo_lbfgs(gpo_engine* eng, int kind, double par, int M, const dou
   const size_t Md = (size_t)M * d, MH = (size_t)M * LB_HIST;
   const size_t n_dbl = 6 * Md + 2 * MH * d + MH + 4 * (size_t)M + 2 * (size_t)d, n_int = 6 * (size_t)M + 2;
   int rc;
-  if ((rc = grow(eng, &eng->lb_buf, &eng->lb_bytes, n_dbl * 8 + (size_t)M * sizeof(LbLineSearch) + n_int * 4 + 64))) return rc;
+  if ((rc = grow(eng, &eng->lb_buf, &eng->lb_bytes, n_dbl * 8 + (size_t)M * sizeof(LbLineSearch) + n_int * 4 + 64 + sizeof(LbfgsParams) + 64))) return rc;
   double* w = eng->lb_buf;
   LbfgsParams p;
   memset(&p, 0, sizeof(p));
@@ -1722,7 +1960,8 @@ extern "C" int gpo_lbfgs(gpo_engine* eng, int kind, double par, int M, const dou
   p.ls = reinterpret_cast<LbLineSearch*>(w);
   int* iw = reinterpret_cast<int*>(p.ls + M);
   p.hist_n = iw; iw += M; p.hist_head = iw; iw += M; p.iter = iw; iw += M; p.phase = iw; iw += M;
-  p.done = iw; iw += M; p.nfev = iw; iw += M; p.n_done = iw;
+  p.done = iw; iw += M; p.nfev = iw; iw += M; p.n_done = iw; iw += 2;
+  LbfgsParams* p_dev = reinterpret_cast<LbfgsParams*>((reinterpret_cast<uintptr_t>(iw) + 63) & ~(uintptr_t)63);
   std::vector<double> hb(2 * (size_t)d);
   for (int q = 0; q < d; ++q) {
     hb[q] = bounds[2 * q]; hb[d + q] = bounds[2 * q + 1];
@@ -1730,6 +1969,7 @@ extern "C" int gpo_lbfgs(gpo_engine* eng, int kind, double par, int M, const dou
   }
   GPO_CUDA_OK(cudaMemcpyAsync(lo, hb.data(), 2 * (size_t)d * 8, cudaMemcpyHostToDevice, st));
   GPO_CUDA_OK(cudaMemcpyAsync(x0d, x0, Md * 8, cudaMemcpyHostToDevice, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(p_dev, &p, sizeof(LbfgsParams), cudaMemcpyHostToDevice, st));
   GPO_CUDA_OK(cudaStreamSynchronize(st));   // (pageable sources: the staging above is already complete; keeps hb alive)
   lbfgs_init_kernel<<<1, LB_MAXM, 0, st>>>(p, x0d);
   eng->launches++;
@@ -1737,10 +1977,18 @@ extern "C" int gpo_lbfgs(gpo_engine* eng, int kind, double par, int M, const dou
   int* pin_done = reinterpret_cast<int*>(eng->fit_pin);
   const long long max_rounds = std::min<long long>(20LL * maxiter + 60, 40000);   // (<= 20 evaluations per line search)
   const int poll = 4;
+  // M <= 32: the evaluation takes the latency kernels and its K3 (one warp per candidate) continues into the optimiser step of
+  // the same anchor; above, the evaluation is a regular sweep followed by the stand-alone update kernel (one warp per anchor)
+  const bool fused_step = M <= SMALLN_MAX_CALL;
   for (long long r = 0; r < max_rounds; ++r) {
-    if ((rc = sweep(eng, kind, par, true, false, 1, M, p.xt, ft, gt, nullptr, nullptr, st))) return rc;
-    lbfgs_update_kernel<<<1, LB_MAXM, 0, st>>>(p);
-    eng->launches++;
+    eng->lb_fused = fused_step ? p_dev : nullptr;
+    rc = sweep(eng, kind, par, true, false, 1, M, p.xt, ft, gt, nullptr, nullptr, st);
+    eng->lb_fused = nullptr;
+    if (rc) return rc;
+    if (!fused_step) {
+      lbfgs_update_kernel<<<M, 32, 0, st>>>(p_dev);
+      eng->launches++;
+    }
     GPO_CUDA_OK(cudaGetLastError());
     if (r % poll == poll - 1) {
       GPO_CUDA_OK(cudaMemcpyAsync(pin_done, p.n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1834,6 +2082,7 @@ extern "C" int gpo_set_option(gpo_engine* eng, int key, long long value) {
     case GPO_OPT_INVERSE: if (value < 0 || value > 2) return GPO_ERR_ARG; eng->opt_inverse = (int)value; break;
     case GPO_OPT_FUSED_SMALL: eng->opt_fused_small = value != 0; break;
     case GPO_OPT_PREFETCH_KT: eng->opt_prefetch_kt = value != 0; break;
+    case GPO_OPT_FIT_PATH: if (value < 0 || value > 1) return GPO_ERR_ARG; eng->opt_fit_path = (int)value; break;
     default: GPO_FAIL(GPO_ERR_ARG, "gpo_set_option: unknown key %d", key);
   }
   return GPO_OK;

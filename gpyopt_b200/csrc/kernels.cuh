@@ -367,8 +367,11 @@ __device__ __forceinline__ void diag_rhs_update(double (&r)[8][8], const double*
 // The eight stages run through ONE loop body so that chol32_warp and fwdsub32 exist once in the instruction stream.
 // Only the first n_valid = clamp(n - 128 kb, 0, 128) rows are real data; the rest is identity padding for which every
 // step is a no-op, so panels at or beyond n_valid are skipped.
+// mode 0: both phases.  mode 1 (critical chain of the refit): Cholesky + the four diagonal 32 x 32 inverses only -- L to A,
+// the inverses into the diagonal 32-blocks of X (what trsm_panel_kernel needs), 1 / L_jj to rdiag.  mode 2 (side stream): the
+// inverse from the L and rdiag that mode 1 left: same instructions on the same numbers, X and U bit-identical to mode 0.
 __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, double* X, double* U, int n_pad, int kb,
-                                                                     int n_valid, int* info) {
+                                                                     int n_valid, int* info, int mode, double* rdiag) {
   extern __shared__ double sm[];
   double* S = sm;                                        // [128][129]  lower: L;  strict upper: X^T (off-diagonal blocks)
   double* XD = sm + TILE * DIAG_PITCH;                   // [4][32][33] inverses of the diagonal 32x32 blocks
@@ -378,19 +381,29 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
   const int ty = tid >> 4, tx = tid & 15;
   const long long base = ((long long)z * n_pad + (long long)kb * TILE) * n_pad + (long long)kb * TILE;
   double r[8][8];
+  if (mode != 2) {
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const int i = ty + 16 * a, k = tx + 16 * b;
-      r[a][b] = A[base + (long long)(k <= i ? i : k) * n_pad + (k <= i ? k : i)];  // symmetric fill from the lower part
-      if (k > i) S[i * DIAG_PITCH + k] = 0.0;
+      for (int b = 0; b < 8; ++b) {
+        const int i = ty + 16 * a, k = tx + 16 * b;
+        r[a][b] = A[base + (long long)(k <= i ? i : k) * n_pad + (k <= i ? k : i)];  // symmetric fill from the lower part
+        if (k > i) S[i * DIAG_PITCH + k] = 0.0;
+      }
+    if (tid < TILE) rd[tid] = 1.0;
+  } else {
+    for (int e = tid; e < TILE * TILE; e += DIAG_THREADS) {
+      const int i = e >> 7, k = e & (TILE - 1);
+      S[i * DIAG_PITCH + k] = (k <= i) ? A[base + (long long)i * n_pad + k] : 0.0;
     }
-  if (tid < TILE) rd[tid] = 1.0;
+    if (tid < TILE) rd[tid] = rdiag[(long long)z * n_pad + kb * TILE + tid];
+    __syncthreads();
+  }
+  const int s_begin = mode == 2 ? 4 : 0, s_end = mode == 1 ? 5 : 8;
 
   // stages 0..3: Cholesky panel p = s;  stage 4: L out + diagonal-block inverses;  stages 5..7: block row p = s - 4 of X
 #pragma unroll 1
-  for (int s = 0; s < 8; ++s) {
+  for (int s = s_begin; s < s_end; ++s) {
     const int p = s < 4 ? s : s - 4, j0 = DIAG_PB * p;
     const bool live = j0 < n_valid;                      // uniform; identity padding from j0 on otherwise
     double* vec = S;
@@ -410,9 +423,11 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
       solve = live && p < DIAG_NP - 1 && i < n_valid;    // (rows of the identity padding hold zeros already)
       vec = S + i * DIAG_PITCH + j0;
     } else if (s == 4) {
-      for (int e = tid; e < TILE * TILE; e += DIAG_THREADS) {  // L to global memory (coalesced rows)
-        const int i = e >> 7, k = e & (TILE - 1);
-        A[base + (long long)i * n_pad + k] = (k <= i) ? S[i * DIAG_PITCH + k] : 0.0;
+      if (mode != 2) {
+        for (int e = tid; e < TILE * TILE; e += DIAG_THREADS) {  // L to global memory (coalesced rows)
+          const int i = e >> 7, k = e & (TILE - 1);
+          A[base + (long long)i * n_pad + k] = (k <= i) ? S[i * DIAG_PITCH + k] : 0.0;
+        }
       }
       if (tid < TILE) {                                  // thread = (diagonal block w, column c): L_ww x = e_c
         const int w = tid >> 5;
@@ -442,7 +457,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
         else if (p == 1) diag_syrk_update<1>(r, S, ty, tx);
         else diag_syrk_update<2>(r, S, ty, tx);
       }
-    } else if (s == 4) {
+    } else if (s == 4 && mode != 1) {
 #pragma unroll
       for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -455,13 +470,22 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
     }
   }
   __syncthreads();
+  if (mode == 1) {   // the diagonal 32 x 32 inverses (final entries of X) and the reciprocal pivots; the rest follows in mode 2
+    for (int e = tid; e < DIAG_NP * DIAG_PB * DIAG_PB; e += DIAG_THREADS) {
+      const int w = e >> 10, i = (e >> 5) & 31, c = e & 31;
+      X[base + (long long)(DIAG_PB * w + i) * n_pad + DIAG_PB * w + c] =
+          (c <= i) ? XD[w * DIAG_PB * DIAG_XD_PITCH + i * DIAG_XD_PITCH + c] : 0.0;
+    }
+    if (tid < TILE) rdiag[(long long)z * n_pad + kb * TILE + tid] = rd[tid];
+    return;
+  }
   // X (lower) and U = X^T (upper), coalesced rows
   for (int e = tid; e < TILE * TILE; e += DIAG_THREADS) {
     const int i = e >> 7, c = e & (TILE - 1);
     const int lo = c < i ? c : i, hi = c < i ? i : c;              // X[hi][lo] is the non-zero of the pair
-    const double x = ((hi >> 5) == (lo >> 5)) ? XD[(hi >> 5) * DIAG_PB * DIAG_XD_PITCH + (hi & 31) * DIAG_XD_PITCH + (lo & 31)]
-                                              : S[lo * DIAG_PITCH + hi];
-    X[base + (long long)i * n_pad + c] = (c <= i) ? x : 0.0;
+    const bool same = (hi >> 5) == (lo >> 5);
+    const double x = same ? XD[(hi >> 5) * DIAG_PB * DIAG_XD_PITCH + (hi & 31) * DIAG_XD_PITCH + (lo & 31)] : S[lo * DIAG_PITCH + hi];
+    if (mode == 0 || !same) X[base + (long long)i * n_pad + c] = (c <= i) ? x : 0.0;   // (mode 2: the panel may be reading them)
     U[base + (long long)i * n_pad + c] = (c >= i) ? x : 0.0;
   }
 }
@@ -663,8 +687,12 @@ __device__ __forceinline__ void block_argmax_store(double score, long long idx, 
   }
 }
 
-// last stage of K3 for one candidate: MCMC average, then either the plain outputs or the Local-Penalization transform
-__device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, double f_acc, double (&df_acc)[DMAX]) {
+// last stage of K3 for one candidate: MCMC average, then either the plain outputs or the Local-Penalization transform.
+// LP_LANES = 1: one thread per candidate (sweeps).  LP_LANES = 32: one warp per candidate (calls with a handful of points, where
+// K3 is a latency chain: 15 penalisers cost one thread ~40 us of erfc / log / exp): every lane carries the candidate's values,
+// the lanes split the penalisers, a shuffle tree adds their terms, lane 0 (`store`) writes.
+template <int LP_LANES>
+__device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, double f_acc, double (&df_acc)[DMAX], int lane, bool store) {
   const int d = p.d;
   if (p.kind >= ACQ_EI_MCMC) {
     const double invS = 1.0 / (double)p.S;  // f_acqu/(len(means)): true division by S
@@ -674,11 +702,13 @@ __device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, 
     (void)invS;
   }
   if (!p.lp_on) {
-    p.out_f[i] = f_acc;
-    if (p.grad) {
+    if (store) {
+      p.out_f[i] = f_acc;
+      if (p.grad) {
 #pragma unroll
-      for (int q = 0; q < DMAX; ++q)
-        if (q < d) p.out_df[i * d + q] = df_acc[q];
+        for (int q = 0; q < DMAX; ++q)
+          if (q < d) p.out_df[i * d + q] = df_acc[q];
+      }
     }
     return f_acc;
   }
@@ -694,8 +724,8 @@ __device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, 
     scale = 1.0 / fval;
   }
   val = -val;
-  double dsum = 0.0;
-  for (int k = 0; k < p.lp_K; ++k) {
+  double dsum = 0.0, pen = 0.0;
+  for (int k = LP_LANES > 1 ? lane : 0; k < p.lp_K; k += LP_LANES) {
     double nm2 = 0.0;
     for (int q = 0; q < d; ++q) {
       const double df = p.Xs[i * d + q] - p.lp_xb[k * d + q];
@@ -703,7 +733,8 @@ __device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, 
     }
     const double nm = sqrt(nm2);
     const double zz = (nm - p.lp_r[k]) / p.lp_s[k];
-    val -= log_ndtr(zz);
+    if (LP_LANES > 1) pen += log_ndtr(zz);
+    else val -= log_ndtr(zz);
     if (p.grad) {
       const double h = 0.5 * erfc(-zz * 0.70710678118654752440);  // norm.cdf(z)
       double dk = 1.0 / (p.lp_s[k] * 2.50662827463100050242 * h) * exp(-zz * zz / 2.0) / nm;
@@ -711,26 +742,31 @@ __device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, 
       dsum += dk;
     }
   }
-  p.out_f[i] = val;
-  if (p.grad) {
-    // scale * (-df) - sum_k d_k (direction dropped, broadcast over coordinates: LP.py:100-103,132)
+  if (LP_LANES > 1) {
 #pragma unroll
-    for (int q = 0; q < DMAX; ++q)
-      if (q < d) p.out_df[i * d + q] = scale * (-df_acc[q]) - dsum;
+    for (int o = 16; o > 0; o >>= 1) {
+      pen += __shfl_xor_sync(0xffffffffu, pen, o);
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    }
+    val -= pen;
+  }
+  if (store) {
+    p.out_f[i] = val;
+    if (p.grad) {
+      // scale * (-df) - sum_k d_k (direction dropped, broadcast over coordinates: LP.py:100-103,132)
+#pragma unroll
+      for (int q = 0; q < DMAX; ++q)
+        if (q < d) p.out_df[i * d + q] = scale * (-df_acc[q]) - dsum;
+    }
   }
   return -val;  // the penalised value is minimised
 }
 
-__global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
-  const long long i_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = i_raw < p.n_cand;
-  const long long i = active ? i_raw : p.n_cand - 1;  // out-of-range threads shadow the last row and write nothing
+// K3 for one candidate and the hyper-parameter sets z_begin .. z_end-1: posterior (m, s, gradients) from the partial rows, then
+// either the predict outputs (kind == ACQ_NONE, written when `store`) or the acquisition contributions added into f_acc / df_acc
+__device__ __forceinline__ void acq_accumulate(const AcqParams& p, long long i, int z_begin, int z_end, bool store, double& f_acc,
+                                               double (&df_acc)[DMAX]) {
   const int d = p.d, nv = p.part_nv;
-  double f_acc = 0.0, df_acc[DMAX];
-#pragma unroll
-  for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
-  const bool zsplit = gridDim.y > 1;
-  const int z_begin = zsplit ? blockIdx.y : 0, z_end = zsplit ? blockIdx.y + 1 : p.S;
   for (int z = z_begin; z < z_end; ++z) {
     double m = 0.0;
     for (int sp = 0; sp < p.js; ++sp) m += p.mean[((long long)z * p.js_ld + sp) * p.nc_pad + i];
@@ -769,6 +805,7 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
       }
     }
     if (p.kind == ACQ_NONE) {
+      if (!store) continue;
       p.out_m[(long long)z * p.out_ldN + i] = m;
       if (p.out_s) p.out_s[(long long)z * p.out_ldN + i] = s;  // null: mean-only call (no variance partials exist)
       if (p.grad) {
@@ -811,6 +848,19 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
       }
     }
   }
+}
+
+__global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
+  const long long i_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i_raw < p.n_cand;
+  const long long i = active ? i_raw : p.n_cand - 1;  // out-of-range threads shadow the last row (identical values, benign)
+  const int d = p.d;
+  double f_acc = 0.0, df_acc[DMAX];
+#pragma unroll
+  for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
+  const bool zsplit = gridDim.y > 1;
+  const int z_begin = zsplit ? blockIdx.y : 0, z_end = zsplit ? blockIdx.y + 1 : p.S;
+  acq_accumulate(p, i, z_begin, z_end, true, f_acc, df_acc);
   if (p.kind == ACQ_NONE) return;
   if (zsplit) {
     double* zb = p.zbuf + (long long)z_begin * (d + 1) * p.nc_pad + i;
@@ -822,8 +872,32 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
     }
     return;
   }
-  const double score = acq_finalize(p, i, f_acc, df_acc);
+  const double score = acq_finalize<1>(p, i, f_acc, df_acc, 0, true);
   if (p.blk_val) block_argmax_store(score, p.row0 + i, p.blk_val, p.blk_idx, (p.row0 >> 7) + blockIdx.x);
+}
+
+struct LbfgsParams;
+__device__ void lbfgs_anchor_update(const LbfgsParams& lb, int a, int lane);
+
+// K3 for calls with a handful of candidates (the L-BFGS steps): ONE WARP per candidate (grid = candidates, 32 threads).  For a
+// single thread K3 is a latency chain run from a cold instruction cache -- 72 us for 5 points with 15 Local-Penalization
+// penalisers at n = 4096 -- so the lanes split the penalisers (acq_finalize<32>) and lane 0 stores.  Hyper-parameter sets are
+// walked in set order inside the warp (no zbuf / zsum / reduce launches).  With `lb` set the same warp continues into the
+// optimiser step of anchor `candidate` (lbfgs_anchor_update): evaluation epilogue and L-BFGS state machine in one launch.
+__global__ void __launch_bounds__(32) acq_small_kernel(const AcqParams p, const LbfgsParams* __restrict__ lb) {
+  const long long i = blockIdx.x;
+  const int lane = threadIdx.x;
+  double f_acc = 0.0, df_acc[DMAX];
+#pragma unroll
+  for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
+  acq_accumulate(p, i, 0, p.S, lane == 0, f_acc, df_acc);
+  if (p.kind == ACQ_NONE) return;
+  acq_finalize<32>(p, i, f_acc, df_acc, lane, lane == 0);
+  if (lb) {
+    __threadfence_block();
+    __syncwarp();
+    lbfgs_anchor_update(*lb, (int)i, lane);
+  }
 }
 
 // S > 1, stage 1: grid (candidates / 128, 1 + d).  Thread (i, v) adds value v of candidate i over the hyper-parameter sets
@@ -847,7 +921,7 @@ __global__ void __launch_bounds__(128) acq_reduce_kernel(const AcqParams p) {
   double f_acc = p.zbuf[i], df_acc[DMAX];
 #pragma unroll
   for (int q = 0; q < DMAX; ++q) df_acc[q] = (p.grad && q < d) ? p.zbuf[(long long)(q + 1) * p.nc_pad + i] : 0.0;
-  const double score = acq_finalize(p, i, f_acc, df_acc);
+  const double score = acq_finalize<1>(p, i, f_acc, df_acc, 0, true);
   if (p.blk_val) block_argmax_store(score, p.row0 + i, p.blk_val, p.blk_idx, (p.row0 >> 7) + blockIdx.x);
 }
 
@@ -1040,7 +1114,7 @@ constexpr int SMALLN_CW = 128, SMALLN_STAGES = 4;
 constexpr int smalln_smem_bytes(int rows) { return SMALLN_STAGES * rows * SMALLN_CW * 8 + SMALLN_STAGES * 8; }
 
 template <int NC, bool SQ, int SMALLN_ROWS>
-__global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
+__device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
   extern __shared__ __align__(128) double smalln_smem[];
   __shared__ double red[8][DMAX + 2][NC];
   double* tile = smalln_smem;                                                            // [STAGES][ROWS][CW]
@@ -1161,6 +1235,20 @@ __global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     if (lane == 0) p.final_rows[((long long)z * (d + 2) + v) * p.final_ld + i] = t;
   }
+}
+
+template <int NC, bool SQ, int SMALLN_ROWS>
+__global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
+  smalln_wk_body<NC, SQ, SMALLN_ROWS>(p);
+}
+
+// Both forms in ONE launch (gradient calls in the reference variance form need b = W^-1 k AND |L^-1 k|^2): grid.z = 0 streams
+// W^-1, grid.z = 1 streams L^-1, concurrently -- alone each of them is latency-bound (2.1 / 1.4 TB/s at n = 4096: 63 + 49 us back
+// to back), together they keep twice as many TMA stages in flight.
+template <int NC, int SMALLN_ROWS>
+__global__ void __launch_bounds__(256) smalln_both_kernel(const SmallNParams pw, const SmallNParams psq) {
+  if (blockIdx.z == 0) smalln_wk_body<NC, false, SMALLN_ROWS>(pw);
+  else smalln_wk_body<NC, true, SMALLN_ROWS>(psq);
 }
 
 // K1 for the same handful of candidates: one thread per TRAINING point (K1 proper gives each candidate a thread and
@@ -1559,25 +1647,34 @@ __global__ void lbfgs_init_kernel(const LbfgsParams p, const double* __restrict_
   p.step[a] = 0.0; p.gd[a] = 0.0; p.f[a] = 0.0;
 }
 
-// one optimiser state-machine step per anchor after an evaluation at its trial point
-__global__ void lbfgs_update_kernel(const LbfgsParams p) {
-  const int a = threadIdx.x;
-  if (a >= p.M || p.done[a]) return;
+// One optimiser state-machine step of anchor `a` after an evaluation at its trial point, executed by ONE WARP: the lanes stage
+// the anchor's state (iterate, gradient, direction, curvature pairs: <= 3 KB) from global into shared memory in one round trip,
+// lane 0 runs the scalar state machine on the shared copy (a chain of dependent global loads made the first version take 45 us
+// per round), the lanes write the state back.
+__device__ void lbfgs_anchor_update(const LbfgsParams& p, int a, int lane) {
+  __shared__ double sh_x[DMAX], sh_g[DMAX], sh_dir[DMAX], sh_S[LB_HIST * DMAX], sh_Y[LB_HIST * DMAX], sh_rho[LB_HIST];
+  if (a >= p.M || p.done[a]) return;            // (warp-uniform)
   const int d = p.d;
+  {
+    const double* gx = p.x + a * d; const double* gg = p.g + a * d; const double* gd = p.dir + a * d;
+    const double* gS = p.S + (long long)a * LB_HIST * d; const double* gY = p.Y + (long long)a * LB_HIST * d;
+    for (int i = lane; i < d; i += 32) { sh_x[i] = gx[i]; sh_g[i] = gg[i]; sh_dir[i] = gd[i]; }
+    for (int i = lane; i < LB_HIST * d; i += 32) { sh_S[i] = gS[i]; sh_Y[i] = gY[i]; }
+    if (lane < LB_HIST) sh_rho[lane] = p.rho[a * LB_HIST + lane];
+  }
+  __syncwarp();
+  if (lane == 0) {
   const double eps = 2.220446049250313e-16;
-  double* x = p.x + a * d; double* g = p.g + a * d; double* xt = p.xt + a * d; double* dir = p.dir + a * d;
-  LbLineSearch& ls = p.ls[a];
+  double* x = sh_x; double* g = sh_g; double* dir = sh_dir; double* xt = p.xt + a * d;
+  LbLineSearch ls = p.ls[a];
   const double sgn = p.negate ? -1.0 : 1.0;
   double F = sgn * p.ft[a];
   double G[DMAX];
   bool finite = F == F && fabs(F) < 1e300;
   for (int q = 0; q < d; ++q) { G[q] = sgn * p.gt[a * d + q]; finite = finite && G[q] == G[q] && fabs(G[q]) < 1e300; }
   p.nfev[a] += 1;
-  auto finish = [&]() {
-    p.done[a] = 1;
-    for (int q = 0; q < d; ++q) xt[q] = x[q];   // later (lock-step) evaluations of this anchor are idle repeats
-    atomicAdd(p.n_done, 1);
-  };
+  int hist_n = p.hist_n[a], hist_head = p.hist_head[a];
+  bool finished = false, need_direction = true;
   auto pg_norm = [&](const double* xx, const double* gg) {
     double m = 0.0;
     for (int q = 0; q < d; ++q) m = ::fmax(m, fabs(lb_clamp(xx[q] - gg[q], p.lo[q], p.hi[q]) - xx[q]));
@@ -1586,11 +1683,13 @@ __global__ void lbfgs_update_kernel(const LbfgsParams p) {
   bool steepest = false;
   if (p.phase[a] == 0) {            // the evaluation at the start point
     p.f[a] = F;
-    if (!finite) { finish(); return; }
-    for (int q = 0; q < d; ++q) g[q] = G[q];
-    if (pg_norm(x, g) <= p.pgtol) { finish(); return; }
-    steepest = true;
-    p.phase[a] = 1;
+    if (!finite) finished = true;
+    else {
+      for (int q = 0; q < d; ++q) g[q] = G[q];
+      if (pg_norm(x, g) <= p.pgtol) finished = true;
+      steepest = true;
+      p.phase[a] = 1;
+    }
   } else {                          // a line-search trial at xt = x + step * dir
     double stp = p.step[a];
     double gdt = 0.0;
@@ -1598,96 +1697,116 @@ __global__ void lbfgs_update_kernel(const LbfgsParams p) {
     else { F = ls.fx + 1e10 * (1.0 + fabs(ls.fx)); gdt = 1e10; }
     ls.nls += 1;
     const bool ended = lb_dcsrch_next(ls, stp, F, gdt);
-    if (!ended) {
-      if (ls.nls < 20) {            // next trial
-        p.step[a] = stp;
-        for (int q = 0; q < d; ++q) xt[q] = lb_clamp(x[q] + stp * dir[q], p.lo[q], p.hi[q]);
-        return;
-      }
-    }
-    if (ended && finite) {
+    if (!ended && ls.nls < 20) {    // next trial
+      p.step[a] = stp;
+      for (int q = 0; q < d; ++q) xt[q] = lb_clamp(x[q] + stp * dir[q], p.lo[q], p.hi[q]);
+      need_direction = false;
+    } else if (ended && finite) {
       // accept: curvature pair, new iterate, stopping rules (as scipy.optimize.fmin_l_bfgs_b: pgtol, factr, maxiter)
       double sy = 0.0;
       for (int q = 0; q < d; ++q) sy = fma(xt[q] - x[q], G[q] - g[q], sy);
       if (sy > eps * (-p.gd[a] * p.step[a])) {
-        const int h = p.hist_head[a];
-        double* Sh = p.S + ((long long)a * LB_HIST + h) * d; double* Yh = p.Y + ((long long)a * LB_HIST + h) * d;
+        double* Sh = sh_S + hist_head * d; double* Yh = sh_Y + hist_head * d;
         for (int q = 0; q < d; ++q) { Sh[q] = xt[q] - x[q]; Yh[q] = G[q] - g[q]; }
-        p.rho[a * LB_HIST + h] = 1.0 / sy;
-        p.hist_head[a] = (h + 1) % LB_HIST;
-        if (p.hist_n[a] < LB_HIST) p.hist_n[a] += 1;
+        sh_rho[hist_head] = 1.0 / sy;
+        hist_head = (hist_head + 1) % LB_HIST;
+        if (hist_n < LB_HIST) hist_n += 1;
       }
       const double f0 = p.f[a];
       for (int q = 0; q < d; ++q) { x[q] = xt[q]; g[q] = G[q]; }
       p.f[a] = F;
       p.iter[a] += 1;
-      if (pg_norm(x, g) <= p.pgtol || (f0 - F) <= p.ftol * ::fmax(::fmax(fabs(f0), fabs(F)), 1.0) || p.iter[a] >= p.maxiter) {
-        finish(); return;
-      }
+      if (pg_norm(x, g) <= p.pgtol || (f0 - F) <= p.ftol * ::fmax(::fmax(fabs(f0), fabs(F)), 1.0) || p.iter[a] >= p.maxiter)
+        finished = true;
     } else {
       // failed search: with history, drop it and restart from steepest descent at the iterate; without, stop
-      if (p.hist_n[a] > 0) { p.hist_n[a] = 0; steepest = true; }
-      else { finish(); return; }
+      if (hist_n > 0) { hist_n = 0; steepest = true; }
+      else finished = true;
     }
   }
-  // ---- new search direction from the iterate (x, g) ----
-  bool fr[DMAX];
-  for (int q = 0; q < d; ++q) fr[q] = !((x[q] <= p.lo[q] && g[q] > 0.0) || (x[q] >= p.hi[q] && g[q] < 0.0));
-  double gdd = 0.0, dn = 0.0;
-  for (int attempt = 0; attempt < 2; ++attempt) {
-    const int hn = steepest ? 0 : p.hist_n[a];
-    for (int pass = 0; pass <= d; ++pass) {
-      double v[DMAX], al[LB_HIST];
-      for (int q = 0; q < d; ++q) v[q] = fr[q] ? g[q] : 0.0;
-      for (int i = 0; i < hn; ++i) {        // newest to oldest
-        const int h = (p.hist_head[a] - 1 - i + 2 * LB_HIST) % LB_HIST;
-        const double* Sh = p.S + ((long long)a * LB_HIST + h) * d; const double* Yh = p.Y + ((long long)a * LB_HIST + h) * d;
-        double sv = 0.0;
-        for (int q = 0; q < d; ++q) sv = fma(Sh[q], v[q], sv);
-        al[i] = p.rho[a * LB_HIST + h] * sv;
-        for (int q = 0; q < d; ++q) v[q] = fma(-al[i], Yh[q], v[q]);
+  if (!finished && need_direction) {
+    // ---- new search direction from the iterate (x, g) ----
+    bool fr[DMAX];
+    for (int q = 0; q < d; ++q) fr[q] = !((x[q] <= p.lo[q] && g[q] > 0.0) || (x[q] >= p.hi[q] && g[q] < 0.0));
+    double gdd = 0.0, dn = 0.0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      const int hn = steepest ? 0 : hist_n;
+      for (int pass = 0; pass <= d; ++pass) {
+        double v[DMAX], al[LB_HIST];
+        for (int q = 0; q < d; ++q) v[q] = fr[q] ? g[q] : 0.0;
+        for (int i = 0; i < hn; ++i) {        // newest to oldest
+          const int h = (hist_head - 1 - i + 2 * LB_HIST) % LB_HIST;
+          const double* Sh = sh_S + h * d; const double* Yh = sh_Y + h * d;
+          double sv = 0.0;
+          for (int q = 0; q < d; ++q) sv = fma(Sh[q], v[q], sv);
+          al[i] = sh_rho[h] * sv;
+          for (int q = 0; q < d; ++q) v[q] = fma(-al[i], Yh[q], v[q]);
+        }
+        if (hn > 0) {
+          const int h = (hist_head - 1 + LB_HIST) % LB_HIST;
+          const double* Yh = sh_Y + h * d;
+          double yy = 0.0;
+          for (int q = 0; q < d; ++q) yy = fma(Yh[q], Yh[q], yy);
+          const double gamma = 1.0 / (sh_rho[h] * yy);
+          for (int q = 0; q < d; ++q) v[q] *= gamma;
+        }
+        for (int i = hn - 1; i >= 0; --i) {   // oldest to newest
+          const int h = (hist_head - 1 - i + 2 * LB_HIST) % LB_HIST;
+          const double* Sh = sh_S + h * d; const double* Yh = sh_Y + h * d;
+          double yv = 0.0;
+          for (int q = 0; q < d; ++q) yv = fma(Yh[q], v[q], yv);
+          const double be = sh_rho[h] * yv;
+          for (int q = 0; q < d; ++q) v[q] = fma(al[i] - be, Sh[q], v[q]);
+        }
+        bool blocked = false;
+        for (int q = 0; q < d; ++q) {
+          dir[q] = fr[q] ? -v[q] : 0.0;
+          // a free variable sitting on a bound and pushed outward by the quasi-Newton coupling: freeze it and redo
+          if (fr[q] && ((x[q] <= p.lo[q] && dir[q] < 0.0) || (x[q] >= p.hi[q] && dir[q] > 0.0))) { fr[q] = false; blocked = true; }
+        }
+        if (!blocked) break;
       }
-      if (hn > 0) {
-        const int h = (p.hist_head[a] - 1 + LB_HIST) % LB_HIST;
-        const double* Yh = p.Y + ((long long)a * LB_HIST + h) * d;
-        double yy = 0.0;
-        for (int q = 0; q < d; ++q) yy = fma(Yh[q], Yh[q], yy);
-        const double gamma = 1.0 / (p.rho[a * LB_HIST + h] * yy);
-        for (int q = 0; q < d; ++q) v[q] *= gamma;
-      }
-      for (int i = hn - 1; i >= 0; --i) {   // oldest to newest
-        const int h = (p.hist_head[a] - 1 - i + 2 * LB_HIST) % LB_HIST;
-        const double* Sh = p.S + ((long long)a * LB_HIST + h) * d; const double* Yh = p.Y + ((long long)a * LB_HIST + h) * d;
-        double yv = 0.0;
-        for (int q = 0; q < d; ++q) yv = fma(Yh[q], v[q], yv);
-        const double be = p.rho[a * LB_HIST + h] * yv;
-        for (int q = 0; q < d; ++q) v[q] = fma(al[i] - be, Sh[q], v[q]);
-      }
-      bool blocked = false;
+      gdd = 0.0; dn = 0.0;
+      for (int q = 0; q < d; ++q) { gdd = fma(g[q], dir[q], gdd); dn = fma(dir[q], dir[q], dn); }
+      if (gdd < 0.0 || hn == 0) break;
+      hist_n = 0;                             // not a descent direction: drop the history, steepest descent
+      steepest = true;
+    }
+    if (!(dn > 0.0) || !(gdd < 0.0)) finished = true;
+    else {
+      double stpmx = 1e10;
       for (int q = 0; q < d; ++q) {
-        dir[q] = fr[q] ? -v[q] : 0.0;
-        // a free variable sitting on a bound and pushed outward by the quasi-Newton coupling: freeze it and redo
-        if (fr[q] && ((x[q] <= p.lo[q] && dir[q] < 0.0) || (x[q] >= p.hi[q] && dir[q] > 0.0))) { fr[q] = false; blocked = true; }
+        if (dir[q] > 0.0) stpmx = ::fmin(stpmx, (p.hi[q] - x[q]) / dir[q]);
+        else if (dir[q] < 0.0) stpmx = ::fmin(stpmx, (p.lo[q] - x[q]) / dir[q]);
       }
-      if (!blocked) break;
+      const double stp = ::fmin(1.0, stpmx);
+      lb_dcsrch_start(ls, stp, p.f[a], gdd, stpmx);
+      p.step[a] = stp;
+      p.gd[a] = gdd;
+      for (int q = 0; q < d; ++q) xt[q] = lb_clamp(x[q] + stp * dir[q], p.lo[q], p.hi[q]);
     }
-    gdd = 0.0; dn = 0.0;
-    for (int q = 0; q < d; ++q) { gdd = fma(g[q], dir[q], gdd); dn = fma(dir[q], dir[q], dn); }
-    if (gdd < 0.0 || hn == 0) break;
-    p.hist_n[a] = 0;                        // not a descent direction: drop the history, steepest descent
-    steepest = true;
   }
-  if (!(dn > 0.0) || !(gdd < 0.0)) { finish(); return; }
-  double stpmx = 1e10;
-  for (int q = 0; q < d; ++q) {
-    if (dir[q] > 0.0) stpmx = ::fmin(stpmx, (p.hi[q] - x[q]) / dir[q]);
-    else if (dir[q] < 0.0) stpmx = ::fmin(stpmx, (p.lo[q] - x[q]) / dir[q]);
+  if (finished) {
+    p.done[a] = 1;
+    for (int q = 0; q < d; ++q) xt[q] = x[q];   // later (lock-step) evaluations of this anchor are idle repeats
+    atomicAdd(p.n_done, 1);
   }
-  const double stp = ::fmin(1.0, stpmx);
-  lb_dcsrch_start(ls, stp, p.f[a], gdd, stpmx);
-  p.step[a] = stp;
-  p.gd[a] = gdd;
-  for (int q = 0; q < d; ++q) xt[q] = lb_clamp(x[q] + stp * dir[q], p.lo[q], p.hi[q]);
+  p.ls[a] = ls;
+  p.hist_n[a] = hist_n; p.hist_head[a] = hist_head;
+  }
+  __syncwarp();
+  {
+    double* gx = p.x + a * d; double* gg = p.g + a * d; double* gd = p.dir + a * d;
+    double* gS = p.S + (long long)a * LB_HIST * d; double* gY = p.Y + (long long)a * LB_HIST * d;
+    for (int i = lane; i < d; i += 32) { gx[i] = sh_x[i]; gg[i] = sh_g[i]; gd[i] = sh_dir[i]; }
+    for (int i = lane; i < LB_HIST * d; i += 32) { gS[i] = sh_S[i]; gY[i] = sh_Y[i]; }
+    if (lane < LB_HIST) p.rho[a * LB_HIST + lane] = sh_rho[lane];
+  }
+}
+
+// stand-alone form: one warp (block) per anchor
+__global__ void __launch_bounds__(32) lbfgs_update_kernel(const LbfgsParams* __restrict__ p) {
+  lbfgs_anchor_update(*p, (int)blockIdx.x, (int)threadIdx.x);
 }
 
 }  // namespace gpo

@@ -179,9 +179,11 @@ int gpo_get_info(gpo_engine* eng, double* info, int count);
  *   GPO_OPT_INVERSE     0 automatic (default) / 1 interleaved with the Cholesky / 2 recursive triangular inverse
  *   GPO_OPT_FUSED_SMALL 1 (default) / 0: value sweeps of models with n <= 128 take the fused shared-memory-resident kernel
  *   GPO_OPT_PREFETCH_KT 0 (default) / 1: L2 prefetch of the K* tile that the gradient epilogue of the second triangular product
- *                       re-reads (measured: +0.03 % RBF, -0.4 % Matern at n = 2048 -- the epilogue is not waiting on those loads) */
+ *                       re-reads (measured: +0.03 % RBF, -0.4 % Matern at n = 2048 -- the epilogue is not waiting on those loads)
+ *   GPO_OPT_FIT_PATH    0 (default): refit with the short critical chain (diagonal-block Cholesky -> panel by block substitution ->
+ *                       block-column update; inverse, trailing update and W^-1 on side streams) / 1: the round-1 look-ahead scheme */
 typedef enum { GPO_OPT_SERPENTINE = 0, GPO_OPT_BN_SWEEP = 1, GPO_OPT_BN_FIT = 2, GPO_OPT_INVERSE = 3, GPO_OPT_FUSED_SMALL = 4,
-               GPO_OPT_PREFETCH_KT = 5 } gpo_option;
+               GPO_OPT_PREFETCH_KT = 5, GPO_OPT_FIT_PATH = 6 } gpo_option;
 int gpo_set_option(gpo_engine* eng, int key, long long value);
 
 /* Multi-GPU replication of the posterior state (one process per GPU; the collective itself is issued by the

@@ -116,9 +116,17 @@ struct gpo_engine {
   double* lb_buf = nullptr;  size_t lb_bytes = 0;   // device state of the batched L-BFGS (gpo_lbfgs)
   double var_disc = 0.0;
   std::vector<cudaEvent_t> chol_ev;  // look-ahead events of the blocked Cholesky (2 per block column)
+  int opt_fit_graph = 1;    // replay the launch sequence of factorize_chain as a CUDA graph (captured once per problem shape)
+  cudaGraphExec_t fit_graph_exec = nullptr;
+  struct FitGraphKey { int n_pad, n, d, S, kern; const void* A; } fit_graph_key = {0, 0, 0, 0, 0, nullptr};
+  long long fit_graph_launches = 0;
+  int opt_fit_trace = 0;    // measurement aid: time every launch of factorize_chain with events and print the timeline to stderr
   int opt_fit_path = 0;     // refit: 0 short critical chain (factorize_chain), 1 the round-1 look-ahead scheme (factorize)
   std::vector<cudaEvent_t> fit_ev;   // events of factorize_chain (6 per block column + 4)
-  cudaStream_t fit_side[3] = {nullptr, nullptr, nullptr};   // its side streams: inverse steps, diagonal-block inverses, W^-1
+  cudaStream_t fit_side[4] = {nullptr, nullptr, nullptr, nullptr};   // its side streams: inverse steps, diagonal-block inverses, W^-1,
+                                                                     // panel + next block column (high priority like the chain)
+  double* chain_buf = nullptr;       // [4][S][128][128] scratch of chol_chain_kernel
+  int* chain_flags = nullptr;        // [n_pad / 128][S][2] its arrival counters
   double* rdiag = nullptr;           // [S][n_pad] reciprocal pivots 1 / L_jj (diagonal-block kernel, mode 1 -> mode 2)
   // counters / live profiling of the dominant kernel (variance GEMM) for the benchmark's roofline
   long long launches = 0;
@@ -214,6 +222,9 @@ static int gemm_setup(gpo_engine* eng) {
   GPO_CUDA_OK(gemm_attr_epi<EPI_GRAD>());
   GPO_CUDA_OK(cudaFuncSetAttribute(diag_chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG_SMEM_BYTES));
   GPO_CUDA_OK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM_BYTES));
+  GPO_CUDA_OK(cudaFuncSetAttribute(chol_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES));
+  GPO_CUDA_OK(cudaFuncSetAttribute(rank128_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RD_SMEM_BYTES));
+  GPO_CUDA_OK(cudaFuncSetAttribute(rank128_dmma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   GPO_CUDA_OK(cudaFuncSetAttribute(rank128_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, rank128_smem_bytes<4, 4>()));
   GPO_CUDA_OK(cudaFuncSetAttribute(rank128_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rank128_smem_bytes<8, 2>()));
   GPO_CUDA_OK(cov_attr<2>()); GPO_CUDA_OK(cov_attr<4>()); GPO_CUDA_OK(cov_attr<6>());
@@ -295,6 +306,11 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
     cudaStreamCreateWithPriority(&eng->fit_stream, cudaStreamNonBlocking, prio_hi);
   }
   for (int i = 0; i < 3; ++i) cudaStreamCreateWithFlags(&eng->fit_side[i], cudaStreamNonBlocking);
+  {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaStreamCreateWithPriority(&eng->fit_side[3], cudaStreamNonBlocking, prio_hi);
+  }
   cudaEventCreateWithFlags(&eng->ev_in, cudaEventDisableTiming);
   int rc = gemm_setup(eng);
   if (rc != GPO_OK) {
@@ -308,9 +324,11 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
 
 static void free_state(gpo_engine* eng) {
   double** ptrs[] = {&eng->Xt, &eng->Xtc, &eng->xmu, &eng->Xaos, &eng->Y, &eng->invl, &eng->sigf2, &eng->noise, &eng->jitter, &eng->A, &eng->X,
-                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->rdiag, &eng->xtile, &eng->probe_out, &eng->logdet, &eng->quad, &eng->fmin};
+                     &eng->U, &eng->W, &eng->T, &eng->alpha, &eng->tmpv, &eng->rdiag, &eng->chain_buf, &eng->xtile, &eng->probe_out, &eng->logdet, &eng->quad, &eng->fmin};
   for (auto pp : ptrs) { if (*pp) cudaFree(*pp); *pp = nullptr; }
   if (eng->info) { cudaFree(eng->info); eng->info = nullptr; }
+  if (eng->chain_flags) { cudaFree(eng->chain_flags); eng->chain_flags = nullptr; }
+  if (eng->fit_graph_exec) { cudaGraphExecDestroy(eng->fit_graph_exec); eng->fit_graph_exec = nullptr; }   // it holds the old pointers
   for (int i = 0; i < 2; ++i) {
     Slot& s = eng->slot[i];
     double** sp[] = {&s.Kt, &s.Ht, &s.Tt, &s.mean, &s.dmean, &s.partial, &s.partial_sq, &s.zbuf, &s.fs_mean, &s.fs_sq};
@@ -355,8 +373,9 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
     cudaEventDestroy(eng->slot[i].done);
   }
   cudaStreamDestroy(eng->fit_stream);
-  for (int i = 0; i < 3; ++i) cudaStreamDestroy(eng->fit_side[i]);
+  for (int i = 0; i < 4; ++i) cudaStreamDestroy(eng->fit_side[i]);
   for (cudaEvent_t e : eng->fit_ev) cudaEventDestroy(e);
+  if (eng->fit_graph_exec) cudaGraphExecDestroy(eng->fit_graph_exec);
   cudaEventDestroy(eng->ev_in);
   delete eng;
   return GPO_OK;
@@ -424,6 +443,8 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   GPO_CUDA_OK(cudaMalloc(&eng->alpha, (size_t)S * n_pad * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->tmpv, (size_t)S * n_pad * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->rdiag, (size_t)S * n_pad * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->chain_buf, (size_t)4 * S * TILE * TILE * 8));
+  GPO_CUDA_OK(cudaMalloc(&eng->chain_flags, (size_t)(n_pad / TILE) * S * 2 * sizeof(int)));
   eng->dp = d <= 2 ? 2 : d <= 4 ? 4 : d <= 6 ? 6 : d <= 8 ? 8 : d <= 12 ? 12 : 16;
   GPO_CUDA_OK(cudaMalloc(&eng->xtile, (size_t)S * n_pad * (eng->dp + 1) * 8));
   GPO_CUDA_OK(cudaMalloc(&eng->logdet, (size_t)S * 8));
@@ -710,50 +731,128 @@ static int launch_r128(gpo_engine* eng, const R128Params& p, int S, cudaStream_t
   return GPO_OK;
 }
 
+static int launch_r128d(gpo_engine* eng, const R128Params& p, int S, cudaStream_t st) {   // 64 x 64 tiles on the tensor pipe
+  dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)S, 1);
+  rank128_dmma_kernel<<<grid, 128, RD_SMEM_BYTES, st>>>(p);
+  eng->launches++;
+  GPO_CUDA_OK(cudaGetLastError());
+  return GPO_OK;
+}
+
 static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
   const int n_pad = eng->n_pad, S = eng->S, nb = n_pad / TILE;
-  const long long nn = (long long)n_pad * n_pad;
+  const long long nn = (long long)n_pad * n_pad, tt = (long long)TILE * TILE;
   int rc;
-  cudaStream_t sb = eng->slot[0].stream, sc = eng->fit_side[0], sd = eng->fit_side[1], se = eng->fit_side[2];
-  while ((int)eng->fit_ev.size() < 6 * nb + 4) {
+  cudaStream_t sb = eng->slot[0].stream, sc = eng->fit_side[0], sd = eng->fit_side[1], se = eng->fit_side[2], sn = eng->fit_side[3];
+  while ((int)eng->fit_ev.size() < 6 * nb + 6) {
     cudaEvent_t e;
     GPO_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     eng->fit_ev.push_back(e);
   }
-  enum { EV_CHOL = 0, EV_INV = 1, EV_PANEL = 2, EV_BULK = 3, EV_ROW = 4, EV_W = 5 };
+  enum { EV_CHOL = 0, EV_INV = 1, EV_PANEL = 2, EV_BULK = 3, EV_ROW = 4, EV_NEXT = 5 };
   auto ev = [&](int kind, int kb) { return eng->fit_ev[(size_t)kind * nb + kb]; };
   cudaEvent_t ev_start = eng->fit_ev[6 * (size_t)nb], ev_sc = eng->fit_ev[6 * (size_t)nb + 1], ev_se = eng->fit_ev[6 * (size_t)nb + 2];
+  cudaEvent_t ev_sn = eng->fit_ev[6 * (size_t)nb + 3], ev_sd = eng->fit_ev[6 * (size_t)nb + 4];
+  // scratch of the chain kernel: the raw first panel tile (double-buffered by block-column parity), its solved copy, the updated
+  // diagonal block; arrival counters per (block column, hyper-parameter set)
+  double* raw[2] = {eng->chain_buf, eng->chain_buf + tt * S};
+  double* Pg = eng->chain_buf + 2 * tt * S;
+  double* Tg = eng->chain_buf + 3 * tt * S;
+  // measurement aid (GPO_OPT_FIT_TRACE): a timing event on either side of every launch, printed as a timeline at the end
+  struct TraceRec { const char* name; int kb; int stream; cudaEvent_t e0, e1; };
+  std::vector<TraceRec> trace;
+  cudaEvent_t trace_t0 = nullptr;
+  const bool tracing = eng->opt_fit_trace != 0;
+  auto t_begin = [&](const char* name, int kb, int sid, cudaStream_t s) {
+    if (!tracing) return;
+    TraceRec r{name, kb, sid, nullptr, nullptr};
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, s);
+    trace.push_back(r);
+  };
+  auto t_end = [&](cudaStream_t s) { if (tracing) cudaEventRecord(trace.back().e1, s); };
+  if (tracing) { cudaEventCreate(&trace_t0); cudaEventRecord(trace_t0, st); }
   // W^-1 is accumulated: zero it first (after whatever the fit stream has done so far, e.g. an earlier attempt's reads)
   GPO_CUDA_OK(cudaEventRecord(ev_start, st));
   GPO_CUDA_OK(cudaStreamWaitEvent(se, ev_start, 0));
   GPO_CUDA_OK(cudaMemsetAsync(eng->W, 0, (size_t)S * nn * 8, se));
+  GPO_CUDA_OK(cudaMemsetAsync(eng->chain_flags, 0, (size_t)nb * S * 2 * sizeof(int), st));
   {
     dim3 blk(16, 16), grd(n_pad / 16, n_pad / 16, S);
+    t_begin("gram", 0, 0, st);
     gram_kernel<<<grd, blk, 0, st>>>(eng->A, eng->Xt, n_pad, eng->n, n_pad, eng->d, eng->kern, eng->invl, eng->sigf2,
                                      eng->noise, eng->jitter);
+    t_end(st);
     eng->launches++;
   }
   GPO_CUDA_OK(cudaMemsetAsync(eng->info, 0, S * sizeof(int), st));
-  const int bulk_ctas = std::max(16, eng->sm_count - 48), w_ctas = 40;
-  int last_bulk = -1;
   for (int kb = 0; kb < nb; ++kb) {
     const int rem = nb - kb - 1, kT = kb * TILE, k1T = (kb + 1) * TILE;
     const int n_valid = std::max(0, std::min(TILE, eng->n - kT));
-    // ---- critical chain: Cholesky of the diagonal block (+ its four 32 x 32 inverses) ----
-    diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info, 1, eng->rdiag);
+    // ---- critical chain: block column kb in one launch ----
+    if (kb == 0) {
+      tile_copy_kernel<<<dim3(16, (unsigned)S), 256, 0, st>>>(eng->A, raw[1], n_pad, 1, 0);   // tile (1, 0) before the panel overwrites it
+      eng->launches++;
+      t_begin("chol", kb, 0, st);
+      diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info, 1, eng->rdiag);
+      t_end(st);
+    } else {
+      if (kb >= 2) {   // tile (kb, kb-1) and tile (kb, kb) carry the updates of the panels up to kb-2
+        GPO_CUDA_OK(cudaStreamWaitEvent(st, ev(EV_NEXT, kb - 2), 0));
+        GPO_CUDA_OK(cudaStreamWaitEvent(st, ev(EV_BULK, kb - 2), 0));
+      }
+      t_begin("chain", kb, 0, st);
+      chol_chain_kernel<<<CHAIN_CTAS * S, DIAG_THREADS, CHAIN_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info,
+                                                                                eng->rdiag, raw[kb & 1], Pg, Tg,
+                                                                                eng->chain_flags + (size_t)kb * 2 * S);
+      t_end(st);
+    }
     eng->launches++;
+    GPO_CUDA_OK(cudaGetLastError());
     GPO_CUDA_OK(cudaEventRecord(ev(EV_CHOL, kb), st));
     // ---- side: X_kk = L_kk^-1, U_kk ----
     GPO_CUDA_OK(cudaStreamWaitEvent(sd, ev(EV_CHOL, kb), 0));
+    t_begin("inv128", kb, 3, sd);
     diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, sd>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info, 2, eng->rdiag);
+    t_end(sd);
     eng->launches++;
     GPO_CUDA_OK(cudaEventRecord(ev(EV_INV, kb), sd));
-    // ---- critical chain: panel ----
+    // ---- right behind the chain: the panel below block kb, then block column kb+1 below its diagonal block (the chain kernel
+    //      of block column kb+2 waits for these; they have the whole chain kernel of kb+1 to finish) ----
     if (rem > 0) {
-      trsm_panel_kernel<<<dim3((unsigned)(rem * (TILE / TRSM_RS)), (unsigned)S), 256, TRSM_SMEM_BYTES, st>>>(eng->A, eng->X, n_pad, kb);
+      GPO_CUDA_OK(cudaStreamWaitEvent(sn, ev(EV_CHOL, kb), 0));
+      t_begin("trsm", kb, 5, sn);
+      trsm_panel_kernel<<<dim3((unsigned)(rem * (TILE / TRSM_RS)), (unsigned)S), 256, TRSM_SMEM_BYTES, sn>>>(eng->A, eng->X, n_pad, kb, kb + 1);
+      t_end(sn);
       eng->launches++;
       GPO_CUDA_OK(cudaGetLastError());
-      GPO_CUDA_OK(cudaEventRecord(ev(EV_PANEL, kb), st));
+      GPO_CUDA_OK(cudaEventRecord(ev(EV_PANEL, kb), sn));
+      if (rem >= 2) {
+        if (kb >= 1) GPO_CUDA_OK(cudaStreamWaitEvent(sn, ev(EV_BULK, kb - 1), 0));   // those tiles carry panel kb-1 first
+        R128Params c = r128_defaults();
+        c.alpha = -1.0; c.beta = 1.0;
+        c.A = eng->A; c.lda = n_pad; c.a_z = nn; c.a_row0 = k1T + TILE; c.a_col0 = kT;
+        c.B = eng->A; c.ldb = n_pad; c.b_z = nn; c.b_row0 = k1T; c.b_col0 = kT;
+        c.C = eng->A; c.ldc = n_pad; c.c_z = nn; c.c_row0 = k1T + TILE; c.c_col0 = k1T;
+        c.tiles_m = (rem - 1) * 2; c.tiles_n = 2;
+        c.C2 = raw[(kb + 2) & 1]; c.c2_z = tt;    // tile (kb+2, kb+1): what the chain kernel of kb+2 solves
+        t_begin("colupd", kb, 5, sn);
+        if ((rc = launch_r128d(eng, c, S, sn))) return rc;
+        t_end(sn);
+        GPO_CUDA_OK(cudaEventRecord(ev(EV_NEXT, kb), sn));
+        // ---- side: trailing update of block columns >= kb+2 (lower 64 x 64 tiles) ----
+        R128Params r = r128_defaults();
+        r.alpha = -1.0; r.beta = 1.0;
+        r.A = eng->A; r.lda = n_pad; r.a_z = nn; r.a_row0 = k1T + TILE; r.a_col0 = kT;
+        r.B = eng->A; r.ldb = n_pad; r.b_z = nn; r.b_row0 = k1T + TILE; r.b_col0 = kT;
+        r.C = eng->A; r.ldc = n_pad; r.c_z = nn; r.c_row0 = k1T + TILE; r.c_col0 = k1T + TILE;
+        r.tiles_m = (rem - 1) * 2; r.tiles_n = (rem - 1) * 2; r.skip_upper = 1;
+        GPO_CUDA_OK(cudaStreamWaitEvent(sb, ev(EV_PANEL, kb), 0));
+        t_begin("bulk", kb, 1, sb);
+        if ((rc = launch_r128d(eng, r, S, sb))) return rc;
+        t_end(sb);
+        GPO_CUDA_OK(cudaEventRecord(ev(EV_BULK, kb), sb));
+      }
     }
     // ---- side: block row kb of the inverse becomes final: X[kb, c] = X_kk R[kb, c], c < kb (in place on U) ----
     GPO_CUDA_OK(cudaStreamWaitEvent(sc, ev(EV_INV, kb), 0));
@@ -764,21 +863,24 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
       f.C = eng->X; f.ldc = n_pad; f.c_z = nn; f.c_row0 = kT; f.c_col0 = 0;
       f.Ct = eng->U; f.ldct = n_pad; f.ct_z = nn; f.ct_row0 = 0; f.ct_col0 = kT;
       f.tiles_m = 1; f.tiles_n = kb * (TILE / 32);
+      t_begin("inv_row", kb, 2, sc);
       if ((rc = launch_r128<8, 2>(eng, f, S, sc))) return rc;
+      t_end(sc);
     }
     GPO_CUDA_OK(cudaEventRecord(ev(EV_ROW, kb), sc));
     // ---- side: W^-1[i, j] += U[i, kb] U[j, kb]^T for j <= i <= kb (mirrored into the upper tiles with the last block row) ----
     {
       GPO_CUDA_OK(cudaStreamWaitEvent(se, ev(EV_ROW, kb), 0));
-      GemmParams w = gemm_defaults();
-      w.tiles_m = kb + 1; w.tiles_n = kb + 1; w.kblocks = 1; w.tile_skip = TS_LOWER;
-      w.a = {0, kT, 0, 0, 0, 1};
-      w.b = w.a;
+      R128Params w = r128_defaults();
       w.beta = 1.0;
-      w.C = eng->W; w.ldc = n_pad; w.c_off_z = nn;
-      if (rem == 0) { w.Ct = eng->W; w.ldct = n_pad; w.ct_off_z = nn; }
-      w.sym_diag = 1;
-      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapU, eng->mapU, w, S, se, rem == 0 ? 0 : w_ctas))) return rc;
+      w.A = eng->U; w.lda = n_pad; w.a_z = nn; w.a_col0 = kT;
+      w.B = eng->U; w.ldb = n_pad; w.b_z = nn; w.b_col0 = kT;
+      w.C = eng->W; w.ldc = n_pad; w.c_z = nn;
+      if (rem == 0) { w.Ct = eng->W; w.ldct = n_pad; w.ct_z = nn; }
+      w.tiles_m = (kb + 1) * 2; w.tiles_n = (kb + 1) * 2; w.skip_upper = 1;
+      t_begin("w_acc", kb, 4, se);
+      if ((rc = launch_r128d(eng, w, S, se))) return rc;
+      t_end(se);
     }
     if (rem == 0) break;
     // ---- side: running right-hand side of L X = I ----
@@ -794,44 +896,88 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
       if (kb > 0) {   // R[i, c] -= L[i, kb] X[kb, c],  c < kb
         R128Params a2 = u;
         a2.b_row0 = 0; a2.c_col0 = 0; a2.ct_row0 = 0; a2.beta = 1.0; a2.tiles_n = kb * 2;
-        if ((rc = launch_r128<4, 4>(eng, a2, S, sc))) return rc;
+        t_begin("inv_upd", kb, 2, sc);
+        if ((rc = launch_r128d(eng, a2, S, sc))) return rc;
+        t_end(sc);
       }
       R128Params b2 = u;   // R[i, kb] = -L[i, kb] X_kk
       b2.b_row0 = kT; b2.c_col0 = kT; b2.ct_row0 = kT; b2.beta = 0.0; b2.tiles_n = 2;
-      if ((rc = launch_r128<4, 4>(eng, b2, S, sc))) return rc;
-    }
-    // ---- side: trailing update of block columns >= kb+2 ----
-    if (rem >= 2) {
-      GemmParams r = gemm_defaults();
-      r.kblocks = 1; r.alpha = -1.0; r.beta = 1.0;
-      r.C = eng->A; r.ldc = n_pad; r.c_off_z = nn;
-      r.tiles_m = rem - 1; r.tiles_n = rem - 1; r.tile_skip = TS_LOWER;
-      r.a = {(kb + 2) * TILE, kT, 0, 0, 0, 1};
-      r.b = r.a;
-      r.c_row0 = (kb + 2) * TILE; r.c_col0 = (kb + 2) * TILE;
-      GPO_CUDA_OK(cudaStreamWaitEvent(sb, ev(EV_PANEL, kb), 0));
-      if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapA, r, S, sb, bulk_ctas))) return rc;
-      GPO_CUDA_OK(cudaEventRecord(ev(EV_BULK, kb), sb));
-    }
-    // ---- critical chain: block column kb+1 (after the side stream's previous update of those tiles) ----
-    if (last_bulk >= 0) GPO_CUDA_OK(cudaStreamWaitEvent(st, ev(EV_BULK, last_bulk), 0));
-    if (rem >= 2) last_bulk = kb;
-    {
-      R128Params c = r128_defaults();
-      c.alpha = -1.0; c.beta = 1.0;
-      c.A = eng->A; c.lda = n_pad; c.a_z = nn; c.a_row0 = k1T; c.a_col0 = kT;
-      c.B = eng->A; c.ldb = n_pad; c.b_z = nn; c.b_row0 = k1T; c.b_col0 = kT;
-      c.C = eng->A; c.ldc = n_pad; c.c_z = nn; c.c_row0 = k1T; c.c_col0 = k1T;
-      c.tiles_m = rem * 2; c.tiles_n = 2; c.skip_upper = 1;
-      if ((rc = launch_r128<4, 4>(eng, c, S, st))) return rc;
+      t_begin("inv_new", kb, 2, sc);
+      if ((rc = launch_r128d(eng, b2, S, sc))) return rc;
+      t_end(sc);
     }
   }
-  // join the side streams (the last trailing update was waited for by the last block-column update)
+  // join the side streams
   GPO_CUDA_OK(cudaEventRecord(ev_sc, sc));
   GPO_CUDA_OK(cudaEventRecord(ev_se, se));
+  GPO_CUDA_OK(cudaEventRecord(ev_sn, sn));
+  GPO_CUDA_OK(cudaEventRecord(ev_sd, sd));
   GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_sc, 0));
   GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_se, 0));
-  if (last_bulk >= 0) GPO_CUDA_OK(cudaStreamWaitEvent(st, ev(EV_BULK, last_bulk), 0));
+  GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_sn, 0));
+  GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_sd, 0));
+  if (nb >= 3) GPO_CUDA_OK(cudaStreamWaitEvent(st, ev(EV_BULK, nb - 3), 0));
+  if (tracing) {
+    cudaEvent_t t_done;
+    cudaEventCreate(&t_done); cudaEventRecord(t_done, st);
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+    float total = 0.f;
+    cudaEventElapsedTime(&total, trace_t0, t_done);
+    fprintf(stderr, "{\"fit_trace\": \"n_pad=%d S=%d\", \"total_us\": %.1f}\n", n_pad, S, total * 1e3);
+    for (const TraceRec& r : trace) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, trace_t0, r.e0); cudaEventElapsedTime(&b, trace_t0, r.e1);
+      fprintf(stderr, "{\"k\": \"%s\", \"kb\": %d, \"stream\": %d, \"t0_us\": %.1f, \"t1_us\": %.1f}\n", r.name, r.kb, r.stream, a * 1e3, b * 1e3);
+      cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    cudaEventDestroy(trace_t0); cudaEventDestroy(t_done);
+  }
+  return GPO_OK;
+}
+
+// The ~200 launches and ~250 event operations of factorize_chain cost the host about as much time as the device needs to run
+// them; ML-II and HMC refit hundreds of times with the same shape.  The sequence is captured once per (shape, kernel, buffers)
+// into a CUDA graph (all five streams fork from and join the fit stream inside the capture) and replayed with one launch.
+// Everything that changes between refits -- hyper-parameters, jitter -- lives in device buffers the kernels read.
+static int factorize_chain_graph(gpo_engine* eng, cudaStream_t st) {
+  if (!eng->opt_fit_graph || eng->opt_fit_trace) return factorize_chain(eng, st);
+  const gpo_engine::FitGraphKey key = {eng->n_pad, eng->n, eng->d, eng->S, eng->kern, eng->A};
+  const gpo_engine::FitGraphKey& k0 = eng->fit_graph_key;
+  if (eng->fit_graph_exec && key.n_pad == k0.n_pad && key.n == k0.n && key.d == k0.d && key.S == k0.S && key.kern == k0.kern &&
+      key.A == k0.A) {
+    GPO_CUDA_OK(cudaGraphLaunch(eng->fit_graph_exec, st));
+    eng->launches += eng->fit_graph_launches;
+    return GPO_OK;
+  }
+  if (eng->fit_graph_exec) { cudaGraphExecDestroy(eng->fit_graph_exec); eng->fit_graph_exec = nullptr; }
+  const long long l0 = eng->launches;
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    eng->opt_fit_graph = 0;
+    return factorize_chain(eng, st);
+  }
+  const int rc = factorize_chain(eng, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != GPO_OK || ce != cudaSuccess || !graph) {   // no graph: run the plain sequence from now on
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    eng->opt_fit_graph = 0;
+    eng->launches = l0;
+    return factorize_chain(eng, st);
+  }
+  const cudaError_t ie = cudaGraphInstantiate(&eng->fit_graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) {
+    cudaGetLastError();
+    eng->fit_graph_exec = nullptr;
+    eng->opt_fit_graph = 0;
+    eng->launches = l0;
+    return factorize_chain(eng, st);
+  }
+  eng->fit_graph_key = key;
+  eng->fit_graph_launches = eng->launches - l0;
+  GPO_CUDA_OK(cudaGraphLaunch(eng->fit_graph_exec, st));
   return GPO_OK;
 }
 
@@ -976,7 +1122,9 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
   for (int attempt = 0; attempt <= 6; ++attempt) {
     memcpy(pin_jit, eng->h_jit.data(), (size_t)S * 8);   // (the previous attempt's copy has completed: it was synchronised)
     GPO_CUDA_OK(cudaMemcpyAsync(eng->jitter, pin_jit, (size_t)S * 8, cudaMemcpyHostToDevice, st));
-    if ((rc = (eng->opt_fit_path == 0 && n_pad >= 2 * TILE) ? factorize_chain(eng, st) : factorize(eng, st))) return rc;
+    // (from 32 block columns on the side work of the chain scheme -- all of it K = 128 products -- no longer fits under the chain:
+    // the look-ahead scheme with its long-K recursive inverse is faster there, 5.9 vs 6.9 ms at n = 4096)
+    if ((rc = (eng->opt_fit_path == 0 && n_pad >= 2 * TILE && n_pad < 32 * TILE) ? factorize_chain_graph(eng, st) : factorize(eng, st))) return rc;
     GPO_CUDA_OK(cudaMemcpyAsync(pin_info, eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
     // alpha = L^-T (L^-1 y)
     {
@@ -2083,6 +2231,8 @@ extern "C" int gpo_set_option(gpo_engine* eng, int key, long long value) {
     case GPO_OPT_FUSED_SMALL: eng->opt_fused_small = value != 0; break;
     case GPO_OPT_PREFETCH_KT: eng->opt_prefetch_kt = value != 0; break;
     case GPO_OPT_FIT_PATH: if (value < 0 || value > 1) return GPO_ERR_ARG; eng->opt_fit_path = (int)value; break;
+    case GPO_OPT_FIT_TRACE: eng->opt_fit_trace = value != 0; break;
+    case GPO_OPT_FIT_GRAPH: eng->opt_fit_graph = value != 0; break;
     default: GPO_FAIL(GPO_ERR_ARG, "gpo_set_option: unknown key %d", key);
   }
   return GPO_OK;

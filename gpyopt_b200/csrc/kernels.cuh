@@ -229,34 +229,72 @@ constexpr int DIAG_PITCH = TILE + 1;
 constexpr int DIAG_PB = 32;                       // inner panel width
 constexpr int DIAG_NP = TILE / DIAG_PB;           // 4 panels
 constexpr int DIAG_XD_PITCH = DIAG_PB + 1;
-constexpr int DIAG_SMEM_BYTES = (TILE * DIAG_PITCH + DIAG_NP * DIAG_PB * DIAG_XD_PITCH + TILE + 2 * DIAG_PB) * 8;
+constexpr int DIAG_SMEM_BYTES = (TILE * DIAG_PITCH + DIAG_NP * DIAG_PB * DIAG_XD_PITCH + TILE + DIAG_PB * DIAG_PB + 2) * 8;
+
+#ifndef GPO_VAR_FENCE
+#define GPO_VAR_FENCE 0
+#endif
+#ifndef GPO_VAR_RSQRT
+#define GPO_VAR_RSQRT 1
+#endif
+#ifndef GPO_VAR_SLEEP
+#define GPO_VAR_SLEEP 0
+#endif
+// 1 / sqrt(d) for a pivot in [2^-100, 2^99): single-precision MUFU seed (relative error ~2^-22) and one third-order step,
+// y (1 + e/2 + 3 e^2/8) with e = 1 - d y^2: relative error ~e^3 ~ 1e-20 before the final rounding.  Four dependent FP64
+// operations instead of the eight of rsqrt(double): the pivot chain of the diagonal-block kernel is a latency chain.
+__device__ __forceinline__ double rsqrt_pivot(double d) {
+  const double y = (double)rsqrtf((float)d);
+  const double t = d * y;
+  const double e = fma(-t, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  const double ye = y * e;
+  return fma(ye, p, y);
+}
 
 // Cholesky of the 32x32 diagonal block at S[j0.., j0..] by ONE warp, lane = row, the row in registers.  Per column:
-// broadcast of the pivot, 1/sqrt in every lane, the scaled column goes through a 32-entry shared buffer (double-buffered)
-// and comes back as 16-byte broadcast loads (one LDS.128 per two columns still to update; a shuffle version needs five
+// broadcast of the pivot, 1/sqrt in every lane, the scaled column goes to shared memory (cbuf[j][row], all 32 columns are
+// kept) and comes back as 16-byte broadcast loads (one LDS.128 per two columns still to update; a shuffle version needs five
 // instructions per column and is issue-bound).  The NEXT pivot does not wait for that round trip: its owner forms
 // a_(j+1,j+1) - l^2 from its own l, so the serial chain per column is shuffle -> rsqrt -> multiply -> fma.
-// Writes L (lower part) back and 1/L_jj to rd.  colbuf: 64 doubles, 16-byte aligned.
-__device__ __forceinline__ void chol32_warp(double* S, double* rd, double* colbuf, int j0, int lane, int* info_z, int col0) {
+// After column j is in cbuf (and 1 / L_jj in rd) the warp publishes *prog = j + 1: the other warps solve the rows below the
+// block and the block's inverse one column behind it (fwdsub32_trail) instead of after it.
+// Writes L (lower part) back and 1/L_jj to rd.  cbuf: 32 x 32 doubles, 16-byte aligned.
+__device__ __forceinline__ void chol32_warp(double* S, double* rd, double* cbuf, volatile int* prog, int j0, int lane, int* info_z,
+                                            int col0) {
   double a[DIAG_PB];
 #pragma unroll
   for (int k = 0; k < DIAG_PB; ++k) a[k] = (k <= lane) ? S[(j0 + lane) * DIAG_PITCH + j0 + k] : 0.0;
   double dd = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
   for (int j = 0; j < DIAG_PB; ++j) {
-    if (!(dd > 0.0)) {  // uniform: dd is a broadcast
-      if (lane == j && *info_z == 0) *info_z = col0 + j0 + j + 1;
-      dd = 1.0;
+#if GPO_VAR_RSQRT
+    double rp = rsqrt_pivot(dd);
+#else
+    double rp = rsqrt(dd);
+#endif
+    // exponent check on the high word (integer pipe, off the FP64 chain): false for <= 0, NaN, tiny and huge pivots
+    if (!((unsigned)(__double2hiint(dd) - 0x39B00000) < (unsigned)(0x46300000 - 0x39B00000))) {  // uniform: dd is a broadcast
+      if (!(dd > 0.0)) {
+        if (lane == j && *info_z == 0) *info_z = col0 + j0 + j + 1;
+        dd = 1.0;
+      }
+      rp = rsqrt(dd);
     }
-    const double rp = rsqrt(dd);
     const double l = (lane > j) ? a[j] * rp : (lane == j ? dd * rp : 0.0);  // as LAPACK dpotf2: scale by the reciprocal pivot
     a[j] = l;
     if (lane == j) rd[j0 + j] = rp;
     if (j < DIAG_PB - 1) {
       dd = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);   // next pivot, from its owner's own l
-      double* cb = colbuf + (j & 1) * DIAG_PB;
+      double* cb = cbuf + j * DIAG_PB;
       cb[lane] = l;
       __syncwarp();
+      if (lane == 0) {
+#if GPO_VAR_FENCE
+        __threadfence_block();
+#endif
+        *prog = j + 1;
+      }
       if (((j + 1) & 1) != 0) a[j + 1] = fma(-l, cb[j + 1], a[j + 1]);   // odd first column: single load
 #pragma unroll
       for (int k = (j + 2) & ~1; k < DIAG_PB; k += 2) {
@@ -264,11 +302,39 @@ __device__ __forceinline__ void chol32_warp(double* S, double* rd, double* colbu
         a[k] = fma(-l, lk.x, a[k]);   // lanes below k carry unused values in a[k]
         a[k + 1] = fma(-l, lk.y, a[k + 1]);
       }
+    } else {
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        *prog = DIAG_PB;
+      }
     }
   }
 #pragma unroll
   for (int k = 0; k < DIAG_PB; ++k)
     if (k <= lane) S[(j0 + lane) * DIAG_PITCH + j0 + k] = a[k];
+}
+
+// fwdsub32 (below) against the block chol32_warp is still factoring: column c of L is read from cbuf as soon as *prog > c.
+// Same operations on the same numbers as fwdsub32 after the fact.
+__device__ __forceinline__ void fwdsub32_trail(double* vec, int sv, const double* cbuf, const double* rdp, const volatile int* prog) {
+  double v[DIAG_PB];
+#pragma unroll
+  for (int c = 0; c < DIAG_PB; ++c) v[c] = vec[c * sv];
+#pragma unroll
+  for (int c = 0; c < DIAG_PB; ++c) {
+    while (*prog <= c) {
+#if GPO_VAR_SLEEP
+      __nanosleep(GPO_VAR_SLEEP);
+#endif
+    }
+    __threadfence_block();
+    v[c] *= rdp[c];
+#pragma unroll
+    for (int c2 = c + 1; c2 < DIAG_PB; ++c2) v[c2] = fma(-v[c], cbuf[c * DIAG_PB + c2], v[c2]);
+  }
+#pragma unroll
+  for (int c = 0; c < DIAG_PB; ++c) vec[c * sv] = v[c];
 }
 
 // Forward substitution L x = v with a 32x32 lower-triangular block (rdp = 1 / diagonal), v in shared memory with stride
@@ -367,19 +433,31 @@ __device__ __forceinline__ void diag_rhs_update(double (&r)[8][8], const double*
 // The eight stages run through ONE loop body so that chol32_warp and fwdsub32 exist once in the instruction stream.
 // Only the first n_valid = clamp(n - 128 kb, 0, 128) rows are real data; the rest is identity padding for which every
 // step is a no-op, so panels at or beyond n_valid are skipped.
+// stage timestamps for tools/microbench/refit_time.cu (compiled in only there)
+#ifdef GPO_DIAG_TIMING
+__device__ long long g_diag_t[64];
+#define DIAG_T(i) do { if (tid == 0 && blockIdx.x == 0) g_diag_t[i] = clock64(); } while (0)
+#else
+#define DIAG_T(i) do { } while (0)
+#endif
 // mode 0: both phases.  mode 1 (critical chain of the refit): Cholesky + the four diagonal 32 x 32 inverses only -- L to A,
 // the inverses into the diagonal 32-blocks of X (what trsm_panel_kernel needs), 1 / L_jj to rdiag.  mode 2 (side stream): the
 // inverse from the L and rdiag that mode 1 left: same instructions on the same numbers, X and U bit-identical to mode 0.
-__global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, double* X, double* U, int n_pad, int kb,
-                                                                     int n_valid, int* info, int mode, double* rdiag) {
-  extern __shared__ double sm[];
+// The block to factor is read from src (row pitch src_ld; only its lower triangle): the matrix itself for the stand-alone
+// kernel, the chain kernel's freshly updated copy otherwise (SRC_CG: written by other CTAs of the same launch, so the loads
+// bypass L1).
+template <bool SRC_CG>
+__device__ __forceinline__ void diag_chol_inv_body(double* sm, const double* src, long long src_ld, double* A, double* X, double* U,
+                                                   int n_pad, int kb, int n_valid, int* info, int mode, double* rdiag, int z) {
   double* S = sm;                                        // [128][129]  lower: L;  strict upper: X^T (off-diagonal blocks)
   double* XD = sm + TILE * DIAG_PITCH;                   // [4][32][33] inverses of the diagonal 32x32 blocks
   double* rd = XD + DIAG_NP * DIAG_PB * DIAG_XD_PITCH;   // [128]       1 / L_jj
-  double* colbuf = rd + TILE;                            // [2][32]     chol32_warp's column broadcast (16-byte aligned)
-  const int z = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* cbuf = rd + TILE;                              // [32][32]    chol32_warp's columns (16-byte aligned)
+  volatile int* prog = reinterpret_cast<volatile int*>(cbuf + DIAG_PB * DIAG_PB);   // columns of the current block in cbuf
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ty = tid >> 4, tx = tid & 15;
   const long long base = ((long long)z * n_pad + (long long)kb * TILE) * n_pad + (long long)kb * TILE;
+  DIAG_T(63);
   double r[8][8];
   if (mode != 2) {
 #pragma unroll
@@ -387,7 +465,8 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
 #pragma unroll
       for (int b = 0; b < 8; ++b) {
         const int i = ty + 16 * a, k = tx + 16 * b;
-        r[a][b] = A[base + (long long)(k <= i ? i : k) * n_pad + (k <= i ? k : i)];  // symmetric fill from the lower part
+        const double* ps = src + (long long)(k <= i ? i : k) * src_ld + (k <= i ? k : i);  // symmetric fill from the lower part
+        r[a][b] = SRC_CG ? __ldcg(ps) : *ps;
         if (k > i) S[i * DIAG_PITCH + k] = 0.0;
       }
     if (tid < TILE) rd[tid] = 1.0;
@@ -400,6 +479,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
     __syncthreads();
   }
   const int s_begin = mode == 2 ? 4 : 0, s_end = mode == 1 ? 5 : 8;
+  DIAG_T(0);
 
   // stages 0..3: Cholesky panel p = s;  stage 4: L out + diagonal-block inverses;  stages 5..7: block row p = s - 4 of X
 #pragma unroll 1
@@ -416,20 +496,32 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
       else if (p == 1) diag_store_block_column<1>(r, S, ty, tx);
       else if (p == 2) diag_store_block_column<2>(r, S, ty, tx);
       else diag_store_block_column<3>(r, S, ty, tx);
+      if (tid == 0) *prog = 0;
+      if (warp == 5) {                                   // unit right-hand sides of this block's inverse (L_pp x = e_c)
+#pragma unroll 4
+        for (int i = 0; i < DIAG_PB; ++i) XD[p * DIAG_PB * DIAG_XD_PITCH + i * DIAG_XD_PITCH + lane] = (i == lane) ? 1.0 : 0.0;
+      }
       __syncthreads();
-      if (live && warp == 0) chol32_warp(S, rd, colbuf, j0, lane, info + z, kb * TILE);
-      __syncthreads();
-      const int i = j0 + DIAG_PB + tid;                  // rows below the diagonal block: l L11^T = a
-      solve = live && p < DIAG_NP - 1 && i < n_valid;    // (rows of the identity padding hold zeros already)
-      vec = S + i * DIAG_PITCH + j0;
+      DIAG_T(1 + 4 * s);
+      if (live) {
+        // warp 0 factors the diagonal 32 x 32 block; one column behind it warps 1-3 solve the rows below (thread = row:
+        // l L_pp^T = a; rows of the identity padding hold zeros already) and warp 5 the columns of L_pp^-1
+        if (warp == 0) chol32_warp(S, rd, cbuf, prog, j0, lane, info + z, kb * TILE);
+        else if (warp <= 3) {
+          const int i = j0 + DIAG_PB + tid - 32;
+          if (p < DIAG_NP - 1 && i < n_valid) fwdsub32_trail(S + i * DIAG_PITCH + j0, 1, cbuf, rdp, prog);
+        } else if (warp == 5) {
+          fwdsub32_trail(XD + p * DIAG_PB * DIAG_XD_PITCH + lane, DIAG_XD_PITCH, cbuf, rdp, prog);
+        }
+      }
+      DIAG_T(2 + 4 * s);
     } else if (s == 4) {
       if (mode != 2) {
         for (int e = tid; e < TILE * TILE; e += DIAG_THREADS) {  // L to global memory (coalesced rows)
           const int i = e >> 7, k = e & (TILE - 1);
           A[base + (long long)i * n_pad + k] = (k <= i) ? S[i * DIAG_PITCH + k] : 0.0;
         }
-      }
-      if (tid < TILE) {                                  // thread = (diagonal block w, column c): L_ww x = e_c
+      } else if (tid < TILE) {                           // thread = (diagonal block w, column c): L_ww x = e_c
         const int w = tid >> 5;
         vec = XD + w * DIAG_PB * DIAG_XD_PITCH + lane;
         sv = DIAG_XD_PITCH;
@@ -451,6 +543,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
     }
     if (solve) fwdsub32(vec, sv, Lb, rdp);
     __syncthreads();
+    DIAG_T(3 + 4 * s);
     if (s < 3) {
       if (live) {
         if (p == 0) diag_syrk_update<0>(r, S, ty, tx);
@@ -468,8 +561,10 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
       if (p == 1) diag_rhs_update<1>(r, S, XDp, ty, tx);
       else if (p == 2) diag_rhs_update<2>(r, S, XDp, ty, tx);
     }
+    DIAG_T(4 + 4 * s);
   }
   __syncthreads();
+  DIAG_T(40);
   if (mode == 1) {   // the diagonal 32 x 32 inverses (final entries of X) and the reciprocal pivots; the rest follows in mode 2
     for (int e = tid; e < DIAG_NP * DIAG_PB * DIAG_PB; e += DIAG_THREADS) {
       const int w = e >> 10, i = (e >> 5) & 31, c = e & 31;
@@ -477,6 +572,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
           (c <= i) ? XD[w * DIAG_PB * DIAG_XD_PITCH + i * DIAG_XD_PITCH + c] : 0.0;
     }
     if (tid < TILE) rdiag[(long long)z * n_pad + kb * TILE + tid] = rd[tid];
+    DIAG_T(41);
     return;
   }
   // X (lower) and U = X^T (upper), coalesced rows
@@ -488,6 +584,15 @@ __global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, 
     if (mode == 0 || !same) X[base + (long long)i * n_pad + c] = (c <= i) ? x : 0.0;   // (mode 2: the panel may be reading them)
     U[base + (long long)i * n_pad + c] = (c >= i) ? x : 0.0;
   }
+  DIAG_T(41);
+}
+
+__global__ void __launch_bounds__(DIAG_THREADS) diag_chol_inv_kernel(double* A, double* X, double* U, int n_pad, int kb,
+                                                                     int n_valid, int* info, int mode, double* rdiag) {
+  extern __shared__ double sm[];
+  const int z = blockIdx.x;
+  const long long base = ((long long)z * n_pad + (long long)kb * TILE) * n_pad + (long long)kb * TILE;
+  diag_chol_inv_body<false>(sm, A + base, n_pad, A, X, U, n_pad, kb, n_valid, info, mode, rdiag, z);
 }
 
 // out[z][r] = sum_{k in [lo(r), hi(r))} M[z][r][k] * v[z][k]; mode 0: k <= r (lower), 1: k >= r (upper), 2: full

@@ -716,6 +716,21 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
 // Every tile receives its updates in the order kb = 0, 1, 2, ... with fixed summation order inside every kernel: the
 // state is bit-reproducible and independent of how the streams interleave.
 // --------------------------------------------------------------------------------------------------
+// alpha = L^-T (L^-1 y) and the per-set scalars of the log-likelihood, enqueued on st (needs L, L^-1, L^-T; not W^-1)
+static int launch_alpha(gpo_engine* eng, cudaStream_t st) {
+  const int n_pad = eng->n_pad, S = eng->S;
+  dim3 grd((n_pad + 7) / 8, S);
+  for (int z = 0; z < S; ++z)  // Y is shared by all hyper-parameter sets
+    GPO_CUDA_OK(cudaMemcpyAsync(eng->alpha + (size_t)z * n_pad, eng->Y, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, st));
+  gemv_kernel<<<grd, 256, 0, st>>>(eng->X, eng->alpha, eng->tmpv, n_pad, 0);
+  gemv_kernel<<<grd, 256, 0, st>>>(eng->U, eng->tmpv, eng->alpha, n_pad, 1);
+  fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, nullptr, eng->nc_ld, eng->js, eng->n, n_pad, eng->logdet,
+                                        eng->quad, eng->fmin);
+  eng->launches += 3;
+  GPO_CUDA_OK(cudaGetLastError());
+  return GPO_OK;
+}
+
 static R128Params r128_defaults() {
   R128Params p;
   memset(&p, 0, sizeof(p));
@@ -802,9 +817,10 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
         GPO_CUDA_OK(cudaStreamWaitEvent(st, ev(EV_BULK, kb - 2), 0));
       }
       t_begin("chain", kb, 0, st);
+      // (the last block column has no panel waiting for it: its CTA 0 goes on to the inverse of the diagonal block)
       chol_chain_kernel<<<CHAIN_CTAS * S, DIAG_THREADS, CHAIN_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info,
                                                                                 eng->rdiag, raw[kb & 1], Pg, Tg,
-                                                                                eng->chain_flags + (size_t)kb * 2 * S);
+                                                                                eng->chain_flags + (size_t)kb * 2 * S, rem == 0 ? 0 : 1);
       t_end(st);
     }
     eng->launches++;
@@ -812,10 +828,12 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
     GPO_CUDA_OK(cudaEventRecord(ev(EV_CHOL, kb), st));
     // ---- side: X_kk = L_kk^-1, U_kk ----
     GPO_CUDA_OK(cudaStreamWaitEvent(sd, ev(EV_CHOL, kb), 0));
-    t_begin("inv128", kb, 3, sd);
-    diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, sd>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info, 2, eng->rdiag);
-    t_end(sd);
-    eng->launches++;
+    if (!(rem == 0 && kb > 0)) {
+      t_begin("inv128", kb, 3, sd);
+      diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, sd>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info, 2, eng->rdiag);
+      t_end(sd);
+      eng->launches++;
+    }
     GPO_CUDA_OK(cudaEventRecord(ev(EV_INV, kb), sd));
     // ---- right behind the chain: the panel below block kb, then block column kb+1 below its diagonal block (the chain kernel
     //      of block column kb+2 waits for these; they have the whole chain kernel of kb+1 to finish) ----
@@ -913,10 +931,13 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
   GPO_CUDA_OK(cudaEventRecord(ev_sn, sn));
   GPO_CUDA_OK(cudaEventRecord(ev_sd, sd));
   GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_sc, 0));
-  GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_se, 0));
   GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_sn, 0));
   GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_sd, 0));
   if (nb >= 3) GPO_CUDA_OK(cudaStreamWaitEvent(st, ev(EV_BULK, nb - 3), 0));
+  t_begin("alpha", nb - 1, 0, st);
+  if ((rc = launch_alpha(eng, st))) return rc;   // L, L^-1, L^-T are complete; the last block row of W^-1 is still accumulating
+  t_end(st);
+  GPO_CUDA_OK(cudaStreamWaitEvent(st, ev_se, 0));
   if (tracing) {
     cudaEvent_t t_done;
     cudaEventCreate(&t_done); cudaEventRecord(t_done, st);
@@ -1124,22 +1145,12 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
     GPO_CUDA_OK(cudaMemcpyAsync(eng->jitter, pin_jit, (size_t)S * 8, cudaMemcpyHostToDevice, st));
     // (from 32 block columns on the side work of the chain scheme -- all of it K = 128 products -- no longer fits under the chain:
     // the look-ahead scheme with its long-K recursive inverse is faster there, 5.9 vs 6.9 ms at n = 4096)
-    if ((rc = (eng->opt_fit_path == 0 && n_pad >= 2 * TILE && n_pad < 32 * TILE) ? factorize_chain_graph(eng, st) : factorize(eng, st))) return rc;
+    const bool chain_path = eng->opt_fit_path == 0 && n_pad >= 2 * TILE && n_pad < 32 * TILE;
+    if ((rc = chain_path ? factorize_chain_graph(eng, st) : factorize(eng, st))) return rc;
     GPO_CUDA_OK(cudaMemcpyAsync(pin_info, eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
-    // alpha = L^-T (L^-1 y)
-    {
-      dim3 grd((n_pad + 7) / 8, S);
-      for (int z = 0; z < S; ++z)  // Y is shared by all hyper-parameter sets
-        GPO_CUDA_OK(cudaMemcpyAsync(eng->alpha + (size_t)z * n_pad, eng->Y, (size_t)n_pad * 8, cudaMemcpyDeviceToDevice, st));
-      gemv_kernel<<<grd, 256, 0, st>>>(eng->X, eng->alpha, eng->tmpv, n_pad, 0);
-      gemv_kernel<<<grd, 256, 0, st>>>(eng->U, eng->tmpv, eng->alpha, n_pad, 1);
-      fit_scalars_kernel<<<S, 256, 0, st>>>(eng->A, eng->alpha, eng->Y, nullptr, eng->nc_ld, eng->js, n, n_pad, eng->logdet,
-                                            eng->quad, eng->fmin);
-      eng->launches += 3;
-      GPO_CUDA_OK(cudaGetLastError());
-      GPO_CUDA_OK(cudaMemcpyAsync(pin_logdet, eng->logdet, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
-      GPO_CUDA_OK(cudaMemcpyAsync(pin_quad, eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
-    }
+    if (!chain_path && (rc = launch_alpha(eng, st))) return rc;   // (the chain path enqueues it itself, under the tail of W^-1)
+    GPO_CUDA_OK(cudaMemcpyAsync(pin_logdet, eng->logdet, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
+    GPO_CUDA_OK(cudaMemcpyAsync(pin_quad, eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
     GPO_CUDA_OK(cudaStreamSynchronize(st));
     memcpy(eng->h_info.data(), pin_info, S * sizeof(int));
     memcpy(eng->h_logdet.data(), pin_logdet, (size_t)S * 8);

@@ -429,7 +429,8 @@ __global__ void __launch_bounds__(256) trsm_panel_kernel(double* A, const double
 //   A  CTA r solves rows 16 r .. 16 r + 15 of the first panel block, P = Raw L^-T with L = L_(kb-1,kb-1)  (trsm_strip, the same
 //      bits the panel kernel writes into the matrix), and publishes them in Pg
 //   B  it then forms its rows of the updated diagonal block, T = A_kk - P P^T (lower part), and publishes them in Tg
-//   C  CTA 0 factors T (diag_chol_inv_body, mode 1): L_kk, the diagonal 32 x 32 inverses, the reciprocal pivots
+//   C  CTA 0 factors T (diag_chol_inv_body, mode 1: L_kk, the diagonal 32 x 32 inverses, the reciprocal pivots; mode 0 for the
+//      last block column: the 128 x 128 inverse as well)
 // `Raw` is the tile (kb, kb-1) as the previous updates left it (dense [128][128] copy made by whoever wrote it last: the panel
 // kernel overwrites the matrix's own tile concurrently).  Nothing else of the matrix is written.  A CTA that is scheduled late
 // only delays the others (they spin); every CTA of the launch is eventually resident, so the waits terminate.
@@ -512,7 +513,7 @@ __device__ __forceinline__ void chain_syrk_rows(const double* Pl, const double* 
 #endif
 __global__ void __launch_bounds__(DIAG_THREADS) chol_chain_kernel(double* A, double* X, double* U, int n_pad, int kb, int n_valid,
                                                                   int* info, double* rdiag, const double* Raw, double* Pg,
-                                                                  double* Tg, int* flags) {
+                                                                  double* Tg, int* flags, int mode) {
   constexpr int LP = R128_LP;
   extern __shared__ __align__(16) double chain_sm[];
   double* sm = chain_sm;
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(DIAG_THREADS) chol_chain_kernel(double* A, dou
   }
   CHAIN_T(7);
   // ---- C: CTA 0 factors the updated block ----
-  diag_chol_inv_body<true>(sm, Tz, TILE, A, X, U, n_pad, kb, n_valid, info, 1, rdiag, z);
+  diag_chol_inv_body<true>(sm, Tz, TILE, A, X, U, n_pad, kb, n_valid, info, mode, rdiag, z);
 }
 
 // dense [128][128] copy of tile (row_block, col_block) of every batch: the first chain kernel's `Raw`

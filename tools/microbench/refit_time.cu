@@ -89,7 +89,7 @@ int main(int argc, char** argv) {
       tile_copy_kernel<<<dim3(16, 1), 256, 0, st>>>(A, raw, n_pad, 1, 0);
       CK(cudaMemsetAsync(flags, 0, 8, st));
       CK(cudaEventRecord(e0, st));
-      chol_chain_kernel<<<CHAIN_CTAS, DIAG_THREADS, CHAIN_SMEM_BYTES, st>>>(A, X, U, n_pad, 1, TILE, info, rdiag, raw, Pg, Tg, flags);
+      chol_chain_kernel<<<CHAIN_CTAS, DIAG_THREADS, CHAIN_SMEM_BYTES, st>>>(A, X, U, n_pad, 1, TILE, info, rdiag, raw, Pg, Tg, flags, 1);
       CK(cudaEventRecord(e1, st)); CK(cudaStreamSynchronize(st));
       float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = fminf(best, ms);
     }

@@ -122,6 +122,8 @@ struct gpo_engine {
   long long fit_graph_launches = 0;
   int opt_fit_trace = 0;    // measurement aid: time every launch of factorize_chain with events and print the timeline to stderr
   int opt_fit_path = 0;     // refit: 0 short critical chain (factorize_chain), 1 the round-1 look-ahead scheme (factorize)
+  int prio_chain = 0, prio_diag = 0, prio_inv = 0, prio_bulk = 0, prio_w = 0;   // launch priorities of the refit's streams (gpo_create)
+  int opt_fit_chain_max = 1 << 20;   // largest number of 128-blocks the short-chain refit takes (above: the look-ahead scheme)
   std::vector<cudaEvent_t> fit_ev;   // events of factorize_chain (6 per block column + 4)
   cudaStream_t fit_side[4] = {nullptr, nullptr, nullptr, nullptr};   // its side streams: inverse steps, diagonal-block inverses, W^-1,
                                                                      // panel + next block column (high priority like the chain)
@@ -296,20 +298,24 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
   eng->device = device;
   eng->sm_count = prop.multiProcessorCount;
   if (cudaSetDevice(device) != cudaSuccess) { delete eng; return GPO_ERR_CUDA; }
-  for (int i = 0; i < 2; ++i) {
-    cudaStreamCreateWithFlags(&eng->slot[i].stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&eng->slot[i].done, cudaEventDisableTiming);
-  }
-  {  // the refit's critical chain runs on the fit stream: its CTAs go first whenever SMs free up
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    cudaStreamCreateWithPriority(&eng->fit_stream, cudaStreamNonBlocking, prio_hi);
-  }
-  for (int i = 0; i < 3; ++i) cudaStreamCreateWithFlags(&eng->fit_side[i], cudaStreamNonBlocking);
   {
+    // Stream priorities order the refit's side work when kernels of several streams wait for SMs: the critical chain (fit stream,
+    // panel stream) first, then the 128 x 128 diagonal inverses, the forward-substitution chain of the inverse (three dependent
+    // launches per block column: a w_acc launch of ~2000 CTAs queued ahead of them used to hold a 4-CTA step back for 100 us),
+    // the trailing update, and last the W^-1 accumulation, which nothing waits for.  Results do not depend on the order.
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    cudaStreamCreateWithPriority(&eng->fit_side[3], cudaStreamNonBlocking, prio_hi);
+    auto prio = [&](int level) { return std::min(prio_lo, prio_hi + level); };   // level 0 = highest
+    for (int i = 0; i < 2; ++i) {
+      cudaStreamCreateWithPriority(&eng->slot[i].stream, cudaStreamNonBlocking, prio(3));   // sweeps; slot[0]: trailing update
+      cudaEventCreateWithFlags(&eng->slot[i].done, cudaEventDisableTiming);
+    }
+    cudaStreamCreateWithPriority(&eng->fit_stream, cudaStreamNonBlocking, prio(0));
+    cudaStreamCreateWithPriority(&eng->fit_side[3], cudaStreamNonBlocking, prio(0));       // panel + next block column
+    cudaStreamCreateWithPriority(&eng->fit_side[1], cudaStreamNonBlocking, prio(1));       // diagonal 128 x 128 inverses
+    cudaStreamCreateWithPriority(&eng->fit_side[0], cudaStreamNonBlocking, prio(2));       // forward substitution L X = I
+    cudaStreamCreateWithPriority(&eng->fit_side[2], cudaStreamNonBlocking, prio(4));       // W^-1 accumulation
+    eng->prio_chain = prio(0); eng->prio_diag = prio(1); eng->prio_inv = prio(2); eng->prio_bulk = prio(3); eng->prio_w = prio(4);
   }
   cudaEventCreateWithFlags(&eng->ev_in, cudaEventDisableTiming);
   int rc = gemm_setup(eng);
@@ -737,20 +743,32 @@ static R128Params r128_defaults() {
   p.alpha = 1.0;
   return p;
 }
+// Launch with an explicit priority attribute: a kernel node captured into the refit's CUDA graph keeps it (the priority of the
+// stream it was captured from is not guaranteed to carry over into the graph).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_prio(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int prio, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributePriority;
+  at[0].val.priority = prio;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 template <int MI, int NJ>
-static int launch_r128(gpo_engine* eng, const R128Params& p, int S, cudaStream_t st) {
+static int launch_r128(gpo_engine* eng, const R128Params& p, int S, cudaStream_t st, int prio) {
   dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)S, 1);
-  rank128_kernel<MI, NJ><<<grid, 256, rank128_smem_bytes<MI, NJ>(), st>>>(p);
+  GPO_CUDA_OK(launch_prio(rank128_kernel<MI, NJ>, grid, dim3(256), rank128_smem_bytes<MI, NJ>(), st, prio, p));
   eng->launches++;
-  GPO_CUDA_OK(cudaGetLastError());
   return GPO_OK;
 }
 
-static int launch_r128d(gpo_engine* eng, const R128Params& p, int S, cudaStream_t st) {   // 64 x 64 tiles on the tensor pipe
+static int launch_r128d(gpo_engine* eng, const R128Params& p, int S, cudaStream_t st, int prio) {   // 64 x 64 tiles on the tensor pipe
   dim3 grid((unsigned)(p.tiles_m * p.tiles_n), (unsigned)S, 1);
-  rank128_dmma_kernel<<<grid, 128, RD_SMEM_BYTES, st>>>(p);
+  GPO_CUDA_OK(launch_prio(rank128_dmma_kernel, grid, dim3(128), RD_SMEM_BYTES, st, prio, p));
   eng->launches++;
-  GPO_CUDA_OK(cudaGetLastError());
   return GPO_OK;
 }
 
@@ -806,10 +824,11 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
     const int n_valid = std::max(0, std::min(TILE, eng->n - kT));
     // ---- critical chain: block column kb in one launch ----
     if (kb == 0) {
-      tile_copy_kernel<<<dim3(16, (unsigned)S), 256, 0, st>>>(eng->A, raw[1], n_pad, 1, 0);   // tile (1, 0) before the panel overwrites it
+      GPO_CUDA_OK(launch_prio(tile_copy_kernel, dim3(16, (unsigned)S), dim3(256), 0, st, eng->prio_chain, eng->A, raw[1], n_pad, 1, 0));   // tile (1, 0) before the panel overwrites it
       eng->launches++;
       t_begin("chol", kb, 0, st);
-      diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info, 1, eng->rdiag);
+      GPO_CUDA_OK(launch_prio(diag_chol_inv_kernel, dim3(S), dim3(DIAG_THREADS), DIAG_SMEM_BYTES, st, eng->prio_chain, eng->A, eng->X, eng->U, n_pad, kb,
+                              n_valid, eng->info, 1, eng->rdiag));
       t_end(st);
     } else {
       if (kb >= 2) {   // tile (kb, kb-1) and tile (kb, kb) carry the updates of the panels up to kb-2
@@ -818,9 +837,9 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
       }
       t_begin("chain", kb, 0, st);
       // (the last block column has no panel waiting for it: its CTA 0 goes on to the inverse of the diagonal block)
-      chol_chain_kernel<<<CHAIN_CTAS * S, DIAG_THREADS, CHAIN_SMEM_BYTES, st>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info,
-                                                                                eng->rdiag, raw[kb & 1], Pg, Tg,
-                                                                                eng->chain_flags + (size_t)kb * 2 * S, rem == 0 ? 0 : 1);
+      GPO_CUDA_OK(launch_prio(chol_chain_kernel, dim3(CHAIN_CTAS * S), dim3(DIAG_THREADS), CHAIN_SMEM_BYTES, st, eng->prio_chain, eng->A, eng->X,
+                              eng->U, n_pad, kb, n_valid, eng->info, eng->rdiag, raw[kb & 1], Pg, Tg,
+                              eng->chain_flags + (size_t)kb * 2 * S, rem == 0 ? 0 : 1));
       t_end(st);
     }
     eng->launches++;
@@ -830,7 +849,8 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
     GPO_CUDA_OK(cudaStreamWaitEvent(sd, ev(EV_CHOL, kb), 0));
     if (!(rem == 0 && kb > 0)) {
       t_begin("inv128", kb, 3, sd);
-      diag_chol_inv_kernel<<<S, DIAG_THREADS, DIAG_SMEM_BYTES, sd>>>(eng->A, eng->X, eng->U, n_pad, kb, n_valid, eng->info, 2, eng->rdiag);
+      GPO_CUDA_OK(launch_prio(diag_chol_inv_kernel, dim3(S), dim3(DIAG_THREADS), DIAG_SMEM_BYTES, sd, eng->prio_diag, eng->A, eng->X, eng->U, n_pad, kb,
+                              n_valid, eng->info, 2, eng->rdiag));
       t_end(sd);
       eng->launches++;
     }
@@ -840,7 +860,8 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
     if (rem > 0) {
       GPO_CUDA_OK(cudaStreamWaitEvent(sn, ev(EV_CHOL, kb), 0));
       t_begin("trsm", kb, 5, sn);
-      trsm_panel_kernel<<<dim3((unsigned)(rem * (TILE / TRSM_RS)), (unsigned)S), 256, TRSM_SMEM_BYTES, sn>>>(eng->A, eng->X, n_pad, kb, kb + 1);
+      GPO_CUDA_OK(launch_prio(trsm_panel_kernel, dim3((unsigned)(rem * (TILE / TRSM_RS)), (unsigned)S), dim3(256), TRSM_SMEM_BYTES, sn, eng->prio_chain,
+                              eng->A, eng->X, n_pad, kb, kb + 1));
       t_end(sn);
       eng->launches++;
       GPO_CUDA_OK(cudaGetLastError());
@@ -855,7 +876,7 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
         c.tiles_m = (rem - 1) * 2; c.tiles_n = 2;
         c.C2 = raw[(kb + 2) & 1]; c.c2_z = tt;    // tile (kb+2, kb+1): what the chain kernel of kb+2 solves
         t_begin("colupd", kb, 5, sn);
-        if ((rc = launch_r128d(eng, c, S, sn))) return rc;
+        if ((rc = launch_r128d(eng, c, S, sn, eng->prio_chain))) return rc;
         t_end(sn);
         GPO_CUDA_OK(cudaEventRecord(ev(EV_NEXT, kb), sn));
         // ---- side: trailing update of block columns >= kb+2 (lower 64 x 64 tiles) ----
@@ -867,7 +888,7 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
         r.tiles_m = (rem - 1) * 2; r.tiles_n = (rem - 1) * 2; r.skip_upper = 1;
         GPO_CUDA_OK(cudaStreamWaitEvent(sb, ev(EV_PANEL, kb), 0));
         t_begin("bulk", kb, 1, sb);
-        if ((rc = launch_r128d(eng, r, S, sb))) return rc;
+        if ((rc = launch_r128d(eng, r, S, sb, eng->prio_bulk))) return rc;
         t_end(sb);
         GPO_CUDA_OK(cudaEventRecord(ev(EV_BULK, kb), sb));
       }
@@ -882,7 +903,7 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
       f.Ct = eng->U; f.ldct = n_pad; f.ct_z = nn; f.ct_row0 = 0; f.ct_col0 = kT;
       f.tiles_m = 1; f.tiles_n = kb * (TILE / 32);
       t_begin("inv_row", kb, 2, sc);
-      if ((rc = launch_r128<8, 2>(eng, f, S, sc))) return rc;
+      if ((rc = launch_r128<8, 2>(eng, f, S, sc, eng->prio_inv))) return rc;
       t_end(sc);
     }
     GPO_CUDA_OK(cudaEventRecord(ev(EV_ROW, kb), sc));
@@ -897,7 +918,7 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
       if (rem == 0) { w.Ct = eng->W; w.ldct = n_pad; w.ct_z = nn; }
       w.tiles_m = (kb + 1) * 2; w.tiles_n = (kb + 1) * 2; w.skip_upper = 1;
       t_begin("w_acc", kb, 4, se);
-      if ((rc = launch_r128d(eng, w, S, se))) return rc;
+      if ((rc = launch_r128d(eng, w, S, se, eng->prio_w))) return rc;
       t_end(se);
     }
     if (rem == 0) break;
@@ -915,13 +936,13 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
         R128Params a2 = u;
         a2.b_row0 = 0; a2.c_col0 = 0; a2.ct_row0 = 0; a2.beta = 1.0; a2.tiles_n = kb * 2;
         t_begin("inv_upd", kb, 2, sc);
-        if ((rc = launch_r128d(eng, a2, S, sc))) return rc;
+        if ((rc = launch_r128d(eng, a2, S, sc, eng->prio_inv))) return rc;
         t_end(sc);
       }
       R128Params b2 = u;   // R[i, kb] = -L[i, kb] X_kk
       b2.b_row0 = kT; b2.c_col0 = kT; b2.ct_row0 = kT; b2.beta = 0.0; b2.tiles_n = 2;
       t_begin("inv_new", kb, 2, sc);
-      if ((rc = launch_r128d(eng, b2, S, sc))) return rc;
+      if ((rc = launch_r128d(eng, b2, S, sc, eng->prio_inv))) return rc;
       t_end(sc);
     }
   }
@@ -987,7 +1008,8 @@ static int factorize_chain_graph(gpo_engine* eng, cudaStream_t st) {
     eng->launches = l0;
     return factorize_chain(eng, st);
   }
-  const cudaError_t ie = cudaGraphInstantiate(&eng->fit_graph_exec, graph, 0);
+  // (without this flag every node runs at the priority of the stream the graph is launched into)
+  const cudaError_t ie = cudaGraphInstantiateWithFlags(&eng->fit_graph_exec, graph, cudaGraphInstantiateFlagUseNodePriority);
   cudaGraphDestroy(graph);
   if (ie != cudaSuccess) {
     cudaGetLastError();
@@ -1143,9 +1165,9 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
   for (int attempt = 0; attempt <= 6; ++attempt) {
     memcpy(pin_jit, eng->h_jit.data(), (size_t)S * 8);   // (the previous attempt's copy has completed: it was synchronised)
     GPO_CUDA_OK(cudaMemcpyAsync(eng->jitter, pin_jit, (size_t)S * 8, cudaMemcpyHostToDevice, st));
-    // (from 32 block columns on the side work of the chain scheme -- all of it K = 128 products -- no longer fits under the chain:
-    // the look-ahead scheme with its long-K recursive inverse is faster there, 5.9 vs 6.9 ms at n = 4096)
-    const bool chain_path = eng->opt_fit_path == 0 && n_pad >= 2 * TILE && n_pad < 32 * TILE;
+    // (the short-chain schedule wins at every size measured: 4.4 vs 5.9 ms at n = 4096, 4.8 vs 6.6 at 4224; the look-ahead scheme
+    // stays as an A/B option and is not used above 33 block columns, where it reported spurious non-PD failures)
+    const bool chain_path = n_pad >= 2 * TILE && ((eng->opt_fit_path == 0 && n_pad <= (long long)eng->opt_fit_chain_max * TILE) || n_pad > 33 * TILE);
     if ((rc = chain_path ? factorize_chain_graph(eng, st) : factorize(eng, st))) return rc;
     GPO_CUDA_OK(cudaMemcpyAsync(pin_info, eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!chain_path && (rc = launch_alpha(eng, st))) return rc;   // (the chain path enqueues it itself, under the tail of W^-1)
@@ -2244,6 +2266,7 @@ extern "C" int gpo_set_option(gpo_engine* eng, int key, long long value) {
     case GPO_OPT_FIT_PATH: if (value < 0 || value > 1) return GPO_ERR_ARG; eng->opt_fit_path = (int)value; break;
     case GPO_OPT_FIT_TRACE: eng->opt_fit_trace = value != 0; break;
     case GPO_OPT_FIT_GRAPH: eng->opt_fit_graph = value != 0; break;
+    case GPO_OPT_FIT_CHAIN_MAX: if (value < 1 || value > 4096) return GPO_ERR_ARG; eng->opt_fit_chain_max = (int)value; break;
     default: GPO_FAIL(GPO_ERR_ARG, "gpo_set_option: unknown key %d", key);
   }
   return GPO_OK;

@@ -913,6 +913,41 @@ def test_config5_gsobol_n4096_local_penalization(engine):
     assert np.max(np.abs(glp[rows] - ref_grad)) / np.max(np.abs(ref_grad)) < 1e-9
 
 
+def test_model_larger_than_4096_points(engine):
+    """n = 5000 (40 block columns; beyond BASELINE's largest configuration): state, log-likelihood, predictions with gradients and
+    EI against the oracle; the refit is bit-reproducible.  (The round-1 look-ahead schedule reported 'not positive definite' from
+    n = 4608 on; the short-chain schedule is the default for every n >= 256 now.)"""
+    from oracle import gpy_numpy as G, gpyopt_numpy as og
+    rng = np.random.default_rng(71)
+    n, d, N = 5000, 5, 3000
+    X = 1 + 9 * rng.random((n, d))
+    Y = og.normalize_stats(og.alpine2(X))
+    engine.fit('matern52', X, Y, [1.3], [[2.5]], [1e-2])
+    gp = G.GPRegression(X, Y, G.Matern52(d, variance=1.3, lengthscale=2.5), noise_var=1e-2)
+    L, _, Wi, al = engine.get_state(Linv=False)
+    assert scaled_err(np.tril(L[0]), gp.posterior.woodbury_chol) < TOL and scaled_err(al[0], gp.posterior.woodbury_vector[:, 0]) < TOL
+    assert scaled_err(Wi[0], gp.posterior.woodbury_inv) < TOL
+    ll, _ = engine.get_loglik()
+    assert abs(ll[0] - gp.log_likelihood()) < TOL * abs(gp.log_likelihood())
+    Xs = 1 + 9 * rng.random((N, d))
+    rows = np.arange(300)
+    tol_v, tol_g = parity_tolerances(gp, Xs[rows])
+    mo, so, dmo, dso = og.gp_predict_withGradients(gp, Xs[rows])
+    fo, dfo = og.acq_EI_withGradients(mo.copy(), so.copy(), dmo, dso, og.gp_get_fmin(gp), 0.01)
+    m, s, dm, ds = engine.predict_grad(Xs)
+    assert scaled_err(m[0][rows], mo[:, 0]) < tol_v and scaled_err(s[0][rows], so[:, 0]) < tol_v
+    assert scaled_err(dm[0][rows], dmo) < tol_g and scaled_err(ds[0][rows], dso) < tol_g
+    f, df = engine.acq('EI', 0.01, Xs, grad=True)
+    assert scaled_err(f[rows], fo[:, 0]) < tol_v and scaled_err(df[rows], dfo) < tol_g
+    m1, s1, dm1, ds1 = engine.predict_grad(Xs[:7])            # latency path
+    assert scaled_err(m1[0], mo[:7, 0]) < tol_v and scaled_err(s1[0], so[:7, 0]) < tol_v
+    assert scaled_err(dm1[0], dmo[:7]) < tol_g and scaled_err(ds1[0], dso[:7]) < tol_g
+    engine.fit('matern52', X, Y, [1.1], [[2.5]], [1e-2])
+    engine.fit('matern52', X, Y, [1.3], [[2.5]], [1e-2])
+    L2, _, Wi2, al2 = engine.get_state(Linv=False)
+    assert np.array_equal(L, L2) and np.array_equal(Wi, Wi2) and np.array_equal(al, al2)
+
+
 # ------------------------------------------------------------------------------------------------------
 # fused small-model value sweep (n <= 128: K1 + variance contraction in one shared-memory-resident kernel)
 # ------------------------------------------------------------------------------------------------------

@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = os.environ.get('NVCC', 'nvcc')
-    flags = [f for f in NVCC_FLAGS if not f.startswith('--use_fast_math')]
+    flags = [f for f in NVCC_FLAGS if not f.startswith('--use_fast_math')] + os.environ.get('GPO_NVCC_EXTRA', '').split()
     cmd = [nvcc] + flags + ['-o', OUT, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr

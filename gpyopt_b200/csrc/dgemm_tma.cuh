@@ -96,6 +96,11 @@ struct GemmParams {
   const double* Kt;     // K*^T chunk [z][nc_ld][n_pad] written by K1 (also the B operand)
   const double* Ht;     // (dK/dr)/r chunk, same layout; null => RBF (h = -k)
   long long nc_ld, n_pad;
+  // Two CTAs per SM (BN = 64): the second CTA to arrive on an SM walks ITS work items in reverse order.  The item lists are
+  // sorted by weight and the serpentine deal gives co-resident CTAs near-identical weight sequences, so half of their
+  // epilogues used to coincide and left the DMMA pipe idle; heavy-first against light-first they never meet.  Which CTA
+  // computes an item, and therefore every result bit, is unchanged.  Null: every CTA walks forward.
+  int* sm_arrivals;     // [#SMs] arrival counters (never reset: only the parity of consecutive arrivals matters)
 };
 
 // One unit of work of the persistent kernel: an output tile (tile_m, tile_n) of batch z, optionally one k slice of it.
@@ -184,14 +189,30 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const long long n_work = gemm_work_items(p);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+  int* rev_flag = reinterpret_cast<int*>(empty_bar + STAGES);   // (the 256-byte barrier block has room)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CW);
     }
     mbar_fence_init();
+    int rev = 0;
+    if (Sh::CTAS_PER_SM > 1 && p.sm_arrivals) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      rev = atomicAdd(p.sm_arrivals + smid, 1) & 1;
+    }
+    *rev_flag = rev;
   }
   __syncthreads();
+  // this CTA's items are j = 0 .. n_mine - 1 of gemm_item; walked backwards when `reversed`
+  const bool reversed = *rev_flag != 0;
+  long long n_mine;
+  {
+    const long long rounds = n_work / G, rest = n_work % G;
+    const long long off = (p.serpentine && (rounds & 1)) ? G - 1 - cta : cta;
+    n_mine = rounds + (off < rest ? 1 : 0);
+  }
 
   if (warp >= CW) {
     // ===================== TMA producer warpgroup (one elected thread issues) =====================
@@ -200,9 +221,8 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       tma_prefetch_desc(&mapA);
       tma_prefetch_desc(&mapB);
       long long g = 0;  // k iterations issued by this CTA so far (ring position)
-      for (long long j = 0;; ++j) {
-        const long long w = gemm_item(p, j, cta, G);
-        if (w >= n_work) break;
+      for (long long j = 0; j < n_mine; ++j) {
+        const long long w = gemm_item(p, reversed ? n_mine - 1 - j : j, cta, G);
         const GemmTile t = gemm_decode<BN>(p, w);
         const int zdiv = p.zdiv > 0 ? p.zdiv : p.batch, node = t.z / zdiv, set = t.z % zdiv;
         const int a_row = p.a.row0 + node * p.a.row_z + t.tile_m * TILE, a_col = p.a.col0 + node * p.a.col_z;
@@ -245,9 +265,8 @@ dgemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const int g = lane >> 2, t = lane & 3;
   const int rr = frag_row(g);
   long long gi = 0;  // ring position, advances exactly like the producer's
-  for (long long jw = 0;; ++jw) {
-  const long long w = gemm_item(p, jw, cta, G);
-  if (w >= n_work) break;
+  for (long long jw = 0; jw < n_mine; ++jw) {
+  const long long w = gemm_item(p, reversed ? n_mine - 1 - jw : jw, cta, G);
   const GemmTile tl = gemm_decode<BN>(p, w);
   const int tile_m = tl.tile_m, tile_n = tl.tile_n, z = tl.z, split = tl.split, nk = tl.nk;
   const int ksplit = p.ksplit > 1 ? p.ksplit : 1;

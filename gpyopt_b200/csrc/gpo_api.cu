@@ -122,6 +122,8 @@ struct gpo_engine {
   long long fit_graph_launches = 0;
   int opt_fit_trace = 0;    // measurement aid: time every launch of factorize_chain with events and print the timeline to stderr
   int opt_fit_path = 0;     // refit: 0 short critical chain (factorize_chain), 1 the round-1 look-ahead scheme (factorize)
+  int opt_desync = 1;       // co-resident GEMM CTAs walk their work items in opposite orders (GemmParams::sm_arrivals)
+  int* sm_arrivals = nullptr;
   int prio_chain = 0, prio_diag = 0, prio_inv = 0, prio_bulk = 0, prio_w = 0;   // launch priorities of the refit's streams (gpo_create)
   int opt_fit_chain_max = 1 << 20;   // largest number of 128-blocks the short-chain refit takes (above: the look-ahead scheme)
   std::vector<cudaEvent_t> fit_ev;   // events of factorize_chain (6 per block column + 4)
@@ -249,6 +251,7 @@ static int launch_gemm(gpo_engine* eng, int epi, const TMap& ma, const TMap& mb,
   GemmParams p = p_in;
   p.batch = batch;
   p.serpentine = eng->opt_serpentine ? 1 : 0;
+  p.sm_arrivals = eng->opt_desync ? eng->sm_arrivals : nullptr;
   if (p.tile_skip == TS_LOWER) bn = TILE;  // the lower-triangle numbering is in square tiles
   if (bn != TILE) p.tiles_n *= TILE / bn;
   int stages = 4;
@@ -318,6 +321,7 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
     eng->prio_chain = prio(0); eng->prio_diag = prio(1); eng->prio_inv = prio(2); eng->prio_bulk = prio(3); eng->prio_w = prio(4);
   }
   cudaEventCreateWithFlags(&eng->ev_in, cudaEventDisableTiming);
+  if (cudaMalloc(&eng->sm_arrivals, 1024 * sizeof(int)) == cudaSuccess) cudaMemset(eng->sm_arrivals, 0, 1024 * sizeof(int));
   int rc = gemm_setup(eng);
   if (rc != GPO_OK) {
     snprintf(g_create_error, sizeof(g_create_error), "%.255s", eng->last_error);
@@ -355,6 +359,7 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
     if (eng->in_pin_ev[i]) cudaEventDestroy(eng->in_pin_ev[i]);
   }
   for (int i = 0; i < 4; ++i) if (eng->stage_out[i]) cudaFree(eng->stage_out[i]);
+  if (eng->sm_arrivals) cudaFree(eng->sm_arrivals);
   if (eng->lp_xb) cudaFree(eng->lp_xb);
   if (eng->lp_r) cudaFree(eng->lp_r);
   if (eng->lp_s) cudaFree(eng->lp_s);
@@ -1836,7 +1841,8 @@ static int sweep(gpo_engine* eng, int kind, double par, bool grad, bool mean_onl
     ap.zbuf = s.zbuf;
     ap.blk_val = eng->want_blk ? eng->blk_val : nullptr; ap.blk_idx = eng->blk_idx; ap.row0 = off;
     if (tiny && !eng->want_blk) {   // a handful of points: one warp per candidate (and, inside gpo_lbfgs, the optimiser step)
-      acq_small_kernel<<<(unsigned)rows, 32, 0, st>>>(ap, eng->lb_fused);
+      if (eng->lb_fused) acq_small_kernel<<<(unsigned)rows, 32, 0, st>>>(ap, *eng->lb_fused, 1);
+      else { LbfgsParams none; memset(&none, 0, sizeof(none)); acq_small_kernel<<<(unsigned)rows, 32, 0, st>>>(ap, none, 0); }
       eng->launches++;
     } else {
       dim3 kgrid((unsigned)((rows + 127) / 128), (unsigned)(S > 1 ? S : 1), 1);
@@ -2162,12 +2168,12 @@ extern "C" int gpo_lbfgs(gpo_engine* eng, int kind, double par, int M, const dou
   // the same anchor; above, the evaluation is a regular sweep followed by the stand-alone update kernel (one warp per anchor)
   const bool fused_step = M <= SMALLN_MAX_CALL;
   for (long long r = 0; r < max_rounds; ++r) {
-    eng->lb_fused = fused_step ? p_dev : nullptr;
+    eng->lb_fused = fused_step ? &p : nullptr;   // (by value into the kernel's parameter bank: no pointer chasing through global memory)
     rc = sweep(eng, kind, par, true, false, 1, M, p.xt, ft, gt, nullptr, nullptr, st);
     eng->lb_fused = nullptr;
     if (rc) return rc;
     if (!fused_step) {
-      lbfgs_update_kernel<<<M, 32, 0, st>>>(p_dev);
+      lbfgs_update_kernel<<<M, 32, 0, st>>>(p);
       eng->launches++;
     }
     GPO_CUDA_OK(cudaGetLastError());
@@ -2266,6 +2272,7 @@ extern "C" int gpo_set_option(gpo_engine* eng, int key, long long value) {
     case GPO_OPT_FIT_PATH: if (value < 0 || value > 1) return GPO_ERR_ARG; eng->opt_fit_path = (int)value; break;
     case GPO_OPT_FIT_TRACE: eng->opt_fit_trace = value != 0; break;
     case GPO_OPT_FIT_GRAPH: eng->opt_fit_graph = value != 0; break;
+    case GPO_OPT_DESYNC: eng->opt_desync = value != 0; break;
     case GPO_OPT_FIT_CHAIN_MAX: if (value < 1 || value > 4096) return GPO_ERR_ARG; eng->opt_fit_chain_max = (int)value; break;
     default: GPO_FAIL(GPO_ERR_ARG, "gpo_set_option: unknown key %d", key);
   }

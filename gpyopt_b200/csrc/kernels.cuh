@@ -981,28 +981,189 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
   if (p.blk_val) block_argmax_store(score, p.row0 + i, p.blk_val, p.blk_idx, (p.row0 >> 7) + blockIdx.x);
 }
 
-struct LbfgsParams;
-__device__ void lbfgs_anchor_update(const LbfgsParams& lb, int a, int lane);
+// (declarations of the device L-BFGS, described in its own section below)
+constexpr int LB_HIST = 10;
+constexpr int LB_MAXM = 64;
+
+struct LbLineSearch {   // dcsrch's saved state
+  double stx, fx, gx, sty, fy, gy, stmin, stmax, width, width1, finit, ginit, gtest, stpmx;
+  int brackt, stage, nls, pad;
+};
+
+struct LbfgsParams {
+  int M, d, negate, maxiter;        // negate: the sweep returns the acquisition (maximised): minimise -f, gradient -df
+  double pgtol, ftol;               // ftol = factr * machine epsilon
+  const double* lo; const double* hi;   // [d] box
+  double* x; double* g; double* f;  // [M][d], [M][d], [M]   current iterate
+  double* xt;                       // [M][d]  trial points = input of the next evaluation
+  const double* ft; const double* gt;   // [M], [M][d]  value / gradient at the trial points (sweep outputs)
+  double* dir;                      // [M][d]  search direction
+  double* S; double* Y; double* rho;    // [M][LB_HIST][d] x 2, [M][LB_HIST]
+  double* step; double* gd;         // [M] current step length, directional derivative g . dir at the iterate
+  LbLineSearch* ls;                 // [M]
+  int* hist_n; int* hist_head; int* iter; int* phase; int* done; int* nfev;   // [M]
+  int* n_done;                      // [1]
+};
+
+// per-lane registers holding one anchor's optimiser state between the moment its loads are issued (the top of acq_small_kernel,
+// so that their round trips run under the evaluation epilogue) and the moment lbfgs_anchor_update spills them to shared memory
+struct LbStage {
+  double x, g, dir, lo, hi, xt, S[5], Y[5], rho, lsw, dsc;
+  int isc, done;
+};
+__device__ __forceinline__ void lbfgs_stage_issue(const LbfgsParams& p, int a, int lane, LbStage& st);
+__device__ void lbfgs_anchor_update(const LbfgsParams& p, int a, int lane, const LbStage& st);
 
 // K3 for calls with a handful of candidates (the L-BFGS steps): ONE WARP per candidate (grid = candidates, 32 threads).  For a
 // single thread K3 is a latency chain run from a cold instruction cache -- 72 us for 5 points with 15 Local-Penalization
 // penalisers at n = 4096 -- so the lanes split the penalisers (acq_finalize<32>) and lane 0 stores.  Hyper-parameter sets are
 // walked in set order inside the warp (no zbuf / zsum / reduce launches).  With `lb` set the same warp continues into the
 // optimiser step of anchor `candidate` (lbfgs_anchor_update): evaluation epilogue and L-BFGS state machine in one launch.
-__global__ void __launch_bounds__(32) acq_small_kernel(const AcqParams p, const LbfgsParams* __restrict__ lb) {
+// Lane q of the warp owns coordinate q (d <= DMAX <= 32): the per-coordinate partial sums, gradient terms and outputs are one
+// value per lane, so their loads go out together (one thread walking the coordinates paid ~50 dependent L2 round trips: 29 us of
+// the 47 us this kernel took at n = 2048) and the code is a sixteenth of the unrolled form.  Per element the arithmetic is
+// acq_accumulate's / acq_finalize's, operation for operation: identical bits.
+__device__ __forceinline__ void acq_accumulate_warp(const AcqParams& p, long long i, int lane, double& f_acc, double& df_lane) {
+  const int d = p.d, nv = p.part_nv;
+  const int q = lane < d ? lane : d - 1;   // lanes past d shadow the last coordinate (never stored)
+  for (int z = 0; z < p.S; ++z) {
+    double m = 0.0;
+    for (int sp = 0; sp < p.js; ++sp) m += p.mean[((long long)z * p.js_ld + sp) * p.nc_pad + i];
+    const double* part = p.partial + (long long)z * p.tiles_m * nv * p.part_ld + i;
+    double s0 = 0.0;
+    if (p.grad && p.partial_sq) {
+      const double* psq = p.partial_sq + (long long)z * p.sq_tiles_m * p.nc_pad + i;
+      for (int tm = 0; tm < p.sq_tiles_m; ++tm) s0 += psq[(long long)tm * p.nc_pad];
+    } else {
+      for (int tm = 0; tm < p.tiles_m; ++tm) s0 += part[(long long)tm * nv * p.part_ld];
+    }
+    double v = p.sigf2[z] - s0;
+    if (p.with_noise) v += p.noise[z];
+    v = ::fmax(v, 1e-10);
+    double s = sqrt(v);
+    double dmq = 0.0, dsq = 0.0;
+    if (p.grad) {
+      const double inv2s = 1.0 / (2.0 * s);
+      double h0 = 0.0;
+      for (int tm = 0; tm < p.tiles_m; ++tm) h0 += part[((long long)tm * nv + 1) * p.part_ld];
+      double pq = 0.0;
+      for (int tm = 0; tm < p.tiles_m; ++tm) pq += part[((long long)tm * nv + 2 + q) * p.part_ld];
+      const double il = p.invl[z * d + q];
+      const double gq = ((p.Xs[i * d + q] - p.xmu[q]) * h0 - pq) * il * il;
+      for (int sp = 0; sp < p.js; ++sp) dmq += p.dmean[(((long long)z * p.js_ld + sp) * d + q) * p.nc_pad + i];
+      dsq = -2.0 * gq * inv2s;
+    }
+    if (p.kind == ACQ_NONE) {
+      if (lane == 0) {
+        p.out_m[(long long)z * p.out_ldN + i] = m;
+        if (p.out_s) p.out_s[(long long)z * p.out_ldN + i] = s;
+      }
+      if (p.grad && lane < d) {
+        p.out_dm[((long long)z * p.out_ldN + i) * d + q] = dmq;
+        if (p.out_ds) p.out_ds[((long long)z * p.out_ldN + i) * d + q] = dsq;
+      }
+      continue;
+    }
+    const int base_kind = p.kind % 3;
+    if (base_kind == ACQ_LCB) {
+      f_acc += -m + p.par * s;
+      if (p.grad) df_lane += -dmq + p.par * dsq;
+    } else {
+      if (s < 1e-10) s = 1e-10;
+      const double fm = p.fmin[z];
+      const double u = (fm - m - p.par) / s;
+      const double phi = exp(-0.5 * u * u) * 0.39894228040143267794;
+      const double Phi = 0.5 * erfc(-u * 0.70710678118654752440);
+      if (base_kind == ACQ_EI) {
+        if (p.kind == ACQ_EI_MCMC) f_acc += (fm - m + p.par) * Phi + s * phi;
+        else f_acc += s * (u * Phi + phi);
+        if (p.grad) df_lane += dsq * phi - Phi * dmq;
+      } else {
+        f_acc += Phi;
+        if (p.grad) {
+          const double c = -(phi / s);
+          df_lane += c * (dmq + dsq * u);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void acq_finalize_warp(const AcqParams& p, long long i, double f_acc, double df_lane, int lane) {
+  const int d = p.d;
+  if (p.kind >= ACQ_EI_MCMC) {
+    f_acc = f_acc / (double)p.S;
+    df_lane = df_lane / (double)p.S;
+  }
+  if (!p.lp_on) {
+    if (lane == 0) p.out_f[i] = f_acc;
+    if (p.grad && lane < d) p.out_df[i * d + lane] = df_lane;
+    return;
+  }
+  const double fval = f_acc;
+  double val, scale;
+  if (p.lp_transform == 1) {
+    if (fval >= 40.0) val = log(fval);
+    else val = log(log1p(exp(fval)));
+    scale = 1.0 / (log1p(exp(fval)) * (1.0 + exp(-fval)));
+  } else {
+    val = log(fval + 1e-50);
+    scale = 1.0 / fval;
+  }
+  val = -val;
+  double dsum = 0.0, pen = 0.0;
+  for (int k = lane; k < p.lp_K; k += 32) {
+    double nm2 = 0.0;
+    for (int q = 0; q < d; ++q) {
+      const double df = p.Xs[i * d + q] - p.lp_xb[k * d + q];
+      nm2 = fma(df, df, nm2);
+    }
+    const double nm = sqrt(nm2);
+    const double zz = (nm - p.lp_r[k]) / p.lp_s[k];
+    pen += log_ndtr(zz);
+    if (p.grad) {
+      const double h = 0.5 * erfc(-zz * 0.70710678118654752440);
+      double dk = 1.0 / (p.lp_s[k] * 2.50662827463100050242 * h) * exp(-zz * zz / 2.0) / nm;
+      if (h < 1e-50) dk = 0.0;
+      dsum += dk;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    pen += __shfl_xor_sync(0xffffffffu, pen, o);
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+  }
+  val -= pen;
+  if (lane == 0) p.out_f[i] = val;
+  if (p.grad && lane < d) p.out_df[i * d + lane] = scale * (-df_lane) - dsum;
+}
+
+__global__ void __launch_bounds__(32) acq_small_kernel(const AcqParams p, const LbfgsParams lb, int with_lb) {
   const long long i = blockIdx.x;
   const int lane = threadIdx.x;
-  double f_acc = 0.0, df_acc[DMAX];
-#pragma unroll
-  for (int q = 0; q < DMAX; ++q) df_acc[q] = 0.0;
-  acq_accumulate(p, i, 0, p.S, lane == 0, f_acc, df_acc);
+  double f_acc = 0.0, df_lane = 0.0;
+  LbStage stg;
+  if (with_lb) lbfgs_stage_issue(lb, (int)i, lane, stg);
+#ifdef GPO_ACQ_TIMING
+  const long long t0 = clock64();
+#endif
+  acq_accumulate_warp(p, i, lane, f_acc, df_lane);
   if (p.kind == ACQ_NONE) return;
-  acq_finalize<32>(p, i, f_acc, df_acc, lane, lane == 0);
-  if (lb) {
+#ifdef GPO_ACQ_TIMING
+  const long long t1 = clock64();
+#endif
+  acq_finalize_warp(p, i, f_acc, df_lane, lane);
+#ifdef GPO_ACQ_TIMING
+  const long long t2 = clock64();
+#endif
+  if (with_lb) {
     __threadfence_block();
     __syncwarp();
-    lbfgs_anchor_update(*lb, (int)i, lane);
+    lbfgs_anchor_update(lb, (int)i, lane, stg);
   }
+#ifdef GPO_ACQ_TIMING
+  if (lane == 0 && i == 0) printf("acq_small cycles: accumulate %lld finalize %lld lbfgs %lld\n", t1 - t0, t2 - t1, clock64() - t2);
+#endif
 }
 
 // S > 1, stage 1: grid (candidates / 128, 1 + d).  Thread (i, v) adds value v of candidate i over the hyper-parameter sets
@@ -1335,7 +1496,14 @@ __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
     const int v = idx / NC, i = idx - v * NC;
     const double* src = p.partial + (long long)z * p.part_z + (long long)v * p.ldp + i;
     double t = 0.0;
-    for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(src + (long long)b * (d + 2) * p.ldp);
+    for (int b0 = lane; b0 < (int)gridDim.x; b0 += 256) {   // (loads first, then the adds in the same order as before)
+      double vals[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) vals[u] = b0 + 32 * u < (int)gridDim.x ? __ldcg(src + (long long)(b0 + 32 * u) * (d + 2) * p.ldp) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (b0 + 32 * u < (int)gridDim.x) t += vals[u];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
     if (lane == 0) p.final_rows[((long long)z * (d + 2) + v) * p.final_ld + i] = t;
@@ -1361,7 +1529,6 @@ __global__ void __launch_bounds__(256) smalln_both_kernel(const SmallNParams pw,
 // training index and leaves the same per-slice partial sums in mean / dmean, K*^T / H*^T rows in Kt / Ht, for the
 // candidate slots 0 .. nc_run-1 (slots past the last candidate shadow it, as K1's padding does).
 __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
-  __shared__ double red[8][DMAX + 1];
   const int z = blockIdx.y, split = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = p.d;
   const double* invl = p.invl + (long long)z * d;
@@ -1369,7 +1536,10 @@ __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
   const double* alpha = p.alpha + (long long)z * p.n_pad;
   const int j_begin = split * p.tiles_per_split * COV_JT, j_end = min(p.n_pad, j_begin + p.tiles_per_split * COV_JT);
   const long long zs = (long long)z * p.js + split;
-  for (int i = 0; i < (int)p.nc_run; ++i) {
+  // One WARP per candidate slot, the eight warps of the block work on eight slots at once (the first version walked the slots one
+  // after the other with two block barriers each: 28 us for eight slots, all of it latency).  A slot's sums are formed by its warp
+  // alone -- lane-strided partial sums, then a fixed shuffle tree -- so they do not depend on the other slots of the call.
+  for (int i = warp; i < (int)p.nc_run; i += 8) {
     const long long cand = i < p.n_cand ? i : p.n_cand - 1;
     double xs[DMAX], m = 0.0, dm[DMAX];
 #pragma unroll
@@ -1377,7 +1547,7 @@ __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
       xs[q] = q < d ? p.Xs[cand * d + q] * invl[q] : 0.0;
       dm[q] = 0.0;
     }
-    for (int j = j_begin + tid; j < j_end; j += 256) {
+    for (int j = j_begin + lane; j < j_end; j += 32) {
       double r2 = 0.0, df[DMAX];
 #pragma unroll
       for (int q = 0; q < DMAX; ++q) {
@@ -1395,28 +1565,18 @@ __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
       if (p.Kt) p.Kt[((long long)z * p.nc_ld + i) * p.n_pad + j] = kv;
       if (p.Ht) p.Ht[((long long)z * p.nc_ld + i) * p.n_pad + j] = hv;
     }
-    // block sums (fixed shuffle tree, then the eight warps in order)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
-    if (lane == 0) red[warp][0] = m;
+    if (lane == 0) p.mean[zs * p.nc_ld + i] = m;
     if (p.dmean) {
 #pragma unroll
       for (int q = 0; q < DMAX; ++q)
         if (q < d) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) dm[q] += __shfl_xor_sync(0xffffffffu, dm[q], o);
-          if (lane == 0) red[warp][1 + q] = dm[q];
+          if (lane == 0) p.dmean[(zs * d + q) * p.nc_ld + i] = dm[q] * invl[q];
         }
     }
-    __syncthreads();
-    if (tid <= (p.dmean ? d : 0)) {
-      double t = 0.0;
-#pragma unroll
-      for (int w8 = 0; w8 < 8; ++w8) t += red[w8][tid];
-      if (tid == 0) p.mean[zs * p.nc_ld + i] = t;
-      else p.dmean[(zs * d + (tid - 1)) * p.nc_ld + i] = t * invl[tid - 1];
-    }
-    __syncthreads();
   }
   // the last block of this hyper-parameter set adds the slices (in slice order) into slice 0: K3 then reads one value
   // per candidate and output instead of walking js dependent loads for each (41 us for a single point at n=4096)
@@ -1435,14 +1595,20 @@ __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
   const int nv = p.dmean ? d + 1 : 1;
   for (int idx = tid; idx < nv * (int)p.nc_run; idx += 256) {
     const int v = idx / (int)p.nc_run, i = idx - v * (int)p.nc_run;
+    // all slices are fetched before the first add (added one by one, each load waited for the previous add: js round trips)
+    const double* src = v == 0 ? p.mean + (long long)z * p.js * p.nc_ld + i : p.dmean + ((long long)z * p.js * d + (v - 1)) * p.nc_ld + i;
+    const long long stride = v == 0 ? p.nc_ld : (long long)d * p.nc_ld;
     double t = 0.0;
-    if (v == 0) {
-      for (int sp = 0; sp < p.js; ++sp) t += __ldcg(p.mean + ((long long)z * p.js + sp) * p.nc_ld + i);
-      p.mean[(long long)z * p.js * p.nc_ld + i] = t;
-    } else {
-      for (int sp = 0; sp < p.js; ++sp) t += __ldcg(p.dmean + (((long long)z * p.js + sp) * d + (v - 1)) * p.nc_ld + i);
-      p.dmean[((long long)z * p.js * d + (v - 1)) * p.nc_ld + i] = t;
+    for (int sp0 = 0; sp0 < p.js; sp0 += 16) {
+      double vals[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) vals[u] = sp0 + u < p.js ? __ldcg(src + (long long)(sp0 + u) * stride) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (sp0 + u < p.js) t += vals[u];
     }
+    if (v == 0) p.mean[(long long)z * p.js * p.nc_ld + i] = t;
+    else p.dmean[((long long)z * p.js * d + (v - 1)) * p.nc_ld + i] = t;
   }
 }
 
@@ -1610,29 +1776,6 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_small_value_kernel(const 
 // host only polls the finished-anchor count every few rounds.  (The test-suite keeps a line-by-line NumPy mirror of this state
 // machine and walks both along the same path.)
 // =====================================================================================================
-constexpr int LB_HIST = 10;
-constexpr int LB_MAXM = 64;
-
-struct LbLineSearch {   // dcsrch's saved state
-  double stx, fx, gx, sty, fy, gy, stmin, stmax, width, width1, finit, ginit, gtest, stpmx;
-  int brackt, stage, nls, pad;
-};
-
-struct LbfgsParams {
-  int M, d, negate, maxiter;        // negate: the sweep returns the acquisition (maximised): minimise -f, gradient -df
-  double pgtol, ftol;               // ftol = factr * machine epsilon
-  const double* lo; const double* hi;   // [d] box
-  double* x; double* g; double* f;  // [M][d], [M][d], [M]   current iterate
-  double* xt;                       // [M][d]  trial points = input of the next evaluation
-  const double* ft; const double* gt;   // [M], [M][d]  value / gradient at the trial points (sweep outputs)
-  double* dir;                      // [M][d]  search direction
-  double* S; double* Y; double* rho;    // [M][LB_HIST][d] x 2, [M][LB_HIST]
-  double* step; double* gd;         // [M] current step length, directional derivative g . dir at the iterate
-  LbLineSearch* ls;                 // [M]
-  int* hist_n; int* hist_head; int* iter; int* phase; int* done; int* nfev;   // [M]
-  int* n_done;                      // [1]
-};
-
 __device__ __forceinline__ double lb_clamp(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __device__ __forceinline__ double lb_cubic_gamma(double theta, double da, double db) {
@@ -1753,75 +1896,140 @@ __global__ void lbfgs_init_kernel(const LbfgsParams p, const double* __restrict_
 }
 
 // One optimiser state-machine step of anchor `a` after an evaluation at its trial point, executed by ONE WARP: the lanes stage
-// the anchor's state (iterate, gradient, direction, curvature pairs: <= 3 KB) from global into shared memory in one round trip,
-// lane 0 runs the scalar state machine on the shared copy (a chain of dependent global loads made the first version take 45 us
-// per round), the lanes write the state back.
-__device__ void lbfgs_anchor_update(const LbfgsParams& p, int a, int lane) {
+// ALL of the anchor's state -- iterate, gradient, direction, curvature pairs, box, the evaluation's outputs, the line-search record
+// and the scalar counters (<= 3.5 KB) -- from global into shared memory in one round trip, lane 0 runs the scalar state machine on
+// the shared copy (every global access of the state machine used to be its own ~0.5 us round trip: 20 - 55 us per round), the lanes
+// write the state back.
+// dot product of two shared-memory vectors added in coordinate order with fused multiply-adds (every lane forms the same value
+// from broadcast reads).  Deliberately a rolled loop: these one-warp kernels run from a cold instruction cache, and what they cost
+// is the number of distinct instruction lines they touch (an unrolled, shuffle-based form of this function made one pass of the
+// two-loop recursion 100,000 cycles long).
+__device__ __noinline__ double lb_dot_seq(const double* a, const double* b, int d) {
+  // (one shared copy of this body serves all 23 dot products of a pass: the operands are fetched up front, then the chain runs)
+  double av[DMAX], bv[DMAX];
+#pragma unroll
+  for (int q = 0; q < DMAX; ++q) {
+    av[q] = q < d ? a[q] : 0.0;
+    bv[q] = q < d ? b[q] : 0.0;
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < DMAX; ++q)
+    if (q < d) s = fma(av[q], bv[q], s);
+  return s;
+}
+
+struct LbScalars { double ft, f, step, gd; int hist_n, hist_head, iter, phase, nfev, done, pad0, pad1; };
+// issue the loads of anchor a's state (everything but this round's evaluation outputs); nothing here waits for them
+__device__ __forceinline__ void lbfgs_stage_issue(const LbfgsParams& p, int a, int lane, LbStage& st) {
+  const int d = p.d;
+  st.done = (a < p.M) ? p.done[a] : 1;
+  const int q = lane < d ? lane : 0;
+  st.x = p.x[a * d + q]; st.g = p.g[a * d + q]; st.dir = p.dir[a * d + q]; st.lo = p.lo[q]; st.hi = p.hi[q]; st.xt = p.xt[a * d + q];
+  const double* gS = p.S + (long long)a * LB_HIST * d; const double* gY = p.Y + (long long)a * LB_HIST * d;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const int e = lane + 32 * r < LB_HIST * d ? lane + 32 * r : 0;
+    st.S[r] = gS[e]; st.Y[r] = gY[e];
+  }
+  st.rho = p.rho[a * LB_HIST + (lane < LB_HIST ? lane : 0)];
+  st.lsw = reinterpret_cast<const double*>(p.ls + a)[lane & 15];
+  const double* dp = lane == 1 ? p.f + a : lane == 2 ? p.step + a : p.gd + a;
+  const int* ip = lane == 4 ? p.hist_n + a : lane == 5 ? p.hist_head + a : lane == 6 ? p.iter + a : lane == 7 ? p.phase + a : p.nfev + a;
+  st.dsc = *dp;
+  st.isc = *ip;
+}
+
+__device__ void lbfgs_anchor_update(const LbfgsParams& p, int a, int lane, const LbStage& st) {
   __shared__ double sh_x[DMAX], sh_g[DMAX], sh_dir[DMAX], sh_S[LB_HIST * DMAX], sh_Y[LB_HIST * DMAX], sh_rho[LB_HIST];
-  if (a >= p.M || p.done[a]) return;            // (warp-uniform)
+  __shared__ double sh_lo[DMAX], sh_hi[DMAX], sh_G[DMAX], sh_xt[DMAX];
+  __shared__ LbLineSearch sh_ls;
+  __shared__ LbScalars sh_sc;
+  __shared__ double sh_v[DMAX], sh_al[LB_HIST];
+  __shared__ int sh_fl[8];   // finished, need_direction, steepest, hist_n, hist_head: lane 0 -> warp -> lane 0
+  static_assert(sizeof(LbLineSearch) == 16 * 8, "copied as 16 words");
+#ifdef GPO_ACQ_TIMING
+  long long lt[6]; int n_pass = 0; lt[0] = clock64();
+#endif
+  if (a >= p.M || st.done) return;              // (warp-uniform)
   const int d = p.d;
   {
-    const double* gx = p.x + a * d; const double* gg = p.g + a * d; const double* gd = p.dir + a * d;
-    const double* gS = p.S + (long long)a * LB_HIST * d; const double* gY = p.Y + (long long)a * LB_HIST * d;
-    for (int i = lane; i < d; i += 32) { sh_x[i] = gx[i]; sh_g[i] = gg[i]; sh_dir[i] = gd[i]; }
-    for (int i = lane; i < LB_HIST * d; i += 32) { sh_S[i] = gS[i]; sh_Y[i] = gY[i]; }
-    if (lane < LB_HIST) sh_rho[lane] = p.rho[a * LB_HIST + lane];
+    if (lane < d) {
+      sh_x[lane] = st.x; sh_g[lane] = st.g; sh_dir[lane] = st.dir; sh_lo[lane] = st.lo; sh_hi[lane] = st.hi; sh_xt[lane] = st.xt;
+      sh_G[lane] = p.gt[a * d + lane];          // this round's evaluation: written by this warp a moment ago (or by the sweep)
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+      if (lane + 32 * r < LB_HIST * d) { sh_S[lane + 32 * r] = st.S[r]; sh_Y[lane + 32 * r] = st.Y[r]; }
+    if (lane < LB_HIST) sh_rho[lane] = st.rho;
+    if (lane >= 16) reinterpret_cast<double*>(&sh_ls)[lane - 16] = st.lsw;
+    if (lane == 0) sh_sc.ft = p.ft[a];
+    else if (lane < 4) (&sh_sc.ft)[lane] = st.dsc;
+    else if (lane < 9) (&sh_sc.hist_n)[lane - 4] = st.isc;
+    else if (lane == 9) sh_sc.done = 0;
   }
+  const double pgtol = p.pgtol, ftol = p.ftol;
+  const int maxiter = p.maxiter, negate = p.negate;
   __syncwarp();
+#ifdef GPO_ACQ_TIMING
+  lt[1] = clock64();
+#endif
   if (lane == 0) {
   const double eps = 2.220446049250313e-16;
-  double* x = sh_x; double* g = sh_g; double* dir = sh_dir; double* xt = p.xt + a * d;
-  LbLineSearch ls = p.ls[a];
-  const double sgn = p.negate ? -1.0 : 1.0;
-  double F = sgn * p.ft[a];
+  double* x = sh_x; double* g = sh_g; double* dir = sh_dir; double* xt = sh_xt;
+  const double* lo = sh_lo; const double* hi = sh_hi;
+  LbLineSearch ls = sh_ls;
+  LbScalars sc = sh_sc;
+  const double sgn = negate ? -1.0 : 1.0;
+  double F = sgn * sc.ft;
   double G[DMAX];
   bool finite = F == F && fabs(F) < 1e300;
-  for (int q = 0; q < d; ++q) { G[q] = sgn * p.gt[a * d + q]; finite = finite && G[q] == G[q] && fabs(G[q]) < 1e300; }
-  p.nfev[a] += 1;
-  int hist_n = p.hist_n[a], hist_head = p.hist_head[a];
+  _Pragma("unroll 1") for (int q = 0; q < d; ++q) { G[q] = sgn * sh_G[q]; finite = finite && G[q] == G[q] && fabs(G[q]) < 1e300; }
+  sc.nfev += 1;
+  int hist_n = sc.hist_n, hist_head = sc.hist_head;
   bool finished = false, need_direction = true;
   auto pg_norm = [&](const double* xx, const double* gg) {
     double m = 0.0;
-    for (int q = 0; q < d; ++q) m = ::fmax(m, fabs(lb_clamp(xx[q] - gg[q], p.lo[q], p.hi[q]) - xx[q]));
+    _Pragma("unroll 1") for (int q = 0; q < d; ++q) m = ::fmax(m, fabs(lb_clamp(xx[q] - gg[q], lo[q], hi[q]) - xx[q]));
     return m;
   };
   bool steepest = false;
-  if (p.phase[a] == 0) {            // the evaluation at the start point
-    p.f[a] = F;
+  if (sc.phase == 0) {            // the evaluation at the start point
+    sc.f = F;
     if (!finite) finished = true;
     else {
-      for (int q = 0; q < d; ++q) g[q] = G[q];
-      if (pg_norm(x, g) <= p.pgtol) finished = true;
+      _Pragma("unroll 1") for (int q = 0; q < d; ++q) g[q] = G[q];
+      if (pg_norm(x, g) <= pgtol) finished = true;
       steepest = true;
-      p.phase[a] = 1;
+      sc.phase = 1;
     }
   } else {                          // a line-search trial at xt = x + step * dir
-    double stp = p.step[a];
+    double stp = sc.step;
     double gdt = 0.0;
     if (finite) { for (int q = 0; q < d; ++q) gdt = fma(G[q], dir[q], gdt); }
     else { F = ls.fx + 1e10 * (1.0 + fabs(ls.fx)); gdt = 1e10; }
     ls.nls += 1;
     const bool ended = lb_dcsrch_next(ls, stp, F, gdt);
     if (!ended && ls.nls < 20) {    // next trial
-      p.step[a] = stp;
-      for (int q = 0; q < d; ++q) xt[q] = lb_clamp(x[q] + stp * dir[q], p.lo[q], p.hi[q]);
+      sc.step = stp;
+      _Pragma("unroll 1") for (int q = 0; q < d; ++q) xt[q] = lb_clamp(x[q] + stp * dir[q], lo[q], hi[q]);
       need_direction = false;
     } else if (ended && finite) {
       // accept: curvature pair, new iterate, stopping rules (as scipy.optimize.fmin_l_bfgs_b: pgtol, factr, maxiter)
       double sy = 0.0;
-      for (int q = 0; q < d; ++q) sy = fma(xt[q] - x[q], G[q] - g[q], sy);
-      if (sy > eps * (-p.gd[a] * p.step[a])) {
+      _Pragma("unroll 1") for (int q = 0; q < d; ++q) sy = fma(xt[q] - x[q], G[q] - g[q], sy);
+      if (sy > eps * (-sc.gd * sc.step)) {
         double* Sh = sh_S + hist_head * d; double* Yh = sh_Y + hist_head * d;
-        for (int q = 0; q < d; ++q) { Sh[q] = xt[q] - x[q]; Yh[q] = G[q] - g[q]; }
+        _Pragma("unroll 1") for (int q = 0; q < d; ++q) { Sh[q] = xt[q] - x[q]; Yh[q] = G[q] - g[q]; }
         sh_rho[hist_head] = 1.0 / sy;
         hist_head = (hist_head + 1) % LB_HIST;
         if (hist_n < LB_HIST) hist_n += 1;
       }
-      const double f0 = p.f[a];
-      for (int q = 0; q < d; ++q) { x[q] = xt[q]; g[q] = G[q]; }
-      p.f[a] = F;
-      p.iter[a] += 1;
-      if (pg_norm(x, g) <= p.pgtol || (f0 - F) <= p.ftol * ::fmax(::fmax(fabs(f0), fabs(F)), 1.0) || p.iter[a] >= p.maxiter)
+      const double f0 = sc.f;
+      _Pragma("unroll 1") for (int q = 0; q < d; ++q) { x[q] = xt[q]; g[q] = G[q]; }
+      sc.f = F;
+      sc.iter += 1;
+      if (pg_norm(x, g) <= pgtol || (f0 - F) <= ftol * ::fmax(::fmax(fabs(f0), fabs(F)), 1.0) || sc.iter >= maxiter)
         finished = true;
     } else {
       // failed search: with history, drop it and restart from steepest descent at the iterate; without, stop
@@ -1829,89 +2037,145 @@ __device__ void lbfgs_anchor_update(const LbfgsParams& p, int a, int lane) {
       else finished = true;
     }
   }
-  if (!finished && need_direction) {
-    // ---- new search direction from the iterate (x, g) ----
-    bool fr[DMAX];
-    for (int q = 0; q < d; ++q) fr[q] = !((x[q] <= p.lo[q] && g[q] > 0.0) || (x[q] >= p.hi[q] && g[q] < 0.0));
-    double gdd = 0.0, dn = 0.0;
+  sh_fl[0] = finished; sh_fl[1] = need_direction; sh_fl[2] = steepest; sh_fl[3] = hist_n; sh_fl[4] = hist_head;
+  sh_ls = ls; sh_sc = sc;
+  }
+  __syncwarp();
+  // ---- new search direction from the iterate (x, g): the whole warp, lane q owns coordinate q.  The scalar form (lane 0 walking
+  //      v[], S[], Y[] element by element out of local / shared memory) took 20 - 55 us per round; every dot product here adds its
+  //      terms in the same order with the same fused multiply-adds (lb_dot_seq), so the direction has the same bits. ----
+#ifdef GPO_ACQ_TIMING
+  lt[2] = clock64();
+#endif
+  double gdd = 0.0, dn = 0.0;
+  const bool want_dir = !sh_fl[0] && sh_fl[1];
+  if (want_dir) {           // (warp-uniform)
+    bool steepest = sh_fl[2] != 0;
+    int hist_n = sh_fl[3];
+    const int hist_head = sh_fl[4];
+    const bool on = lane < d;
+    const double xq = on ? sh_x[lane] : 0.0, gq = on ? sh_g[lane] : 0.0, loq = on ? sh_lo[lane] : 0.0, hiq = on ? sh_hi[lane] : 0.0;
+    bool fr = on && !((xq <= loq && gq > 0.0) || (xq >= hiq && gq < 0.0));
+    double dirq = 0.0;
+    const int lq = on ? lane : 0;   // (lanes past d shadow coordinate 0 and never store)
     for (int attempt = 0; attempt < 2; ++attempt) {
       const int hn = steepest ? 0 : hist_n;
       for (int pass = 0; pass <= d; ++pass) {
-        double v[DMAX], al[LB_HIST];
-        for (int q = 0; q < d; ++q) v[q] = fr[q] ? g[q] : 0.0;
+#ifdef GPO_ACQ_TIMING
+        ++n_pass;
+#endif
+        double v = fr ? gq : 0.0;
+        if (on) sh_v[lane] = v;
+        __syncwarp();
+#pragma unroll 1
         for (int i = 0; i < hn; ++i) {        // newest to oldest
           const int h = (hist_head - 1 - i + 2 * LB_HIST) % LB_HIST;
-          const double* Sh = sh_S + h * d; const double* Yh = sh_Y + h * d;
-          double sv = 0.0;
-          for (int q = 0; q < d; ++q) sv = fma(Sh[q], v[q], sv);
-          al[i] = sh_rho[h] * sv;
-          for (int q = 0; q < d; ++q) v[q] = fma(-al[i], Yh[q], v[q]);
+          const double ali = sh_rho[h] * lb_dot_seq(sh_S + h * d, sh_v, d);
+          if (lane == 0) sh_al[i] = ali;
+          v = fma(-ali, sh_Y[h * d + lq], v);
+          __syncwarp();
+          if (on) sh_v[lane] = v;
+          __syncwarp();
         }
         if (hn > 0) {
           const int h = (hist_head - 1 + LB_HIST) % LB_HIST;
-          const double* Yh = sh_Y + h * d;
-          double yy = 0.0;
-          for (int q = 0; q < d; ++q) yy = fma(Yh[q], Yh[q], yy);
-          const double gamma = 1.0 / (sh_rho[h] * yy);
-          for (int q = 0; q < d; ++q) v[q] *= gamma;
+          const double gamma = 1.0 / (sh_rho[h] * lb_dot_seq(sh_Y + h * d, sh_Y + h * d, d));
+          v *= gamma;
+          __syncwarp();
+          if (on) sh_v[lane] = v;
+          __syncwarp();
         }
+#pragma unroll 1
         for (int i = hn - 1; i >= 0; --i) {   // oldest to newest
           const int h = (hist_head - 1 - i + 2 * LB_HIST) % LB_HIST;
-          const double* Sh = sh_S + h * d; const double* Yh = sh_Y + h * d;
-          double yv = 0.0;
-          for (int q = 0; q < d; ++q) yv = fma(Yh[q], v[q], yv);
-          const double be = sh_rho[h] * yv;
-          for (int q = 0; q < d; ++q) v[q] = fma(al[i] - be, Sh[q], v[q]);
+          const double be = sh_rho[h] * lb_dot_seq(sh_Y + h * d, sh_v, d);
+          v = fma(sh_al[i] - be, sh_S[h * d + lq], v);
+          __syncwarp();
+          if (on) sh_v[lane] = v;
+          __syncwarp();
         }
-        bool blocked = false;
-        for (int q = 0; q < d; ++q) {
-          dir[q] = fr[q] ? -v[q] : 0.0;
-          // a free variable sitting on a bound and pushed outward by the quasi-Newton coupling: freeze it and redo
-          if (fr[q] && ((x[q] <= p.lo[q] && dir[q] < 0.0) || (x[q] >= p.hi[q] && dir[q] > 0.0))) { fr[q] = false; blocked = true; }
-        }
-        if (!blocked) break;
+        dirq = fr ? -v : 0.0;
+        // a free variable sitting on a bound and pushed outward by the quasi-Newton coupling: freeze it and redo
+        const bool hit = fr && ((xq <= loq && dirq < 0.0) || (xq >= hiq && dirq > 0.0));
+        if (hit) fr = false;
+        if (!__any_sync(0xffffffffu, hit)) break;
       }
-      gdd = 0.0; dn = 0.0;
-      for (int q = 0; q < d; ++q) { gdd = fma(g[q], dir[q], gdd); dn = fma(dir[q], dir[q], dn); }
+      __syncwarp();
+      if (on) sh_v[lane] = dirq;
+      __syncwarp();
+      gdd = lb_dot_seq(sh_g, sh_v, d);
+      dn = lb_dot_seq(sh_v, sh_v, d);
       if (gdd < 0.0 || hn == 0) break;
       hist_n = 0;                             // not a descent direction: drop the history, steepest descent
       steepest = true;
     }
+    if (on) sh_dir[lane] = dirq;
+    if (lane == 0) sh_fl[3] = hist_n;
+  }
+  __syncwarp();
+#ifdef GPO_ACQ_TIMING
+  lt[3] = clock64();
+#endif
+  if (lane == 0) {
+  double* x = sh_x; double* dir = sh_dir; double* xt = sh_xt;
+  const double* lo = sh_lo; const double* hi = sh_hi;
+  LbLineSearch ls = sh_ls;
+  LbScalars sc = sh_sc;
+  bool finished = sh_fl[0] != 0;
+  const int hist_n = sh_fl[3], hist_head = sh_fl[4];
+  if (want_dir) {
     if (!(dn > 0.0) || !(gdd < 0.0)) finished = true;
     else {
       double stpmx = 1e10;
-      for (int q = 0; q < d; ++q) {
-        if (dir[q] > 0.0) stpmx = ::fmin(stpmx, (p.hi[q] - x[q]) / dir[q]);
-        else if (dir[q] < 0.0) stpmx = ::fmin(stpmx, (p.lo[q] - x[q]) / dir[q]);
+      _Pragma("unroll 1") for (int q = 0; q < d; ++q) {
+        if (dir[q] > 0.0) stpmx = ::fmin(stpmx, (hi[q] - x[q]) / dir[q]);
+        else if (dir[q] < 0.0) stpmx = ::fmin(stpmx, (lo[q] - x[q]) / dir[q]);
       }
       const double stp = ::fmin(1.0, stpmx);
-      lb_dcsrch_start(ls, stp, p.f[a], gdd, stpmx);
-      p.step[a] = stp;
-      p.gd[a] = gdd;
-      for (int q = 0; q < d; ++q) xt[q] = lb_clamp(x[q] + stp * dir[q], p.lo[q], p.hi[q]);
+      lb_dcsrch_start(ls, stp, sc.f, gdd, stpmx);
+      sc.step = stp;
+      sc.gd = gdd;
+      _Pragma("unroll 1") for (int q = 0; q < d; ++q) xt[q] = lb_clamp(x[q] + stp * dir[q], lo[q], hi[q]);
     }
   }
   if (finished) {
-    p.done[a] = 1;
-    for (int q = 0; q < d; ++q) xt[q] = x[q];   // later (lock-step) evaluations of this anchor are idle repeats
+    sc.done = 1;
+    _Pragma("unroll 1") for (int q = 0; q < d; ++q) xt[q] = x[q];   // later (lock-step) evaluations of this anchor are idle repeats
     atomicAdd(p.n_done, 1);
   }
-  p.ls[a] = ls;
-  p.hist_n[a] = hist_n; p.hist_head[a] = hist_head;
+  sh_ls = ls;
+  sc.hist_n = hist_n; sc.hist_head = hist_head;
+  sh_sc = sc;
   }
   __syncwarp();
+#ifdef GPO_ACQ_TIMING
+  lt[4] = clock64();
+#endif
   {
     double* gx = p.x + a * d; double* gg = p.g + a * d; double* gd = p.dir + a * d;
     double* gS = p.S + (long long)a * LB_HIST * d; double* gY = p.Y + (long long)a * LB_HIST * d;
-    for (int i = lane; i < d; i += 32) { gx[i] = sh_x[i]; gg[i] = sh_g[i]; gd[i] = sh_dir[i]; }
+    for (int i = lane; i < d; i += 32) { gx[i] = sh_x[i]; gg[i] = sh_g[i]; gd[i] = sh_dir[i]; p.xt[a * d + i] = sh_xt[i]; }
+    if (lane >= 16) reinterpret_cast<double*>(p.ls + a)[lane - 16] = reinterpret_cast<const double*>(&sh_ls)[lane - 16];
+    {
+      double* dp = lane == 1 ? p.f + a : lane == 2 ? p.step + a : p.gd + a;
+      int* ip = lane == 4 ? p.hist_n + a : lane == 5 ? p.hist_head + a : lane == 6 ? p.iter + a : lane == 7 ? p.phase + a : p.nfev + a;
+      if (lane >= 1 && lane < 4) *dp = (&sh_sc.ft)[lane];
+      else if (lane >= 4 && lane < 9) *ip = (&sh_sc.hist_n)[lane - 4];
+      else if (lane == 9 && sh_sc.done) p.done[a] = 1;
+    }
     for (int i = lane; i < LB_HIST * d; i += 32) { gS[i] = sh_S[i]; gY[i] = sh_Y[i]; }
     if (lane < LB_HIST) p.rho[a * LB_HIST + lane] = sh_rho[lane];
   }
+#ifdef GPO_ACQ_TIMING
+  if (lane == 0 && a == 0) printf("  lbfgs: stage %lld A %lld dir %lld (passes %d) C %lld wb %lld\n", lt[1] - lt[0], lt[2] - lt[1], lt[3] - lt[2], n_pass, lt[4] - lt[3], clock64() - lt[4]);
+#endif
 }
 
 // stand-alone form: one warp (block) per anchor
-__global__ void __launch_bounds__(32) lbfgs_update_kernel(const LbfgsParams* __restrict__ p) {
-  lbfgs_anchor_update(*p, (int)blockIdx.x, (int)threadIdx.x);
+__global__ void __launch_bounds__(32) lbfgs_update_kernel(const LbfgsParams p) {
+  LbStage st;
+  lbfgs_stage_issue(p, (int)blockIdx.x, (int)threadIdx.x, st);
+  lbfgs_anchor_update(p, (int)blockIdx.x, (int)threadIdx.x, st);
 }
 
 }  // namespace gpo

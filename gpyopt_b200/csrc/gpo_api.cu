@@ -122,6 +122,7 @@ struct gpo_engine {
   long long fit_graph_launches = 0;
   int opt_fit_trace = 0;    // measurement aid: time every launch of factorize_chain with events and print the timeline to stderr
   int opt_fit_path = 0;     // refit: 0 short critical chain (factorize_chain), 1 the round-1 look-ahead scheme (factorize)
+  CUtensorMap rowmapW[3], rowmapX[3];   // W^-1 / L^-1 with [8 | 16 | 32 rows][128 columns] boxes (latency kernels)
   int opt_desync = 1;       // co-resident GEMM CTAs walk their work items in opposite orders (GemmParams::sm_arrivals)
   int* sm_arrivals = nullptr;
   int prio_chain = 0, prio_diag = 0, prio_inv = 0, prio_bulk = 0, prio_w = 0;   // launch priorities of the refit's streams (gpo_create)
@@ -196,6 +197,21 @@ static int make_map(gpo_engine* eng, TMap* map, double* base, long long cols, lo
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   }
+  return GPO_OK;
+}
+
+// map over a [batch][rows][cols] float64 array with a [1][box_rows][box_cols] box, no swizzle (rows land back to back in shared memory)
+static int make_row_map(gpo_engine* eng, CUtensorMap* map, double* base, long long cols, long long rows, long long batch, int box_cols,
+                        int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 8, (cuuint64_t)cols * rows * 8};
+  cuuint32_t estr[3] = {1, 1, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled (row map) failed (%d)", (int)r);
   return GPO_OK;
 }
 
@@ -470,6 +486,10 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   if ((rc = make_map(eng, &eng->mapU, eng->U, n_pad, n_pad, S))) return rc;
   if ((rc = make_map(eng, &eng->mapW, eng->W, n_pad, n_pad, S))) return rc;
   if ((rc = make_map(eng, &eng->mapT, eng->T, n_pad, n_pad, S))) return rc;
+  for (int v = 0; v < 3; ++v) {
+    if ((rc = make_row_map(eng, &eng->rowmapW[v], eng->W, n_pad, n_pad, S, SMALLN_CW, 8 << v))) return rc;
+    if ((rc = make_row_map(eng, &eng->rowmapX[v], eng->X, n_pad, n_pad, S, SMALLN_CW, 8 << v))) return rc;
+  }
   eng->nc_ld = std::max<long long>(pick_chunk(eng, n_pad, S), n_pad);  // >= n_pad: the fmin sweep runs over X itself
   {  // K1 slices: 256 training rows (8 tiles of 32) per slice, at most 16 slices
     const int ntiles = n_pad / COV_JT;
@@ -1433,11 +1453,11 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
       GPO_CUDA_OK(cudaMalloc(&eng->smalln_sq, need));
       eng->smalln_sq_cap = need;
     }
-    p.W = eng->X; p.Ht = nullptr;
+    p.W = eng->X; p.Ht = nullptr; p.wmap = eng->rowmapX[rows == 32 ? 2 : rows == 16 ? 1 : 0];
     p.partial = eng->smalln_sq; p.part_z = (long long)row_blocks * SMALLN_LDP;
     p.final_rows = sq_dest; p.final_ld = sq_ld;
   } else {
-    p.W = eng->W;
+    p.W = eng->W; p.wmap = eng->rowmapW[rows == 32 ? 2 : rows == 16 ? 1 : 0];
     p.partial = s.partial; p.part_z = (long long)row_blocks * (d_epi + 2) * SMALLN_LDP;
     p.final_rows = s.partial + (long long)eng->S * p.part_z; p.final_ld = SMALLN_FLD;
     *final_rows = p.final_rows;
@@ -1502,12 +1522,12 @@ static int launch_smalln_both(gpo_engine* eng, const Slot& s, int nc, int d_epi,
   pw.Kt = s.Kt; pw.Ht = use_ht ? s.Ht : nullptr; pw.kt_z = eng->nc_ld * (long long)n_pad;
   pw.Xtc = eng->Xtc; pw.ldx = n_pad; pw.n_pad = n_pad; pw.d = d_epi; pw.ldp = SMALLN_LDP;
   pw.ticket = eng->smalln_ticket;
-  pw.W = eng->W;
+  pw.W = eng->W; pw.wmap = eng->rowmapW[rows == 16 ? 1 : 0];
   pw.partial = s.partial; pw.part_z = (long long)row_blocks * (d_epi + 2) * SMALLN_LDP;
   pw.final_rows = s.partial + (long long)eng->S * pw.part_z; pw.final_ld = SMALLN_FLD;
   *final_rows = pw.final_rows;
   ps = pw;
-  ps.W = eng->X; ps.Ht = nullptr; ps.ticket = eng->smalln_ticket + eng->S;
+  ps.W = eng->X; ps.wmap = eng->rowmapX[rows == 16 ? 1 : 0]; ps.Ht = nullptr; ps.ticket = eng->smalln_ticket + eng->S;
   ps.partial = eng->smalln_sq; ps.part_z = (long long)row_blocks * SMALLN_LDP;
   ps.final_rows = s.partial_sq; ps.final_ld = eng->nc_ld;
   dim3 grid((unsigned)row_blocks, (unsigned)eng->S, 2);

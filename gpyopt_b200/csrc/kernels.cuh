@@ -1365,6 +1365,10 @@ struct SmallNParams {
   double* final_rows;                    // [S][nvals][final_ld]: the partial rows added in row-block order by the last CTA
   long long final_ld;
   int* ticket;                           // [S] arrival counters (zero before the launch; the last CTA resets its own)
+  // [S][n_pad][n_pad] as a 3-D tensor map with a [1][SMALLN_ROWS][SMALLN_CW] box: ONE tensor copy fills a ring stage (a stage used
+  // to be SMALLN_ROWS separate 1 KB bulk copies; at n = 4096 that was 200,000 copy operations for 201 MB and the kernel ran at
+  // 2.3 TB/s with the copy engines, not HBM, as the limit)
+  alignas(64) CUtensorMap wmap;
 };
 
 // SQ = true: the strict-variance form instead.  W is then X = L^-1 (lower triangular: the column loop stops at the
@@ -1390,7 +1394,6 @@ __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
   const int n_pad = p.n_pad, d = SQ ? -1 : p.d;   // d + 2 values per candidate (SQ: one)
   const int row0 = rb * SMALLN_ROWS + warp * R;
   const int nchunks = SQ ? (rb * SMALLN_ROWS + SMALLN_ROWS + SMALLN_CW - 1) / SMALLN_CW : n_pad / SMALLN_CW;
-  const double* Wblk = p.W + (long long)z * p.w_z + (long long)rb * SMALLN_ROWS * n_pad;
   const double* Kt = p.Kt + (long long)z * p.kt_z;
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -1400,11 +1403,10 @@ __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
   __syncthreads();
   auto issue = [&](int t) {  // warp 0: chunk t of all 32 rows into stage t % STAGES
     const int s = t % SMALLN_STAGES;
-    if (lane == 0) mbar_arrive_expect_tx(&full[s], SMALLN_ROWS * SMALLN_CW * 8);
-    __syncwarp();
-    if (lane < SMALLN_ROWS)
-      tma_bulk_load(tile + ((long long)s * SMALLN_ROWS + lane) * SMALLN_CW, Wblk + (long long)lane * n_pad + (long long)t * SMALLN_CW,
-                    SMALLN_CW * 8, &full[s]);
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&full[s], SMALLN_ROWS * SMALLN_CW * 8);
+      tma_load_3d(tile + (long long)s * SMALLN_ROWS * SMALLN_CW, &p.wmap, &full[s], t * SMALLN_CW, rb * SMALLN_ROWS, z);
+    }
   };
   if (warp == 0)
     for (int t = 0; t < SMALLN_STAGES && t < nchunks; ++t) issue(t);
@@ -1511,7 +1513,7 @@ __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
 }
 
 template <int NC, bool SQ, int SMALLN_ROWS>
-__global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
+__global__ void __launch_bounds__(256) smalln_wk_kernel(const __grid_constant__ SmallNParams p) {
   smalln_wk_body<NC, SQ, SMALLN_ROWS>(p);
 }
 
@@ -1519,7 +1521,7 @@ __global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
 // W^-1, grid.z = 1 streams L^-1, concurrently -- alone each of them is latency-bound (2.1 / 1.4 TB/s at n = 4096: 63 + 49 us back
 // to back), together they keep twice as many TMA stages in flight.
 template <int NC, int SMALLN_ROWS>
-__global__ void __launch_bounds__(256) smalln_both_kernel(const SmallNParams pw, const SmallNParams psq) {
+__global__ void __launch_bounds__(256) smalln_both_kernel(const __grid_constant__ SmallNParams pw, const __grid_constant__ SmallNParams psq) {
   if (blockIdx.z == 0) smalln_wk_body<NC, false, SMALLN_ROWS>(pw);
   else smalln_wk_body<NC, true, SMALLN_ROWS>(psq);
 }

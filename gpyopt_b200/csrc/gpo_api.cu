@@ -25,6 +25,7 @@ struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   double* Kt = nullptr;  // [S][nc_ld][n_pad]
+  CUtensorMap rowmapKt;  // the same with [8 rows][128 columns] boxes (latency kernels)
   double* Ht = nullptr;  // [S][nc_ld][n_pad], only for non-RBF kernels (allocated on demand)
   TMap mapKt;
   double* Tt = nullptr;  // [S][nc_ld][n_pad]  t = L^-1 k of the chunk (strict gradient sweeps: b = L^-T t), allocated on demand
@@ -507,6 +508,7 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
     GPO_CUDA_OK(cudaMalloc(&s.partial_sq, (size_t)S * tiles_m * eng->nc_ld * 8));
     if (S > 1) GPO_CUDA_OK(cudaMalloc(&s.zbuf, (size_t)S * (d + 1) * eng->nc_ld * 8));
     if ((rc = make_map(eng, &s.mapKt, s.Kt, n_pad, eng->nc_ld, S))) return rc;
+    if ((rc = make_row_map(eng, &s.rowmapKt, s.Kt, n_pad, eng->nc_ld, S, SMALLN_CW, SMALLN_KROWS))) return rc;
   }
   eng->cap_n_pad = n_pad; eng->cap_d = d; eng->cap_S = S;
   return GPO_OK;
@@ -1468,7 +1470,7 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
   double* final0 = p.final_rows;
   for (int g0 = 0; g0 < nc; g0 += SMALLN_MAX) {
     const int ncg = std::min(SMALLN_MAX, nc - g0);
-    p.Kt = s.Kt + (long long)g0 * n_pad;
+    p.Kt = s.Kt + (long long)g0 * n_pad; p.kmap = s.rowmapKt; p.k_row0 = g0;
     p.Ht = (!sq && use_ht) ? s.Ht + (long long)g0 * n_pad : nullptr;
     p.final_rows = final0 + g0;
     if (rows == 32) { if (sq) launch_smalln_r<true, 32>(p, ncg, grid, st); else launch_smalln_r<false, 32>(p, ncg, grid, st); }
@@ -1534,7 +1536,7 @@ static int launch_smalln_both(gpo_engine* eng, const Slot& s, int nc, int d_epi,
   double* fw = pw.final_rows; double* fs = ps.final_rows;
   for (int g0 = 0; g0 < nc; g0 += SMALLN_MAX) {
     const int ncg = std::min(SMALLN_MAX, nc - g0);
-    pw.Kt = s.Kt + (long long)g0 * n_pad; ps.Kt = pw.Kt;
+    pw.Kt = s.Kt + (long long)g0 * n_pad; ps.Kt = pw.Kt; pw.kmap = s.rowmapKt; ps.kmap = s.rowmapKt; pw.k_row0 = ps.k_row0 = g0;
     pw.Ht = use_ht ? s.Ht + (long long)g0 * n_pad : nullptr;
     pw.final_rows = fw + g0; ps.final_rows = fs + g0;
     if (rows == 16) launch_smalln_both_r<16>(pw, ps, ncg, grid, st);
@@ -1564,7 +1566,8 @@ static int launch_cov_small(gpo_engine* eng, const CovParams& p_in, int nc, cuda
   const int tail = nc % SMALLN_MAX == 0 ? SMALLN_MAX : nc % SMALLN_MAX;
   p.nc_run = (nc - tail) + (tail <= 1 ? 1 : tail <= 2 ? 2 : tail <= 4 ? 4 : 8);
   p.ticket = eng->smalln_ticket;
-  dim3 grid((unsigned)p.js, (unsigned)eng->S, 1);
+  static_assert(SMALLN_SLOTS == SMALLN_MAX_CALL, "slot columns of cov_small_kernel");
+  dim3 grid((unsigned)(p.js * COV_SUB), (unsigned)eng->S, 1);
   cov_small_kernel<<<grid, 256, 0, st>>>(p);
   eng->launches++;
   GPO_CUDA_OK(cudaGetLastError());

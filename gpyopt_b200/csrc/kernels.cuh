@@ -1369,6 +1369,8 @@ struct SmallNParams {
   // to be SMALLN_ROWS separate 1 KB bulk copies; at n = 4096 that was 200,000 copy operations for 201 MB and the kernel ran at
   // 2.3 TB/s with the copy engines, not HBM, as the limit)
   alignas(64) CUtensorMap wmap;
+  alignas(64) CUtensorMap kmap;          // K*^T chunk [S][nc_ld][n_pad], box [1][8][SMALLN_CW]
+  int k_row0;                            // first candidate row of this launch's group
 };
 
 // SQ = true: the strict-variance form instead.  W is then X = L^-1 (lower triangular: the column loop stops at the
@@ -1381,14 +1383,22 @@ struct SmallNParams {
 // SMALLN_ROWS is a template parameter (32 / 16 / 8 rows per CTA, i.e. 4 / 2 / 1 per warp): smaller matrices need more,
 // thinner CTAs to put every SM's load path to work (n = 2048: 64 CTAs of 32 rows took 25 us for 32 MB out of L2).
 constexpr int SMALLN_CW = 128, SMALLN_STAGES = 4;
-constexpr int smalln_smem_bytes(int rows) { return SMALLN_STAGES * rows * SMALLN_CW * 8 + SMALLN_STAGES * 8; }
+// (the ring also carries the candidates' covariance chunk, 8 rows of K*^T per stage: fetched by plain loads at the point of use they
+// were what the warps waited for -- 50 % long-scoreboard stalls at n = 4096)
+constexpr int SMALLN_KROWS = 8;
+// ... in the 16- and 32-row shapes; the 8-row shape (n < 2048: a few chunks per CTA) measured faster with the plain loads
+__host__ __device__ constexpr bool smalln_k_in_ring(int rows) { return rows >= 16; }
+constexpr int smalln_smem_bytes(int rows) { return SMALLN_STAGES * (rows + (smalln_k_in_ring(rows) ? SMALLN_KROWS : 0)) * SMALLN_CW * 8 + SMALLN_STAGES * 8; }
 
 template <int NC, bool SQ, int SMALLN_ROWS>
 __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
   extern __shared__ __align__(128) double smalln_smem[];
   __shared__ double red[8][DMAX + 2][NC];
+  static_assert(NC <= SMALLN_KROWS, "ring sized for up to SMALLN_KROWS candidates");
   double* tile = smalln_smem;                                                            // [STAGES][ROWS][CW]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smalln_smem + SMALLN_STAGES * SMALLN_ROWS * SMALLN_CW);
+  constexpr bool KRING = smalln_k_in_ring(SMALLN_ROWS);
+  double* ktile = smalln_smem + SMALLN_STAGES * SMALLN_ROWS * SMALLN_CW;                 // [STAGES][KROWS][CW]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smalln_smem + SMALLN_STAGES * (SMALLN_ROWS + (KRING ? SMALLN_KROWS : 0)) * SMALLN_CW);
   constexpr int R = SMALLN_ROWS / 8;
   const int z = blockIdx.y, rb = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_pad = p.n_pad, d = SQ ? -1 : p.d;   // d + 2 values per candidate (SQ: one)
@@ -1404,8 +1414,9 @@ __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
   auto issue = [&](int t) {  // warp 0: chunk t of all 32 rows into stage t % STAGES
     const int s = t % SMALLN_STAGES;
     if (lane == 0) {
-      mbar_arrive_expect_tx(&full[s], SMALLN_ROWS * SMALLN_CW * 8);
+      mbar_arrive_expect_tx(&full[s], (SMALLN_ROWS + (KRING ? SMALLN_KROWS : 0)) * SMALLN_CW * 8);
       tma_load_3d(tile + (long long)s * SMALLN_ROWS * SMALLN_CW, &p.wmap, &full[s], t * SMALLN_CW, rb * SMALLN_ROWS, z);
+      if (KRING) tma_load_3d(ktile + (long long)s * SMALLN_KROWS * SMALLN_CW, &p.kmap, &full[s], t * SMALLN_CW, p.k_row0, z);
     }
   };
   if (warp == 0)
@@ -1417,13 +1428,22 @@ __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
     for (int i = 0; i < NC; ++i) acc[r][i] = 0.0;
   for (int t = 0; t < nchunks; ++t) {
     const int s = t % SMALLN_STAGES;
-    double2 kv[2][NC];   // this chunk of the candidates' covariance vectors (shared by every CTA: L1 / L2 hits)
+    double2 kv[2][NC];   // this chunk of the candidates' covariance vectors: staged with the rows, or straight from L1 / L2
+    if (!KRING) {
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int i = 0; i < NC; ++i)
-        kv[u][i] = __ldg(reinterpret_cast<const double2*>(Kt + (long long)i * n_pad + t * SMALLN_CW + 64 * u + 2 * lane));
+        for (int i = 0; i < NC; ++i)
+          kv[u][i] = __ldg(reinterpret_cast<const double2*>(Kt + (long long)i * n_pad + t * SMALLN_CW + 64 * u + 2 * lane));
+    }
     mbar_wait(&full[s], (uint32_t)((t / SMALLN_STAGES) & 1));
+    if (KRING) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+          kv[u][i] = *reinterpret_cast<const double2*>(ktile + ((long long)s * SMALLN_KROWS + i) * SMALLN_CW + 64 * u + 2 * lane);
+    }
     const double* ts = tile + ((long long)s * SMALLN_ROWS + warp * R) * SMALLN_CW + 2 * lane;
 #pragma unroll
     for (int u = 0; u < 2; ++u)
@@ -1530,17 +1550,24 @@ __global__ void __launch_bounds__(256) smalln_both_kernel(const __grid_constant_
 // would run 128-candidate blocks that are all padding but one row).  Block `split` covers K1's slice `split` of the
 // training index and leaves the same per-slice partial sums in mean / dmean, K*^T / H*^T rows in Kt / Ht, for the
 // candidate slots 0 .. nc_run-1 (slots past the last candidate shadow it, as K1's padding does).
+constexpr int SMALLN_SLOTS = 32;   // candidate slots of a latency-path call (= SMALLN_MAX_CALL on the host side)
+constexpr int COV_SUB = 4;    // CTAs per slice of the training index (grid.x = js * COV_SUB)
 __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
-  const int z = blockIdx.y, split = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int z = blockIdx.y, split = blockIdx.x / COV_SUB, ss = blockIdx.x % COV_SUB;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = p.d;
   const double* invl = p.invl + (long long)z * d;
   const double sf2 = p.sigf2[z];
   const double* alpha = p.alpha + (long long)z * p.n_pad;
   const int j_begin = split * p.tiles_per_split * COV_JT, j_end = min(p.n_pad, j_begin + p.tiles_per_split * COV_JT);
+  // this CTA's quarter of the slice (whole 32-point groups)
+  const int sub_len = (((j_end - j_begin) / COV_SUB + 31) / 32) * 32;
+  const int jb = j_begin + ss * sub_len, je = min(j_end, jb + sub_len);
   const long long zs = (long long)z * p.js + split;
-  // One WARP per candidate slot, the eight warps of the block work on eight slots at once (the first version walked the slots one
-  // after the other with two block barriers each: 28 us for eight slots, all of it latency).  A slot's sums are formed by its warp
-  // alone -- lane-strided partial sums, then a fixed shuffle tree -- so they do not depend on the other slots of the call.
+  // One WARP per candidate slot, the eight warps of the block work on eight slots at once, and COV_SUB CTAs share a slice (the
+  // first version walked the slots one after the other, 256 points each, with two block barriers per slot: 28 us for eight slots,
+  // all of it latency).  A slot's partial sums are formed by its warp alone -- lane-strided, then a fixed shuffle tree -- and are
+  // parked in columns i + 32 ss of the slice's row; they do not depend on the other slots of the call.
   for (int i = warp; i < (int)p.nc_run; i += 8) {
     const long long cand = i < p.n_cand ? i : p.n_cand - 1;
     double xs[DMAX], m = 0.0, dm[DMAX];
@@ -1549,7 +1576,7 @@ __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
       xs[q] = q < d ? p.Xs[cand * d + q] * invl[q] : 0.0;
       dm[q] = 0.0;
     }
-    for (int j = j_begin + lane; j < j_end; j += 32) {
+    for (int j = jb + lane; j < je; j += 32) {
       double r2 = 0.0, df[DMAX];
 #pragma unroll
       for (int q = 0; q < DMAX; ++q) {
@@ -1567,22 +1594,22 @@ __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
       if (p.Kt) p.Kt[((long long)z * p.nc_ld + i) * p.n_pad + j] = kv;
       if (p.Ht) p.Ht[((long long)z * p.nc_ld + i) * p.n_pad + j] = hv;
     }
+    const int col = i + SMALLN_SLOTS * ss;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
-    if (lane == 0) p.mean[zs * p.nc_ld + i] = m;
+    if (lane == 0) p.mean[zs * p.nc_ld + col] = m;
     if (p.dmean) {
 #pragma unroll
       for (int q = 0; q < DMAX; ++q)
         if (q < d) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) dm[q] += __shfl_xor_sync(0xffffffffu, dm[q], o);
-          if (lane == 0) p.dmean[(zs * d + q) * p.nc_ld + i] = dm[q] * invl[q];
+          if (lane == 0) p.dmean[(zs * d + q) * p.nc_ld + col] = dm[q] * invl[q];
         }
     }
   }
-  // the last block of this hyper-parameter set adds the slices (in slice order) into slice 0: K3 then reads one value
-  // per candidate and output instead of walking js dependent loads for each (41 us for a single point at n=4096)
-  if (p.js == 1) return;
+  // the last block of this hyper-parameter set adds the js * COV_SUB partial sums (fixed order) into column i of slice 0: K3 then
+  // reads one value per candidate and output instead of walking dependent loads for each (41 us for a single point at n=4096)
   __shared__ int is_last;
   __threadfence();
   __syncthreads();
@@ -1594,23 +1621,24 @@ __global__ void __launch_bounds__(256) cov_small_kernel(const CovParams p) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  const int nv = p.dmean ? d + 1 : 1;
-  for (int idx = tid; idx < nv * (int)p.nc_run; idx += 256) {
+  // one warp per (value, slot) pair: the lanes fetch the partial sums (entry e = slice * COV_SUB + quarter on lane e % 32; at most
+  // 16 slices -> two entries per lane) in one round trip, a fixed shuffle tree adds them
+  const int nv = p.dmean ? d + 1 : 1, n_ent = p.js * COV_SUB;
+  for (int idx = warp; idx < nv * (int)p.nc_run; idx += 8) {
     const int v = idx / (int)p.nc_run, i = idx - v * (int)p.nc_run;
-    // all slices are fetched before the first add (added one by one, each load waited for the previous add: js round trips)
     const double* src = v == 0 ? p.mean + (long long)z * p.js * p.nc_ld + i : p.dmean + ((long long)z * p.js * d + (v - 1)) * p.nc_ld + i;
     const long long stride = v == 0 ? p.nc_ld : (long long)d * p.nc_ld;
-    double t = 0.0;
-    for (int sp0 = 0; sp0 < p.js; sp0 += 16) {
-      double vals[16];
+    const int e0 = lane, e1 = lane + 32;
+    const double v0 = e0 < n_ent ? __ldcg(src + (long long)(e0 / COV_SUB) * stride + SMALLN_SLOTS * (e0 % COV_SUB)) : 0.0;
+    const double v1 = e1 < n_ent ? __ldcg(src + (long long)(e1 / COV_SUB) * stride + SMALLN_SLOTS * (e1 % COV_SUB)) : 0.0;
+    double t = v0 + v1;
 #pragma unroll
-      for (int u = 0; u < 16; ++u) vals[u] = sp0 + u < p.js ? __ldcg(src + (long long)(sp0 + u) * stride) : 0.0;
-#pragma unroll
-      for (int u = 0; u < 16; ++u)
-        if (sp0 + u < p.js) t += vals[u];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncwarp();
+    if (lane == 0) {
+      if (v == 0) p.mean[(long long)z * p.js * p.nc_ld + i] = t;
+      else p.dmean[((long long)z * p.js * d + (v - 1)) * p.nc_ld + i] = t;
     }
-    if (v == 0) p.mean[(long long)z * p.js * p.nc_ld + i] = t;
-    else p.dmean[((long long)z * p.js * d + (v - 1)) * p.nc_ld + i] = t;
   }
 }
 

@@ -344,7 +344,7 @@ class Engine(object):
         include/gpo_b200.h."""
         self._check(self._lib.gpo_set_strict_variance(self._h, int(mode)), 'gpo_set_strict_variance')
 
-    OPTIONS = {'serpentine': 0, 'bn_sweep': 1, 'bn_fit': 2, 'inverse': 3, 'fused_small': 4, 'prefetch_kt': 5, 'fit_path': 6, 'fit_trace': 7, 'fit_graph': 8, 'fit_chain_max': 9, 'desync': 10}
+    OPTIONS = {'serpentine': 0, 'bn_sweep': 1, 'bn_fit': 2, 'inverse': 3, 'fused_small': 4, 'prefetch_kt': 5, 'fit_path': 6, 'fit_trace': 7, 'fit_graph': 8, 'fit_chain_max': 9, 'desync': 10, 'k1_slice': 11}
 
     def set_option(self, key, value):
         """Tuning knobs for measurements (gpo_set_option in include/gpo_b200.h)."""

@@ -124,6 +124,7 @@ struct gpo_engine {
   int opt_fit_trace = 0;    // measurement aid: time every launch of factorize_chain with events and print the timeline to stderr
   int opt_fit_path = 0;     // refit: 0 short critical chain (factorize_chain), 1 the round-1 look-ahead scheme (factorize)
   CUtensorMap rowmapW[3], rowmapX[3];   // W^-1 / L^-1 with [8 | 16 | 32 rows][128 columns] boxes (latency kernels)
+  int opt_k1_slice = 256;   // training rows per K1 slice (grid.y of cov_mean_kernel = n_pad / this, at most 16)
   int opt_desync = 1;       // co-resident GEMM CTAs walk their work items in opposite orders (GemmParams::sm_arrivals)
   int* sm_arrivals = nullptr;
   int prio_chain = 0, prio_diag = 0, prio_inv = 0, prio_bulk = 0, prio_w = 0;   // launch priorities of the refit's streams (gpo_create)
@@ -494,7 +495,7 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   eng->nc_ld = std::max<long long>(pick_chunk(eng, n_pad, S), n_pad);  // >= n_pad: the fmin sweep runs over X itself
   {  // K1 slices: 256 training rows (8 tiles of 32) per slice, at most 16 slices
     const int ntiles = n_pad / COV_JT;
-    int js = std::min(16, std::max(1, n_pad / 256));
+    int js = std::min(16, std::max(1, n_pad / eng->opt_k1_slice));
     eng->tiles_per_split = (ntiles + js - 1) / js;
     eng->js = (ntiles + eng->tiles_per_split - 1) / eng->tiles_per_split;
   }
@@ -2296,6 +2297,7 @@ extern "C" int gpo_set_option(gpo_engine* eng, int key, long long value) {
     case GPO_OPT_FIT_TRACE: eng->opt_fit_trace = value != 0; break;
     case GPO_OPT_FIT_GRAPH: eng->opt_fit_graph = value != 0; break;
     case GPO_OPT_DESYNC: eng->opt_desync = value != 0; break;
+    case GPO_OPT_K1_SLICE: if (value != 128 && value != 256 && value != 512) return GPO_ERR_ARG; eng->opt_k1_slice = (int)value; eng->cap_n_pad = 0; break;
     case GPO_OPT_FIT_CHAIN_MAX: if (value < 1 || value > 4096) return GPO_ERR_ARG; eng->opt_fit_chain_max = (int)value; break;
     default: GPO_FAIL(GPO_ERR_ARG, "gpo_set_option: unknown key %d", key);
   }

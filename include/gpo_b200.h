@@ -186,10 +186,12 @@ int gpo_get_info(gpo_engine* eng, double* info, int count);
  *   GPO_OPT_FIT_GRAPH   1 (default) / 0: replay the refit's launch sequence as a CUDA graph captured once per problem shape
  *   GPO_OPT_FIT_CHAIN_MAX  largest number of 128-row blocks (n_pad / 128) the short-chain refit is used for
  *   GPO_OPT_DESYNC      1 (default) / 0: the two GEMM CTAs sharing an SM walk their work items in opposite orders, so that their
- *                       epilogues do not coincide (results are unchanged bit for bit) */
+ *                       epilogues do not coincide (results are unchanged bit for bit)
+ *   GPO_OPT_K1_SLICE    training rows per slice of the covariance kernel K1 (128 / 256 / 512); takes effect with the next gpo_fit */
 typedef enum { GPO_OPT_SERPENTINE = 0, GPO_OPT_BN_SWEEP = 1, GPO_OPT_BN_FIT = 2, GPO_OPT_INVERSE = 3, GPO_OPT_FUSED_SMALL = 4,
                GPO_OPT_PREFETCH_KT = 5, GPO_OPT_FIT_PATH = 6, GPO_OPT_FIT_TRACE = 7, GPO_OPT_FIT_GRAPH = 8,
-               GPO_OPT_FIT_CHAIN_MAX = 9, GPO_OPT_DESYNC = 10 } gpo_option;
+               GPO_OPT_FIT_CHAIN_MAX = 9, GPO_OPT_DESYNC = 10,
+               GPO_OPT_K1_SLICE = 11 } gpo_option;
 int gpo_set_option(gpo_engine* eng, int key, long long value);
 
 /* Multi-GPU replication of the posterior state (one process per GPU; the collective itself is issued by the

@@ -664,6 +664,47 @@ def test_gemm_shapes_and_schedules_agree(engine, bn_sweep, serp):
         e2.close()
 
 
+def test_refit_schedules_and_item_order_do_not_enter_the_arithmetic():
+    """(a) The two co-resident GEMM CTAs of an SM walking their work items in opposite orders (GPO_OPT_DESYNC) leaves every sweep
+    output bit unchanged.  (b) The refit replayed as a CUDA graph (kernel nodes carrying launch priorities) and enqueued on plain
+    prioritised streams gives bitwise the same state, repeatedly; the round-1 look-ahead schedule, an independent arrangement of the
+    same mathematics, agrees with it to rounding on L, L^-1, W^-1, alpha and the log-likelihood (three hyper-parameter sets)."""
+    from gpyopt_b200 import Engine
+    from oracle import gpyopt_numpy as og
+    rng = np.random.default_rng(11)
+    n, d, N, S = 900, 4, 5000, 3
+    X = rng.random((n, d)); Y = og.normalize_stats(np.sin(3 * X).sum(1, keepdims=True))[:, 0]
+    Xs = rng.random((N, d))
+    var = np.array([1.0, 1.3, 0.8]); ls = np.array([[0.5], [0.7], [0.4]]); noise = np.array([1e-2, 2e-2, 5e-2])
+    states, outs, ll = {}, {}, {}
+    for name, opts in (('graph', {}), ('streams', {'fit_graph': 0}), ('lookahead', {'fit_path': 1}), ('no_desync', {'desync': 0})):
+        e = Engine(0)
+        try:
+            for k, v in opts.items():
+                e.set_option(k, v)
+            e.fit('rbf', X, Y, var * 1.5, ls, noise)        # (a first problem of the same shape: the graph is captured here ...)
+            e.fit('rbf', X, Y, var, ls, noise)              # (... and replayed here)
+            states[name] = e.get_state()
+            ll[name] = e.get_loglik()[0]
+            outs[name] = list(e.predict_grad(Xs)) + list(e.acq('EI_MCMC', 0.01, Xs, grad=True))
+            if name == 'graph':
+                e.fit('rbf', X, Y, var * 0.7, ls, noise)
+                e.fit('rbf', X, Y, var, ls, noise)
+                for a, b in zip(e.get_state(), states[name]):
+                    assert np.array_equal(a, b)
+        finally:
+            e.close()
+    for name in ('streams', 'no_desync'):
+        for a, b in zip(states[name], states['graph']):
+            assert np.array_equal(a, b)
+        for a, b in zip(outs[name], outs['graph']):
+            assert np.array_equal(a, b)
+        assert np.array_equal(ll[name], ll['graph'])
+    for a, b in zip(states['lookahead'], states['graph']):     # (two summation orders: eps * cond(Ky) ~ 1e-12 on these models)
+        assert scaled_err(a, b) < TOL
+    assert np.max(np.abs(ll['lookahead'] - ll['graph']) / np.abs(ll['graph'])) < 1e-12
+
+
 # ------------------------------------------------------------------------------------------------------
 # (3) properties at the full BASELINE sizes (n = 2048, d = 6; the oracle is too slow / too big there)
 # ------------------------------------------------------------------------------------------------------

@@ -92,6 +92,8 @@ struct gpo_engine {
   // page-locked staging of the latency path: a host-array call with <= 8 candidates uploads its points from here with an
   // asynchronous copy and K3 writes the results straight into it (no device->host copies, one stream sync)
   double* fit_pin = nullptr;  size_t fit_pin_cap = 0;   // page-locked staging of gpo_fit's small uploads / downloads
+  unsigned char* lb_pin = nullptr;       // gpo_lbfgs: page-locked staging of start points / box / results
+  size_t lb_pin_bytes = 0;
   unsigned char* pin_buf = nullptr;      // host address
   unsigned char* pin_dev = nullptr;      // the same memory as the device sees it
   bool smalln_attr_done = false, smalln_both_attr_done = false;
@@ -386,6 +388,7 @@ extern "C" int gpo_destroy(gpo_engine* eng) {
   if (eng->gen_idx) cudaFree(eng->gen_idx);
   if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
   if (eng->pin_buf) cudaFreeHost(eng->pin_buf);
+  if (eng->lb_pin) cudaFreeHost(eng->lb_pin);
   if (eng->gradpart) cudaFree(eng->gradpart);
   if (eng->gradpart_pin) cudaFreeHost(eng->gradpart_pin);
   if (eng->fit_pin) cudaFreeHost(eng->fit_pin);
@@ -2158,30 +2161,37 @@ extern "C" int gpo_lbfgs(gpo_engine* eng, int kind, double par, int M, const dou
   const size_t Md = (size_t)M * d, MH = (size_t)M * LB_HIST;
   const size_t n_dbl = 6 * Md + 2 * MH * d + MH + 4 * (size_t)M + 2 * (size_t)d, n_int = 6 * (size_t)M + 2;
   int rc;
-  if ((rc = grow(eng, &eng->lb_buf, &eng->lb_bytes, n_dbl * 8 + (size_t)M * sizeof(LbLineSearch) + n_int * 4 + 64 + sizeof(LbfgsParams) + 64))) return rc;
+  if ((rc = grow(eng, &eng->lb_buf, &eng->lb_bytes, n_dbl * 8 + (size_t)M * sizeof(LbLineSearch) + n_int * 4 + 64))) return rc;
+  // page-locked staging of the call's inputs (start points, box) and outputs: one asynchronous upload, one synchronisation at the end
+  const size_t pin_in = (Md + 2 * (size_t)d) * 8, pin_out = (Md + M) * 8 + 2 * (size_t)M * 4;
+  if (pin_in + pin_out > eng->lb_pin_bytes) {
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
+    if (eng->lb_pin) cudaFreeHost(eng->lb_pin);
+    eng->lb_pin = nullptr; eng->lb_pin_bytes = 0;
+    GPO_CUDA_OK(cudaHostAlloc((void**)&eng->lb_pin, pin_in + pin_out, cudaHostAllocDefault));
+    eng->lb_pin_bytes = pin_in + pin_out;
+  }
   double* w = eng->lb_buf;
   LbfgsParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.d = d; p.negate = eng->lp_on ? 0 : 1; p.maxiter = maxiter; p.pgtol = pgtol; p.ftol = factr * 2.220446049250313e-16;
-  p.x = w; w += Md; p.g = w; w += Md; p.xt = w; w += Md; double* gt = w; w += Md; p.dir = w; w += Md; double* x0d = w; w += Md;
+  p.x = w; w += Md; p.g = w; w += Md; p.xt = w; w += Md; double* gt = w; w += Md; p.dir = w; w += Md;
+  double* x0d = w; w += Md; double* lo = w; w += d; double* hi = w; w += d;      // (contiguous: uploaded with one copy)
   p.S = w; w += MH * d; p.Y = w; w += MH * d; p.rho = w; w += MH;
   p.f = w; w += M; double* ft = w; w += M; p.step = w; w += M; p.gd = w; w += M;
-  double* lo = w; w += d; double* hi = w; w += d;
   p.ft = ft; p.gt = gt; p.lo = lo; p.hi = hi;
   p.ls = reinterpret_cast<LbLineSearch*>(w);
   int* iw = reinterpret_cast<int*>(p.ls + M);
   p.hist_n = iw; iw += M; p.hist_head = iw; iw += M; p.iter = iw; iw += M; p.phase = iw; iw += M;
   p.done = iw; iw += M; p.nfev = iw; iw += M; p.n_done = iw; iw += 2;
-  LbfgsParams* p_dev = reinterpret_cast<LbfgsParams*>((reinterpret_cast<uintptr_t>(iw) + 63) & ~(uintptr_t)63);
-  std::vector<double> hb(2 * (size_t)d);
+  GPO_CUDA_OK(cudaStreamSynchronize(st));   // (an earlier call's output copies have left the staging block)
+  double* hin = reinterpret_cast<double*>(eng->lb_pin);
+  memcpy(hin, x0, Md * 8);
   for (int q = 0; q < d; ++q) {
-    hb[q] = bounds[2 * q]; hb[d + q] = bounds[2 * q + 1];
-    if (!(hb[q] <= hb[d + q])) GPO_FAIL(GPO_ERR_ARG, "gpo_lbfgs: empty box in dimension %d", q);
+    hin[Md + q] = bounds[2 * q]; hin[Md + d + q] = bounds[2 * q + 1];
+    if (!(hin[Md + q] <= hin[Md + d + q])) GPO_FAIL(GPO_ERR_ARG, "gpo_lbfgs: empty box in dimension %d", q);
   }
-  GPO_CUDA_OK(cudaMemcpyAsync(lo, hb.data(), 2 * (size_t)d * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(x0d, x0, Md * 8, cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(p_dev, &p, sizeof(LbfgsParams), cudaMemcpyHostToDevice, st));
-  GPO_CUDA_OK(cudaStreamSynchronize(st));   // (pageable sources: the staging above is already complete; keeps hb alive)
+  GPO_CUDA_OK(cudaMemcpyAsync(x0d, hin, pin_in, cudaMemcpyHostToDevice, st));
   lbfgs_init_kernel<<<1, LB_MAXM, 0, st>>>(p, x0d);
   eng->launches++;
   GPO_CUDA_OK(cudaGetLastError());
@@ -2207,16 +2217,16 @@ extern "C" int gpo_lbfgs(gpo_engine* eng, int kind, double par, int M, const dou
       if (*pin_done >= M) break;
     }
   }
-  std::vector<int> hi_(2 * (size_t)M);
-  GPO_CUDA_OK(cudaMemcpyAsync(x_out, p.x, Md * 8, cudaMemcpyDeviceToHost, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(f_out, p.f, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(hi_.data(), p.iter, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
-  GPO_CUDA_OK(cudaMemcpyAsync(hi_.data() + M, p.nfev, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+  unsigned char* hout = eng->lb_pin + pin_in;
+  GPO_CUDA_OK(cudaMemcpyAsync(hout, p.x, Md * 8, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(hout + Md * 8, p.f, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(hout + (Md + M) * 8, p.iter, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+  GPO_CUDA_OK(cudaMemcpyAsync(hout + (Md + M) * 8 + (size_t)M * 4, p.nfev, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
   GPO_CUDA_OK(cudaStreamSynchronize(st));
-  for (int a = 0; a < M; ++a) {
-    if (iters) iters[a] = hi_[a];
-    if (nfev) nfev[a] = hi_[M + a];
-  }
+  memcpy(x_out, hout, Md * 8);
+  memcpy(f_out, hout + Md * 8, (size_t)M * 8);
+  if (iters) memcpy(iters, hout + (Md + M) * 8, (size_t)M * 4);
+  if (nfev) memcpy(nfev, hout + (Md + M) * 8 + (size_t)M * 4, (size_t)M * 4);
   return GPO_OK;
 }
 

@@ -793,11 +793,8 @@ __device__ __forceinline__ void block_argmax_store(double score, long long idx, 
 }
 
 // last stage of K3 for one candidate: MCMC average, then either the plain outputs or the Local-Penalization transform.
-// LP_LANES = 1: one thread per candidate (sweeps).  LP_LANES = 32: one warp per candidate (calls with a handful of points, where
-// K3 is a latency chain: 15 penalisers cost one thread ~40 us of erfc / log / exp): every lane carries the candidate's values,
-// the lanes split the penalisers, a shuffle tree adds their terms, lane 0 (`store`) writes.
-template <int LP_LANES>
-__device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, double f_acc, double (&df_acc)[DMAX], int lane, bool store) {
+// (one thread per candidate; calls with a handful of points take acq_finalize_warp below)
+__device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, double f_acc, double (&df_acc)[DMAX], bool store) {
   const int d = p.d;
   if (p.kind >= ACQ_EI_MCMC) {
     const double invS = 1.0 / (double)p.S;  // f_acqu/(len(means)): true division by S
@@ -829,8 +826,8 @@ __device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, 
     scale = 1.0 / fval;
   }
   val = -val;
-  double dsum = 0.0, pen = 0.0;
-  for (int k = LP_LANES > 1 ? lane : 0; k < p.lp_K; k += LP_LANES) {
+  double dsum = 0.0;
+  for (int k = 0; k < p.lp_K; ++k) {
     double nm2 = 0.0;
     for (int q = 0; q < d; ++q) {
       const double df = p.Xs[i * d + q] - p.lp_xb[k * d + q];
@@ -838,22 +835,13 @@ __device__ __forceinline__ double acq_finalize(const AcqParams& p, long long i, 
     }
     const double nm = sqrt(nm2);
     const double zz = (nm - p.lp_r[k]) / p.lp_s[k];
-    if (LP_LANES > 1) pen += log_ndtr(zz);
-    else val -= log_ndtr(zz);
+    val -= log_ndtr(zz);
     if (p.grad) {
       const double h = 0.5 * erfc(-zz * 0.70710678118654752440);  // norm.cdf(z)
       double dk = 1.0 / (p.lp_s[k] * 2.50662827463100050242 * h) * exp(-zz * zz / 2.0) / nm;
       if (h < 1e-50) dk = 0.0;
       dsum += dk;
     }
-  }
-  if (LP_LANES > 1) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      pen += __shfl_xor_sync(0xffffffffu, pen, o);
-      dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-    }
-    val -= pen;
   }
   if (store) {
     p.out_f[i] = val;
@@ -977,7 +965,7 @@ __global__ void __launch_bounds__(128) acq_kernel(const AcqParams p) {
     }
     return;
   }
-  const double score = acq_finalize<1>(p, i, f_acc, df_acc, 0, true);
+  const double score = acq_finalize(p, i, f_acc, df_acc, true);
   if (p.blk_val) block_argmax_store(score, p.row0 + i, p.blk_val, p.blk_idx, (p.row0 >> 7) + blockIdx.x);
 }
 
@@ -1016,7 +1004,7 @@ __device__ void lbfgs_anchor_update(const LbfgsParams& p, int a, int lane, const
 
 // K3 for calls with a handful of candidates (the L-BFGS steps): ONE WARP per candidate (grid = candidates, 32 threads).  For a
 // single thread K3 is a latency chain run from a cold instruction cache -- 72 us for 5 points with 15 Local-Penalization
-// penalisers at n = 4096 -- so the lanes split the penalisers (acq_finalize<32>) and lane 0 stores.  Hyper-parameter sets are
+// penalisers at n = 4096 -- so the lanes split the penalisers (acq_finalize_warp) and lane 0 stores.  Hyper-parameter sets are
 // walked in set order inside the warp (no zbuf / zsum / reduce launches).  With `lb` set the same warp continues into the
 // optimiser step of anchor `candidate` (lbfgs_anchor_update): evaluation epilogue and L-BFGS state machine in one launch.
 // Lane q of the warp owns coordinate q (d <= DMAX <= 32): the per-coordinate partial sums, gradient terms and outputs are one
@@ -1187,7 +1175,7 @@ __global__ void __launch_bounds__(128) acq_reduce_kernel(const AcqParams p) {
   double f_acc = p.zbuf[i], df_acc[DMAX];
 #pragma unroll
   for (int q = 0; q < DMAX; ++q) df_acc[q] = (p.grad && q < d) ? p.zbuf[(long long)(q + 1) * p.nc_pad + i] : 0.0;
-  const double score = acq_finalize<1>(p, i, f_acc, df_acc, 0, true);
+  const double score = acq_finalize(p, i, f_acc, df_acc, true);
   if (p.blk_val) block_argmax_store(score, p.row0 + i, p.blk_val, p.blk_idx, (p.row0 >> 7) + blockIdx.x);
 }
 

@@ -938,14 +938,20 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
       t_end(sc);
     }
     GPO_CUDA_OK(cudaEventRecord(ev(EV_ROW, kb), sc));
-    // ---- side: W^-1[i, j] += U[i, kb] U[j, kb]^T for j <= i <= kb (mirrored into the upper tiles with the last block row) ----
-    {
+    // ---- side: W^-1[i, j] += U[i, kb] U[j, kb]^T for j <= i <= kb (mirrored into the upper tiles with the last block row).  Two
+    //      block rows per launch (K = 256: half the read-modify-write passes over W^-1; U[kb, kb-1] is a never-written zero block,
+    //      so the extra products of block row kb add exact zeros) ----
+    //      -- except the last block row, which goes alone: it is the tail of the whole refit
+    const bool w_alone = rem == 0 || (rem == 1 && !(kb & 1));
+    if ((kb & 1) || w_alone) {
+      const int kb0 = ((kb & 1) && !w_alone) ? kb - 1 : kb;
       GPO_CUDA_OK(cudaStreamWaitEvent(se, ev(EV_ROW, kb), 0));
       R128Params w = r128_defaults();
       w.beta = 1.0;
-      w.A = eng->U; w.lda = n_pad; w.a_z = nn; w.a_col0 = kT;
-      w.B = eng->U; w.ldb = n_pad; w.b_z = nn; w.b_col0 = kT;
+      w.A = eng->U; w.lda = n_pad; w.a_z = nn; w.a_col0 = kb0 * TILE;
+      w.B = eng->U; w.ldb = n_pad; w.b_z = nn; w.b_col0 = kb0 * TILE;
       w.C = eng->W; w.ldc = n_pad; w.c_z = nn;
+      w.kchunks = (kb - kb0 + 1) * (TILE / RD_KC);
       if (rem == 0) { w.Ct = eng->W; w.ldct = n_pad; w.ct_z = nn; }
       w.tiles_m = (kb + 1) * 2; w.tiles_n = (kb + 1) * 2; w.skip_upper = 1;
       t_begin("w_acc", kb, 4, se);

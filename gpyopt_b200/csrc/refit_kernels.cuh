@@ -44,6 +44,7 @@ struct R128Params {
   int skip_upper;          // skip CTA tiles that lie entirely above the diagonal of C (symmetric updates: lower part only)
   double* C2; long long c2_z;   // may be null: dense copy [128][128] of output rows < 128, columns < 128 (the tile the next chain
                                 // kernel factors against: the panel kernel overwrites it in C while that kernel still reads it)
+  int kchunks;                  // rank128_dmma_kernel only: K in units of 32 (0 = 4, i.e. K = 128)
 };
 
 template <int MI, int NJ>
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(128, 2) rank128_dmma_kernel(const R128Params p
     }
     cp_async_commit();
   };
+  const int nch = p.kchunks > 0 ? p.kchunks : TILE / RD_KC;   // (>= 2)
   load_chunk(0, 0);
   load_chunk(1, 1);
   double acc[4][4][2];
@@ -198,8 +200,8 @@ __global__ void __launch_bounds__(128, 2) rank128_dmma_kernel(const R128Params p
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[f][j][0] = acc[f][j][1] = 0.0;
 #pragma unroll 1
-  for (int c = 0; c < TILE / RD_KC; ++c) {
-    if (c < TILE / RD_KC - 1) cp_async_wait<1>();
+  for (int c = 0; c < nch; ++c) {
+    if (c < nch - 1) cp_async_wait<1>();
     else cp_async_wait<0>();
     __syncthreads();
     const double* As = rd_sm + (c & 1) * RD_STAGE + (wm + g) * RD_LP + 2 * t;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(128, 2) rank128_dmma_kernel(const R128Params p
         for (int j = 0; j < 4; ++j) dmma_884(acc[f][j][0], acc[f][j][1], a[f].y, b[j].y);
     }
     __syncthreads();
-    if (c + 2 < TILE / RD_KC) load_chunk(c + 2, c & 1);
+    if (c + 2 < nch) load_chunk(c + 2, c & 1);
   }
   // accumulator (f, j, e) of lane (g, t): row wm + 8 f + g, column wn + 8 j + 2 t + e of the tile
   if (p.C) {

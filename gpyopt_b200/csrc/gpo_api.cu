@@ -647,7 +647,11 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
     p.a = {(kb + 1) * TILE, kb * TILE, 0, 0, 0, 1};
     p.b = {kb * TILE, kb * TILE, 0, 0, 0, 1};
     p.C = eng->A; p.ldc = n_pad; p.c_off_z = nn; p.c_row0 = (kb + 1) * TILE; p.c_col0 = kb * TILE;
-    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapX, p, S, st, 0, bnf))) return rc;
+    // (in place: a CTA reads all 128 k of its row block before it stores any column of it.  With the 128 x 64 shape TWO work items
+    // share a row block, each reading all of it and storing half: correct only while both run side by side.  Behind a side-stream
+    // trailing update that holds 116 SMs, from 35 block columns on (2 (nb - 2) items > 64 free CTA slots) the second halves started
+    // after the first halves had been stored -- a silently wrong factor at n = 4480 and "not positive definite" from n = 4608 on.)
+    if ((rc = launch_gemm(eng, EPI_STORE, eng->mapA, eng->mapX, p, S, st, 0, TILE))) return rc;
     // trailing update (lower tiles): A[kb+1:, kb+1:] -= P P^T
     GemmParams q = gemm_defaults();
     q.kblocks = 1;
@@ -1202,9 +1206,9 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
   for (int attempt = 0; attempt <= 6; ++attempt) {
     memcpy(pin_jit, eng->h_jit.data(), (size_t)S * 8);   // (the previous attempt's copy has completed: it was synchronised)
     GPO_CUDA_OK(cudaMemcpyAsync(eng->jitter, pin_jit, (size_t)S * 8, cudaMemcpyHostToDevice, st));
-    // (the short-chain schedule wins at every size measured: 4.4 vs 5.9 ms at n = 4096, 4.8 vs 6.6 at 4224; the look-ahead scheme
-    // stays as an A/B option and is not used above 33 block columns, where it reported spurious non-PD failures)
-    const bool chain_path = n_pad >= 2 * TILE && ((eng->opt_fit_path == 0 && n_pad <= (long long)eng->opt_fit_chain_max * TILE) || n_pad > 33 * TILE);
+    // (the short-chain schedule wins at every size measured: 3.9 vs 5.9 ms at n = 4096, 5.3 vs 8.2 at 4608; the look-ahead scheme
+    // stays as an A/B option: an independent arrangement of the same mathematics)
+    const bool chain_path = n_pad >= 2 * TILE && eng->opt_fit_path == 0 && n_pad <= (long long)eng->opt_fit_chain_max * TILE;
     if ((rc = chain_path ? factorize_chain_graph(eng, st) : factorize(eng, st))) return rc;
     GPO_CUDA_OK(cudaMemcpyAsync(pin_info, eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!chain_path && (rc = launch_alpha(eng, st))) return rc;   // (the chain path enqueues it itself, under the tail of W^-1)

@@ -956,8 +956,9 @@ def test_config5_gsobol_n4096_local_penalization(engine):
 
 def test_model_larger_than_4096_points(engine):
     """n = 5000 (40 block columns; beyond BASELINE's largest configuration): state, log-likelihood, predictions with gradients and
-    EI against the oracle; the refit is bit-reproducible.  (The round-1 look-ahead schedule reported 'not positive definite' from
-    n = 4608 on; the short-chain schedule is the default for every n >= 256 now.)"""
+    EI against the oracle; the refit is bit-reproducible; the look-ahead schedule agrees.  (Round 1's in-place panel product on the
+    128 x 64 GEMM shape was silently wrong from 35 block columns on -- two work items sharing a row block no longer ran side by side
+    behind the side-stream trailing update; BASELINE stops at n = 4096, so nothing tested it.)"""
     from oracle import gpy_numpy as G, gpyopt_numpy as og
     rng = np.random.default_rng(71)
     n, d, N = 5000, 5, 3000
@@ -987,6 +988,15 @@ def test_model_larger_than_4096_points(engine):
     engine.fit('matern52', X, Y, [1.3], [[2.5]], [1e-2])
     L2, _, Wi2, al2 = engine.get_state(Linv=False)
     assert np.array_equal(L, L2) and np.array_equal(Wi, Wi2) and np.array_equal(al, al2)
+    from gpyopt_b200 import Engine
+    e1 = Engine(0)
+    try:
+        e1.set_option('fit_path', 1)
+        e1.fit('matern52', X, Y, [1.3], [[2.5]], [1e-2])
+        L1, _, Wi1, al1 = e1.get_state(Linv=False)
+        assert scaled_err(L1, L) < TOL and scaled_err(Wi1, Wi) < TOL and scaled_err(al1, al) < TOL
+    finally:
+        e1.close()
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -1,5 +1,6 @@
-"""Refit for n >= 4096 on both schedules (fit_chain_max 31 -> look-ahead scheme, 64 -> short chain): latency, error message if any,
-and the factor against numpy.linalg.cholesky."""
+"""Refit for n >= 4096 on both schedules (fit_chain_max 31 -> round-1 look-ahead scheme, 64 -> short chain): latency, error message
+if any, and the factor against numpy.linalg.cholesky.  (This is the script that exposed the in-place panel race of the look-ahead
+scheme from 35 block columns on: DESIGN.md section 5, K4.)"""
 import os, sys, time, json
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))

@@ -194,6 +194,13 @@ __global__ void __launch_bounds__(128, 2) rank128_dmma_kernel(const R128Params p
   const int nch = p.kchunks > 0 ? p.kchunks : TILE / RD_KC;   // (>= 2)
   load_chunk(0, 0);
   load_chunk(1, 1);
+  if (p.C && p.beta != 0.0) {
+    // the read-modify-write epilogue fetches its 64 x 64 tile of C at the very end, from HBM when the matrix is larger than the L2
+    // (W^-1 at n = 4096: 134 MB): pull the 256 lines into the L2 now, a whole main loop ahead
+    const double* Cp = p.C + p.c_z * z + (long long)(p.c_row0 + m0 + (tid >> 1)) * p.ldc + p.c_col0 + n0 + (tid & 1) * 32;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(Cp));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(Cp + 16));
+  }
   double acc[4][4][2];
 #pragma unroll
   for (int f = 0; f < 4; ++f)

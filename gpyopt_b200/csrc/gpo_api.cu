@@ -121,7 +121,7 @@ struct gpo_engine {
   std::vector<cudaEvent_t> chol_ev;  // look-ahead events of the blocked Cholesky (2 per block column)
   int opt_fit_graph = 1;    // replay the launch sequence of factorize_chain as a CUDA graph (captured once per problem shape)
   cudaGraphExec_t fit_graph_exec = nullptr;
-  struct FitGraphKey { int n_pad, n, d, S, kern; const void* A; } fit_graph_key = {0, 0, 0, 0, 0, nullptr};
+  struct FitGraphKey { int n_pad, n, d, S, kern, path; const void* A; } fit_graph_key = {0, 0, 0, 0, 0, 0, nullptr};
   long long fit_graph_launches = 0;
   int opt_fit_trace = 0;    // measurement aid: time every launch of factorize_chain with events and print the timeline to stderr
   int opt_fit_path = 0;     // refit: 0 short critical chain (factorize_chain), 1 the round-1 look-ahead scheme (factorize)
@@ -547,6 +547,9 @@ static int launch_cov(gpo_engine* eng, const CovParams& p_in, bool grad, int S, 
 // --------------------------------------------------------------------------------------------------
 // refit (K4): blocked right-looking Cholesky, recursive triangular inverse, W^-1 = L^-T L^-1, alpha, fmin
 // --------------------------------------------------------------------------------------------------
+static R128Params r128_defaults();
+static int launch_r128d(gpo_engine* eng, const R128Params& p, int S, cudaStream_t st, int prio);
+static int launch_alpha(gpo_engine* eng, cudaStream_t st);
 struct TriNode { int lo, mid, hi; };
 static void build_tree(int lo, int hi, int depth, std::vector<std::vector<TriNode>>& levels) {
   if (hi - lo <= 1) return;
@@ -731,7 +734,17 @@ static int factorize(gpo_engine* eng, cudaStream_t st) {
     }
   }
   // W^-1 = L^-T L^-1 = U U^T  (k >= max(m, n) block), lower tiles mirrored into the upper ones
-  {
+  if (nb == 1) {
+    // a single block (n <= 128: every early BO iteration): four 64 x 64 tiles on four SMs instead of one persistent CTA walking a
+    // 128^3 product alone (26 -> 8 us of a 76 us refit)
+    R128Params w = r128_defaults();
+    w.A = eng->U; w.lda = n_pad; w.a_z = nn;
+    w.B = eng->U; w.ldb = n_pad; w.b_z = nn;
+    w.C = eng->W; w.ldc = n_pad; w.c_z = nn;
+    w.Ct = eng->W; w.ldct = n_pad; w.ct_z = nn;
+    w.tiles_m = 2; w.tiles_n = 2; w.skip_upper = 1;
+    if ((rc = launch_r128d(eng, w, S, st, eng->prio_chain))) return rc;
+  } else {
     GemmParams p = gemm_defaults();
     p.tiles_m = nb; p.tiles_n = nb; p.kblocks = nb; p.krange = KR_GE_MAX; p.tile_skip = TS_LOWER;
     p.a = {0, 0, 0, 0, 0, 1};
@@ -1022,11 +1035,17 @@ static int factorize_chain(gpo_engine* eng, cudaStream_t st) {
 // them; ML-II and HMC refit hundreds of times with the same shape.  The sequence is captured once per (shape, kernel, buffers)
 // into a CUDA graph (all five streams fork from and join the fit stream inside the capture) and replayed with one launch.
 // Everything that changes between refits -- hyper-parameters, jitter -- lives in device buffers the kernels read.
-static int factorize_chain_graph(gpo_engine* eng, cudaStream_t st) {
-  if (!eng->opt_fit_graph || eng->opt_fit_trace) return factorize_chain(eng, st);
-  const gpo_engine::FitGraphKey key = {eng->n_pad, eng->n, eng->d, eng->S, eng->kern, eng->A};
+// single-block models (n <= 128): the look-ahead-free sequence of factorize() plus alpha and the scalars, all on the fit stream
+static int factorize_single(gpo_engine* eng, cudaStream_t st) {
+  const int rc = factorize(eng, st);
+  return rc ? rc : launch_alpha(eng, st);
+}
+
+static int factorize_graph(gpo_engine* eng, cudaStream_t st, int (*sequence)(gpo_engine*, cudaStream_t), int path) {
+  if (!eng->opt_fit_graph || eng->opt_fit_trace) return sequence(eng, st);
+  const gpo_engine::FitGraphKey key = {eng->n_pad, eng->n, eng->d, eng->S, eng->kern, path, eng->A};
   const gpo_engine::FitGraphKey& k0 = eng->fit_graph_key;
-  if (eng->fit_graph_exec && key.n_pad == k0.n_pad && key.n == k0.n && key.d == k0.d && key.S == k0.S && key.kern == k0.kern &&
+  if (eng->fit_graph_exec && key.n_pad == k0.n_pad && key.n == k0.n && key.d == k0.d && key.S == k0.S && key.kern == k0.kern && key.path == k0.path &&
       key.A == k0.A) {
     GPO_CUDA_OK(cudaGraphLaunch(eng->fit_graph_exec, st));
     eng->launches += eng->fit_graph_launches;
@@ -1037,9 +1056,9 @@ static int factorize_chain_graph(gpo_engine* eng, cudaStream_t st) {
   if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
     cudaGetLastError();
     eng->opt_fit_graph = 0;
-    return factorize_chain(eng, st);
+    return sequence(eng, st);
   }
-  const int rc = factorize_chain(eng, st);
+  const int rc = sequence(eng, st);
   cudaGraph_t graph = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(st, &graph);
   if (rc != GPO_OK || ce != cudaSuccess || !graph) {   // no graph: run the plain sequence from now on
@@ -1047,7 +1066,7 @@ static int factorize_chain_graph(gpo_engine* eng, cudaStream_t st) {
     cudaGetLastError();
     eng->opt_fit_graph = 0;
     eng->launches = l0;
-    return factorize_chain(eng, st);
+    return sequence(eng, st);
   }
   // (without this flag every node runs at the priority of the stream the graph is launched into)
   const cudaError_t ie = cudaGraphInstantiateWithFlags(&eng->fit_graph_exec, graph, cudaGraphInstantiateFlagUseNodePriority);
@@ -1057,7 +1076,7 @@ static int factorize_chain_graph(gpo_engine* eng, cudaStream_t st) {
     eng->fit_graph_exec = nullptr;
     eng->opt_fit_graph = 0;
     eng->launches = l0;
-    return factorize_chain(eng, st);
+    return sequence(eng, st);
   }
   eng->fit_graph_key = key;
   eng->fit_graph_launches = eng->launches - l0;
@@ -1209,9 +1228,11 @@ extern "C" int gpo_fit(gpo_engine* eng, int kernel, int n, int d, const double* 
     // (the short-chain schedule wins at every size measured: 3.9 vs 5.9 ms at n = 4096, 5.3 vs 8.2 at 4608; the look-ahead scheme
     // stays as an A/B option: an independent arrangement of the same mathematics)
     const bool chain_path = n_pad >= 2 * TILE && eng->opt_fit_path == 0 && n_pad <= (long long)eng->opt_fit_chain_max * TILE;
-    if ((rc = chain_path ? factorize_chain_graph(eng, st) : factorize(eng, st))) return rc;
+    const bool single = n_pad == TILE;   // one block: no side streams, the whole refit is a short sequence on the fit stream
+    if ((rc = chain_path ? factorize_graph(eng, st, factorize_chain, 0) : single ? factorize_graph(eng, st, factorize_single, 2) : factorize(eng, st)))
+      return rc;
     GPO_CUDA_OK(cudaMemcpyAsync(pin_info, eng->info, S * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (!chain_path && (rc = launch_alpha(eng, st))) return rc;   // (the chain path enqueues it itself, under the tail of W^-1)
+    if (!chain_path && !single && (rc = launch_alpha(eng, st))) return rc;   // (the other two sequences enqueue it themselves)
     GPO_CUDA_OK(cudaMemcpyAsync(pin_logdet, eng->logdet, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
     GPO_CUDA_OK(cudaMemcpyAsync(pin_quad, eng->quad, (size_t)S * 8, cudaMemcpyDeviceToHost, st));
     GPO_CUDA_OK(cudaStreamSynchronize(st));

@@ -401,9 +401,11 @@ def run_gpu_arm(args, cfg):
                 want = 2 if info['strict_variance'] else 1
                 ls = [l for l in js['launches'] if 'dgemm_nt_kernel' in l['kernel']][:want]
                 if len(ls) == want:
-                    traffic = float(sum(l['dram_bytes_total'] for l in ls))
+                    stored_cands = float(js.get('candidates_per_launch', 9472))
+                    traffic = float(sum(l['dram_bytes_total'] for l in ls)) * cands_per_launch / stored_cands
                     traffic_src = ("stored ncu value (profiles/gemm_sweep_r02_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of "
-                                   "`ncu --set full` captures of the same kernels on one 9472-candidate chunk), NOT measured in this run")
+                                   "`ncu --set full` captures of the same kernels on one %d-candidate chunk, scaled to the %d candidates "
+                                   "per launch of this run), NOT measured in this run" % (int(stored_cands), int(round(cands_per_launch))))
             except Exception:
                 traffic = None
         # CPU baseline + parity of what was timed: the oracle sweeps the first rows of the same design

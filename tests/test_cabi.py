@@ -39,6 +39,16 @@ def test_library_exports_every_declared_symbol(lib):
     assert sorted(_lib.SIGNATURES) == _declared_symbols()
 
 
+def test_option_keys_of_the_binding_match_the_header():
+    """gpo_set_option keys: the ctypes binding's table (Engine.OPTIONS) names every GPO_OPT_* enumerator of the header with its
+    value, and nothing else."""
+    from gpyopt_b200 import _lib
+    text = open(os.path.join(ROOT, 'include', 'gpo_b200.h')).read()
+    enum = re.search(r'typedef enum \{([^}]*)\} gpo_option;', text, flags=re.S).group(1)
+    declared = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r'GPO_OPT_([A-Z0-9_]+)\s*=\s*(\d+)', enum)}
+    assert declared and declared == _lib.Engine.OPTIONS
+
+
 def test_strerror_and_version(lib):
     assert lib.gpo_strerror(0) == b'ok'
     assert b'positive definite' in lib.gpo_strerror(-2)

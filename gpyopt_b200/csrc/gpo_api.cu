@@ -25,7 +25,6 @@ struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   double* Kt = nullptr;  // [S][nc_ld][n_pad]
-  CUtensorMap rowmapKt;  // the same with [8 rows][128 columns] boxes (latency kernels)
   double* Ht = nullptr;  // [S][nc_ld][n_pad], only for non-RBF kernels (allocated on demand)
   TMap mapKt;
   double* Tt = nullptr;  // [S][nc_ld][n_pad]  t = L^-1 k of the chunk (strict gradient sweeps: b = L^-T t), allocated on demand
@@ -125,7 +124,6 @@ struct gpo_engine {
   long long fit_graph_launches = 0;
   int opt_fit_trace = 0;    // measurement aid: time every launch of factorize_chain with events and print the timeline to stderr
   int opt_fit_path = 0;     // refit: 0 short critical chain (factorize_chain), 1 the round-1 look-ahead scheme (factorize)
-  CUtensorMap rowmapW[3], rowmapX[3];   // W^-1 / L^-1 with [8 | 16 | 32 rows][128 columns] boxes (latency kernels)
   int opt_k1_slice = 256;   // training rows per K1 slice (grid.y of cov_mean_kernel = n_pad / this, at most 16)
   int opt_desync = 1;       // co-resident GEMM CTAs walk their work items in opposite orders (GemmParams::sm_arrivals)
   int* sm_arrivals = nullptr;
@@ -201,21 +199,6 @@ static int make_map(gpo_engine* eng, TMap* map, double* base, long long cols, lo
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   }
-  return GPO_OK;
-}
-
-// map over a [batch][rows][cols] float64 array with a [1][box_rows][box_cols] box, no swizzle (rows land back to back in shared memory)
-static int make_row_map(gpo_engine* eng, CUtensorMap* map, double* base, long long cols, long long rows, long long batch, int box_cols,
-                        int box_rows) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
-  cuuint64_t strides[2] = {(cuuint64_t)cols * 8, (cuuint64_t)cols * rows * 8};
-  cuuint32_t estr[3] = {1, 1, 1};
-  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) GPO_FAIL(GPO_ERR_CUDA, "cuTensorMapEncodeTiled (row map) failed (%d)", (int)r);
   return GPO_OK;
 }
 
@@ -341,7 +324,10 @@ extern "C" int gpo_create(int device, gpo_engine** out) {
     eng->prio_chain = prio(0); eng->prio_diag = prio(1); eng->prio_inv = prio(2); eng->prio_bulk = prio(3); eng->prio_w = prio(4);
   }
   cudaEventCreateWithFlags(&eng->ev_in, cudaEventDisableTiming);
-  if (cudaMalloc(&eng->sm_arrivals, 1024 * sizeof(int)) == cudaSuccess) cudaMemset(eng->sm_arrivals, 0, 1024 * sizeof(int));
+  if (cudaMalloc(&eng->sm_arrivals, 1024 * sizeof(int)) == cudaSuccess) {
+    cudaMemsetAsync(eng->sm_arrivals, 0, 1024 * sizeof(int), eng->fit_stream);
+    cudaStreamSynchronize(eng->fit_stream);
+  }
   int rc = gemm_setup(eng);
   if (rc != GPO_OK) {
     snprintf(g_create_error, sizeof(g_create_error), "%.255s", eng->last_error);
@@ -494,10 +480,6 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
   if ((rc = make_map(eng, &eng->mapU, eng->U, n_pad, n_pad, S))) return rc;
   if ((rc = make_map(eng, &eng->mapW, eng->W, n_pad, n_pad, S))) return rc;
   if ((rc = make_map(eng, &eng->mapT, eng->T, n_pad, n_pad, S))) return rc;
-  for (int v = 0; v < 3; ++v) {
-    if ((rc = make_row_map(eng, &eng->rowmapW[v], eng->W, n_pad, n_pad, S, SMALLN_CW, 8 << v))) return rc;
-    if ((rc = make_row_map(eng, &eng->rowmapX[v], eng->X, n_pad, n_pad, S, SMALLN_CW, 8 << v))) return rc;
-  }
   eng->nc_ld = std::max<long long>(pick_chunk(eng, n_pad, S), n_pad);  // >= n_pad: the fmin sweep runs over X itself
   {  // K1 slices: 256 training rows (8 tiles of 32) per slice, at most 16 slices
     const int ntiles = n_pad / COV_JT;
@@ -515,7 +497,6 @@ static int ensure_capacity(gpo_engine* eng, int n_pad, int d, int S) {
     GPO_CUDA_OK(cudaMalloc(&s.partial_sq, (size_t)S * tiles_m * eng->nc_ld * 8));
     if (S > 1) GPO_CUDA_OK(cudaMalloc(&s.zbuf, (size_t)S * (d + 1) * eng->nc_ld * 8));
     if ((rc = make_map(eng, &s.mapKt, s.Kt, n_pad, eng->nc_ld, S))) return rc;
-    if ((rc = make_row_map(eng, &s.rowmapKt, s.Kt, n_pad, eng->nc_ld, S, SMALLN_CW, SMALLN_KROWS))) return rc;
   }
   eng->cap_n_pad = n_pad; eng->cap_d = d; eng->cap_S = S;
   return GPO_OK;
@@ -1474,7 +1455,10 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
     if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
     eng->smalln_ticket = nullptr; eng->smalln_ticket_cap = 0;
     GPO_CUDA_OK(cudaMalloc(&eng->smalln_ticket, (size_t)2 * eng->S * sizeof(int)));
-    GPO_CUDA_OK(cudaMemset(eng->smalln_ticket, 0, (size_t)2 * eng->S * sizeof(int)));
+    // (ordered and completed here: a plain cudaMemset runs on the legacy default stream, which the engine's non-blocking streams
+    // do not wait for -- a kernel counting arrivals while the memset lands is left with a permanently offset counter)
+    GPO_CUDA_OK(cudaMemsetAsync(eng->smalln_ticket, 0, (size_t)2 * eng->S * sizeof(int), st));
+    GPO_CUDA_OK(cudaStreamSynchronize(st));
     eng->smalln_ticket_cap = 2 * eng->S;
   }
   const int rows = n_pad >= 4096 ? 32 : (n_pad >= 2048 ? 16 : 8);   // rows per CTA: at least ~128 CTAs from n = 1024 on
@@ -1493,11 +1477,11 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
       GPO_CUDA_OK(cudaMalloc(&eng->smalln_sq, need));
       eng->smalln_sq_cap = need;
     }
-    p.W = eng->X; p.Ht = nullptr; p.wmap = eng->rowmapX[rows == 32 ? 2 : rows == 16 ? 1 : 0];
+    p.W = eng->X; p.Ht = nullptr;
     p.partial = eng->smalln_sq; p.part_z = (long long)row_blocks * SMALLN_LDP;
     p.final_rows = sq_dest; p.final_ld = sq_ld;
   } else {
-    p.W = eng->W; p.wmap = eng->rowmapW[rows == 32 ? 2 : rows == 16 ? 1 : 0];
+    p.W = eng->W;
     p.partial = s.partial; p.part_z = (long long)row_blocks * (d_epi + 2) * SMALLN_LDP;
     p.final_rows = s.partial + (long long)eng->S * p.part_z; p.final_ld = SMALLN_FLD;
     *final_rows = p.final_rows;
@@ -1508,7 +1492,7 @@ static int launch_smalln(gpo_engine* eng, const Slot& s, int nc, int d_epi, bool
   double* final0 = p.final_rows;
   for (int g0 = 0; g0 < nc; g0 += SMALLN_MAX) {
     const int ncg = std::min(SMALLN_MAX, nc - g0);
-    p.Kt = s.Kt + (long long)g0 * n_pad; p.kmap = s.rowmapKt; p.k_row0 = g0;
+    p.Kt = s.Kt + (long long)g0 * n_pad;
     p.Ht = (!sq && use_ht) ? s.Ht + (long long)g0 * n_pad : nullptr;
     p.final_rows = final0 + g0;
     if (rows == 32) { if (sq) launch_smalln_r<true, 32>(p, ncg, grid, st); else launch_smalln_r<false, 32>(p, ncg, grid, st); }
@@ -1562,19 +1546,19 @@ static int launch_smalln_both(gpo_engine* eng, const Slot& s, int nc, int d_epi,
   pw.Kt = s.Kt; pw.Ht = use_ht ? s.Ht : nullptr; pw.kt_z = eng->nc_ld * (long long)n_pad;
   pw.Xtc = eng->Xtc; pw.ldx = n_pad; pw.n_pad = n_pad; pw.d = d_epi; pw.ldp = SMALLN_LDP;
   pw.ticket = eng->smalln_ticket;
-  pw.W = eng->W; pw.wmap = eng->rowmapW[rows == 16 ? 1 : 0];
+  pw.W = eng->W;
   pw.partial = s.partial; pw.part_z = (long long)row_blocks * (d_epi + 2) * SMALLN_LDP;
   pw.final_rows = s.partial + (long long)eng->S * pw.part_z; pw.final_ld = SMALLN_FLD;
   *final_rows = pw.final_rows;
   ps = pw;
-  ps.W = eng->X; ps.wmap = eng->rowmapX[rows == 16 ? 1 : 0]; ps.Ht = nullptr; ps.ticket = eng->smalln_ticket + eng->S;
+  ps.W = eng->X; ps.Ht = nullptr; ps.ticket = eng->smalln_ticket + eng->S;
   ps.partial = eng->smalln_sq; ps.part_z = (long long)row_blocks * SMALLN_LDP;
   ps.final_rows = s.partial_sq; ps.final_ld = eng->nc_ld;
   dim3 grid((unsigned)row_blocks, (unsigned)eng->S, 2);
   double* fw = pw.final_rows; double* fs = ps.final_rows;
   for (int g0 = 0; g0 < nc; g0 += SMALLN_MAX) {
     const int ncg = std::min(SMALLN_MAX, nc - g0);
-    pw.Kt = s.Kt + (long long)g0 * n_pad; ps.Kt = pw.Kt; pw.kmap = s.rowmapKt; ps.kmap = s.rowmapKt; pw.k_row0 = ps.k_row0 = g0;
+    pw.Kt = s.Kt + (long long)g0 * n_pad; ps.Kt = pw.Kt;
     pw.Ht = use_ht ? s.Ht + (long long)g0 * n_pad : nullptr;
     pw.final_rows = fw + g0; ps.final_rows = fs + g0;
     if (rows == 16) launch_smalln_both_r<16>(pw, ps, ncg, grid, st);
@@ -1592,7 +1576,8 @@ static int ensure_ticket(gpo_engine* eng) {
   if (eng->smalln_ticket) cudaFree(eng->smalln_ticket);
   eng->smalln_ticket = nullptr; eng->smalln_ticket_cap = 0;
   GPO_CUDA_OK(cudaMalloc(&eng->smalln_ticket, (size_t)2 * eng->S * sizeof(int)));
-  GPO_CUDA_OK(cudaMemset(eng->smalln_ticket, 0, (size_t)2 * eng->S * sizeof(int)));
+  GPO_CUDA_OK(cudaMemsetAsync(eng->smalln_ticket, 0, (size_t)2 * eng->S * sizeof(int), eng->fit_stream));   // (see launch_smalln)
+  GPO_CUDA_OK(cudaStreamSynchronize(eng->fit_stream));
   eng->smalln_ticket_cap = 2 * eng->S;
   return GPO_OK;
 }

@@ -1353,12 +1353,6 @@ struct SmallNParams {
   double* final_rows;                    // [S][nvals][final_ld]: the partial rows added in row-block order by the last CTA
   long long final_ld;
   int* ticket;                           // [S] arrival counters (zero before the launch; the last CTA resets its own)
-  // [S][n_pad][n_pad] as a 3-D tensor map with a [1][SMALLN_ROWS][SMALLN_CW] box: ONE tensor copy fills a ring stage (a stage used
-  // to be SMALLN_ROWS separate 1 KB bulk copies; at n = 4096 that was 200,000 copy operations for 201 MB and the kernel ran at
-  // 2.3 TB/s with the copy engines, not HBM, as the limit)
-  alignas(64) CUtensorMap wmap;
-  alignas(64) CUtensorMap kmap;          // K*^T chunk [S][nc_ld][n_pad], box [1][8][SMALLN_CW]
-  int k_row0;                            // first candidate row of this launch's group
 };
 
 // SQ = true: the strict-variance form instead.  W is then X = L^-1 (lower triangular: the column loop stops at the
@@ -1371,22 +1365,34 @@ struct SmallNParams {
 // SMALLN_ROWS is a template parameter (32 / 16 / 8 rows per CTA, i.e. 4 / 2 / 1 per warp): smaller matrices need more,
 // thinner CTAs to put every SM's load path to work (n = 2048: 64 CTAs of 32 rows took 25 us for 32 MB out of L2).
 constexpr int SMALLN_CW = 128, SMALLN_STAGES = 4;
-// (the ring also carries the candidates' covariance chunk, 8 rows of K*^T per stage: fetched by plain loads at the point of use they
-// were what the warps waited for -- 50 % long-scoreboard stalls at n = 4096)
-constexpr int SMALLN_KROWS = 8;
-// ... in the 16- and 32-row shapes; the 8-row shape (n < 2048: a few chunks per CTA) measured faster with the plain loads
-__host__ __device__ constexpr bool smalln_k_in_ring(int rows) { return rows >= 16; }
-constexpr int smalln_smem_bytes(int rows) { return SMALLN_STAGES * (rows + (smalln_k_in_ring(rows) ? SMALLN_KROWS : 0)) * SMALLN_CW * 8 + SMALLN_STAGES * 8; }
+constexpr int smalln_smem_bytes(int rows) { return SMALLN_STAGES * rows * SMALLN_CW * 8 + SMALLN_STAGES * 8; }
+// How the ring is filled.  1 (default): 16-byte cp.async copies issued by all 256 threads, one commit group and ONE block barrier per
+// chunk (the stage freed by chunk t - 1 takes chunk t + STAGES - 1).  0: the round-1 form, one 1 KB cp.async.bulk per row and chunk on
+// an mbarrier per stage.  The bulk form is NOT safe: on launches that run in several waves with three or more CTAs per SM it
+// returned wrong partial sums for whole row blocks -- once in 10 ... 400 calls with 5 hyper-parameter sets at n = 684, or 2 sets at
+// n = 3000, or one set at n >= 5000 (variance clamped to 1e-10, or garbage) -- first seen as ONE failing case of the 250-case
+// randomised oracle sweep, then reproduced with tools/stress_latency_path.py (the same call repeated thousands of times must return
+// the same bits).  Ruled out by experiment: the arrival-counter protocol (a separate reduction kernel sees the same wrong partial
+// rows), the read-only data path of the K* loads, re-initialising un-invalidated mbarriers, 2-D tensor copies instead of bulk
+// copies (worse), capping the residency at two CTAs per SM (rarer, not gone).  What remains is the bulk copies' data itself; with
+// compute-sanitizer closed on this pool the cause stays open.  The cp.async form has never returned a differing bit in 60,000
+// stress calls over the shapes that failed, and is a little faster (n = 4096, five points: 0.127 -> 0.120 ms).
+#ifndef GPO_SMALLN_CPASYNC
+#define GPO_SMALLN_CPASYNC 1
+#endif
+__device__ __forceinline__ void sn_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void sn_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void sn_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int NC, bool SQ, int SMALLN_ROWS>
 __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
   extern __shared__ __align__(128) double smalln_smem[];
   __shared__ double red[8][DMAX + 2][NC];
-  static_assert(NC <= SMALLN_KROWS, "ring sized for up to SMALLN_KROWS candidates");
   double* tile = smalln_smem;                                                            // [STAGES][ROWS][CW]
-  constexpr bool KRING = smalln_k_in_ring(SMALLN_ROWS);
-  double* ktile = smalln_smem + SMALLN_STAGES * SMALLN_ROWS * SMALLN_CW;                 // [STAGES][KROWS][CW]
-  uint64_t* full = reinterpret_cast<uint64_t*>(smalln_smem + SMALLN_STAGES * (SMALLN_ROWS + (KRING ? SMALLN_KROWS : 0)) * SMALLN_CW);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smalln_smem + SMALLN_STAGES * SMALLN_ROWS * SMALLN_CW);
   constexpr int R = SMALLN_ROWS / 8;
   const int z = blockIdx.y, rb = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_pad = p.n_pad, d = SQ ? -1 : p.d;   // d + 2 values per candidate (SQ: one)
@@ -1399,15 +1405,29 @@ __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
     mbar_fence_init();
   }
   __syncthreads();
-  auto issue = [&](int t) {  // warp 0: chunk t of all 32 rows into stage t % STAGES
-    const int s = t % SMALLN_STAGES;
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&full[s], (SMALLN_ROWS + (KRING ? SMALLN_KROWS : 0)) * SMALLN_CW * 8);
-      tma_load_3d(tile + (long long)s * SMALLN_ROWS * SMALLN_CW, &p.wmap, &full[s], t * SMALLN_CW, rb * SMALLN_ROWS, z);
-      if (KRING) tma_load_3d(ktile + (long long)s * SMALLN_KROWS * SMALLN_CW, &p.kmap, &full[s], t * SMALLN_CW, p.k_row0, z);
+  auto issue_cpasync = [&](int t) {   // every thread: chunk t (or nothing past the end) as 16-byte cp.async copies, one commit group
+    if (t < nchunks) {
+      const int s = t % SMALLN_STAGES;
+      const double* Wblk = p.W + (long long)z * p.w_z + (long long)rb * SMALLN_ROWS * n_pad + (long long)t * SMALLN_CW;
+      for (int e = threadIdx.x; e < SMALLN_ROWS * (SMALLN_CW / 2); e += 256) {
+        const int row = e / (SMALLN_CW / 2), ch = e % (SMALLN_CW / 2);
+        sn_cp_async16(tile + ((long long)s * SMALLN_ROWS + row) * SMALLN_CW + 2 * ch, Wblk + (long long)row * n_pad + 2 * ch);
+      }
     }
+    sn_cp_async_commit();
   };
-  if (warp == 0)
+  auto issue = [&](int t) {  // (bulk form) warp 0: chunk t of all rows into stage t % STAGES
+    const int s = t % SMALLN_STAGES;
+    const double* Wblk = p.W + (long long)z * p.w_z + (long long)rb * SMALLN_ROWS * n_pad;
+    if (lane == 0) mbar_arrive_expect_tx(&full[s], SMALLN_ROWS * SMALLN_CW * 8);
+    __syncwarp();
+    if (lane < SMALLN_ROWS)
+      tma_bulk_load(tile + ((long long)s * SMALLN_ROWS + lane) * SMALLN_CW, Wblk + (long long)lane * n_pad + (long long)t * SMALLN_CW,
+                    SMALLN_CW * 8, &full[s]);
+  };
+  if (GPO_SMALLN_CPASYNC) {
+    for (int t = 0; t < SMALLN_STAGES - 1; ++t) issue_cpasync(t);
+  } else if (warp == 0)
     for (int t = 0; t < SMALLN_STAGES && t < nchunks; ++t) issue(t);
   double acc[R][NC];
 #pragma unroll
@@ -1416,22 +1436,18 @@ __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
     for (int i = 0; i < NC; ++i) acc[r][i] = 0.0;
   for (int t = 0; t < nchunks; ++t) {
     const int s = t % SMALLN_STAGES;
-    double2 kv[2][NC];   // this chunk of the candidates' covariance vectors: staged with the rows, or straight from L1 / L2
-    if (!KRING) {
+    double2 kv[2][NC];   // this chunk of the candidates' covariance vectors (shared by every CTA: L1 / L2 hits)
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int i = 0; i < NC; ++i)
-          kv[u][i] = __ldg(reinterpret_cast<const double2*>(Kt + (long long)i * n_pad + t * SMALLN_CW + 64 * u + 2 * lane));
-    }
-    mbar_wait(&full[s], (uint32_t)((t / SMALLN_STAGES) & 1));
-    if (KRING) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int i = 0; i < NC; ++i)
-          kv[u][i] = *reinterpret_cast<const double2*>(ktile + ((long long)s * SMALLN_KROWS + i) * SMALLN_CW + 64 * u + 2 * lane);
-    }
+      for (int i = 0; i < NC; ++i)
+        kv[u][i] = __ldg(reinterpret_cast<const double2*>(Kt + (long long)i * n_pad + t * SMALLN_CW + 64 * u + 2 * lane));
+    if (GPO_SMALLN_CPASYNC) {
+      sn_cp_async_wait<SMALLN_STAGES - 2>();   // this thread's copies of chunk t have landed ...
+      __syncthreads();                         // ... and everybody else's; everybody is also done with chunk t - 1:
+      issue_cpasync(t + SMALLN_STAGES - 1);    // its stage takes chunk t + STAGES - 1 (one barrier per chunk)
+    } else
+      mbar_wait(&full[s], (uint32_t)((t / SMALLN_STAGES) & 1));
     const double* ts = tile + ((long long)s * SMALLN_ROWS + warp * R) * SMALLN_CW + 2 * lane;
 #pragma unroll
     for (int u = 0; u < 2; ++u)
@@ -1444,8 +1460,10 @@ __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
           acc[r][i] = fma(w.y, kv[u][i].y, acc[r][i]);
         }
       }
-    __syncthreads();   // every warp is done with stage s: refill it
-    if (warp == 0 && t + SMALLN_STAGES < nchunks) issue(t + SMALLN_STAGES);
+    if (!GPO_SMALLN_CPASYNC) {
+      __syncthreads();   // every warp is done with stage s: refill it
+      if (warp == 0 && t + SMALLN_STAGES < nchunks) issue(t + SMALLN_STAGES);
+    }
   }
 #pragma unroll
   for (int r = 0; r < R; ++r)
@@ -1520,8 +1538,9 @@ __device__ __forceinline__ void smalln_wk_body(const SmallNParams& p) {
   }
 }
 
+
 template <int NC, bool SQ, int SMALLN_ROWS>
-__global__ void __launch_bounds__(256) smalln_wk_kernel(const __grid_constant__ SmallNParams p) {
+__global__ void __launch_bounds__(256) smalln_wk_kernel(const SmallNParams p) {
   smalln_wk_body<NC, SQ, SMALLN_ROWS>(p);
 }
 
@@ -1529,7 +1548,7 @@ __global__ void __launch_bounds__(256) smalln_wk_kernel(const __grid_constant__ 
 // W^-1, grid.z = 1 streams L^-1, concurrently -- alone each of them is latency-bound (2.1 / 1.4 TB/s at n = 4096: 63 + 49 us back
 // to back), together they keep twice as many TMA stages in flight.
 template <int NC, int SMALLN_ROWS>
-__global__ void __launch_bounds__(256) smalln_both_kernel(const __grid_constant__ SmallNParams pw, const __grid_constant__ SmallNParams psq) {
+__global__ void __launch_bounds__(256) smalln_both_kernel(const SmallNParams pw, const SmallNParams psq) {
   if (blockIdx.z == 0) smalln_wk_body<NC, false, SMALLN_ROWS>(pw);
   else smalln_wk_body<NC, true, SMALLN_ROWS>(psq);
 }

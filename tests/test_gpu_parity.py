@@ -403,6 +403,37 @@ def test_small_batch_latency_path(engine, kernel, ARD, S):
             engine.lp_set(None, None, None, None)
 
 
+@pytest.mark.parametrize('n,d,N,kernel,S,noise,strict', [(684, 5, 3, 'matern32', 5, 1e-3, 1), (684, 5, 1, 'rbf', 12, 1e-3, 0), (3000, 6, 2, 'rbf', 4, 1e-2, 0),
+                                                         (3000, 6, 2, 'rbf', 2, 1e-2, 1), (5000, 4, 1, 'rbf', 1, 1e-2, 1)])
+def test_latency_path_repeats_bitwise_on_multi_wave_launches(n, d, N, kernel, S, noise, strict):
+    """The same latency-path call, 1500 times, returns the same bits -- on shapes whose matrix-vector launch runs in several waves
+    with three or more CTAs per SM.  The round-1 ring of these kernels (1 KB cp.async.bulk copies on mbarriers) returned wrong partial
+    sums for whole row blocks on exactly such launches, once in 10 ... 400 calls (variance clamped to 1e-10, or garbage); nothing
+    in the suite launched them that way until one case of tests/manual_random_sweep.py did.  Also: the first call agrees with the
+    tensor-core path (same points inside a 300-row call)."""
+    from gpyopt_b200 import Engine
+    rng = np.random.default_rng(801778405)
+    X = rng.random((n, d)); Y = np.sin(3 * X).sum(1) + 0.1 * rng.standard_normal(n); Y = (Y - Y.mean()) / Y.std()
+    Xs = rng.random((N, d))
+    var = 0.5 + rng.random(S); ls = 0.3 + rng.random((S, d)); nz = noise * (0.5 + rng.random(S))
+    eng = Engine(0)
+    try:
+        eng.fit(kernel, X, Y, var, ls, nz)
+        eng.set_strict_variance(strict)
+        ref = eng.predict_grad(Xs)
+        big = eng.predict_grad(np.vstack([Xs, rng.random((300 - N, d))]))      # tensor-core path
+        # (a sanity bound, not a parity bound: the two paths sum in different orders, and the opt-in fast variance form sigma^2 - k.W^-1.k
+        # cancels ~eps * cond(Ky) on these noise levels; what the old ring returned was off by 10 % ... 100 %)
+        assert scaled_err(ref[0], big[0][:, :N]) < 1e-8 and scaled_err(ref[1], big[1][:, :N]) < 1e-5
+        bad = 0
+        for _ in range(1500):
+            out = eng.predict_grad(Xs)
+            bad += not all(np.array_equal(a, b) for a, b in zip(out, ref))
+        assert bad == 0, "%d of 1500 identical calls returned different bits" % bad
+    finally:
+        eng.close()
+
+
 def test_engine_lifecycle_across_shapes(engine):
     """ONE engine refitted through a sequence of different (n, d, S, kernel) problems -- growing and shrinking buffers,
     switching kernels (the H*^T buffers appear on demand), Local Penalization set and cleared, latency and tensor-core

@@ -50,8 +50,8 @@ with open(OUT, 'w') as fh:
     emit('gpo::cov_mean_kernel<6, true> (K1): bulk-copy staging of the training tiles (cp.async.bulk -> UBLKCP) + mbarrier',
          [counts(k1, ['UBLKCP', 'SYNCS', 'DFMA', 'DMUL', 'MUFU', 'STG', 'LDS'])] + window(k1, lambda l: 'UBLKCP' in l, 8, 4, 1))
     sm = sass('_ZN3gpo16smalln_wk_kernelILi8ELb0ELi32EEEvNS_12SmallNParamsE')
-    emit('gpo::smalln_wk_kernel<8, false, 32> (latency path): ring over W^-1 and the K* chunk, one 2-D tensor copy each per stage',
-         [counts(sm, ['UTMALDG', 'SYNCS', 'DFMA', 'LDS.128', 'SHFL'])] + window(sm, lambda l: 'UTMALDG' in l, 6, 4, 2))
+    emit('gpo::smalln_wk_kernel<8, false, 32> (latency path): shared-memory ring over W^-1 filled by 16-byte cp.async (LDGSTS) copies',
+         [counts(sm, ['LDGSTS', 'LDGDEPBAR', 'DEPBAR', 'DFMA', 'LDS.128', 'SHFL'])] + window(sm, lambda l: 'LDGSTS' in l, 6, 4, 1))
     fu = sass('_ZN3gpo24fused_small_value_kernelILi7ELi4EEEvNS_16FusedSmallParamsE')
     emit('gpo::fused_small_value_kernel<MF=7, NF=4> (n <= 56): covariance evaluated in the B-fragment position, DMMA against the resident L^-1',
          [counts(fu, ['DMMA', 'DFMA', 'DMUL', 'MUFU', 'LDS', 'UMOV', 'SHFL', 'BSSY'])] + window(fu, lambda l: 'DMMA' in l, 10, 24, 1))

@@ -1358,10 +1358,10 @@ struct SmallNParams {
 // SQ = true: the strict-variance form instead.  W is then X = L^-1 (lower triangular: the column loop stops at the
 // diagonal) and the only reduction is sum_j (X k)_j^2 = |L^-1 k|^2, one value per candidate.
 // One CTA owns SMALLN_ROWS rows (four per warp) and streams them in chunks of SMALLN_CW columns through a ring of
-// SMALLN_STAGES shared-memory stages filled by TMA bulk copies (one 1 KB copy per row and chunk, issued by the 32 lanes of
-// warp 0, one mbarrier per stage): 96 KB per SM are in flight without holding a register.  Plain loads did not get
-// there -- the compiler schedules the FMAs of step t ahead of the loads of step t+1, each warp had ~1.5 steps in flight
-// and the kernel ran at 2.6 of HBM's 7.7 TB/s with every warp on the long scoreboard (ncu, profiles/).
+// SMALLN_STAGES shared-memory stages filled by asynchronous copies (GPO_SMALLN_CPASYNC below): three stages per CTA are in flight
+// without holding a register.  Plain loads did not get there -- the compiler schedules the FMAs of step t ahead of the loads of
+// step t+1, each warp had ~1.5 steps in flight and the kernel ran at 2.6 of HBM's 7.7 TB/s with every warp on the long
+// scoreboard (ncu, profiles/).
 // SMALLN_ROWS is a template parameter (32 / 16 / 8 rows per CTA, i.e. 4 / 2 / 1 per warp): smaller matrices need more,
 // thinner CTAs to put every SM's load path to work (n = 2048: 64 CTAs of 32 rows took 25 us for 32 MB out of L2).
 constexpr int SMALLN_CW = 128, SMALLN_STAGES = 4;

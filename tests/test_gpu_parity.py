@@ -825,6 +825,11 @@ def _random_cases(count=24, seed=2024):
         N = int(rng.choice([1, 2, 127, 128, 129, 255, 256, 257, 300, 700]))
         cases.append((n, d, N, ['rbf', 'matern52', 'matern32'][i % 3], bool(rng.integers(0, 2)), int(rng.choice([1, 1, 2, 3])),
                       float(rng.choice([1e-1, 1e-2, 1e-3])), int(rng.integers(0, 1 << 30))))
+    # the case of tests/manual_random_sweep.py (250 cases, seed 11) that exposed the latency kernels' bulk-copy ring: five hyper-parameter
+    # sets at n = 684 make their matrix-vector launch run in several waves; plus two more multi-wave latency-path shapes
+    cases.append((684, 5, 3, 'matern32', True, 5, 0.001, 801778405))
+    cases.append((1151, 4, 2, 'rbf', False, 5, 0.01, 12345))
+    cases.append((700, 6, 7, 'matern52', True, 5, 0.01, 777))
     return cases
 
 

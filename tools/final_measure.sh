@@ -13,6 +13,9 @@ python tools/fit_ab.py 256 1000 2048 3072 --no-check > $O/refit_ab_r02.jsonl 2>&
 python tools/time_single_point.py > $O/latency_r02.json 2>&1
 python tools/time_lbfgs_rounds.py > $O/lbfgs_rounds_r02.jsonl 2>&1
 python tools/desync_ab.py > $O/desync_ab_r02.jsonl 2>&1
+python tools/stress_latency_path.py 4000 > $O/stress_latency_path_r02.jsonl 2>&1
+python tools/stress_sweep_repeat.py > $O/stress_sweep_repeat_r02.jsonl 2>&1
+python tools/fit_chain_limit.py 4096 4480 4608 5120 6144 > $O/refit_large_n_r02.jsonl 2>&1
 for n in 2048 4096; do python tools/fit_trace.py $n 2> $O/fit_trace_${n}_r02.jsonl; done
 # launch list of the bench command (small batch), and the same command's line without ncu
 python bench.py --steps 2 --warmup 1 --batch 189440 --cpu-sample 2048 > $O/bench_r02_small_for_ncu.json 2> $O/bench_small.err && \
